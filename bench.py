@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- text-line-pixels/sec of one full training step of clstm's hot path on B200.
+
+A "step" = one pass of the hot path over one minibatch of synthetic text lines:
+    forward (bidi NPLSTM + Softmax) -> CTC alignment -> backward -> [grad all-reduce] -> clip+SGD update -> decode
+Workload (BASELINE.json configs[1], "cfg2"): nhidden=100, H=48, T=500, 32 lines per GPU, 83 classes, fp32.
+Multi-GPU: one process per GPU (torchrun), lines sharded 32 per rank (weak scaling), one NCCL all-reduce of the
+flat fp32 derivative buffer per step issued from inside libclstm_b200.so.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1     # the reference's CPU path (oracle port)
+
+Prints ONE JSON line (rank 0).  `value` = whole-job px/s with the batch resident in HBM; `e2e` = the same through
+clstm_b200_train_step with pinned host buffers (H2D of the lines, D2H of the decoded result inside the timed
+region); `roofline` for the dominant kernel from live CUDA-event phase timings; `cpu_baseline` = the CPU oracle
+port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from clstm_b200 import synth  # noqa: E402
+
+LR, MOM, CLIP = 1e-4, 0.9, 100.0   # clstmocrtrain defaults (clstmocrtrain.cc:99-115), gradient_clip clstm.cc:204
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nhidden", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=32, help="lines per GPU")
+    ap.add_argument("--T", type=int, default=500)
+    ap.add_argument("--Tmax", type=int, default=0, help="if > T: variable lengths uniform in [T, Tmax]")
+    ap.add_argument("--nclasses", type=int, default=83)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    t = "T=%d" % a.T if a.Tmax <= a.T else "T=%d..%d" % (a.T, a.Tmax)
+    tag = "cfg2 " if (a.nhidden, a.batch, a.T, a.Tmax <= a.T) == (100, 32, 500, True) else ""
+    return "%sbidi-LSTM nhidden=%d H=48 %s batch=%d/GPU nclasses=%d fwd+CTC+bwd+update" % (
+        tag, a.nhidden, t, a.batch, a.nclasses)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batch(a, rank):
+    T = (a.T, a.Tmax) if a.Tmax > a.T else a.T
+    return synth.make_lines(a.batch, T, 48, a.nclasses, seed=1000 + rank)
+
+
+# ------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference(a, budget_s, threads):
+    """Times the CPU oracle port (reference algorithm, oracle/clstm_oracle.cc) on a bounded sample of the
+    workload: `threads` host threads, one line each per repetition."""
+    from oracle import binding as ob
+    net = ob.BidiOracle(48, a.nhidden, a.nclasses, seed=0.222)
+    x, T, labels, L = make_batch(a, 0)
+    nl = max(1, min(a.batch, threads))
+    n_cols = int(T[:nl].sum())
+    xs, Ts, Ls = x[: n_cols], T[:nl], L[:nl]
+    labs = labels[: int(L[:nl].sum())]
+    t = net.train_lines(xs, Ts, labs, Ls, LR, MOM, threads=threads, reps=1)      # warm-up + calibration
+    reps = int(max(1, min(50, budget_s / max(t, 1e-3))))
+    t = net.train_lines(xs, Ts, labs, Ls, LR, MOM, threads=threads, reps=reps)
+    px = reps * n_cols * 48
+    return {"value": px / t, "unit": "px/s", "cores": threads, "kind": "port",
+            "sample": "%d line(s) x %d rep(s) of the workload (T=%s), %d host thread(s), fwdbwd per line + one "
+                      "sgd_update per rep; reference's O(T^2) anynan asserts excluded" % (nl, reps, a.T, threads),
+            "seconds": t}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    for _ in range(max(0, a.warmup)):
+        cpu_reference(a, 0.5, cores)
+    t0 = time.time()
+    for _ in range(max(1, a.steps)):
+        vals.append(cpu_reference(a, 2.0, cores))
+    px = sum(v["value"] * v["seconds"] for v in vals)
+    sec = sum(v["seconds"] for v in vals)
+    val = px / sec
+    out = {"impl": "reference", "metric": "text-line-pixels/sec (fwd+bwd+CTC+update)", "value": val, "unit": "px/s",
+           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * sec / max(1, a.steps),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(a), "note": "reference CPU path = oracle port (Eigen absent, "
+                      "reference not buildable); each step = bounded sample, all host threads"},
+           "cpu_baseline": {"value": val, "unit": "px/s", "cores": cores, "kind": "port", "sample": vals[-1]["sample"]},
+           "e2e": {"value": val, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import clstm_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (a.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    net = clstm_b200.Net(48, a.nhidden, a.nclasses, device=local)
+    net.set_params(synth.reference_init(48, a.nhidden, a.nclasses, seed=0.222))
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(clstm_b200.Net.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        net.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    x, T, labels, L = make_batch(a, rank)
+    N = int(T.sum())
+    px_per_step_rank = N * 48
+    # pinned host copies for the end-to-end path
+    hx = clstm_b200.pinned_array(x.shape, np.float32); hx[...] = x
+    stream = torch.cuda.ExternalStream(net.stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def l2_flush():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            l2_flush()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(e0.elapsed_time(e1) for e0, e1 in evs)   # ms
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident-batch measurement (value)
+    net.upload_batch(hx, T, labels, L)
+    step_res = lambda: net.step_resident(LR, MOM, CLIP)  # noqa: E731
+    for _ in range(max(3, a.warmup)):
+        l2_flush(); step_res()
+    net.synchronize()
+    barrier()
+    net.profile(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.time()
+    ms_total = timed(step_res, a.steps)
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1) if sampler else None
+    stats = net.phase_stats()
+    net.profile(False)
+    ms_total = max_over_ranks(ms_total)
+    value = world * px_per_step_rank * a.steps / (ms_total / 1000.0)
+
+    # ---- end to end through the public C-ABI call with host buffers
+    mpl = int(T.max()) // 2 + 1
+    e2e_fn = lambda: net.train_step(hx, T, labels, L, LR, MOM, CLIP, max_per_line=mpl)  # noqa: E731
+    for _ in range(3):
+        e2e_fn()
+    barrier()
+    ms_e2e = max_over_ranks(timed(e2e_fn, a.steps))
+    barrier()
+    e2e = world * px_per_step_rank * a.steps / (ms_e2e / 1000.0)
+    h2d = int(x.nbytes + T.nbytes * 5 + labels.nbytes + 8 * len(T))
+    d2h = int(len(T) * 4 + 2 * len(T) * mpl * 4 + 4)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel from the live phase timings
+    pk = peaks()
+    no, ni, nc = a.nhidden, 48, a.nclasses
+    P = synth.nparams(ni, no, nc)
+    S_lat = float(np.sum(T.astype(np.int64) * (2 * L + 1)))
+    alg = {   # per launch of the phase (one step, this rank): (flops, bytes, bound)
+        "xproj_gemm": (2.0 * 2 * N * 4 * no * ni, None, "tensor"),
+        "lstm_fwd": (2.0 * 2 * N * 4 * no * no, None, "tensor"),
+        "softmax_fwd": (2.0 * N * nc * 2 * no, None, "tensor"),
+        "ctc_align": (None, 8.0 * N * nc, "hbm"),
+        "softmax_bwd": (2.0 * 2 * N * nc * 2 * no, None, "tensor"),
+        "lstm_bwd": (2.0 * 2 * N * 4 * no * no, None, "tensor"),
+        "wgrad_gemm": (2.0 * 2 * N * 4 * no * (ni + no), None, "tensor"),
+        "dx_gemm": (2.0 * 2 * N * 4 * no * ni, None, "tensor"),
+        "sgd_update": (None, 16.0 * P, "hbm"),
+        "decode": (None, 4.0 * N * nc, "hbm"),
+    }
+    kernels = {}
+    for name, (ms, launches) in stats.items():
+        if name in alg and ms > 0:
+            fl, by, bound = alg[name]
+            per = ms / a.steps / 1000.0
+            if bound == "tensor":
+                ach = fl / per / 1e12; peak = pk["bf16_tflops"]; unit = "TFLOP/s"
+            else:
+                ach = by / per / 1e9; peak = pk["hbm_gbs"]; unit = "GB/s"
+            kernels[name] = {"ms_per_step": ms / a.steps, "launches_per_step": launches / a.steps, "bound": bound,
+                             "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    roof = dict(kernels[dom]); roof["kernel"] = dom; roof["traffic"] = None
+    roof["peak_source"] = pk["src"]
+    roof.pop("ms_per_step"); roof.pop("launches_per_step")
+    roof["kernel_ms"] = kernels[dom]["ms_per_step"]
+    launches = int(sum(c for (_, c) in stats.values()))
+
+    out = {"metric": "text-line-pixels/sec (fwd+bwd+CTC+update)", "value": value, "unit": "px/s", "n_gpus": world,
+           "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(a), "lines_per_gpu": a.batch, "global_lines": a.batch * world,
+                      "columns_per_gpu": N, "l2": "flushed between timed steps (256 MiB memset)",
+                      "weights": "reference LCG init (negbiased, 0.01), seed 0.222", "lr": LR, "momentum": MOM,
+                      "lstm_kernel": net.lstm_variant, "parallelism": "dp%d" % world},
+           "e2e": {"value": e2e, "unit": "px/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h},
+           "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels}
+    if world == 1 and not a.no_cpu_baseline:
+        cb = cpu_reference(a, a.cpu_seconds, 1)
+        cb.pop("seconds")
+        out["cpu_baseline"] = cb
+    else:
+        out["cpu_baseline"] = None
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -1,0 +1,876 @@
+// capi.cu -- the extern "C" boundary (include/clstm_b200.h): device-resident bidi net, batch staging,
+// kernel orchestration on one stream, parameter layout conversion, NCCL gradient sum, measurement hooks.
+// No CPU compute path exists here: every entry point needs a CUDA device.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/clstm_b200.h"
+#include "kernels.h"
+
+using namespace cb200;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr)            \
+  do {                       \
+    int r_ = (expr);         \
+    if (r_) return r_;       \
+  } while (0)
+
+enum Phase { PH_H2D, PH_XPROJ, PH_LSTM_FWD, PH_SOFTMAX_FWD, PH_CTC, PH_SOFTMAX_BWD, PH_LSTM_BWD, PH_WGRAD, PH_DX,
+             PH_ALLREDUCE, PH_UPDATE, PH_DECODE, PH_D2H, PH_COUNT };
+const char* kPhaseNames[PH_COUNT] = {"h2d", "xproj_gemm", "lstm_fwd", "softmax_fwd", "ctc_align", "softmax_bwd",
+                                     "lstm_bwd", "wgrad_gemm", "dx_gemm", "allreduce", "sgd_update", "decode", "d2h"};
+
+// ---- minimal NCCL surface, resolved at run time (the library under torch is reused when already loaded) ----
+struct Id128 { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+int load_nccl() {
+  if (g_nccl.lib) return 0;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail("NCCL not found: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail("NCCL symbols missing");
+  g_nccl.lib = h;
+  return 0;
+}
+
+template <class T>
+int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CU(cudaMalloc((void**)p, n * sizeof(T)));
+  return 0;
+}
+template <class T>
+void dev_free(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+}  // namespace
+
+struct clstm_b200_net {
+  clstm_b200_cfg cfg;
+  int ni, no, nc, nf;
+  int num_sms = 148;
+  cudaStream_t st = nullptr;
+
+  // ---- parameters, DEVICE layout: [dir0: Wx(4no x ni) | bias(4no) | R(4no x no)] [dir1: ...] [W1(nc x 2no) | b1(nc)]
+  // rows of the LSTM blocks are gate-interleaved: r = 4*j + g, g: 0=gi(WGI) 1=gf(WGF) 2=go(WGO) 3=ci(WCI)
+  size_t P = 0;
+  size_t oWx[2], oB[2], oR[2], oW1, oB1;
+  float *v = nullptr, *d = nullptr, *g = nullptr;   // weights, Params.d (derivative+momentum), this step's derivatives
+  float* Rt[2] = {nullptr, nullptr};
+  bool g_pending = false;
+
+  // ---- batch capacity and buffers
+  int capN = 0, capB = 0, capLab = 0;
+  long long capLat = 0;
+  float *x = nullptr, *XP[2] = {}, *G[2] = {}, *C[2] = {}, *H = nullptr, *Hprev[2] = {}, *out = nullptr,
+        *aligned = nullptr, *delta = nullptr, *dH = nullptr, *DG[2] = {}, *dx = nullptr;
+  float *lm = nullptr, *lr = nullptr, *rl = nullptr;
+  int* meta = nullptr;          // device: T | off | L | lab_off | order | labels
+  long long* lat_off = nullptr;
+  int* status = nullptr;
+  int* amax[2] = {};
+  float* amaxv[2] = {};
+  int *dcls[2] = {}, *dlocs[2] = {}, *dcnt[2] = {};
+  int capDec = 0;               // max_per_line capacity of the decode buffers
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+  // pinned host staging for metadata and small results
+  int* h_meta = nullptr;
+  long long* h_lat = nullptr;
+  int* h_small = nullptr;       // status + counts
+  cudaEvent_t meta_done = nullptr;   // guards re-use of the pinned staging buffers
+
+  std::vector<int> hT, hOff, hL, hLabOff, hOrder;
+  Lines ln{};
+  bool have_batch = false, have_forward = false, have_labels = false, have_ctc = false, raw_targets = false;
+  const char* variant = "generic";
+
+  // ---- measurement
+  bool prof = false;
+  struct Rec { int ph; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  float ph_ms[PH_COUNT] = {};
+  long long ph_launch[PH_COUNT] = {};
+
+  // ---- communicator
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+namespace {
+
+struct Scope {  // brackets one phase with events when profiling is on
+  clstm_b200_net* n;
+  int ph;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Scope(clstm_b200_net* net, int phase) : n(net), ph(phase) {
+    if (!n->prof) return;
+    a = get();
+    b = get();
+    cudaEventRecord(a, n->st);
+  }
+  cudaEvent_t get() {
+    cudaEvent_t e;
+    if (!n->pool.empty()) { e = n->pool.back(); n->pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  }
+  void launches(int k) { n->ph_launch[ph] += k; }
+  ~Scope() {
+    if (!n->prof) return;
+    cudaEventRecord(b, n->st);
+    n->recs.push_back({ph, a, b});
+  }
+};
+
+void harvest(clstm_b200_net* n) {  // stream must be idle
+  for (auto& r : n->recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) n->ph_ms[r.ph] += ms;
+    n->pool.push_back(r.a);
+    n->pool.push_back(r.b);
+  }
+  n->recs.clear();
+}
+
+int gate_ref_index(int g) {  // position of gate g's matrix inside a direction's reference block [WCI,WGF,WGI,WGO]
+  static const int m[4] = {2, 1, 3, 0};
+  return m[g];
+}
+
+// reference flat (walk_params order, col-major, bias column first) <-> device layout
+void ref_to_dev(const clstm_b200_net* n, const float* ref, float* dev) {
+  const int ni = n->ni, no = n->no, nc = n->nc, nf = n->nf;
+  const size_t msz = (size_t)no * (1 + nf);
+  for (int d = 0; d < 2; d++) {
+    const float* blk = ref + (size_t)d * 4 * msz;
+    for (int g = 0; g < 4; g++) {
+      const float* W = blk + (size_t)gate_ref_index(g) * msz;
+      for (int j = 0; j < no; j++) {
+        const int r = 4 * j + g;
+        dev[n->oB[d] + r] = W[j];
+        for (int i = 0; i < ni; i++) dev[n->oWx[d] + (size_t)r * ni + i] = W[j + (size_t)(1 + i) * no];
+        for (int k = 0; k < no; k++) dev[n->oR[d] + (size_t)r * no + k] = W[j + (size_t)(1 + ni + k) * no];
+      }
+    }
+  }
+  const float* W1 = ref + 8 * msz;
+  for (int c = 0; c < nc; c++) {
+    dev[n->oB1 + c] = W1[c];
+    for (int k = 0; k < 2 * no; k++) dev[n->oW1 + (size_t)c * 2 * no + k] = W1[c + (size_t)(1 + k) * nc];
+  }
+}
+void dev_to_ref(const clstm_b200_net* n, const float* dev, float* ref) {
+  const int ni = n->ni, no = n->no, nc = n->nc, nf = n->nf;
+  const size_t msz = (size_t)no * (1 + nf);
+  for (int d = 0; d < 2; d++) {
+    float* blk = ref + (size_t)d * 4 * msz;
+    for (int g = 0; g < 4; g++) {
+      float* W = blk + (size_t)gate_ref_index(g) * msz;
+      for (int j = 0; j < no; j++) {
+        const int r = 4 * j + g;
+        W[j] = dev[n->oB[d] + r];
+        for (int i = 0; i < ni; i++) W[j + (size_t)(1 + i) * no] = dev[n->oWx[d] + (size_t)r * ni + i];
+        for (int k = 0; k < no; k++) W[j + (size_t)(1 + ni + k) * no] = dev[n->oR[d] + (size_t)r * no + k];
+      }
+    }
+  }
+  float* W1 = ref + 8 * msz;
+  for (int c = 0; c < nc; c++) {
+    W1[c] = dev[n->oB1 + c];
+    for (int k = 0; k < 2 * no; k++) W1[c + (size_t)(1 + k) * nc] = dev[n->oW1 + (size_t)c * 2 * no + k];
+  }
+}
+
+void free_batch(clstm_b200_net* n) {
+  dev_free(n->x); dev_free(n->H); dev_free(n->out); dev_free(n->aligned); dev_free(n->delta); dev_free(n->dH);
+  dev_free(n->dx);
+  for (int d = 0; d < 2; d++) {
+    dev_free(n->XP[d]); dev_free(n->G[d]); dev_free(n->C[d]); dev_free(n->Hprev[d]); dev_free(n->DG[d]);
+    dev_free(n->amax[d]); dev_free(n->amaxv[d]);
+  }
+}
+
+int ensure_columns(clstm_b200_net* n, int N) {
+  if (N <= n->capN) return 0;
+  CU(cudaStreamSynchronize(n->st));
+  free_batch(n);
+  const size_t cap = (size_t)N + N / 8 + 64;
+  const int no = n->no, ni = n->ni, nc = n->nc;
+  TRY(dev_alloc(&n->x, cap * ni));
+  TRY(dev_alloc(&n->H, cap * 2 * no));
+  TRY(dev_alloc(&n->out, cap * nc));
+  TRY(dev_alloc(&n->aligned, cap * nc));
+  TRY(dev_alloc(&n->delta, cap * nc));
+  TRY(dev_alloc(&n->dH, cap * 2 * no));
+  TRY(dev_alloc(&n->dx, cap * ni));
+  for (int d = 0; d < 2; d++) {
+    TRY(dev_alloc(&n->XP[d], cap * 4 * no));
+    TRY(dev_alloc(&n->G[d], cap * 4 * no));
+    TRY(dev_alloc(&n->C[d], cap * no));
+    TRY(dev_alloc(&n->Hprev[d], cap * no));
+    TRY(dev_alloc(&n->DG[d], cap * 4 * no));
+    TRY(dev_alloc(&n->amax[d], cap));
+    TRY(dev_alloc(&n->amaxv[d], cap));
+  }
+  n->capN = (int)cap;
+  return 0;
+}
+int ensure_lines(clstm_b200_net* n, int B, int nlab) {
+  if (B > n->capB || nlab > n->capLab) {
+    CU(cudaStreamSynchronize(n->st));
+    const int cb = std::max(B + B / 4 + 8, n->capB), cl = std::max(nlab + nlab / 4 + 64, n->capLab);
+    dev_free(n->meta); dev_free(n->lat_off);
+    if (n->h_meta) cudaFreeHost(n->h_meta);
+    if (n->h_lat) cudaFreeHost(n->h_lat);
+    if (n->h_small) cudaFreeHost(n->h_small);
+    TRY(dev_alloc(&n->meta, (size_t)5 * cb + cl));
+    TRY(dev_alloc(&n->lat_off, (size_t)cb));
+    CU(cudaHostAlloc((void**)&n->h_meta, ((size_t)5 * cb + cl) * sizeof(int), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&n->h_lat, (size_t)cb * sizeof(long long), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&n->h_small, ((size_t)2 * cb + 8) * sizeof(int), cudaHostAllocDefault));
+    for (int w = 0; w < 2; w++) { dev_free(n->dcnt[w]); TRY(dev_alloc(&n->dcnt[w], (size_t)cb)); }
+    n->capB = cb;
+    n->capLab = cl;
+    n->capDec = 0;  // decode buffers depend on capB
+  }
+  return 0;
+}
+int ensure_decode(clstm_b200_net* n, int max_per_line) {
+  if (max_per_line <= n->capDec) return 0;
+  CU(cudaStreamSynchronize(n->st));
+  for (int w = 0; w < 2; w++) {
+    dev_free(n->dcls[w]); dev_free(n->dlocs[w]);
+    TRY(dev_alloc(&n->dcls[w], (size_t)n->capB * max_per_line));
+    TRY(dev_alloc(&n->dlocs[w], (size_t)n->capB * max_per_line));
+  }
+  n->capDec = max_per_line;
+  return 0;
+}
+int ensure_lattice(clstm_b200_net* n, long long elems) {
+  if (elems <= n->capLat) return 0;
+  CU(cudaStreamSynchronize(n->st));
+  dev_free(n->lm); dev_free(n->lr); dev_free(n->rl);
+  const long long cap = elems + elems / 8 + 1024;
+  TRY(dev_alloc(&n->lm, (size_t)cap));
+  TRY(dev_alloc(&n->lr, (size_t)cap));
+  TRY(dev_alloc(&n->rl, (size_t)cap));
+  n->capLat = cap;
+  return 0;
+}
+
+// Stage line lengths (and optionally transcripts) and publish the Lines view.
+int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const int* L, bool raw = false) {
+  if (B <= 0) return fail("batch must contain at least one line");
+  long long N = 0;
+  for (int b = 0; b < B; b++) {
+    if (T[b] <= 0) return fail("line %d has non-positive length %d", b, T[b]);
+    N += T[b];
+  }
+  if (N > 0x7fffffff / (4LL * std::max(n->no, 16))) return fail("batch too large: %lld columns", N);
+  int nlab = 0;
+  if (L) for (int b = 0; b < B; b++) {
+    if (L[b] < 0) return fail("line %d has negative transcript length", b);
+    if ((raw ? L[b] : 2 * L[b] + 1) > kCtcMaxStates) return fail("transcript of line %d too long (%d labels, max %d)", b, L[b], (kCtcMaxStates - 1) / 2);
+    if (raw && L[b] < 1) return fail("line %d needs at least one target state", b);
+    nlab += L[b];
+  }
+  TRY(ensure_columns(n, (int)N));
+  TRY(ensure_lines(n, B, nlab));
+  if (n->meta_done) CU(cudaEventSynchronize(n->meta_done));   // pinned staging buffers free again?
+  n->hT.assign(T, T + B);
+  n->hOff.resize(B); n->hL.assign(B, 0); n->hLabOff.assign(B, 0); n->hOrder.resize(B);
+  int off = 0, tmax = 0;
+  for (int b = 0; b < B; b++) { n->hOff[b] = off; off += T[b]; tmax = std::max(tmax, T[b]); }
+  std::iota(n->hOrder.begin(), n->hOrder.end(), 0);
+  std::stable_sort(n->hOrder.begin(), n->hOrder.end(), [&](int a, int c) { return T[a] > T[c]; });
+  long long lat = 0;
+  int lo = 0;
+  for (int b = 0; b < B; b++) {
+    if (L) { n->hL[b] = L[b]; n->hLabOff[b] = lo; lo += L[b]; }
+    n->h_lat[b] = lat;
+    lat += (long long)T[b] * (raw ? n->hL[b] : 2 * n->hL[b] + 1);
+  }
+  if (L) {
+    for (int i = 0; i < nlab; i++)
+      if (labels[i] < 0 || labels[i] >= n->nc) return fail("label %d out of range [0,%d)", labels[i], n->nc);
+    TRY(ensure_lattice(n, lat));
+  }
+  int* hm = n->h_meta;
+  const int cb = n->capB;
+  memcpy(hm + 0 * cb, n->hT.data(), B * sizeof(int));
+  memcpy(hm + 1 * cb, n->hOff.data(), B * sizeof(int));
+  memcpy(hm + 2 * cb, n->hL.data(), B * sizeof(int));
+  memcpy(hm + 3 * cb, n->hLabOff.data(), B * sizeof(int));
+  memcpy(hm + 4 * cb, n->hOrder.data(), B * sizeof(int));
+  if (L && nlab) memcpy(hm + 5 * cb, labels, nlab * sizeof(int));
+  CU(cudaMemcpyAsync(n->meta, hm, ((size_t)5 * cb + nlab) * sizeof(int), cudaMemcpyHostToDevice, n->st));
+  CU(cudaMemcpyAsync(n->lat_off, n->h_lat, (size_t)B * sizeof(long long), cudaMemcpyHostToDevice, n->st));
+  if (!n->meta_done) CU(cudaEventCreateWithFlags(&n->meta_done, cudaEventDisableTiming));
+  CU(cudaEventRecord(n->meta_done, n->st));
+  Lines& ln = n->ln;
+  ln.B = B; ln.N = (int)N; ln.Tmax = tmax;
+  ln.T = n->meta; ln.off = n->meta + cb; ln.L = n->meta + 2 * cb; ln.lab_off = n->meta + 3 * cb;
+  ln.order = n->meta + 4 * cb; ln.labels = n->meta + 5 * cb; ln.lat_off = n->lat_off;
+  n->have_batch = true;
+  n->have_labels = (L != nullptr);
+  n->raw_targets = raw;
+  n->have_forward = false;
+  n->have_ctc = false;
+  return 0;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ device passes
+int run_forward(clstm_b200_net* n) {
+  const Lines& ln = n->ln;
+  const int N = ln.N, ni = n->ni, no = n->no, nc = n->nc;
+  {
+    Scope s(n, PH_XPROJ);
+    for (int d = 0; d < 2; d++)
+      s.launches(gemm_f32(n->st, N, 4 * no, ni, n->x, ni, 1, n->v + n->oWx[d], 1, ni, n->XP[d], 4 * no,
+                          n->v + n->oB[d], 0.f, nullptr, 0, n->num_sms));
+  }
+  {
+    Scope s(n, PH_LSTM_FWD);
+    LstmFwdArgs a;
+    a.no = no;
+    for (int d = 0; d < 2; d++) {
+      a.XP[d] = n->XP[d]; a.R[d] = n->v + n->oR[d]; a.Rt[d] = n->Rt[d];
+      a.G[d] = n->G[d]; a.C[d] = n->C[d]; a.Hprev[d] = n->Hprev[d];
+    }
+    a.H = n->H;
+    n->variant = lstm_forward(n->st, ln, a);
+    s.launches(1);
+  }
+  {
+    Scope s(n, PH_SOFTMAX_FWD);
+    s.launches(gemm_f32(n->st, N, nc, 2 * no, n->H, 2 * no, 1, n->v + n->oW1, 1, 2 * no, n->out, nc,
+                        n->v + n->oB1, 0.f, nullptr, 0, n->num_sms));
+    softmax_rows(n->st, n->out, N, nc);
+    s.launches(1);
+  }
+  TRY(check_launch("forward"));
+  n->have_forward = true;
+  n->have_ctc = false;
+  return 0;
+}
+
+int run_ctc(clstm_b200_net* n) {
+  Scope s(n, PH_CTC);
+  CtcArgs a;
+  a.nc = n->nc; a.out = n->out; a.aligned = n->aligned; a.delta = n->delta;
+  a.lmatch = n->lm; a.lr = n->lr; a.rl = n->rl; a.status = n->status; a.raw = n->raw_targets ? 1 : 0;
+  ctc_align(n->st, n->ln, a);
+  s.launches(1);
+  TRY(check_launch("ctc_align"));
+  n->have_ctc = true;
+  return 0;
+}
+
+int run_backward(clstm_b200_net* n) {
+  const Lines& ln = n->ln;
+  const int N = ln.N, ni = n->ni, no = n->no, nc = n->nc;
+  {
+    Scope s(n, PH_SOFTMAX_BWD);   // backward_softmax clstm_compute.cc:346-356
+    s.launches(gemm_f32(n->st, N, 2 * no, nc, n->delta, nc, 1, n->v + n->oW1, 2 * no, 1, n->dH, 2 * no, nullptr,
+                        0.f, nullptr, 0, n->num_sms));
+    s.launches(gemm_f32(n->st, nc, 2 * no, N, n->delta, 1, nc, n->H, 2 * no, 1, n->g + n->oW1, 2 * no, nullptr, 1.f,
+                        n->ws, n->ws_floats, n->num_sms));
+    s.launches(colsum_f32(n->st, N, nc, n->delta, nc, n->g + n->oB1, 1.f, n->ws, n->ws_floats, n->num_sms));
+  }
+  {
+    Scope s(n, PH_LSTM_BWD);
+    LstmBwdArgs a;
+    a.no = no; a.dH = n->dH;
+    for (int d = 0; d < 2; d++) { a.R[d] = n->v + n->oR[d]; a.G[d] = n->G[d]; a.C[d] = n->C[d]; a.DG[d] = n->DG[d]; }
+    lstm_backward(n->st, ln, a);
+    s.launches(1);
+  }
+  {
+    Scope s(n, PH_WGRAD);   // W.d += delta * src^T over all columns (backward_lin1 clstm_compute.cc:297-298)
+    for (int d = 0; d < 2; d++) {
+      s.launches(gemm_f32(n->st, 4 * no, ni, N, n->DG[d], 1, 4 * no, n->x, ni, 1, n->g + n->oWx[d], ni, nullptr, 1.f,
+                          n->ws, n->ws_floats, n->num_sms));
+      s.launches(gemm_f32(n->st, 4 * no, no, N, n->DG[d], 1, 4 * no, n->Hprev[d], no, 1, n->g + n->oR[d], no, nullptr,
+                          1.f, n->ws, n->ws_floats, n->num_sms));
+      s.launches(colsum_f32(n->st, N, 4 * no, n->DG[d], 4 * no, n->g + n->oB[d], 1.f, n->ws, n->ws_floats,
+                            n->num_sms));
+    }
+  }
+  {
+    Scope s(n, PH_DX);      // inputs.d = sum over both directions of Wx^T delta (clstm.cc:537-541)
+    for (int d = 0; d < 2; d++)
+      s.launches(gemm_f32(n->st, N, ni, 4 * no, n->DG[d], 4 * no, 1, n->v + n->oWx[d], ni, 1, n->dx, ni, nullptr,
+                          d ? 1.f : 0.f, nullptr, 0, n->num_sms));
+  }
+  TRY(check_launch("backward"));
+  n->g_pending = true;
+  return 0;
+}
+
+int fold_pending(clstm_b200_net* n) {
+  if (!n->g_pending) return 0;
+  sgd_update(n->st, n->v, n->d, n->g, n->P, 0.f, 0.f, 0.f, 1);
+  n->g_pending = false;
+  return check_launch("fold");
+}
+
+int run_allreduce(clstm_b200_net* n) {
+  if (!n->comm || n->world <= 1) return 0;
+  Scope s(n, PH_ALLREDUCE);
+  int r = g_nccl.AllReduce(n->g, n->g, n->P, /*ncclFloat*/ 7, /*ncclSum*/ 0, n->comm, n->st);
+  s.launches(1);
+  if (r != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  return 0;
+}
+
+int run_update(clstm_b200_net* n, float lr, float mom, float clip) {
+  Scope s(n, PH_UPDATE);
+  sgd_update(n->st, n->v, n->d, n->g, n->P, lr, mom, clip, 0);
+  n->g_pending = false;
+  transpose_R(n->st, n->v + n->oR[0], n->Rt[0], n->v + n->oR[1], n->Rt[1], n->no);
+  s.launches(2);
+  return check_launch("sgd_update");
+}
+
+int run_decode(clstm_b200_net* n, int which, int max_per_line) {
+  TRY(ensure_decode(n, max_per_line));
+  Scope s(n, PH_DECODE);
+  decode_lines(n->st, n->ln, which ? n->aligned : n->out, n->nc, n->amax[which], n->amaxv[which], n->dcls[which],
+               n->dlocs[which], n->dcnt[which], n->capDec);
+  s.launches(1);
+  return check_launch("decode");
+}
+
+int fetch_decode(clstm_b200_net* n, int which, int* classes, int* locs, int* counts, int max_per_line) {
+  const int B = n->ln.B;
+  {
+    Scope s(n, PH_D2H);
+    CU(cudaMemcpyAsync(counts, n->dcnt[which], (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, n->st));
+    if (n->capDec == max_per_line) {
+      CU(cudaMemcpyAsync(classes, n->dcls[which], (size_t)B * max_per_line * sizeof(int), cudaMemcpyDeviceToHost, n->st));
+      CU(cudaMemcpyAsync(locs, n->dlocs[which], (size_t)B * max_per_line * sizeof(int), cudaMemcpyDeviceToHost, n->st));
+    } else {
+      CU(cudaMemcpy2DAsync(classes, (size_t)max_per_line * sizeof(int), n->dcls[which], (size_t)n->capDec * sizeof(int),
+                           (size_t)max_per_line * sizeof(int), B, cudaMemcpyDeviceToHost, n->st));
+      CU(cudaMemcpy2DAsync(locs, (size_t)max_per_line * sizeof(int), n->dlocs[which], (size_t)n->capDec * sizeof(int),
+                           (size_t)max_per_line * sizeof(int), B, cudaMemcpyDeviceToHost, n->st));
+    }
+  }
+  CU(cudaStreamSynchronize(n->st));
+  for (int b = 0; b < B; b++)
+    if (counts[b] > max_per_line) return fail("line %d decodes to %d symbols > max_per_line %d", b, counts[b], max_per_line);
+  return 0;
+}
+
+int check_status(clstm_b200_net* n) {  // stream must be synchronised
+  if (n->h_small[0] != 0) return fail("ctc_align: transcript too long for the device lattice (status %d)", n->h_small[0]);
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* clstm_b200_last_error(void) { return g_err.c_str(); }
+const char* clstm_b200_version(void) { return "clstm_b200 0.1 (sm_100a)"; }
+int clstm_b200_num_phases(void) { return PH_COUNT; }
+const char* clstm_b200_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
+
+int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
+  if (!cfg || !out) return fail("null argument");
+  *out = nullptr;
+  if (cfg->ninput <= 0 || cfg->nhidden <= 0 || cfg->nclasses < 2) return fail("bad dimensions (Softmax requires nclasses>=2, clstm.cc:400)");
+  if (cfg->nclasses > kCtcMaxClasses) return fail("nclasses %d > %d not supported", cfg->nclasses, kCtcMaxClasses);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("no CUDA device available (%s); clstm_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d devices)", cfg->device, ndev);
+  CU(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; this library contains sm_100a code only", cfg->device, prop.major, prop.minor);
+  auto* n = new clstm_b200_net;
+  n->cfg = *cfg;
+  n->ni = cfg->ninput; n->no = cfg->nhidden; n->nc = cfg->nclasses; n->nf = n->ni + n->no;
+  n->num_sms = prop.multiProcessorCount;
+  const int ni = n->ni, no = n->no, nc = n->nc;
+  size_t o = 0;
+  for (int d = 0; d < 2; d++) {
+    n->oWx[d] = o; o += (size_t)4 * no * ni;
+    n->oB[d] = o;  o += (size_t)4 * no;
+    n->oR[d] = o;  o += (size_t)4 * no * no;
+  }
+  n->oW1 = o; o += (size_t)nc * 2 * no;
+  n->oB1 = o; o += nc;
+  n->P = o;
+  if (cudaStreamCreateWithFlags(&n->st, cudaStreamNonBlocking) != cudaSuccess) { delete n; return fail("cudaStreamCreate failed"); }
+  int rc = 0;
+  rc |= dev_alloc(&n->v, n->P); rc |= dev_alloc(&n->d, n->P); rc |= dev_alloc(&n->g, n->P);
+  for (int d = 0; d < 2; d++) rc |= dev_alloc(&n->Rt[d], (size_t)4 * no * no);
+  rc |= dev_alloc(&n->status, 1);
+  // split-K workspace: enough for ~2 waves of 64x64 tiles plus the largest derivative matrix a few times over
+  n->ws_floats = std::max<size_t>((size_t)4 * n->num_sms * 64 * 64, (size_t)8 * 4 * no * std::max(no, ni));
+  rc |= dev_alloc(&n->ws, n->ws_floats);
+  if (rc) { clstm_b200_destroy(n); return 1; }
+  cudaMemsetAsync(n->v, 0, n->P * sizeof(float), n->st);
+  cudaMemsetAsync(n->d, 0, n->P * sizeof(float), n->st);
+  cudaMemsetAsync(n->g, 0, n->P * sizeof(float), n->st);
+  cudaMemsetAsync(n->Rt[0], 0, (size_t)4 * no * no * sizeof(float), n->st);
+  cudaMemsetAsync(n->Rt[1], 0, (size_t)4 * no * no * sizeof(float), n->st);
+  cudaMemsetAsync(n->status, 0, sizeof(int), n->st);
+  if (lstm_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
+  n->variant = lstm_variant_for(no);
+  if (cudaStreamSynchronize(n->st) != cudaSuccess) { clstm_b200_destroy(n); return fail("device initialisation failed"); }
+  *out = n;
+  return 0;
+}
+
+void clstm_b200_destroy(clstm_b200_net* n) {
+  if (!n) return;
+  cudaSetDevice(n->cfg.device);
+  if (n->st) cudaStreamSynchronize(n->st);
+  if (n->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n->comm);
+  free_batch(n);
+  dev_free(n->v); dev_free(n->d); dev_free(n->g); dev_free(n->Rt[0]); dev_free(n->Rt[1]);
+  dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->status);
+  dev_free(n->ws);
+  for (int w = 0; w < 2; w++) { dev_free(n->dcls[w]); dev_free(n->dlocs[w]); dev_free(n->dcnt[w]); }
+  if (n->h_meta) cudaFreeHost(n->h_meta);
+  if (n->h_lat) cudaFreeHost(n->h_lat);
+  if (n->h_small) cudaFreeHost(n->h_small);
+  for (auto& r : n->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : n->pool) cudaEventDestroy(e);
+  if (n->meta_done) cudaEventDestroy(n->meta_done);
+  if (n->st) cudaStreamDestroy(n->st);
+  delete n;
+}
+
+size_t clstm_b200_nparams(const clstm_b200_net* n) { return n ? n->P : 0; }
+
+int clstm_b200_set_params(clstm_b200_net* n, const float* flat, size_t cnt) {
+  if (!n || !flat) return fail("null argument");
+  if (cnt != n->P) return fail("set_params size mismatch: got %zu, net has %zu", cnt, n->P);   // clstm.cc:871
+  CU(cudaSetDevice(n->cfg.device));
+  std::vector<float> dev(n->P);
+  ref_to_dev(n, flat, dev.data());
+  CU(cudaMemcpyAsync(n->v, dev.data(), n->P * sizeof(float), cudaMemcpyHostToDevice, n->st));
+  transpose_R(n->st, n->v + n->oR[0], n->Rt[0], n->v + n->oR[1], n->Rt[1], n->no);
+  CU(cudaStreamSynchronize(n->st));
+  return check_launch("set_params");
+}
+int clstm_b200_get_params(clstm_b200_net* n, float* flat, size_t cnt) {
+  if (!n || !flat) return fail("null argument");
+  if (cnt != n->P) return fail("get_params size mismatch: got %zu, net has %zu", cnt, n->P);
+  CU(cudaSetDevice(n->cfg.device));
+  std::vector<float> dev(n->P);
+  CU(cudaMemcpyAsync(dev.data(), n->v, n->P * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  dev_to_ref(n, dev.data(), flat);
+  return 0;
+}
+int clstm_b200_get_derivs(clstm_b200_net* n, float* flat, size_t cnt) {
+  if (!n || !flat) return fail("null argument");
+  if (cnt != n->P) return fail("get_derivs size mismatch");
+  CU(cudaSetDevice(n->cfg.device));
+  TRY(fold_pending(n));
+  std::vector<float> dev(n->P);
+  CU(cudaMemcpyAsync(dev.data(), n->d, n->P * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  dev_to_ref(n, dev.data(), flat);
+  return 0;
+}
+int clstm_b200_set_derivs(clstm_b200_net* n, const float* flat, size_t cnt) {
+  if (!n || !flat) return fail("null argument");
+  if (cnt != n->P) return fail("set_derivs size mismatch");
+  CU(cudaSetDevice(n->cfg.device));
+  std::vector<float> dev(n->P);
+  ref_to_dev(n, flat, dev.data());
+  CU(cudaMemsetAsync(n->g, 0, n->P * sizeof(float), n->st));
+  n->g_pending = false;
+  CU(cudaMemcpyAsync(n->d, dev.data(), n->P * sizeof(float), cudaMemcpyHostToDevice, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+int clstm_b200_clear_derivs(clstm_b200_net* n) {
+  if (!n) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  CU(cudaMemsetAsync(n->g, 0, n->P * sizeof(float), n->st));
+  CU(cudaMemsetAsync(n->d, 0, n->P * sizeof(float), n->st));
+  n->g_pending = false;
+  return 0;
+}
+
+int clstm_b200_upload_batch(clstm_b200_net* n, const float* x, const int* T, int B, const int* labels, const int* L) {
+  if (!n || !x || !T) return fail("null argument");
+  if (L != nullptr && labels == nullptr) return fail("labels missing");
+  CU(cudaSetDevice(n->cfg.device));
+  Scope s(n, PH_H2D);
+  TRY(stage_lines(n, T, B, labels, L));
+  CU(cudaMemcpyAsync(n->x, x, (size_t)n->ln.N * n->ni * sizeof(float), cudaMemcpyHostToDevice, n->st));
+  return 0;
+}
+
+int clstm_b200_forward(clstm_b200_net* n, const float* x, const int* T, int B, float* out) {
+  TRY(clstm_b200_upload_batch(n, x, T, B, nullptr, nullptr));
+  TRY(run_forward(n));
+  if (out) {
+    Scope s(n, PH_D2H);
+    CU(cudaMemcpyAsync(out, n->out, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  }
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+
+int clstm_b200_ctc_align(clstm_b200_net* n, const int* labels, const int* L, float* aligned) {
+  if (!n || !L) return fail("null argument");
+  if (!n->have_forward) return fail("ctc_align called before forward");
+  CU(cudaSetDevice(n->cfg.device));
+  {
+    // re-stage the metadata with the transcripts; line geometry is unchanged
+    std::vector<int> T = n->hT;
+    if (!labels) {
+      for (size_t b = 0; b < T.size(); b++)
+        if (L[b] != 0) return fail("labels missing");
+      labels = L;   // never dereferenced: every transcript is empty
+    }
+    TRY(stage_lines(n, T.data(), (int)T.size(), labels, L));
+    n->have_forward = true;
+  }
+  CU(cudaMemsetAsync(n->status, 0, sizeof(int), n->st));
+  TRY(run_ctc(n));
+  CU(cudaMemcpyAsync(n->h_small, n->status, sizeof(int), cudaMemcpyDeviceToHost, n->st));
+  if (aligned) {
+    Scope s(n, PH_D2H);
+    CU(cudaMemcpyAsync(aligned, n->aligned, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  }
+  CU(cudaStreamSynchronize(n->st));
+  return check_status(n);
+}
+
+int clstm_b200_ctc_align_states(clstm_b200_net* n, const float* outputs, const int* T, int B, const int* states,
+                                const int* S, float* aligned) {
+  if (!n || !outputs || !T || !states || !S || !aligned) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  TRY(stage_lines(n, T, B, states, S, /*raw=*/true));
+  CU(cudaMemcpyAsync(n->out, outputs, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyHostToDevice, n->st));
+  CU(cudaMemsetAsync(n->status, 0, sizeof(int), n->st));
+  TRY(run_ctc(n));
+  n->have_ctc = false;   // deltas of a free-standing alignment must not feed backward()
+  CU(cudaMemcpyAsync(n->h_small, n->status, sizeof(int), cudaMemcpyDeviceToHost, n->st));
+  CU(cudaMemcpyAsync(aligned, n->aligned, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  return check_status(n);
+}
+
+int clstm_b200_backward(clstm_b200_net* n, const float* deltas, float* din) {
+  if (!n) return fail("null argument");
+  if (!n->have_forward) return fail("backward called before forward");
+  if (!deltas && !n->have_ctc) return fail("backward: no deltas given and no ctc_align result on the device");
+  CU(cudaSetDevice(n->cfg.device));
+  if (deltas) {
+    Scope s(n, PH_H2D);
+    CU(cudaMemcpyAsync(n->delta, deltas, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyHostToDevice, n->st));
+  }
+  TRY(run_backward(n));
+  if (din) {
+    Scope s(n, PH_D2H);
+    CU(cudaMemcpyAsync(din, n->dx, (size_t)n->ln.N * n->ni * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  }
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+
+int clstm_b200_decode(clstm_b200_net* n, int which, int* classes, int* locs, int* counts, int max_per_line) {
+  if (!n || !classes || !locs || !counts) return fail("null argument");
+  if (which < 0 || which > 1 || max_per_line <= 0) return fail("bad argument");
+  if (!n->have_forward || (which == 1 && !n->have_ctc)) return fail("decode: nothing to decode yet");
+  CU(cudaSetDevice(n->cfg.device));
+  TRY(run_decode(n, which, max_per_line));
+  return fetch_decode(n, which, classes, locs, counts, max_per_line);
+}
+
+int clstm_b200_argmax(clstm_b200_net* n, int which, int* idx) {
+  if (!n || !idx) return fail("null argument");
+  if (which < 0 || which > 1) return fail("bad argument");
+  if (!n->have_forward || (which == 1 && !n->have_ctc)) return fail("argmax: nothing to decode yet");
+  CU(cudaSetDevice(n->cfg.device));
+  TRY(run_decode(n, which, std::max(n->capDec, 1)));
+  CU(cudaMemcpyAsync(idx, n->amax[which], (size_t)n->ln.N * sizeof(int), cudaMemcpyDeviceToHost, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+
+int clstm_b200_sgd_update(clstm_b200_net* n, float lr, float momentum, float clip) {
+  if (!n) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  TRY(run_update(n, lr, momentum, clip));
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+
+int clstm_b200_comm_unique_id(void* id128) {
+  if (!id128) return fail("null argument");
+  TRY(load_nccl());
+  int r = g_nccl.GetUniqueId(id128);
+  if (r != 0) return fail("ncclGetUniqueId failed (%d)", r);
+  return 0;
+}
+int clstm_b200_comm_init(clstm_b200_net* n, const void* id128, int rank, int world) {
+  if (!n || !id128) return fail("null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail("bad rank/world");
+  TRY(load_nccl());
+  CU(cudaSetDevice(n->cfg.device));
+  Id128 id;
+  memcpy(&id, id128, sizeof id);
+  int r = g_nccl.CommInitRank(&n->comm, world, id, rank);
+  if (r != 0) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  n->rank = rank;
+  n->world = world;
+  return 0;
+}
+int clstm_b200_allreduce_derivs(clstm_b200_net* n) {
+  if (!n) return fail("null argument");
+  if (!n->comm) return fail("no communicator attached (clstm_b200_comm_init)");
+  CU(cudaSetDevice(n->cfg.device));
+  TRY(run_allreduce(n));
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+
+int clstm_b200_step_resident(clstm_b200_net* n, float lr, float momentum, float clip) {
+  if (!n) return fail("null argument");
+  if (!n->have_batch || !n->have_labels) return fail("step_resident: upload a batch with transcripts first");
+  CU(cudaSetDevice(n->cfg.device));
+  TRY(run_forward(n));
+  TRY(run_ctc(n));
+  TRY(run_backward(n));
+  TRY(run_allreduce(n));
+  TRY(run_update(n, lr, momentum, clip));
+  TRY(run_decode(n, 0, std::max(n->capDec, n->ln.Tmax / 2 + 1)));
+  return 0;
+}
+
+int clstm_b200_fetch_decoded(clstm_b200_net* n, int which, int* classes, int* locs, int* counts, int max_per_line) {
+  if (!n || !classes || !locs || !counts) return fail("null argument");
+  if (which != 0) TRY(run_decode(n, which, std::max(n->capDec, max_per_line)));
+  if (max_per_line > n->capDec) return fail("fetch_decoded: max_per_line %d exceeds the decoded capacity %d", max_per_line, n->capDec);
+  return fetch_decode(n, which, classes, locs, counts, max_per_line);
+}
+
+int clstm_b200_synchronize(clstm_b200_net* n) {
+  if (!n) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  CU(cudaStreamSynchronize(n->st));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("device error: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int clstm_b200_train_step(clstm_b200_net* n, const float* x, const int* T, int B, const int* labels, const int* L,
+                          float lr, float momentum, float clip, float* out, float* aligned, int* classes, int* locs,
+                          int* counts, int max_per_line) {
+  if (!labels || !L) return fail("train_step needs transcripts");
+  TRY(clstm_b200_upload_batch(n, x, T, B, labels, L));
+  CU(cudaMemsetAsync(n->status, 0, sizeof(int), n->st));
+  if (classes && max_per_line > 0) TRY(ensure_decode(n, max_per_line));
+  TRY(clstm_b200_step_resident(n, lr, momentum, clip));
+  CU(cudaMemcpyAsync(n->h_small, n->status, sizeof(int), cudaMemcpyDeviceToHost, n->st));
+  {
+    Scope s(n, PH_D2H);
+    if (out) CU(cudaMemcpyAsync(out, n->out, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+    if (aligned) CU(cudaMemcpyAsync(aligned, n->aligned, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  }
+  if (classes && locs && counts && max_per_line > 0) {
+    TRY(fetch_decode(n, 0, classes, locs, counts, max_per_line));   // synchronises
+  } else {
+    CU(cudaStreamSynchronize(n->st));
+  }
+  return check_status(n);
+}
+
+int clstm_b200_profile(clstm_b200_net* n, int enable) {
+  if (!n) return fail("null argument");
+  CU(cudaStreamSynchronize(n->st));
+  harvest(n);
+  n->prof = enable != 0;
+  for (int i = 0; i < PH_COUNT; i++) { n->ph_ms[i] = 0.f; n->ph_launch[i] = 0; }
+  return 0;
+}
+int clstm_b200_phase_stats(clstm_b200_net* n, float* ms, long long* launches, int cnt) {
+  if (!n) return fail("null argument");
+  CU(cudaStreamSynchronize(n->st));
+  harvest(n);
+  for (int i = 0; i < cnt && i < PH_COUNT; i++) {
+    if (ms) ms[i] = n->ph_ms[i];
+    if (launches) launches[i] = n->ph_launch[i];
+  }
+  return 0;
+}
+void* clstm_b200_stream(clstm_b200_net* n) { return n ? (void*)n->st : nullptr; }
+const char* clstm_b200_lstm_variant(const clstm_b200_net* n) { return n ? n->variant : ""; }
+
+void* clstm_b200_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { fail("cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+void clstm_b200_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// kernels.h -- internal launcher declarations shared by the .cu files of libclstm_b200.so.
+// Everything here is device-side plumbing for the one hot path; the public
+// surface is include/clstm_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace cb200 {
+
+// Per-batch line metadata, all device pointers (filled by capi.cu::upload_meta).
+struct Lines {
+  int B;                 // number of text lines in the batch
+  int N;                 // total columns = sum_b T[b]
+  int Tmax;              // longest line
+  const int* T;          // [B] columns per line
+  const int* off;        // [B] first column of line b in the packed arrays
+  const int* L;          // [B] transcript length
+  const int* lab_off;    // [B] first label of line b
+  const int* labels;     // packed transcripts
+  const long long* lat_off;  // [B] first element of line b's T x S lattice scratch
+  const int* order;      // [B] line indices sorted by decreasing T (longest lines start first)
+};
+
+// ---------------------------------------------------------------- gemm.cu
+// C[M x N] (row-major, ldc) = beta*C + sum_k A(m,k)*B(k,n) (+ bias[n]); A(m,k)=A[m*sam+k*sak], B(k,n)=B[k*sbk+n*sbn].
+// fp32 SIMT tiles; `ws` is split-K workspace of at least splits*M*N floats (may be null => no split).
+// Both return the number of kernels launched.
+int gemm_f32(cudaStream_t st, int M, int N, int K, const float* A, long long sam, long long sak, const float* B,
+              long long sbk, long long sbn, float* C, long long ldc, const float* bias, float beta, float* ws,
+              size_t ws_floats, int num_sms);
+// out[n] = beta*out[n] + sum_m A[m*lda + n]   (column sums of a row-major M x N matrix)
+int colsum_f32(cudaStream_t st, int M, int N, const float* A, long long lda, float* out, float beta, float* ws,
+                size_t ws_floats, int num_sms);
+
+// ---------------------------------------------------------------- lstm.cu
+struct LstmFwdArgs {
+  int no;                 // hidden units per direction
+  const float* XP[2];     // [N][4no] input projection + bias, gate-interleaved rows r = 4*j + g
+  const float* R[2];      // [4no][no] recurrent weights, row-major, rows gate-interleaved
+  const float* Rt[2];     // [no][4no] transposed copy
+  float* G[2];            // [N][4no] gate activations (gi,gf,go,ci)
+  float* C[2];            // [N][no] cell states
+  float* H;               // [N][2no] outputs of both directions (Parallel concat)
+  float* Hprev[2];        // [N][no] output of the previous step in the direction's own time order
+};
+struct LstmBwdArgs {
+  int no;
+  const float* R[2];
+  const float* G[2];
+  const float* C[2];
+  const float* dH;        // [N][2no] d(loss)/d(H) from the softmax layer
+  float* DG[2];           // [N][4no] deltas of the gate pre-activations
+};
+// returns the variant name actually used
+const char* lstm_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a);
+const char* lstm_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
+const char* lstm_variant_for(int no);
+int lstm_configure();   // opt in to large dynamic smem etc.; returns cudaError_t as int
+
+// ---------------------------------------------------------------- ctc.cu
+struct CtcArgs {
+  int nc;
+  const float* out;       // [N][nc] softmax outputs
+  float* aligned;         // [N][nc]
+  float* delta;           // [N][nc] = aligned - out   (clstmhl.h:211-212)
+  float* lmatch;          // lattice scratch, per line T x S
+  float* lr;              // forward lattice
+  float* rl;              // backward lattice
+  int* status;            // device int, set non-zero on unsupported transcript length
+  int raw;                // 1: Lines::L holds the state count S and labels hold one class per state (ctc.cc:136-146)
+};
+void ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a);
+constexpr int kCtcMaxStates = 1024;  // S = 2L+1 must not exceed this
+constexpr int kCtcMaxClasses = 512;  // nclasses limit of the per-warp class accumulators
+
+// ---------------------------------------------------------------- misc.cu
+// out[n][:] = limexp(z[n][:]) / sum  in place (clstm_compute.cc:324-345)
+void softmax_rows(cudaStream_t st, float* z, int N, int nc);
+// d += g; g = 0; d = clamp(d); v += lr*d; d *= mom      (clstm_compute.cc:553-563)
+void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,
+                int fold_only);
+// Rt[k][r] = R[r][k] for both directions
+void transpose_R(cudaStream_t st, const float* R0, float* Rt0, const float* R1, float* Rt1, int no);
+// trivial_decode + argmax per line (ctc.cc:159-194, tensor.h:357-366)
+void decode_lines(cudaStream_t st, const Lines& ln, const float* probs, int nc, int* argmax_idx, float* argmax_val,
+                  int* classes, int* locs, int* counts, int max_per_line);
+
+}  // namespace cb200

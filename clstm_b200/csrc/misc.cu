@@ -1,0 +1,146 @@
+// misc.cu -- the HBM-bound pointwise pieces of the path: softmax normalisation, clip+SGD update, greedy decode.
+#include "kernels.h"
+
+namespace cb200 {
+namespace {
+
+__device__ __forceinline__ float limexp_(float x) {  // tensor.h:78-82
+  if (x < -30.f) return expf(-30.f);
+  if (x > 30.f) return expf(30.f);
+  return expf(x);
+}
+
+// forward_softmax after the linear part (clstm_compute.cc:334-337): z = limexp(z); z /= colsum(z).
+// One warp per column, values kept in registers (nc <= 32*16).
+__global__ void softmax_rows_kernel(float* __restrict__ z, int N, int nc) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = warp; n < N; n += nwarps) {
+    float* row = z + (size_t)n * nc;
+    float v[16];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int c = lane + 32 * i;
+      v[i] = 0.f;
+      if (c < nc) { v[i] = limexp_(row[c]); sum += v[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const int c = lane + 32 * i;
+      if (c < nc) row[c] = v[i] / sum;
+    }
+  }
+}
+
+// Folds this step's derivatives g into the accumulator d (Params.d) and applies sgd_update(Network)
+// (clstm.cc:201-217): clip_gradient then v += lr*d ; d *= momentum  (clstm_compute.cc:553-563).
+__global__ void sgd_update_kernel(float* __restrict__ v, float* __restrict__ d, float* __restrict__ g, size_t n,
+                                  float lr, float mom, float clip, int fold_only) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float di = d[i] + g[i];
+    g[i] = 0.f;
+    if (!fold_only) {
+      if (clip < 1e6f) { di = fminf(di, clip); di = fmaxf(di, -clip); }
+      v[i] = __fadd_rn(v[i], __fmul_rn(di, lr));   // two roundings like the CPU path (no FMA contraction)
+      di = di * mom;
+    }
+    d[i] = di;
+  }
+}
+
+__global__ void transpose_R_kernel(const float* __restrict__ R0, float* __restrict__ Rt0,
+                                   const float* __restrict__ R1, float* __restrict__ Rt1, int no) {
+  __shared__ float tile[32][33];
+  const float* R = blockIdx.z ? R1 : R0;
+  float* Rt = blockIdx.z ? Rt1 : Rt0;
+  const int rows = 4 * no, cols = no;          // R is rows x cols, Rt is cols x rows
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? R[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) Rt[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// argmax (tensor.h:357-366, ties -> last index) for every column of a line, then trivial_decode (ctc.cc:159-194).
+// One CTA per line.  The scan over time is inherently sequential but tiny (one compare per column).
+__global__ void decode_kernel(Lines ln, const float* __restrict__ probs, int nc, int* __restrict__ amax,
+                              float* __restrict__ amax_val, int* __restrict__ classes, int* __restrict__ locs,
+                              int* __restrict__ counts, int max_per_line) {
+  const int b = blockIdx.x;
+  const int T = ln.T[b], off = ln.off[b];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int t = warp; t < T; t += nw) {
+    const float* row = probs + (size_t)(off + t) * nc;
+    float mv = -INFINITY;
+    int mi = -1;
+    for (int c = lane; c < nc; c += 32) {
+      const float x = row[c];
+      if (!(x < mv)) { mv = x; mi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (ov > mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; }
+    }
+    if (lane == 0) { amax[off + t] = mi; amax_val[off + t] = mv; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && classes) {
+    int count = 0;
+    float mv = 0.f;
+    int mc = -1, mt = -1;
+    for (int t = 0; t < T; t++) {
+      const int index = amax[off + t];
+      const float v = amax_val[off + t];
+      if (index == 0) {
+        if (mc != -1 && mc != 0) {
+          if (count < max_per_line) { classes[(size_t)b * max_per_line + count] = mc; locs[(size_t)b * max_per_line + count] = mt; }
+          count++;
+        }
+        mv = 0.f; mc = -1; mt = -1;
+        continue;
+      }
+      if (v > mv) { mv = v; mc = index; mt = t; }
+    }
+    counts[b] = count;
+  }
+}
+}  // namespace
+
+void softmax_rows(cudaStream_t st, float* z, int N, int nc) {
+  if (N <= 0) return;
+  const int threads = 256;
+  int blocks = (N + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  softmax_rows_kernel<<<blocks, threads, 0, st>>>(z, N, nc);
+}
+
+void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,
+                int fold_only) {
+  if (n == 0) return;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sgd_update_kernel<<<blocks, 256, 0, st>>>(v, d, g, n, lr, mom, clip, fold_only);
+}
+
+void transpose_R(cudaStream_t st, const float* R0, float* Rt0, const float* R1, float* Rt1, int no) {
+  dim3 grid((no + 31) / 32, (4 * no + 31) / 32, 2);
+  transpose_R_kernel<<<grid, dim3(32, 8), 0, st>>>(R0, Rt0, R1, Rt1, no);
+}
+
+void decode_lines(cudaStream_t st, const Lines& ln, const float* probs, int nc, int* argmax_idx, float* argmax_val,
+                  int* classes, int* locs, int* counts, int max_per_line) {
+  if (ln.B <= 0) return;
+  decode_kernel<<<ln.B, 256, 0, st>>>(ln, probs, nc, argmax_idx, argmax_val, classes, locs, counts, max_per_line);
+}
+
+}  // namespace cb200

@@ -1,0 +1,183 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Every test drives the CUDA path through the C ABI
+(ctypes -> libclstm_b200.so) and compares with the CPU oracle on the same seeded inputs.
+
+Tolerances: fp32 values within 1e-4 absolute of the oracle (BASELINE.json north_star); CTC alignment indices
+(per-column argmax of `aligned`, trivial_decode classes and locations) bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from clstm_b200 import synth  # noqa: E402
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ffi():
+    import clstm_b200
+    clstm_b200.lib()
+    return clstm_b200
+
+
+def split(a, T):
+    offs = np.concatenate([[0], np.cumsum(T)])
+    return [a[offs[i]:offs[i + 1]] for i in range(len(T))]
+
+
+def make_pair(ffi, oracle, ni, nh, nc, weights, seed=0.222):
+    onet = oracle.BidiOracle(ni, nh, nc, seed=seed)
+    if weights == "trained":
+        onet.set_params(synth.trained_like(onet.nparams, 0.3, seed=7))
+    gnet = ffi.Net(ni, nh, nc)
+    assert gnet.nparams == onet.nparams
+    gnet.set_params(onet.get_params())
+    return onet, gnet
+
+
+CASES = [
+    # ni, nh, nc, B, T, weights
+    (48, 100, 83, 3, (40, 70), "init"),      # register-resident kernels
+    (48, 100, 83, 3, (40, 70), "trained"),
+    (48, 50, 83, 2, (30, 50), "trained"),     # regs, K padded to a multiple of 4
+    (7, 5, 4, 2, (9, 14), "trained"),         # generic kernels, test-deriv.cc-sized net
+    (48, 24, 30, 4, (1, 40), "trained"),      # generic, ragged incl. very short lines
+]
+
+
+@pytest.mark.parametrize("ni,nh,nc,B,T,weights", CASES)
+def test_forward_ctc_backward_parity(ffi, oracle, ni, nh, nc, B, T, weights):
+    x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=3)
+    # transcripts must fit the line: the aligner needs no minimum, but keep L <= T
+    onet, gnet = make_pair(ffi, oracle, ni, nh, nc, weights)
+    assert np.array_equal(gnet.get_params(), onet.get_params())           # layout round trip is exact
+    out = gnet.forward(x, Ts)
+    aligned = gnet.ctc_align(labels, L)
+    din = gnet.backward()
+    gd = gnet.get_derivs()
+    amax = gnet.argmax(1)
+    dec_al = gnet.decode(1)
+    dec_out = gnet.decode(0)
+    xs, outs, als, dins = split(x, Ts), split(out, Ts), split(aligned, Ts), split(din, Ts)
+    labs = split(labels, L)
+    onet.clear_derivs()
+    for b in range(B):
+        o_out, o_al = onet.fwdbwd(xs[b], labs[b])
+        assert np.abs(o_out - outs[b]).max() < TOL
+        # the aligner amplifies output differences; compare it on identical inputs (the GPU's own outputs)
+        o_al_same = oracle.ctc_align_labels(outs[b], labs[b])
+        assert np.abs(o_al_same - als[b]).max() < 2e-5
+        assert np.abs(o_al - als[b]).max() < 5e-3
+        assert np.array_equal(oracle.argmax_rows(o_al_same), split(amax, Ts)[b])
+        cs, locs = oracle.trivial_decode(o_al_same)
+        assert np.array_equal(cs, dec_al[b][0]) and np.array_equal(locs, dec_al[b][1])
+        cs, locs = oracle.trivial_decode(outs[b])
+        assert np.array_equal(cs, dec_out[b][0]) and np.array_equal(locs, dec_out[b][1])
+    od = onet.get_derivs()
+    scale = max(1.0, np.abs(od).max())
+    assert np.abs(od - gd).max() < 5e-3 * scale      # end to end incl. the aligner's amplification
+    # backward in isolation: same deltas into both
+    rng = np.random.default_rng(5)
+    deltas = (rng.standard_normal(out.shape) * 0.1).astype(np.float32)
+    gnet.clear_derivs()
+    gnet.forward(x, Ts)
+    din = gnet.backward(deltas)
+    gd = gnet.get_derivs()
+    onet.clear_derivs()
+    for b in range(B):
+        onet.forward(xs[b])
+        o_din = onet.backward(split(deltas, Ts)[b])
+        assert np.abs(o_din - split(din, Ts)[b]).max() < TOL * max(1.0, np.abs(o_din).max())
+    od = onet.get_derivs()
+    assert np.abs(od - gd).max() < TOL * max(1.0, np.abs(od).max())
+
+
+def test_ctc_known_answers_on_gpu(ffi):
+    # the reference's own golden vectors (test-ctc.cc:47-109) through the CUDA aligner
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ctc_kat.json")))
+    for c in kat["cases"]:
+        outs = np.array(c["outputs"], np.float32)
+        tg = np.array(c["targets"])
+        states = tg.argmax(1).astype(np.int32)
+        net = ffi.Net(8, 4, outs.shape[1])
+        al = net.ctc_align_states(outs, [outs.shape[0]], states, [states.size])
+        assert np.abs(al - np.array(c["expected"])).max() < kat["tolerance"], c["name"]
+
+
+def test_training_steps_track_oracle(ffi, oracle):
+    ni, nh, nc, B = 48, 100, 83, 4
+    x, Ts, labels, L = synth.make_lines(B, (40, 60), ni, nc, seed=11)
+    onet, gnet = make_pair(ffi, oracle, ni, nh, nc, "trained")
+    lr, mom = 1e-3, 0.9
+    for step in range(3):
+        dec, _, _ = gnet.train_step(x, Ts, labels, L, lr, mom)
+        onet.train_lines(x, Ts, labels, L, lr, mom, threads=1, reps=1)
+    gp, op = gnet.get_params(), onet.get_params()
+    assert np.abs(gp - op).max() < 1e-4
+    gd, od = gnet.get_derivs(), onet.get_derivs()
+    assert np.abs(gd - od).max() < 5e-3 * max(1.0, np.abs(od).max())
+
+
+def test_derivs_accumulate_and_momentum(ffi):
+    # Params.d accumulates over backward calls and doubles as the momentum buffer (clstm.cc:201-217)
+    ni, nh, nc = 48, 16, 10
+    x, Ts, labels, L = synth.make_lines(2, 30, ni, nc, seed=2)
+    net = ffi.Net(ni, nh, nc)
+    net.set_params(synth.trained_like(net.nparams, 0.3))
+    net.forward(x, Ts); net.ctc_align(labels, L); net.backward()
+    d1 = net.get_derivs()
+    net.forward(x, Ts); net.ctc_align(labels, L); net.backward()
+    assert np.allclose(net.get_derivs(), 2 * d1, rtol=1e-5, atol=1e-6)
+    p0 = net.get_params()
+    net.sgd_update(1e-2, 0.9, 0.05)
+    clipped = np.clip(2 * d1, -0.05, 0.05)
+    assert np.allclose(net.get_params(), p0 + 1e-2 * clipped, atol=1e-6)
+    assert np.allclose(net.get_derivs(), 0.9 * clipped, rtol=1e-5, atol=1e-7)
+
+
+def test_full_size_properties(ffi):
+    # BASELINE config 2 at full size (nh=100, B=32, T=500): size-independent properties instead of the oracle
+    ni, nh, nc, B, T = 48, 100, 83, 32, 500
+    x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=4)
+    net = ffi.Net(ni, nh, nc)
+    net.set_params(synth.trained_like(net.nparams, 0.1))
+    out = net.forward(x, Ts)
+    al = net.ctc_align(labels, L)
+    assert np.isfinite(out).all() and np.isfinite(al).all()
+    assert np.abs(out.sum(1) - 1).max() < 1e-5 and np.abs(al.sum(1) - 1).max() < 1e-5   # check_normalized batches.h:159
+    # aligned mass only on blank and the line's own transcript classes
+    for b, (a, lab) in enumerate(zip(split(al, Ts), split(labels, L))):
+        mask = np.ones(nc, bool); mask[0] = False; mask[lab] = False
+        assert a[:, mask].max() == 0.0
+    # batch independence: line 5 alone gives the same outputs as inside the batch
+    o5 = net.forward(split(x, Ts)[5], [T])
+    assert np.abs(o5 - split(out, Ts)[5]).max() < 1e-6
+    # reversal symmetry of the wiring: swapping the two directions' weights == time-reversing the input
+    p = net.get_params()
+    blk = 4 * nh * (1 + ni + nh)
+    swapped = p.copy(); swapped[:blk] = p[blk:2 * blk]; swapped[blk:2 * blk] = p[:blk]
+    w1 = p[2 * blk:].reshape(1 + 2 * nh, nc).copy()          # col-major nc x (1+2nh) => rows here are columns
+    w1s = w1.copy(); w1s[1:1 + nh] = w1[1 + nh:]; w1s[1 + nh:] = w1[1:1 + nh]
+    swapped[2 * blk:] = w1s.ravel()
+    net.set_params(swapped)
+    xr = np.concatenate([xx[::-1] for xx in split(x, Ts)], 0)
+    outr = net.forward(xr, Ts)
+    outr = np.concatenate([oo[::-1] for oo in split(outr, Ts)], 0)
+    assert np.abs(outr - out).max() < 1e-5
+
+
+def test_error_behaviour(ffi):
+    net = ffi.Net(48, 16, 10)
+    with pytest.raises(ffi.Error):
+        net.set_params(np.zeros(3, np.float32))                      # size mismatch (clstm.cc:871)
+    with pytest.raises(ffi.Error):
+        net.backward()                                                # backward before forward
+    x, Ts, labels, L = synth.make_lines(1, 20, 48, 10, seed=0)
+    net.forward(x, Ts)
+    with pytest.raises(ffi.Error):
+        net.ctc_align(np.array([12], np.int32), [1])                  # label out of range
+    with pytest.raises(ffi.Error):
+        net.forward(x, [0])                                           # empty line

@@ -118,3 +118,10 @@ def test_training_reduces_ctc_error(oracle):
     out = net.forward(img)
     cs, _ = oracle.trivial_decode(out)
     assert cs.tolist() == labels
+
+
+def test_product_side_init_matches_reference_lcg(oracle):
+    # clstm_b200.synth.reference_init (host side of the product) must reproduce the reference init bit for bit
+    from clstm_b200 import synth
+    net = oracle.BidiOracle(9, 6, 5, seed=0.222)
+    assert np.array_equal(net.get_params(), synth.reference_init(9, 6, 5, seed=0.222))
