@@ -180,4 +180,4 @@ def test_error_behaviour(ffi):
     with pytest.raises(ffi.Error):
         net.ctc_align(np.array([12], np.int32), [1])                  # label out of range
     with pytest.raises(ffi.Error):
-        net.forward(x, [0])                                           # empty line
+        net.forward(x[:0], [0])                                       # empty line
