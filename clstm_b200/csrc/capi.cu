@@ -110,7 +110,12 @@ struct clstm_b200_net {
   float *x = nullptr, *XP[2] = {}, *G[2] = {}, *C[2] = {}, *H = nullptr, *Hprev[2] = {}, *out = nullptr,
         *aligned = nullptr, *delta = nullptr, *dH = nullptr, *DG[2] = {}, *dx = nullptr;
   float *lm = nullptr, *lr = nullptr, *rl = nullptr;
-  int* meta = nullptr;          // device: T | off | L | lab_off | order | labels
+  int* meta = nullptr;          // device: T | off | L | lab_off | order | st_off | labels
+  int* tiles = nullptr;         // device: tile_line | tile_t0
+  int* h_tiles = nullptr;
+  int capTiles = 0;
+  double* tot = nullptr;        // CTC per-state totals
+  int capStates = 0;
   long long* lat_off = nullptr;
   int* status = nullptr;
   int* amax[2] = {};
@@ -125,7 +130,7 @@ struct clstm_b200_net {
   int* h_small = nullptr;       // status + counts
   cudaEvent_t meta_done = nullptr;   // guards re-use of the pinned staging buffers
 
-  std::vector<int> hT, hOff, hL, hLabOff, hOrder;
+  std::vector<int> hT, hOff, hL, hLabOff, hOrder, hStOff;
   Lines ln{};
   bool have_batch = false, have_forward = false, have_labels = false, have_ctc = false, raw_targets = false;
   const char* variant = "generic";
@@ -270,9 +275,12 @@ int ensure_lines(clstm_b200_net* n, int B, int nlab) {
     if (n->h_meta) cudaFreeHost(n->h_meta);
     if (n->h_lat) cudaFreeHost(n->h_lat);
     if (n->h_small) cudaFreeHost(n->h_small);
-    TRY(dev_alloc(&n->meta, (size_t)5 * cb + cl));
+    TRY(dev_alloc(&n->meta, (size_t)6 * cb + cl));
+    dev_free(n->tot);
+    n->capStates = 2 * cl + cb;
+    TRY(dev_alloc(&n->tot, (size_t)n->capStates));
     TRY(dev_alloc(&n->lat_off, (size_t)cb));
-    CU(cudaHostAlloc((void**)&n->h_meta, ((size_t)5 * cb + cl) * sizeof(int), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&n->h_meta, ((size_t)6 * cb + cl) * sizeof(int), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&n->h_lat, (size_t)cb * sizeof(long long), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&n->h_small, ((size_t)2 * cb + 8) * sizeof(int), cudaHostAllocDefault));
     for (int w = 0; w < 2; w++) { dev_free(n->dcnt[w]); TRY(dev_alloc(&n->dcnt[w], (size_t)cb)); }
@@ -280,6 +288,17 @@ int ensure_lines(clstm_b200_net* n, int B, int nlab) {
     n->capLab = cl;
     n->capDec = 0;  // decode buffers depend on capB
   }
+  return 0;
+}
+int ensure_tiles(clstm_b200_net* n, int ntiles) {
+  if (ntiles <= n->capTiles) return 0;
+  CU(cudaStreamSynchronize(n->st));
+  dev_free(n->tiles);
+  if (n->h_tiles) cudaFreeHost(n->h_tiles);
+  const int cap = ntiles + ntiles / 4 + 64;
+  TRY(dev_alloc(&n->tiles, (size_t)2 * cap));
+  CU(cudaHostAlloc((void**)&n->h_tiles, (size_t)2 * cap * sizeof(int), cudaHostAllocDefault));
+  n->capTiles = cap;
   return 0;
 }
 int ensure_decode(clstm_b200_net* n, int max_per_line) {
@@ -331,11 +350,24 @@ int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const
   std::iota(n->hOrder.begin(), n->hOrder.end(), 0);
   std::stable_sort(n->hOrder.begin(), n->hOrder.end(), [&](int a, int c) { return T[a] > T[c]; });
   long long lat = 0;
-  int lo = 0;
+  int lo = 0, so = 0, ntiles = 0;
+  for (int b = 0; b < B; b++) ntiles += (T[b] + 31) / 32;
+  TRY(ensure_tiles(n, ntiles));
+  if (n->meta_done) CU(cudaEventSynchronize(n->meta_done));
+  n->hStOff.assign(B, 0);
+  ntiles = 0;
   for (int b = 0; b < B; b++) {
     if (L) { n->hL[b] = L[b]; n->hLabOff[b] = lo; lo += L[b]; }
+    const int Sb = raw ? n->hL[b] : 2 * n->hL[b] + 1;
+    n->hStOff[b] = so;
+    so += Sb;
     n->h_lat[b] = lat;
-    lat += (long long)T[b] * (raw ? n->hL[b] : 2 * n->hL[b] + 1);
+    lat += (long long)T[b] * Sb;
+    for (int t0 = 0; t0 < T[b]; t0 += 32) {
+      n->h_tiles[ntiles] = b;
+      n->h_tiles[n->capTiles + ntiles] = t0;
+      ntiles++;
+    }
   }
   if (L) {
     for (int i = 0; i < nlab; i++)
@@ -349,15 +381,18 @@ int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const
   memcpy(hm + 2 * cb, n->hL.data(), B * sizeof(int));
   memcpy(hm + 3 * cb, n->hLabOff.data(), B * sizeof(int));
   memcpy(hm + 4 * cb, n->hOrder.data(), B * sizeof(int));
-  if (L && nlab) memcpy(hm + 5 * cb, labels, nlab * sizeof(int));
-  CU(cudaMemcpyAsync(n->meta, hm, ((size_t)5 * cb + nlab) * sizeof(int), cudaMemcpyHostToDevice, n->st));
+  memcpy(hm + 5 * cb, n->hStOff.data(), B * sizeof(int));
+  if (L && nlab) memcpy(hm + 6 * cb, labels, nlab * sizeof(int));
+  CU(cudaMemcpyAsync(n->meta, hm, ((size_t)6 * cb + nlab) * sizeof(int), cudaMemcpyHostToDevice, n->st));
+  CU(cudaMemcpyAsync(n->tiles, n->h_tiles, ((size_t)n->capTiles + ntiles) * sizeof(int), cudaMemcpyHostToDevice, n->st));
   CU(cudaMemcpyAsync(n->lat_off, n->h_lat, (size_t)B * sizeof(long long), cudaMemcpyHostToDevice, n->st));
   if (!n->meta_done) CU(cudaEventCreateWithFlags(&n->meta_done, cudaEventDisableTiming));
   CU(cudaEventRecord(n->meta_done, n->st));
   Lines& ln = n->ln;
   ln.B = B; ln.N = (int)N; ln.Tmax = tmax;
   ln.T = n->meta; ln.off = n->meta + cb; ln.L = n->meta + 2 * cb; ln.lab_off = n->meta + 3 * cb;
-  ln.order = n->meta + 4 * cb; ln.labels = n->meta + 5 * cb; ln.lat_off = n->lat_off;
+  ln.order = n->meta + 4 * cb; ln.st_off = n->meta + 5 * cb; ln.labels = n->meta + 6 * cb; ln.lat_off = n->lat_off;
+  ln.ntiles = ntiles; ln.tile_line = n->tiles; ln.tile_t0 = n->tiles + n->capTiles;
   n->have_batch = true;
   n->have_labels = (L != nullptr);
   n->raw_targets = raw;
@@ -398,7 +433,7 @@ int run_forward(clstm_b200_net* n) {
     Scope s(n, PH_SOFTMAX_FWD);
     s.launches(gemm_f32(n->st, N, nc, 2 * no, n->H, 2 * no, 1, n->v + n->oW1, 1, 2 * no, n->out, nc,
                         n->v + n->oB1, 0.f, nullptr, 0, n->num_sms));
-    softmax_rows(n->st, n->out, N, nc);
+    softmax_rows(n->st, n->out, N, nc, n->amax[0], n->amaxv[0]);
     s.launches(1);
   }
   TRY(check_launch("forward"));
@@ -411,9 +446,8 @@ int run_ctc(clstm_b200_net* n) {
   Scope s(n, PH_CTC);
   CtcArgs a;
   a.nc = n->nc; a.out = n->out; a.aligned = n->aligned; a.delta = n->delta;
-  a.lmatch = n->lm; a.lr = n->lr; a.rl = n->rl; a.status = n->status; a.raw = n->raw_targets ? 1 : 0;
-  ctc_align(n->st, n->ln, a);
-  s.launches(1);
+  a.lmatch = n->lm; a.lr = n->lr; a.rl = n->rl; a.tot = n->tot; a.amax = n->amax[1]; a.amaxv = n->amaxv[1]; a.status = n->status; a.raw = n->raw_targets ? 1 : 0;
+  s.launches(ctc_align(n->st, n->ln, a));
   TRY(check_launch("ctc_align"));
   n->have_ctc = true;
   return 0;
@@ -488,8 +522,8 @@ int run_update(clstm_b200_net* n, float lr, float mom, float clip) {
 int run_decode(clstm_b200_net* n, int which, int max_per_line) {
   TRY(ensure_decode(n, max_per_line));
   Scope s(n, PH_DECODE);
-  decode_lines(n->st, n->ln, which ? n->aligned : n->out, n->nc, n->amax[which], n->amaxv[which], n->dcls[which],
-               n->dlocs[which], n->dcnt[which], n->capDec);
+  decode_lines(n->st, n->ln, n->amax[which], n->amaxv[which], n->dcls[which], n->dlocs[which], n->dcnt[which],
+               n->capDec);
   s.launches(1);
   return check_launch("decode");
 }
@@ -573,7 +607,7 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   cudaMemsetAsync(n->Rt[0], 0, (size_t)4 * no * no * sizeof(float), n->st);
   cudaMemsetAsync(n->Rt[1], 0, (size_t)4 * no * no * sizeof(float), n->st);
   cudaMemsetAsync(n->status, 0, sizeof(int), n->st);
-  if (lstm_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
+  if (lstm_configure() != 0 || ctc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   n->variant = lstm_variant_for(no);
   if (cudaStreamSynchronize(n->st) != cudaSuccess) { clstm_b200_destroy(n); return fail("device initialisation failed"); }
   *out = n;
@@ -588,7 +622,8 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   free_batch(n);
   dev_free(n->v); dev_free(n->d); dev_free(n->g); dev_free(n->Rt[0]); dev_free(n->Rt[1]);
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->status);
-  dev_free(n->ws);
+  dev_free(n->ws); dev_free(n->tiles); dev_free(n->tot);
+  if (n->h_tiles) cudaFreeHost(n->h_tiles);
   for (int w = 0; w < 2; w++) { dev_free(n->dcls[w]); dev_free(n->dlocs[w]); dev_free(n->dcnt[w]); }
   if (n->h_meta) cudaFreeHost(n->h_meta);
   if (n->h_lat) cudaFreeHost(n->h_lat);

@@ -1,16 +1,18 @@
-// ctc.cu -- OCRopus-style CTC alignment, one CTA per text line.
+// ctc.cu -- OCRopus-style CTC alignment on the device.
 //
-// Restates /root/reference/ctc.cc:24-134 (see SURVEY.md Appendix A.4) for one-hot targets built by mktargets
-// (ctc.cc:148-157): S = 2L+1 states, even states = class 0 (blank), odd state s = transcript[(s-1)/2].
-//   phase A  o' = max(1e-5,o) / sum ;  lmatch(t,s) = log o'(t, label_s)                       ctc.cc:68-77
-//   phase B  forward lattice lr and the backward lattice rl (forward algorithm on the doubly flipped lmatch)
-//            with the soft start penalty skip = -5 per state/step and log_add's |x-y|>10 cutoff ctc.cc:24-55
-//   phase C  epath = limexp(lr + rl - max) ; normalised per STATE over TIME                    ctc.cc:83-89
-//   phase D  aligned(t,c) = sum_{s: label_s = c} epath(t,s) ; normalised per t ; delta = aligned - out
-//                                                                                   ctc.cc:92-109, clstmhl.h:211-212
-// The two lattices are the only serial part: each is walked by ONE warp (lane l owns KS consecutive states), so a
-// time step costs one warp shuffle and no block barrier; both warps run concurrently.  Everything else is
-// parallel over (t, s).  Sums the reference accumulates in double are accumulated in double here too.
+// Restates /root/reference/ctc.cc:24-134 (SURVEY.md Appendix A.4) for one-hot targets built by mktargets
+// (ctc.cc:148-157: S = 2L+1 states, even states = class 0, odd state s = transcript[(s-1)/2]) or given explicitly as
+// one class per state (the `Classes& targets` overload, ctc.cc:136-146; "raw" mode, used by the reference's own
+// known-answer tests).  Four kernels; only the lattice recursion is serial:
+//   ctc_lmatch     (grid: 32-column tiles)  o' = max(1e-5,o)/sum ; lmatch(t,s) = log o'(t, class_s)      ctc.cc:68-77
+//   ctc_lattice    (grid: lines, 2 warps)   forward lattice lr and backward lattice rl, skip=-5 soft start,
+//                                           log_add with the |x-y|>10 cutoff                           ctc.cc:24-55
+//   ctc_stats      (grid: lines)            both = lr+rl ; max ; epath = limexp(both-max) ; per-STATE totals over TIME
+//                                                                                                       ctc.cc:83-89
+//   ctc_posterior  (grid: 32-column tiles)  epath /= total_s ; aligned(t,c) = sum_{s: class_s=c} epath(t,s) ;
+//                                           aligned /= row total ; delta = aligned - out   ctc.cc:84-109, clstmhl.h:211
+// Everything the reference accumulates in double is accumulated in double here; its Float sums keep their
+// sequential order where that is free (asum1).  Lattices live in L2-resident global scratch (T x S per line).
 #include "kernels.h"
 
 namespace cb200 {
@@ -21,199 +23,272 @@ __device__ __forceinline__ float limexp_(float x) {  // tensor.h:78-82
   if (x > 30.f) return expf(30.f);
   return expf(x);
 }
-__device__ __forceinline__ float log_add_(float x, float y) {  // tensor.h:86-89
-  if (fabsf(x - y) > 10.f) return fmaxf(x, y);
-  return logf(expf(x - y) + 1.f) + y;
+// log_add for the lattice recursion: same branch structure as tensor.h:86-89, exp/log through the MUFU
+// approximations (abs. error ~1e-7, below the Float resolution of lattice values, which run to O(10^2..10^3)).
+__device__ __forceinline__ float log_add_fast(float x, float y) {
+  const float d = x - y;
+  float e, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d * 1.4426950408889634f));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(e + 1.f));
+  const float r = fmaf(l, 0.6931471805599453f, y);
+  return (fabsf(d) > 10.f) ? fmaxf(x, y) : r;
+}
+__device__ __forceinline__ int state_class(const int* lab, int s, bool raw) {   // mktargets ctc.cc:148-157
+  return raw ? lab[s] : ((s & 1) ? lab[(s - 1) >> 1] : 0);
 }
 
-constexpr int CTC_THREADS = 256;
+constexpr int TC = 32;            // columns per tile
+constexpr int TILE_THREADS = 256;
 
+// ------------------------------------------------------------------------------------------------ lmatch
+// dynamic smem: tile[TC][ncp] | sum[TC] | lblank[TC] | cls[S]
+__global__ void __launch_bounds__(TILE_THREADS) ctc_lmatch_kernel(Lines ln, CtcArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int b = ln.tile_line[blockIdx.x], t0 = ln.tile_t0[blockIdx.x];
+  const int T = ln.T[b], off = ln.off[b], L = ln.L[b];
+  const bool raw = a.raw != 0;
+  const int S = raw ? L : 2 * L + 1;
+  const int nc = a.nc, ncp = nc | 1;                     // odd row stride: conflict-free column walks
+  const int ncols = min(TC, T - t0);
+  float* tile = sm;
+  float* sum_s = sm + TC * ncp;
+  float* lbl_s = sum_s + TC;
+  int* cls_s = reinterpret_cast<int*>(lbl_s + TC);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int* lab = ln.labels + ln.lab_off[b];
+  for (int s = tid; s < S; s += TILE_THREADS) cls_s[s] = state_class(lab, s, raw);
+  const float* __restrict__ src = a.out + (size_t)(off + t0) * nc;
+  for (int i = tid; i < ncols * nc; i += TILE_THREADS) {  // coalesced tile load
+    const int c = i / nc, k = i - c * nc;
+    tile[c * ncp + k] = fmaxf(1e-5f, src[i]);             // out(i) = fmax(lo, outputs)  ctc.cc:70
+  }
+  __syncthreads();
+  if (warp == 0 && lane < ncols) {                        // asum1 (tensor.h:337-342): sequential Float sum
+    const float* row = tile + lane * ncp;
+    float sum = 0.f;
+    for (int i = 0; i < nc; i++) sum += row[i];
+    sum_s[lane] = sum;
+    lbl_s[lane] = (float)log((double)(row[0] / sum));     // blank state: computed once per column
+  }
+  __syncthreads();
+  float* __restrict__ lm = a.lmatch + ln.lat_off[b] + (size_t)t0 * S;
+  for (int i = tid; i < ncols * S; i += TILE_THREADS) {   // memory order == idx order: coalesced stores
+    const int c = i / S, s = i - c * S;
+    float v;
+    if (!raw && !(s & 1)) v = lbl_s[c];
+    else v = (float)log((double)(tile[c * ncp + cls_s[s]] / sum_s[c]));   // double log stored as Float ctc.cc:73-76
+    lm[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ lattice
 // One lattice pass by one warp.  rev=0: lr(t,s).  rev=1: processes i-th step on column T-1-i and state index jj
 // on real state S-1-jj, result stored at rl(T-1-i, S-1-jj)  (forwardbackward, ctc.cc:42-55).
-template <int KS>
+// Lane l owns KS consecutive states; a time step is one shuffle plus KS log_adds.  The lmatch rows are
+// software-prefetched PF steps ahead into a register ring.
+template <int KS, int PF>
 __device__ void lattice_pass(const float* __restrict__ lm, float* __restrict__ out, int T, int S, bool rev) {
   const int lane = threadIdx.x & 31;
   float v[KS];
-  float m_cur[KS], m_nxt[KS];
+  float mq[PF][KS];
 #pragma unroll
-  for (int k = 0; k < KS; k++) {
-    const int jj = lane * KS + k;
-    v[k] = (float)(-5.0 * jj);                       // ctc.cc:30
-    m_cur[k] = 0.f;
-    m_nxt[k] = 0.f;
-  }
+  for (int k = 0; k < KS; k++) v[k] = (float)(-5.0 * (lane * KS + k));      // ctc.cc:30
   auto load_row = [&](int i, float* dst) {
     const int t = rev ? T - 1 - i : i;
     const float* row = lm + (size_t)t * S;
 #pragma unroll
     for (int k = 0; k < KS; k++) {
       const int jj = lane * KS + k;
-      if (jj < S) dst[k] = row[rev ? S - 1 - jj : jj];
+      dst[k] = (jj < S) ? row[rev ? S - 1 - jj : jj] : 0.f;
     }
   };
-  if (T > 0) load_row(0, m_cur);
-  for (int i = 0; i < T; i++) {
-    if (i + 1 < T) load_row(i + 1, m_nxt);
-    float below = __shfl_up_sync(0xffffffffu, v[KS - 1], 1);   // old v(jj-1) of the first state of this lane
-    if (lane == 0) below = (float)(-5.0 * i);                  // w(0) = skip*i   ctc.cc:32
 #pragma unroll
-    for (int k = KS - 1; k >= 0; k--) {
-      const float w = (k == 0) ? below : v[k - 1];             // w(j) = v(j-1) before the update  ctc.cc:33
-      const float same = v[k] + m_cur[k];
-      const float next = w + m_cur[k];
-      v[k] = log_add_(same, next);
+  for (int u = 0; u < PF; u++) {
+    if (u < T) load_row(u, mq[u]);
+    else {
+#pragma unroll
+      for (int k = 0; k < KS; k++) mq[u][k] = 0.f;
     }
-    const int t = rev ? T - 1 - i : i;
-    float* orow = out + (size_t)t * S;
+  }
+  for (int i0 = 0; i0 < T; i0 += PF) {
 #pragma unroll
-    for (int k = 0; k < KS; k++) {
-      const int jj = lane * KS + k;
-      if (jj < S) orow[rev ? S - 1 - jj : jj] = v[k];
+    for (int u = 0; u < PF; u++) {
+      const int i = i0 + u;
+      if (i < T) {
+        float below = __shfl_up_sync(0xffffffffu, v[KS - 1], 1);   // old v(jj-1) of the first state of this lane
+        if (lane == 0) below = -5.f * (float)i;                    // w(0) = skip*i   ctc.cc:32 (exact in Float)
+#pragma unroll
+        for (int k = KS - 1; k >= 0; k--) {
+          const float w = (k == 0) ? below : v[k - 1];             // w(j) = v(j-1) before the update  ctc.cc:33
+          const float same = v[k] + mq[u][k];
+          const float next = w + mq[u][k];
+          v[k] = log_add_fast(same, next);
+        }
+        const int t = rev ? T - 1 - i : i;
+        float* orow = out + (size_t)t * S;
+#pragma unroll
+        for (int k = 0; k < KS; k++) {
+          const int jj = lane * KS + k;
+          if (jj < S) orow[rev ? S - 1 - jj : jj] = v[k];
+        }
+        if (i + PF < T) load_row(i + PF, mq[u]);
+      }
     }
-#pragma unroll
-    for (int k = 0; k < KS; k++) m_cur[k] = m_nxt[k];
   }
 }
 
 __device__ void lattice_dispatch(const float* lm, float* out, int T, int S, bool rev) {
   const int ks = (S + 31) / 32;
-  if (ks <= 1) lattice_pass<1>(lm, out, T, S, rev);
-  else if (ks <= 2) lattice_pass<2>(lm, out, T, S, rev);
-  else if (ks <= 4) lattice_pass<4>(lm, out, T, S, rev);
-  else if (ks <= 8) lattice_pass<8>(lm, out, T, S, rev);
-  else if (ks <= 16) lattice_pass<16>(lm, out, T, S, rev);
-  else lattice_pass<32>(lm, out, T, S, rev);
+  if (ks <= 1) lattice_pass<1, 8>(lm, out, T, S, rev);
+  else if (ks <= 2) lattice_pass<2, 8>(lm, out, T, S, rev);
+  else if (ks <= 4) lattice_pass<4, 4>(lm, out, T, S, rev);
+  else if (ks <= 8) lattice_pass<8, 2>(lm, out, T, S, rev);
+  else if (ks <= 16) lattice_pass<16, 1>(lm, out, T, S, rev);
+  else lattice_pass<32, 1>(lm, out, T, S, rev);
 }
 
-__global__ void __launch_bounds__(CTC_THREADS) ctc_align_kernel(Lines ln, CtcArgs a) {
-  __shared__ int lab_s[kCtcMaxStates];        // class of each state
-  __shared__ float red_s[CTC_THREADS / 32];
-  __shared__ float mx_s;
-  __shared__ double acc_s[(CTC_THREADS / 32) * kCtcMaxClasses];
+__global__ void __launch_bounds__(64) ctc_lattice_kernel(Lines ln, CtcArgs a) {
   const int b = ln.order[blockIdx.x];
-  const int T = ln.T[b], off = ln.off[b], L = ln.L[b];
-  const bool raw = a.raw != 0;                 // raw: ln.L holds S and labels hold one class per state (ctc.cc:136-146)
-  const int S = raw ? L : 2 * L + 1;
-  const int nc = a.nc;
+  const int T = ln.T[b], L = ln.L[b];
+  const int S = a.raw ? L : 2 * L + 1;
+  const float* lm = a.lmatch + ln.lat_off[b];
+  if ((threadIdx.x >> 5) == 0) lattice_dispatch(lm, a.lr + ln.lat_off[b], T, S, false);
+  else lattice_dispatch(lm, a.rl + ln.lat_off[b], T, S, true);
+}
+
+// ------------------------------------------------------------------------------------------------ stats
+// per line: lmatch <- epath = limexp(lr + rl - max) ; tot[s] = max(1e-9, sum_t epath(t,s))  (double)
+__global__ void __launch_bounds__(256) ctc_stats_kernel(Lines ln, CtcArgs a) {
+  __shared__ float red_s[8];
+  __shared__ float mx_s;
+  __shared__ double part_s[4][64];
+  const int b = ln.order[blockIdx.x];
+  const int T = ln.T[b], L = ln.L[b];
+  const int S = a.raw ? L : 2 * L + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (S > kCtcMaxStates || nc > kCtcMaxClasses) {
-    if (tid == 0) atomicExch(a.status, 1);
-    return;
-  }
-  const int* lab = ln.labels + ln.lab_off[b];
-  for (int s = tid; s < S; s += CTC_THREADS)
-    lab_s[s] = raw ? lab[s] : ((s & 1) ? lab[(s - 1) >> 1] : 0);                            // mktargets ctc.cc:148-157
-  __syncthreads();
-  const float* __restrict__ out = a.out + (size_t)off * nc;
-  float* __restrict__ lm = a.lmatch + ln.lat_off[b];
-  float* __restrict__ lr = a.lr + ln.lat_off[b];
-  float* __restrict__ rl = a.rl + ln.lat_off[b];
-
-  // ---- phase A1: one thread per column: asum1 (tensor.h:337-342) is a sequential Float sum, keep its order.
-  //      The sums are parked in the first T entries of rl (rl is not written before phase B).
-  for (int t = tid; t < T; t += CTC_THREADS) {
-    const float* o = out + (size_t)t * nc;
-    float sum = 0.f;
-    for (int i = 0; i < nc; i++) sum += fmaxf(1e-5f, o[i]);
-    rl[t] = sum;
-  }
-  __syncthreads();
-  // ---- phase A2: one warp per column: lmatch(t,s) = log(o'(t,label_s)); the blank log is computed once
-  for (int t = warp; t < T; t += CTC_THREADS / 32) {
-    const float* o = out + (size_t)t * nc;
-    const float sum = rl[t];
-    float lblank = 0.f;
-    if (lane == 0) lblank = (float)log((double)(fmaxf(1e-5f, o[0]) / sum));   // double log, stored as Float ctc.cc:73-76
-    lblank = __shfl_sync(0xffffffffu, lblank, 0);
-    float* lrow = lm + (size_t)t * S;
-    for (int s = lane; s < S; s += 32) {
-      float v = lblank;
-      if (raw || (s & 1)) v = (float)log((double)(fmaxf(1e-5f, o[lab_s[s]]) / sum));
-      lrow[s] = v;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase B: warp 0 = forward lattice, warp 1 = backward lattice
-  if (warp == 0) lattice_dispatch(lm, lr, T, S, false);
-  else if (warp == 1) lattice_dispatch(lm, rl, T, S, true);
-  __syncthreads();
-
-  // ---- phase C: both = lr + rl (kept in lr), global max, epath, per-state normalisation over time
+  const float* __restrict__ lr = a.lr + ln.lat_off[b];
+  const float* __restrict__ rl = a.rl + ln.lat_off[b];
+  float* __restrict__ ep = a.lmatch + ln.lat_off[b];      // lmatch is dead after the lattice passes
   const int TS = T * S;
   float mx = -INFINITY;
-  for (int i = tid; i < TS; i += CTC_THREADS) {
-    const float v = lr[i] + rl[i];
-    lr[i] = v;
-    mx = fmaxf(mx, v);
-  }
+#pragma unroll 4
+  for (int i = tid; i < TS; i += 256) mx = fmaxf(mx, lr[i] + rl[i]);   // both = lr + rl ctc.cc:54 ; amax2 :83
 #pragma unroll
-  for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) red_s[warp] = mx;
   __syncthreads();
   if (tid == 0) {
     float m = red_s[0];
-    for (int i = 1; i < CTC_THREADS / 32; i++) m = fmaxf(m, red_s[i]);
+    for (int i = 1; i < 8; i++) m = fmaxf(m, red_s[i]);
     mx_s = m;
   }
   __syncthreads();
   mx = mx_s;
-  for (int i = tid; i < TS; i += CTC_THREADS) lr[i] = limexp_(lr[i] - mx);      // epath  ctc.cc:83
-  __syncthreads();
-  for (int s = warp; s < S; s += CTC_THREADS / 32) {                             // ctc.cc:84-89
-    double tot = 0.0;
-    for (int t = lane; t < T; t += 32) tot += (double)lr[(size_t)t * S + s];
-#pragma unroll
-    for (int o2 = 16; o2 > 0; o2 >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o2);
-    tot = fmax(1e-9, tot);
-    for (int t = lane; t < T; t += 32) {
-      const size_t i = (size_t)t * S + s;
-      lr[i] = (float)((double)lr[i] / tot);
+  double* __restrict__ tot = a.tot + ln.st_off[b];
+  const int sl = tid & 63, tr = tid >> 6;                 // 64 states x 4 time phases per sweep
+  for (int s0 = 0; s0 < S; s0 += 64) {
+    const int s = s0 + sl;
+    double acc = 0.0;
+    if (s < S) {
+#pragma unroll 4
+      for (int t = tr; t < T; t += 4) {
+        const int i = t * S + s;
+        const float e = limexp_((lr[i] + rl[i]) - mx);    // epath  ctc.cc:83 (kept in the lmatch buffer)
+        ep[i] = e;
+        acc += (double)e;
+      }
     }
+    part_s[tr][sl] = acc;
+    __syncthreads();
+    if (tr == 0 && s < S) tot[s] = fmax(1e-9, (part_s[0][sl] + part_s[1][sl]) + (part_s[2][sl] + part_s[3][sl]));
+    __syncthreads();
   }
-  __syncthreads();
+}
 
-  // ---- phase D: project states onto classes (double accumulators like ctc.cc:96-103), normalise per column,
-  //      emit delta.  One warp per column; per-warp class accumulators in shared memory.
-  float* __restrict__ al = a.aligned + (size_t)off * nc;
-  float* __restrict__ dl = a.delta + (size_t)off * nc;
-  double* acc = acc_s + warp * kCtcMaxClasses;
-  for (int t = warp; t < T; t += CTC_THREADS / 32) {
-    const float* ep = lr + (size_t)t * S;
-    for (int c = lane; c < nc; c += 32) acc[c] = 0.0;
+// ------------------------------------------------------------------------------------------------ posterior
+// dynamic smem: acc[8][nc] doubles | tot[S] doubles | cls[S] ints
+__global__ void __launch_bounds__(TILE_THREADS) ctc_posterior_kernel(Lines ln, CtcArgs a) {
+  extern __shared__ __align__(16) double dsm[];
+  const int b = ln.tile_line[blockIdx.x], t0 = ln.tile_t0[blockIdx.x];
+  const int T = ln.T[b], off = ln.off[b], L = ln.L[b];
+  const bool raw = a.raw != 0;
+  const int S = raw ? L : 2 * L + 1;
+  const int nc = a.nc;
+  const int ncols = min(TC, T - t0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* acc = dsm + warp * nc;
+  double* tot_s = dsm + 8 * nc;
+  int* cls_s = reinterpret_cast<int*>(tot_s + S);
+  const int* lab = ln.labels + ln.lab_off[b];
+  const double* __restrict__ tot = a.tot + ln.st_off[b];
+  for (int s = tid; s < S; s += TILE_THREADS) { cls_s[s] = state_class(lab, s, raw); tot_s[s] = tot[s]; }
+  __syncthreads();
+  const float* __restrict__ ep_l = a.lmatch + ln.lat_off[b];
+  for (int c = warp; c < ncols; c += TILE_THREADS / 32) {
+    const int t = t0 + c;
+    const float* ep = ep_l + (size_t)t * S;
+    for (int k = lane; k < nc; k += 32) acc[k] = 0.0;
     __syncwarp();
+    // epath(t,s) /= total_s (Float /= double, ctc.cc:88), then project onto classes with double accumulators (:96-103)
     if (raw) {
-      for (int s = lane; s < S; s += 32) atomicAdd(&acc[lab_s[s]], (double)ep[s]);
+      for (int s = lane; s < S; s += 32) atomicAdd(&acc[cls_s[s]], (double)(float)((double)ep[s] / tot_s[s]));
       __syncwarp();
     } else {
       double blank = 0.0;                                  // all even states are class 0
-      for (int s = 2 * lane; s < S; s += 64) blank += (double)ep[s];
+      for (int s = 2 * lane; s < S; s += 64) blank += (double)(float)((double)ep[s] / tot_s[s]);
 #pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) blank += __shfl_xor_sync(0xffffffffu, blank, o2);
-      for (int s = 2 * lane + 1; s < S; s += 64) atomicAdd(&acc[lab_s[s]], (double)ep[s]);
+      for (int o = 16; o > 0; o >>= 1) blank += __shfl_xor_sync(0xffffffffu, blank, o);
+      for (int s = 2 * lane + 1; s < S; s += 64) atomicAdd(&acc[cls_s[s]], (double)(float)((double)ep[s] / tot_s[s]));
       __syncwarp();
       if (lane == 0) acc[0] += blank;
       __syncwarp();
     }
-    double tot = 0.0;                                      // row total of the Float-rounded values  ctc.cc:104-109
-    for (int c = lane; c < nc; c += 32) tot += (double)(float)acc[c];
+    double rt = 0.0;                                       // row total of the Float-rounded values  ctc.cc:104-109
+    for (int k = lane; k < nc; k += 32) rt += (double)(float)acc[k];
 #pragma unroll
-    for (int o2 = 16; o2 > 0; o2 >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o2);
-    tot = fmax(tot, 1e-9);
-    const float* o = out + (size_t)t * nc;
-    for (int c = lane; c < nc; c += 32) {
-      const float v = (float)((double)(float)acc[c] / tot);
-      al[(size_t)t * nc + c] = v;
-      dl[(size_t)t * nc + c] = v - o[c];
+    for (int o = 16; o > 0; o >>= 1) rt += __shfl_xor_sync(0xffffffffu, rt, o);
+    rt = fmax(rt, 1e-9);
+    const size_t row = (size_t)(off + t) * nc;
+    float mv = -INFINITY;
+    int mi = -1;
+    for (int k = lane; k < nc; k += 32) {
+      const float v = (float)((double)(float)acc[k] / rt);
+      a.aligned[row + k] = v;
+      a.delta[row + k] = v - a.out[row + k];               // outputs[t].d = aligned - outputs  clstmhl.h:211-212
+      if (!(v < mv)) { mv = v; mi = k; }                   // argmax, ties -> last index (tensor.h:357-366)
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (ov > mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; }
+    }
+    if (lane == 0) { a.amax[off + t] = mi; a.amaxv[off + t] = mv; }
     __syncwarp();
   }
 }
 
 }  // namespace
 
-void ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a) {
-  ctc_align_kernel<<<ln.B, CTC_THREADS, 0, st>>>(ln, a);
+int ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a) {
+  const int ncp = a.nc | 1;
+  const size_t sm_a = (size_t)(TC * ncp + 2 * TC) * sizeof(float) + (size_t)kCtcMaxStates * sizeof(int);
+  const size_t sm_d = (size_t)(8 * a.nc + kCtcMaxStates) * sizeof(double) + (size_t)kCtcMaxStates * sizeof(int);
+  ctc_lmatch_kernel<<<ln.ntiles, TILE_THREADS, sm_a, st>>>(ln, a);
+  ctc_lattice_kernel<<<ln.B, 64, 0, st>>>(ln, a);
+  ctc_stats_kernel<<<ln.B, 256, 0, st>>>(ln, a);
+  ctc_posterior_kernel<<<ln.ntiles, TILE_THREADS, sm_d, st>>>(ln, a);
+  return 4;
+}
+
+int ctc_configure() {
+  // worst case dynamic smem: nc = kCtcMaxClasses
+  const size_t sm_a = (size_t)(TC * (kCtcMaxClasses | 1) + 2 * TC) * sizeof(float) + (size_t)kCtcMaxStates * sizeof(int);
+  const size_t sm_d = (size_t)(8 * kCtcMaxClasses + kCtcMaxStates) * sizeof(double) + (size_t)kCtcMaxStates * sizeof(int);
+  cudaError_t e = cudaFuncSetAttribute(ctc_lmatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(ctc_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_d);
+  return (int)e;
 }
 
 }  // namespace cb200

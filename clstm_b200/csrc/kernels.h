@@ -20,6 +20,10 @@ struct Lines {
   const int* labels;     // packed transcripts
   const long long* lat_off;  // [B] first element of line b's T x S lattice scratch
   const int* order;      // [B] line indices sorted by decreasing T (longest lines start first)
+  const int* st_off;     // [B] first CTC state of line b in the packed per-state arrays
+  int ntiles;            // 32-column tiles over all lines (a tile never crosses a line boundary)
+  const int* tile_line;  // [ntiles] line of the tile
+  const int* tile_t0;    // [ntiles] first column (within the line) of the tile
 };
 
 // ---------------------------------------------------------------- gemm.cu
@@ -67,23 +71,27 @@ struct CtcArgs {
   float* lmatch;          // lattice scratch, per line T x S
   float* lr;              // forward lattice
   float* rl;              // backward lattice
-  int* status;            // device int, set non-zero on unsupported transcript length
+  double* tot;            // per-state totals over time (packed, Lines::st_off)
+  int* amax;              // [N] argmax of aligned per column (tensor.h:357-366 tie rule)
+  float* amaxv;           // [N] its value
+  int* status;            // device int (reserved)
   int raw;                // 1: Lines::L holds the state count S and labels hold one class per state (ctc.cc:136-146)
 };
-void ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a);
+int ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a);   // returns kernels launched
+int ctc_configure();
 constexpr int kCtcMaxStates = 1024;  // S = 2L+1 must not exceed this
 constexpr int kCtcMaxClasses = 512;  // nclasses limit of the per-warp class accumulators
 
 // ---------------------------------------------------------------- misc.cu
 // out[n][:] = limexp(z[n][:]) / sum  in place (clstm_compute.cc:324-345)
-void softmax_rows(cudaStream_t st, float* z, int N, int nc);
+void softmax_rows(cudaStream_t st, float* z, int N, int nc, int* amax, float* amaxv);
 // d += g; g = 0; d = clamp(d); v += lr*d; d *= mom      (clstm_compute.cc:553-563)
 void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,
                 int fold_only);
 // Rt[k][r] = R[r][k] for both directions
 void transpose_R(cudaStream_t st, const float* R0, float* Rt0, const float* R1, float* Rt1, int no);
-// trivial_decode + argmax per line (ctc.cc:159-194, tensor.h:357-366)
-void decode_lines(cudaStream_t st, const Lines& ln, const float* probs, int nc, int* argmax_idx, float* argmax_val,
-                  int* classes, int* locs, int* counts, int max_per_line);
+// trivial_decode per line (ctc.cc:159-194) from the per-column argmax arrays written by softmax_rows / ctc_posterior
+void decode_lines(cudaStream_t st, const Lines& ln, const int* argmax_idx, const float* argmax_val, int* classes,
+                  int* locs, int* counts, int max_per_line);
 
 }  // namespace cb200

@@ -151,194 +151,346 @@ __global__ void lstm_bwd_generic(Lines ln, LstmBwdArgs a) {
 // --------------------------------------------------------------------------------------------------------
 // register-resident kernels
 // --------------------------------------------------------------------------------------------------------
+// Thread layout (forward): quad j = tid>>2 is hidden unit j, lane q = tid&3 of the quad owns, for all FOUR gate
+// rows 4j..4j+3, the quarter k in [q*SL, (q+1)*SL) of the recurrent weights (4 x SL values, register resident,
+// packed f32x2).  Per step a thread reads only ITS quarter of h (SLP/4 LDS.128 instead of NO/4), runs four
+// independent FFMA2 chains (one per gate row), and the quad reduce-scatters the four partial sums with three
+// shuffles so that lane q ends up with the full pre-activation of gate q.
 template <int NO> struct RegCfg {
-  static constexpr int NOP = (NO + 3) & ~3;            // K padded to a multiple of 4 (float4 smem reads)
-  static constexpr int NP = NOP / 2;                   // packed pairs per thread
+  static constexpr int SL = (NO + 3) / 4;              // k-slice length per lane
+  static constexpr int SLP = (SL + 3) & ~3;            // padded to float4 granularity (pad reads hit zeros)
+  static constexpr int NVEC = SLP / 4;                 // LDS.128 per step
+  static constexpr int SSTR = SLP + 4 * (((SLP / 4) & 1) ? 0 : 1);  // slice stride: odd multiple of 16 B => conflict-free
   static constexpr int ROWS = 4 * NO;
   static constexpr int THREADS = (ROWS + 31) & ~31;
+  // backward: k-groups of 4 outputs x 16 row-slices of SLR rows
+  static constexpr int KG = (NO + 3) / 4;
+  static constexpr int SLR = (ROWS + 15) / 16;
+  static constexpr int SLRP = (SLR + 3) & ~3;
+  static constexpr int NVEC_R = SLRP / 4;
+  static constexpr int RSTR = SLRP + 4 * (((SLRP / 4) & 1) ? 0 : 1);
+  static constexpr int THREADS_B = (16 * KG + 31) & ~31;
 };
 
-// Forward.  thread r (< 4*NO) owns row r of R: pre[r] = XP[n][r] + sum_k R[r][k] h[k].
+
+// fast gate math: sigmoid(x) = 1/(1 + 2^(-x*log2e)) with the MUFU approximations (rel. error ~1e-6, far inside the
+// 1e-4 parity bar; tests/test_gpu_parity.py checks it against the libm-based oracle)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ ulonglong2 lds_v2u64(unsigned addr) {
+  ulonglong2 v;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+// per-thread asynchronous global->shared staging (LDGSTS): keeps the streamed operands off the register
+// scoreboards that the shared-memory loads of the recurrence wait on
+__device__ __forceinline__ void cp_async4(unsigned saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kStage = 4;   // depth of the per-thread staging rings
+
 template <int NO>
 __global__ void __launch_bounds__(RegCfg<NO>::THREADS, 1) lstm_fwd_regs(Lines ln, LstmFwdArgs a) {
   typedef RegCfg<NO> Cfg;
-  constexpr int NOP = Cfg::NOP, NP = Cfg::NP, ROWS = Cfg::ROWS;
-  __shared__ __align__(16) float h_s[2][NOP];
+  constexpr int SL = Cfg::SL, NVEC = Cfg::NVEC, SSTR = Cfg::SSTR, ROWS = Cfg::ROWS, THREADS = Cfg::THREADS;
+  constexpr int NPF = SL / 2, TAIL = SL & 1;
+  __shared__ __align__(16) float h_s[2][4 * SSTR];
+  __shared__ float xp_s[kStage][THREADS];                // per-thread ring of staged input projections
   const int tid = threadIdx.x;
   const int b = ln.order[blockIdx.x], d = blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
-  const bool active = tid < ROWS;
-  const int r = active ? tid : ROWS - 1;   // padding threads shadow the last row (results discarded)
-  const int j = r >> 2, g = r & 3;
-  const float* __restrict__ XP = a.XP[d] + r;
-  float* __restrict__ G = a.G[d] + r;
-  float* __restrict__ C = a.C[d] + j;
-  float* __restrict__ Hp = a.Hprev[d] + j;
-  float* __restrict__ H = a.H + d * NO + j;
+  // padding quads (THREADS > ROWS) are exact clones of the last quad: same loads, same stores, same values, so the
+  // whole loop is branch-free straight-line code for every thread
+  const int r = (tid < ROWS) ? tid : ROWS - 4 + (tid & 3);
+  const int j = r >> 2, q = r & 3;
+  const float* __restrict__ XPb = d ? a.XP[1] : a.XP[0];
+  float* __restrict__ Gb = d ? a.G[1] : a.G[0];
+  float* __restrict__ Cb = d ? a.C[1] : a.C[0];
+  float* __restrict__ Hpb = d ? a.Hprev[1] : a.Hprev[0];
+  float* __restrict__ Hb = a.H + d * NO;
 
-  u64 w[NP];
+  u64 w[4][NPF > 0 ? NPF : 1];                           // full pairs of the slice
+  float wt[4];                                           // odd tail element of the slice (SL odd)
   {
-    const float* Rr = a.R[d] + (size_t)r * NO;
+    const float* Rd = d ? a.R[1] : a.R[0];
 #pragma unroll
-    for (int p = 0; p < NP; p++) {
-      const float w0 = (2 * p < NO) ? Rr[2 * p] : 0.f;
-      const float w1 = (2 * p + 1 < NO) ? Rr[2 * p + 1] : 0.f;
-      w[p] = pack2(w0, w1);
+    for (int g = 0; g < 4; g++) {
+      const float* Rr = Rd + (size_t)(4 * j + g) * NO + q * SL;
+#pragma unroll
+      for (int p = 0; p < NPF; p++) {
+        const float w0 = (q * SL + 2 * p < NO) ? Rr[2 * p] : 0.f;
+        const float w1 = (q * SL + 2 * p + 1 < NO) ? Rr[2 * p + 1] : 0.f;
+        w[g][p] = pack2(w0, w1);
+      }
+      wt[g] = (TAIL && q * SL + SL - 1 < NO) ? Rr[SL - 1] : 0.f;
     }
   }
-  for (int k = tid; k < 2 * NOP; k += blockDim.x) (&h_s[0][0])[k] = 0.f;
+  for (int k = tid; k < 2 * 4 * SSTR; k += blockDim.x) (&h_s[0][0])[k] = 0.f;
+
+  const unsigned hs_base = (unsigned)__cvta_generic_to_shared(&h_s[0][0]);
+  constexpr unsigned BUFB = 4 * SSTR * 4;                                  // bytes per h buffer
+  unsigned rd_addr = hs_base + q * (SSTR * 4);                             // this lane's k-slice, buffer 0
+  unsigned wr_addr = hs_base + BUFB + ((j / SL) * SSTR + (j % SL)) * 4;    // h[j] in buffer 1
+  const unsigned xs_addr = (unsigned)__cvta_generic_to_shared(&xp_s[0][tid]);
+
+  // per-lane output stream, one unconditional store per step: q=0 (and its duplicate q=3) -> H[n] = h_t,
+  // q=1 -> C[n] = c_t, q=2 -> Hprev[n] = h_{t-1} (zero at the first step)
+  const int dt = d ? -1 : 1;
+  const int t0 = d ? T - 1 : 0;
+  float* __restrict__ obase = (q == 0 || q == 3) ? Hb : (q == 1) ? Cb : Hpb;
+  const unsigned ostride = (q == 0 || q == 3) ? 2 * NO : NO;
+  unsigned ncol = off + t0;
+
+  // stage the input projection of the first kStage-1 steps
+#pragma unroll
+  for (int u = 0; u < kStage - 1; u++) {
+    if (u < T) cp_async4(xs_addr + u * (THREADS * 4), XPb + (size_t)(ncol + u * dt) * ROWS + r);
+    cp_async_commit();
+  }
   __syncthreads();
 
-  const int dt = d ? -1 : 1;
-  int t = d ? T - 1 : 0;
-  // software prefetch of the input projection, 3 steps ahead
-  float xp0 = 0.f, xp1 = 0.f, xp2 = 0.f;
-  if (T > 0) xp0 = XP[(size_t)(off + t) * ROWS];
-  if (T > 1) xp1 = XP[(size_t)(off + t + dt) * ROWS];
-  if (T > 2) xp2 = XP[(size_t)(off + t + 2 * dt) * ROWS];
-  float c = 0.f;
-  for (int s = 0; s < T; s++, t += dt) {
-    const size_t n = (size_t)off + t;
-    float xp3 = 0.f;
-    if (s + 3 < T) xp3 = XP[(size_t)(off + t + 3 * dt) * ROWS];
-    const ulonglong2* hv = reinterpret_cast<const ulonglong2*>(h_s[s & 1]);
-    u64 acc0 = pack2(xp0, 0.f), acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
-#pragma unroll
-    for (int q = 0; q < NOP / 4; q++) {
-      const ulonglong2 h2 = hv[q];
-      if (q & 1) { ffma2(acc2, w[2 * q], h2.x); ffma2(acc3, w[2 * q + 1], h2.y); }
-      else       { ffma2(acc0, w[2 * q], h2.x); ffma2(acc1, w[2 * q + 1], h2.y); }
+  float c = 0.f, hprev = 0.f;
+  const int m_c = (q == 1) ? -1 : 0, m_p = (q == 2) ? -1 : 0, m_h = ~(m_c | m_p);
+  const bool hi2 = (q & 2) != 0, hi1 = (q & 1) != 0;
+  const float sc = (q == 3) ? -2.f * kLog2e : -kLog2e;
+  int tog = (int)BUFB;
+  for (int s = 0; s < T; s++) {
+    {  // stage step s+kStage-1, then make sure step s has landed (own element only: no cross-thread dependency)
+      const int sn = s + kStage - 1;
+      if (sn < T) cp_async4(xs_addr + (sn & (kStage - 1)) * (THREADS * 4), XPb + (size_t)(ncol + (kStage - 1) * dt) * ROWS + r);
+      cp_async_commit();
+      cp_async_wait<kStage - 1>();
     }
-    float s0, s1, s2, s3, s4, s5, s6, s7;
-    unpack2(acc0, s0, s1); unpack2(acc1, s2, s3); unpack2(acc2, s4, s5); unpack2(acc3, s6, s7);
-    const float pre = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-    // gates: sigmoid for gi,gf,go ; tanh for ci  (forward_full1, clstm.cc:614-617)
-    const float sc = (g == 3) ? 2.f : 1.f;
-    const float sg = 1.0f / (1.0f + expf(-sc * pre));
-    const float act = (g == 3) ? 2.f * sg - 1.f : sg;
-    if (active) G[n * ROWS] = act;
-    const int base = (tid & 31) & ~3;
-    const float gi = __shfl_sync(0xffffffffu, act, base + 0);
-    const float gf = __shfl_sync(0xffffffffu, act, base + 1);
-    const float go = __shfl_sync(0xffffffffu, act, base + 2);
-    const float ci = __shfl_sync(0xffffffffu, act, base + 3);
-    float cn = ci * gi;                                  // forward_statemem clstm_compute.cc:504-508
-    if (s > 0) cn = fmaf(gf, c, cn);
-    c = cn;
-    const float hh = tanhf_(c) * go;                     // forward_nonlingate :530-537
-    if (active) {
-      if (g == 0) { h_s[(s + 1) & 1][j] = hh; H[n * (2 * NO)] = hh; }
-      else if (g == 1) { C[n * NO] = c; }
-      else if (g == 2) {
-        if (s + 1 < T) Hp[(size_t)(off + t + dt) * NO] = hh;
-      } else {
-        if (s == 0) Hp[n * NO] = 0.f;
+    u64 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+    float htail = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; i++) {
+      const ulonglong2 h2 = lds_v2u64(rd_addr + 16 * i);
+      if (2 * i < NPF) {
+        ffma2(acc0, w[0][2 * i], h2.x); ffma2(acc1, w[1][2 * i], h2.x);
+        ffma2(acc2, w[2][2 * i], h2.x); ffma2(acc3, w[3][2 * i], h2.x);
+      } else if (TAIL && 2 * i == NPF) {
+        float dummy; unpack2(h2.x, htail, dummy);
+      }
+      if (2 * i + 1 < NPF) {
+        ffma2(acc0, w[0][2 * i + 1], h2.y); ffma2(acc1, w[1][2 * i + 1], h2.y);
+        ffma2(acc2, w[2][2 * i + 1], h2.y); ffma2(acc3, w[3][2 * i + 1], h2.y);
+      } else if (TAIL && 2 * i + 1 == NPF) {
+        float dummy; unpack2(h2.y, htail, dummy);
       }
     }
-    xp0 = xp1; xp1 = xp2; xp2 = xp3;
+    const float xp = lds_f32(xs_addr + (s & (kStage - 1)) * (THREADS * 4));
+    float lo, hi;
+    unpack2(acc0, lo, hi); const float p0 = fmaf(wt[0], htail, lo + hi);
+    unpack2(acc1, lo, hi); const float p1 = fmaf(wt[1], htail, lo + hi);
+    unpack2(acc2, lo, hi); const float p2 = fmaf(wt[2], htail, lo + hi);
+    unpack2(acc3, lo, hi); const float p3 = fmaf(wt[3], htail, lo + hi);
+    // quad reduce-scatter: lane q ends with the total of gate row q
+    float k0 = hi2 ? p2 : p0, k1 = hi2 ? p3 : p1;
+    const float s0 = hi2 ? p0 : p2, s1 = hi2 ? p1 : p3;
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    float pre = hi1 ? k1 : k0;
+    const float s2 = hi1 ? k0 : k1;
+    pre += __shfl_xor_sync(0xffffffffu, s2, 1);
+    pre += xp;
+    // gates: sigmoid for gi,gf,go ; tanh(x) = 2*sigmoid(2x)-1 for ci  (forward_full1, clstm.cc:614-617)
+    const float sg = rcp_approx(1.0f + ex2_approx(sc * pre));
+    const float act = (q == 3) ? fmaf(2.f, sg, -1.f) : sg;
+    Gb[ncol * ROWS + r] = act;
+    const float gi = __shfl_sync(0xffffffffu, act, 0, 4);
+    const float gf = __shfl_sync(0xffffffffu, act, 1, 4);
+    const float go = __shfl_sync(0xffffffffu, act, 2, 4);
+    const float ci = __shfl_sync(0xffffffffu, act, 3, 4);
+    c = fmaf(gf, c, ci * gi);                            // forward_statemem clstm_compute.cc:504-508 (c = 0 before step 0)
+    const float th = fmaf(2.f, rcp_approx(1.0f + ex2_approx(-2.f * kLog2e * c)), -1.f);
+    const float hh = th * go;                            // forward_nonlingate :530-537
+    sts_f32(wr_addr, hh);                                // all four lanes of the quad hold the same h: same address, same value
+    obase[(size_t)ncol * ostride + j] = __int_as_float((__float_as_int(hh) & m_h) | (__float_as_int(c) & m_c) |
+                                                        (__float_as_int(hprev) & m_p));   // branch-free per-lane select
+    hprev = hh;
+    ncol += dt;
     __syncthreads();
+    rd_addr += tog; wr_addr -= tog; tog = -tog;          // swap the h double buffer
   }
 }
 
-// Backward.  thread (k = tid>>2, p = tid&3) owns R[4i+p][k], i < NO: the part of column k of R that belongs to
-// gate p.  Per step: quad k recomputes the pointwise deltas of hidden unit k (redundantly in its 4 lanes), lane p
-// publishes delta_p, then every thread accumulates its quarter of  dh_prev[k] = sum_r R[r][k] delta[r]  and the
-// quad reduces with two shuffles.
+// Backward.  The serial product is dh_prev[k] = sum_r R[r][k] delta[r] (r < 4*NO gate rows, k < NO).
+// Thread tid: k-group kg = tid>>4 (outputs 4kg..4kg+3), row slice rs = tid&15 (rows rs*SLR .. +SLR): 4 x SLR weights
+// in registers.  Per step it reads its slice of delta (NVEC_R LDS.128), runs four FFMA2 chains (one per output),
+// and the 16 lanes of the k-group reduce with five shuffles, after which the four lanes {4kk..4kk+3} of the group
+// all hold dh_prev[4kg+kk] -- i.e. thread tid holds dh_prev[tid>>2] and plays gate p = tid&3 in the pointwise part.
 template <int NO>
-__global__ void __launch_bounds__(RegCfg<NO>::THREADS, 1) lstm_bwd_regs(Lines ln, LstmBwdArgs a) {
+__global__ void __launch_bounds__(RegCfg<NO>::THREADS_B, 1) lstm_bwd_regs(Lines ln, LstmBwdArgs a) {
   typedef RegCfg<NO> Cfg;
-  constexpr int NOP = Cfg::NOP, NP = Cfg::NP, ROWS = Cfg::ROWS;
-  __shared__ __align__(16) float dg_s[2][4][NOP];        // [buffer][gate][unit]
-  const int tid = threadIdx.x;
+  constexpr int ROWS = Cfg::ROWS, SLR = Cfg::SLR, NVEC = Cfg::NVEC_R, RSTR = Cfg::RSTR, THREADS = Cfg::THREADS_B;
+  constexpr int NPF = SLR / 2, TAIL = SLR & 1;
+  constexpr bool EXACT = (NO % 4) == 0;                  // no padded outputs inside the last k-group
+  extern __shared__ __align__(16) float bsm[];
+  float* dg_s = bsm;                                     // [2][16 * RSTR]  delta double buffer, [row slice][pos]
+  float* st_s = bsm + 2 * 16 * RSTR;                     // [kStage][THREADS][8] per-thread staging ring
+  int tid = threadIdx.x;
   const int b = ln.order[blockIdx.x], d = blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
-  const bool active = tid < ROWS;
-  const int rr = active ? tid : ROWS - 1;
-  const int k = rr >> 2, p = rr & 3;
-  const float* __restrict__ G = a.G[d] + 4 * k;
-  const float* __restrict__ C = a.C[d] + k;
-  const float* __restrict__ dH = a.dH + d * NO + k;
-  float* __restrict__ DG = a.DG[d] + rr;
+  // padding 16-lane groups (THREADS > 16*KG) are exact clones of the last k-group => straight-line code
+  const unsigned st_addr0 = (unsigned)__cvta_generic_to_shared(st_s + (size_t)tid * 8);
+  if (tid >= 16 * Cfg::KG) tid -= 16;
+  const int kraw = tid >> 2, p = tid & 3;
+  const bool active = EXACT || kraw < NO;
+  const int k = active ? kraw : NO - 1;
+  const int kg4 = (tid >> 4) * 4, rs = tid & 15;
+  const float* __restrict__ Gb = d ? a.G[1] : a.G[0];
+  const float* __restrict__ Cb = d ? a.C[1] : a.C[0];
+  const float* __restrict__ dHb = a.dH + d * NO;
+  float* __restrict__ DGb = d ? a.DG[1] : a.DG[0];
+  const int row = 4 * k + p;                             // the delta row this thread publishes
 
-  u64 w[NP];
+  u64 w[4][NPF > 0 ? NPF : 1];
+  float wt[4];
   {
-    const float* R = a.R[d];
+    const float* R = d ? a.R[1] : a.R[0];
 #pragma unroll
-    for (int q = 0; q < NP; q++) {
-      const int i0 = 2 * q, i1 = 2 * q + 1;
-      const float w0 = (i0 < NO) ? R[(size_t)(4 * i0 + p) * NO + k] : 0.f;
-      const float w1 = (i1 < NO) ? R[(size_t)(4 * i1 + p) * NO + k] : 0.f;
-      w[q] = pack2(w0, w1);
+    for (int kk = 0; kk < 4; kk++) {
+      const int kc = kg4 + kk;
+#pragma unroll
+      for (int q = 0; q < NPF; q++) {
+        const int r0 = rs * SLR + 2 * q, r1 = r0 + 1;
+        const float w0 = (r0 < ROWS && kc < NO) ? R[(size_t)r0 * NO + kc] : 0.f;
+        const float w1 = (r1 < ROWS && kc < NO) ? R[(size_t)r1 * NO + kc] : 0.f;
+        w[kk][q] = pack2(w0, w1);
+      }
+      const int rt = rs * SLR + SLR - 1;
+      wt[kk] = (TAIL && rt < ROWS && kc < NO) ? R[(size_t)rt * NO + kc] : 0.f;
     }
   }
-  for (int i = tid; i < 2 * 4 * NOP; i += blockDim.x) (&dg_s[0][0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * 16 * RSTR; i += blockDim.x) dg_s[i] = 0.f;
+
+  const unsigned ds_base = (unsigned)__cvta_generic_to_shared(dg_s);
+  constexpr unsigned BUFB = 16 * RSTR * 4;
+  unsigned rd_addr = ds_base + rs * (RSTR * 4);                                  // this lane's row slice
+  unsigned wr_addr = ds_base + ((row / SLR) * RSTR + (row % SLR)) * 4;           // where delta[row] lives
+  int tog = (int)BUFB;
+  constexpr unsigned STG = THREADS * 32;                                         // bytes per ring stage
+
+  const int dt = d ? 1 : -1;                 // column increment per backward step
+  unsigned ncol = off + (d ? 0 : T - 1);
+  // staged record of a step: {gi,gf,go,ci | c, c_prev, dH, -}; c_prev = cell of the previous FORWARD step
+  auto stage = [&](int u, unsigned col) {   // u = backward step index (0 .. T-1)
+    const unsigned sa = st_addr0 + (u & (kStage - 1)) * STG;
+    cp_async16(sa, Gb + (size_t)col * ROWS + 4 * k);
+    cp_async4(sa + 16, Cb + (size_t)col * NO + k);
+    if (u + 1 < T) cp_async4(sa + 20, Cb + (size_t)(col + dt) * NO + k);
+    cp_async4(sa + 24, dHb + (size_t)col * (2 * NO) + k);
+  };
+#pragma unroll
+  for (int u = 0; u < kStage - 1; u++) {
+    if (u < T) stage(u, ncol + u * dt);
+    cp_async_commit();
+  }
   __syncthreads();
 
-  // walk the direction's forward steps backwards: fs = T-1 .. 0 ; column t = d ? T-1-fs : fs
-  const int dt = d ? 1 : -1;                 // column increment per backward step
-  int t = d ? 0 : T - 1;
   float dhrec = 0.f, dcc = 0.f;
-  // prefetch queue (1 step ahead): gates, cell, previous cell, upstream delta
-  float4 g_n = make_float4(0.f, 0.f, 0.f, 0.f);
-  float c_n = 0.f, dh_n = 0.f;
-  if (T > 0) {
-    const size_t n = (size_t)off + t;
-    g_n = *reinterpret_cast<const float4*>(G + n * ROWS);
-    c_n = C[n * NO];
-    dh_n = dH[n * (2 * NO)];
-  }
-  int buf = 0;
-  for (int fs = T - 1; fs >= 0; fs--, t += dt, buf ^= 1) {
-    const size_t n = (size_t)off + t;
-    const float4 g4 = g_n;
-    const float c = c_n;
-    const float dhu = dh_n;
-    float cprev = 0.f;
-    if (fs > 0) {                            // loads for the next backward step (forward step fs-1)
-      const size_t n1 = (size_t)off + t + dt;
-      g_n = *reinterpret_cast<const float4*>(G + n1 * ROWS);
-      c_n = C[n1 * NO];
-      dh_n = dH[n1 * (2 * NO)];
-      cprev = c_n;   // consumed below only after the loads land; it is the same value as next step's c
+  const bool b8 = (rs & 8) != 0, b4 = (rs & 4) != 0;
+  const bool p_lo = (p & 1) != 0, p_hi = (p & 2) != 0;
+  for (int u = 0; u < T; u++) {              // u-th backward step = forward step fs = T-1-u
+    {
+      const int un = u + kStage - 1;
+      if (un < T) stage(un, ncol + (kStage - 1) * dt);
+      cp_async_commit();
+      cp_async_wait<kStage - 1>();
     }
-    const float gi = g4.x, gf = g4.y, go = g4.z, ci = g4.w;
+    const bool first = (u + 1 == T);         // forward step 0: no previous cell, no forget-gate derivative
+    const unsigned sa = st_addr0 + (u & (kStage - 1)) * STG;
+    const ulonglong2 gq = lds_v2u64(sa);
+    const ulonglong2 cq = lds_v2u64(sa + 16);
+    float gi, gf, go, ci, c, cprev, dhu, unused;
+    unpack2(gq.x, gi, gf); unpack2(gq.y, go, ci);
+    unpack2(cq.x, c, cprev); unpack2(cq.y, dhu, unused);
+    if (first) cprev = 0.f;
     const float dh = dhu + dhrec;
-    const float th = tanhf_(c);                              // backward_nonlingate clstm_compute.cc:539-547
-    const float dgo = th * dh;
-    const float dc = dcc + (1.f - th * th) * (go * dh);
-    float dgf = 0.f;
-    dcc = 0.f;
-    if (fs > 0) {                                            // backward_statemem :509-515
-      dgf = dc * cprev;
-      dcc = dc * gf;
-    }
-    const float dgi = dc * ci, dci = dc * gi;
-    float dl;                                                // backward_nonlin0 :231-267, this lane's gate p
-    if (p == 0) dl = gi * (1.f - gi) * dgi;
-    else if (p == 1) dl = gf * (1.f - gf) * dgf;
-    else if (p == 2) dl = go * (1.f - go) * dgo;
-    else dl = (1.f - ci * ci) * dci;
+    const float th = fmaf(2.f, rcp_approx(1.0f + ex2_approx(-2.f * kLog2e * c)), -1.f);   // tanh(c) as in forward
+    // backward_nonlingate clstm_compute.cc:539-547, backward_statemem :509-515, backward_nonlin0 :231-267
+    const float dc = fmaf(1.f - th * th, go * dh, dcc);
+    dcc = first ? 0.f : dc * gf;
+    // this lane's gate p: value y, its incoming derivative e = A*B, and f'(y); two-level selects, no branches
+    const float y0 = p_lo ? gf : gi, y1 = p_lo ? ci : go;
+    const float y = p_hi ? y1 : y0;
+    const float B0 = p_lo ? cprev : ci, B1 = p_lo ? gi : dh;
+    const float Bv = p_hi ? B1 : B0;
+    const float Av = (p == 2) ? th : dc;
+    const float e = Av * Bv;
+    const float fp = (1.f - y) * ((p == 3) ? (1.f + y) : y);
+    const float dl = fp * e;
     if (active) {
-      dg_s[buf][p][k] = dl;
-      DG[n * ROWS] = dl;
+      sts_f32(wr_addr, dl);
+      DGb[ncol * ROWS + row] = dl;
     }
     __syncthreads();
-    // quarter of dh_{fs-1}[k] = sum_i R[4i+p][k] * delta_p[i]
-    const ulonglong2* dv = reinterpret_cast<const ulonglong2*>(dg_s[buf][p]);
     u64 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+    float dtail = 0.f;
 #pragma unroll
-    for (int q = 0; q < NOP / 4; q++) {
-      const ulonglong2 d2 = dv[q];
-      if (q & 1) { ffma2(acc2, w[2 * q], d2.x); ffma2(acc3, w[2 * q + 1], d2.y); }
-      else       { ffma2(acc0, w[2 * q], d2.x); ffma2(acc1, w[2 * q + 1], d2.y); }
+    for (int i = 0; i < NVEC; i++) {
+      const ulonglong2 d2 = lds_v2u64(rd_addr + 16 * i);
+      if (2 * i < NPF) {
+        ffma2(acc0, w[0][2 * i], d2.x); ffma2(acc1, w[1][2 * i], d2.x);
+        ffma2(acc2, w[2][2 * i], d2.x); ffma2(acc3, w[3][2 * i], d2.x);
+      } else if (TAIL && 2 * i == NPF) {
+        float dummy; unpack2(d2.x, dtail, dummy);
+      }
+      if (2 * i + 1 < NPF) {
+        ffma2(acc0, w[0][2 * i + 1], d2.y); ffma2(acc1, w[1][2 * i + 1], d2.y);
+        ffma2(acc2, w[2][2 * i + 1], d2.y); ffma2(acc3, w[3][2 * i + 1], d2.y);
+      } else if (TAIL && 2 * i + 1 == NPF) {
+        float dummy; unpack2(d2.y, dtail, dummy);
+      }
     }
-    float s0, s1, s2, s3, s4, s5, s6, s7;
-    unpack2(acc0, s0, s1); unpack2(acc1, s2, s3); unpack2(acc2, s4, s5); unpack2(acc3, s6, s7);
-    float part = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    float lo, hi;
+    unpack2(acc0, lo, hi); const float p0 = fmaf(wt[0], dtail, lo + hi);
+    unpack2(acc1, lo, hi); const float p1 = fmaf(wt[1], dtail, lo + hi);
+    unpack2(acc2, lo, hi); const float p2 = fmaf(wt[2], dtail, lo + hi);
+    unpack2(acc3, lo, hi); const float p3 = fmaf(wt[3], dtail, lo + hi);
+    // 16-lane reduce: scatter over bits 8 and 4 (lane group rs>>2 keeps output kk = rs>>2), then all-reduce bits 2,1
+    float k0 = b8 ? p2 : p0, k1 = b8 ? p3 : p1;
+    const float s0 = b8 ? p0 : p2, s1 = b8 ? p1 : p3;
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 8);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+    float part = b4 ? k1 : k0;
+    const float s2 = b4 ? k0 : k1;
+    part += __shfl_xor_sync(0xffffffffu, s2, 4);
     part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
     dhrec = part;
+    ncol += dt;
+    rd_addr += tog; wr_addr += tog; tog = -tog;          // swap the delta double buffer
   }
+}
+
+template <int NO> constexpr size_t bwd_regs_smem() {
+  return (size_t)(2 * 16 * RegCfg<NO>::RSTR + kStage * RegCfg<NO>::THREADS_B * 8) * sizeof(float);
 }
 
 template <int NO>
@@ -347,7 +499,7 @@ void launch_fwd_regs(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
 }
 template <int NO>
 void launch_bwd_regs(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a) {
-  lstm_bwd_regs<NO><<<dim3(ln.B, 2), RegCfg<NO>::THREADS, 0, st>>>(ln, a);
+  lstm_bwd_regs<NO><<<dim3(ln.B, 2), RegCfg<NO>::THREADS_B, bwd_regs_smem<NO>(), st>>>(ln, a);
 }
 
 bool has_regs_variant(int no) { return no == 16 || no == 32 || no == 50 || no == 64 || no == 100; }
@@ -364,6 +516,12 @@ int lstm_configure() {
   cudaError_t e = cudaFuncSetAttribute(lstm_fwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(lstm_bwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e != cudaSuccess) return (int)e;
+#define CB200_BWD_SMEM(N_)                                                                                  \
+  e = cudaFuncSetAttribute(lstm_bwd_regs<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_regs_smem<N_>()); \
+  if (e != cudaSuccess) return (int)e;
+  CB200_BWD_SMEM(16) CB200_BWD_SMEM(32) CB200_BWD_SMEM(50) CB200_BWD_SMEM(64) CB200_BWD_SMEM(100)
+#undef CB200_BWD_SMEM
   return (int)e;
 }
 

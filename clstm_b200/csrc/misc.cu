@@ -12,7 +12,8 @@ __device__ __forceinline__ float limexp_(float x) {  // tensor.h:78-82
 
 // forward_softmax after the linear part (clstm_compute.cc:334-337): z = limexp(z); z /= colsum(z).
 // One warp per column, values kept in registers (nc <= 32*16).
-__global__ void softmax_rows_kernel(float* __restrict__ z, int N, int nc) {
+__global__ void softmax_rows_kernel(float* __restrict__ z, int N, int nc, int* __restrict__ amax,
+                                    float* __restrict__ amaxv) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int n = warp; n < N; n += nwarps) {
@@ -27,11 +28,24 @@ __global__ void softmax_rows_kernel(float* __restrict__ z, int N, int nc) {
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float mv = -INFINITY;
+    int mi = -1;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const int c = lane + 32 * i;
-      if (c < nc) row[c] = v[i] / sum;
+      if (c < nc) {
+        const float o = v[i] / sum;
+        row[c] = o;
+        if (!(o < mv)) { mv = o; mi = c; }                 // per-column argmax, ties -> last index (tensor.h:357-366)
+      }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (ov > mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; }
+    }
+    if (lane == 0) { amax[n] = mi; amaxv[n] = mv; }
   }
 }
 
@@ -69,59 +83,59 @@ __global__ void transpose_R_kernel(const float* __restrict__ R0, float* __restri
   }
 }
 
-// argmax (tensor.h:357-366, ties -> last index) for every column of a line, then trivial_decode (ctc.cc:159-194).
-// One CTA per line.  The scan over time is inherently sequential but tiny (one compare per column).
-__global__ void decode_kernel(Lines ln, const float* __restrict__ probs, int nc, int* __restrict__ amax,
-                              float* __restrict__ amax_val, int* __restrict__ classes, int* __restrict__ locs,
-                              int* __restrict__ counts, int max_per_line) {
+// trivial_decode (ctc.cc:159-194), one CTA per line, from per-column argmax (index, value) arrays.
+__global__ void decode_kernel(Lines ln, const int* __restrict__ amax, const float* __restrict__ amax_val,
+                              int* __restrict__ classes, int* __restrict__ locs, int* __restrict__ counts,
+                              int max_per_line) {
   const int b = blockIdx.x;
   const int T = ln.T[b], off = ln.off[b];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int t = warp; t < T; t += nw) {
-    const float* row = probs + (size_t)(off + t) * nc;
-    float mv = -INFINITY;
-    int mi = -1;
-    for (int c = lane; c < nc; c += 32) {
-      const float x = row[c];
-      if (!(x < mv)) { mv = x; mi = c; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-      if (ov > mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; }
-    }
-    if (lane == 0) { amax[off + t] = mi; amax_val[off + t] = mv; }
-  }
+  // in parallel: a run = maximal stretch of non-blank argmax frames; the thread that
+  // sits on a run's first frame walks the run (runs are a handful of frames), keeps the first strictly largest
+  // probability, and emits (class, frame) iff a blank closes the run.  A block scan orders the emitted symbols.
+  __shared__ int wsum[8];
+  __shared__ int base_s;
+  if (threadIdx.x == 0) base_s = 0;
   __syncthreads();
-  if (threadIdx.x == 0 && classes) {
-    int count = 0;
-    float mv = 0.f;
-    int mc = -1, mt = -1;
-    for (int t = 0; t < T; t++) {
-      const int index = amax[off + t];
-      const float v = amax_val[off + t];
-      if (index == 0) {
-        if (mc != -1 && mc != 0) {
-          if (count < max_per_line) { classes[(size_t)b * max_per_line + count] = mc; locs[(size_t)b * max_per_line + count] = mt; }
-          count++;
-        }
-        mv = 0.f; mc = -1; mt = -1;
-        continue;
+  for (int t0 = 0; t0 < T; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    int flag = 0, mc = -1, mt = -1;
+    if (t < T && amax[off + t] != 0 && (t == 0 || amax[off + t - 1] == 0)) {
+      float mv = 0.f;
+      int u = t;
+      for (; u < T; u++) {
+        const int index = amax[off + u];
+        if (index == 0) break;
+        const float v = amax_val[off + u];
+        if (v > mv) { mv = v; mc = index; mt = u; }
       }
-      if (v > mv) { mv = v; mc = index; mt = t; }
+      flag = (u < T && mc != -1) ? 1 : 0;      // "there should be a 0 at the end anyway": unclosed trailing run is dropped
     }
-    counts[b] = count;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int pre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < nw; w++) { if (w < warp) woff += wsum[w]; tot += wsum[w]; }
+    const int idx = base_s + woff + pre;
+    if (flag && idx < max_per_line) {
+      classes[(size_t)b * max_per_line + idx] = mc;
+      locs[(size_t)b * max_per_line + idx] = mt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) base_s += tot;
+    __syncthreads();
   }
+  if (threadIdx.x == 0) counts[b] = base_s;
 }
 }  // namespace
 
-void softmax_rows(cudaStream_t st, float* z, int N, int nc) {
+void softmax_rows(cudaStream_t st, float* z, int N, int nc, int* amax, float* amaxv) {
   if (N <= 0) return;
   const int threads = 256;
   int blocks = (N + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  softmax_rows_kernel<<<blocks, threads, 0, st>>>(z, N, nc);
+  softmax_rows_kernel<<<blocks, threads, 0, st>>>(z, N, nc, amax, amaxv);
 }
 
 void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,
@@ -137,10 +151,10 @@ void transpose_R(cudaStream_t st, const float* R0, float* Rt0, const float* R1, 
   transpose_R_kernel<<<grid, dim3(32, 8), 0, st>>>(R0, Rt0, R1, Rt1, no);
 }
 
-void decode_lines(cudaStream_t st, const Lines& ln, const float* probs, int nc, int* argmax_idx, float* argmax_val,
-                  int* classes, int* locs, int* counts, int max_per_line) {
+void decode_lines(cudaStream_t st, const Lines& ln, const int* argmax_idx, const float* argmax_val, int* classes,
+                  int* locs, int* counts, int max_per_line) {
   if (ln.B <= 0) return;
-  decode_kernel<<<ln.B, 256, 0, st>>>(ln, probs, nc, argmax_idx, argmax_val, classes, locs, counts, max_per_line);
+  decode_kernel<<<ln.B, 256, 0, st>>>(ln, argmax_idx, argmax_val, classes, locs, counts, max_per_line);
 }
 
 }  // namespace cb200
