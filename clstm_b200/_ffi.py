@@ -54,6 +54,7 @@ EXPORTS = {
     "clstm_b200_phase_stats": (C.c_int, [C.c_void_p, f32p, i64p, C.c_int]),
     "clstm_b200_stream": (C.c_void_p, [C.c_void_p]),
     "clstm_b200_lstm_variant": (C.c_char_p, [C.c_void_p]),
+    "clstm_b200_selftest_gemm": (C.c_int, [C.c_void_p, f32p, C.c_int]),
     "clstm_b200_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "clstm_b200_free_pinned": (None, [C.c_void_p]),
     "clstm_b200_last_error": (C.c_char_p, []),
@@ -251,6 +252,13 @@ class Net:
         cnt = np.zeros(n, np.int64)
         _chk(L.clstm_b200_phase_stats(self.h, ms.ctypes.data_as(f32p), cnt.ctypes.data_as(i64p), n))
         return {L.clstm_b200_phase_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def selftest_gemm(self):
+        err = np.zeros(16, np.float32)
+        k = lib().clstm_b200_selftest_gemm(self.h, err.ctypes.data_as(f32p), 16)
+        if k < 0:
+            raise Error(lib().clstm_b200_last_error().decode())
+        return err[:k]
 
     @property
     def stream(self):

@@ -4,8 +4,11 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -103,6 +106,7 @@ struct clstm_b200_net {
   float *v = nullptr, *d = nullptr, *g = nullptr;   // weights, Params.d (derivative+momentum), this step's derivatives
   float* Rt[2] = {nullptr, nullptr};
   bool g_pending = false;
+  bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
 
   // ---- batch capacity and buffers
   int capN = 0, capB = 0, capLab = 0;
@@ -407,6 +411,51 @@ int check_launch(const char* what) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ dense products
+bool vec_ok(const float* p, long long ld) { return (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0); }
+
+// C[M x N] = beta*C + A[M x K] * B^T (+bias) with A K-contiguous; B either K-contiguous ([N][K], b_mn=false) or
+// MN-contiguous ([K][N], b_mn=true)
+int dense_nt(clstm_b200_net* n, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
+             bool b_mn, float* C, long long ldc, const float* bias, float beta) {
+  if (!n->use_tc) {
+    return gemm_f32(n->st, M, N, K, A, lda, 1, B, b_mn ? ldb : 1, b_mn ? 1 : ldb, C, ldc, bias, beta, nullptr, 0,
+                    n->num_sms);
+  }
+  TcArgs g{};
+  g.M = M; g.N = N;
+  g.a_mode = 0; g.a_k[0] = {A, lda, K}; g.a_vec = vec_ok(A, lda);
+  g.k_nseg = 1; g.k_len[0] = K;
+  if (b_mn) { g.b_mode = 1; g.b_mn[0] = {B, ldb, N}; g.b_nseg = 1; g.b_ones = -1; }
+  else { g.b_mode = 0; g.b_k[0] = {B, ldb, K}; g.b_vec = vec_ok(B, ldb); }
+  g.C = C; g.ldc = ldc; g.bias = bias; g.beta = beta;
+  return gemm_tc(n->st, g, nullptr, n->num_sms);
+}
+
+// derivative product reduced over all columns: out += A^T [B0 | B1 | 1], A [K x M] and B blocks [K x len] row-major
+int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, const float* B0, int n0, const float* B1,
+             int n1, float* out0, float* out1, float* out_bias) {
+  if (!n->use_tc) {
+    int k = gemm_f32(n->st, M, n0, K, A, 1, lda, B0, n0, 1, out0, n0, nullptr, 1.f, n->ws, n->ws_floats, n->num_sms);
+    if (B1) k += gemm_f32(n->st, M, n1, K, A, 1, lda, B1, n1, 1, out1, n1, nullptr, 1.f, n->ws, n->ws_floats, n->num_sms);
+    k += colsum_f32(n->st, K, M, A, lda, out_bias, 1.f, n->ws, n->ws_floats, n->num_sms);
+    return k;
+  }
+  TcArgs g{};
+  g.M = M; g.N = n0 + n1 + 1;
+  g.a_mode = 1; g.a_mn[0] = {A, lda, M};
+  g.b_mode = 1; g.b_mn[0] = {B0, n0, n0}; g.b_nseg = 1;
+  if (B1) { g.b_mn[1] = {B1, n1, n1}; g.b_nseg = 2; }
+  g.b_ones = n0 + n1;
+  g.k_nseg = 1; g.k_len[0] = K;
+  g.beta = 1.f; g.ws = n->ws; g.ws_floats = n->ws_floats;
+  TcOut o{};
+  o.p[0] = out0; o.ld[0] = n0; o.len[0] = n0; o.nseg = 1;
+  if (B1) { o.p[1] = out1; o.ld[1] = n1; o.len[1] = n1; o.nseg = 2; }
+  o.bias = out_bias;
+  return gemm_tc(n->st, g, &o, n->num_sms);
+}
+
 // ------------------------------------------------------------------------------------------------ device passes
 int run_forward(clstm_b200_net* n) {
   const Lines& ln = n->ln;
@@ -414,8 +463,7 @@ int run_forward(clstm_b200_net* n) {
   {
     Scope s(n, PH_XPROJ);
     for (int d = 0; d < 2; d++)
-      s.launches(gemm_f32(n->st, N, 4 * no, ni, n->x, ni, 1, n->v + n->oWx[d], 1, ni, n->XP[d], 4 * no,
-                          n->v + n->oB[d], 0.f, nullptr, 0, n->num_sms));
+      s.launches(dense_nt(n, N, 4 * no, ni, n->x, ni, n->v + n->oWx[d], ni, false, n->XP[d], 4 * no, n->v + n->oB[d], 0.f));
   }
   {
     Scope s(n, PH_LSTM_FWD);
@@ -431,8 +479,7 @@ int run_forward(clstm_b200_net* n) {
   }
   {
     Scope s(n, PH_SOFTMAX_FWD);
-    s.launches(gemm_f32(n->st, N, nc, 2 * no, n->H, 2 * no, 1, n->v + n->oW1, 1, 2 * no, n->out, nc,
-                        n->v + n->oB1, 0.f, nullptr, 0, n->num_sms));
+    s.launches(dense_nt(n, N, nc, 2 * no, n->H, 2 * no, n->v + n->oW1, 2 * no, false, n->out, nc, n->v + n->oB1, 0.f));
     softmax_rows(n->st, n->out, N, nc, n->amax[0], n->amaxv[0]);
     s.launches(1);
   }
@@ -458,11 +505,8 @@ int run_backward(clstm_b200_net* n) {
   const int N = ln.N, ni = n->ni, no = n->no, nc = n->nc;
   {
     Scope s(n, PH_SOFTMAX_BWD);   // backward_softmax clstm_compute.cc:346-356
-    s.launches(gemm_f32(n->st, N, 2 * no, nc, n->delta, nc, 1, n->v + n->oW1, 2 * no, 1, n->dH, 2 * no, nullptr,
-                        0.f, nullptr, 0, n->num_sms));
-    s.launches(gemm_f32(n->st, nc, 2 * no, N, n->delta, 1, nc, n->H, 2 * no, 1, n->g + n->oW1, 2 * no, nullptr, 1.f,
-                        n->ws, n->ws_floats, n->num_sms));
-    s.launches(colsum_f32(n->st, N, nc, n->delta, nc, n->g + n->oB1, 1.f, n->ws, n->ws_floats, n->num_sms));
+    s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->v + n->oW1, 2 * no, true, n->dH, 2 * no, nullptr, 0.f));
+    s.launches(dense_tn(n, nc, N, n->delta, nc, n->H, 2 * no, nullptr, 0, n->g + n->oW1, nullptr, n->g + n->oB1));
   }
   {
     Scope s(n, PH_LSTM_BWD);
@@ -474,20 +518,14 @@ int run_backward(clstm_b200_net* n) {
   }
   {
     Scope s(n, PH_WGRAD);   // W.d += delta * src^T over all columns (backward_lin1 clstm_compute.cc:297-298)
-    for (int d = 0; d < 2; d++) {
-      s.launches(gemm_f32(n->st, 4 * no, ni, N, n->DG[d], 1, 4 * no, n->x, ni, 1, n->g + n->oWx[d], ni, nullptr, 1.f,
-                          n->ws, n->ws_floats, n->num_sms));
-      s.launches(gemm_f32(n->st, 4 * no, no, N, n->DG[d], 1, 4 * no, n->Hprev[d], no, 1, n->g + n->oR[d], no, nullptr,
-                          1.f, n->ws, n->ws_floats, n->num_sms));
-      s.launches(colsum_f32(n->st, N, 4 * no, n->DG[d], 4 * no, n->g + n->oB[d], 1.f, n->ws, n->ws_floats,
-                            n->num_sms));
-    }
+    for (int d = 0; d < 2; d++)
+      s.launches(dense_tn(n, 4 * no, N, n->DG[d], 4 * no, n->x, ni, n->Hprev[d], no, n->g + n->oWx[d], n->g + n->oR[d],
+                          n->g + n->oB[d]));
   }
   {
     Scope s(n, PH_DX);      // inputs.d = sum over both directions of Wx^T delta (clstm.cc:537-541)
     for (int d = 0; d < 2; d++)
-      s.launches(gemm_f32(n->st, N, ni, 4 * no, n->DG[d], 4 * no, 1, n->v + n->oWx[d], ni, 1, n->dx, ni, nullptr,
-                          d ? 1.f : 0.f, nullptr, 0, n->num_sms));
+      s.launches(dense_nt(n, N, ni, 4 * no, n->DG[d], 4 * no, n->v + n->oWx[d], ni, true, n->dx, ni, nullptr, d ? 1.f : 0.f));
   }
   TRY(check_launch("backward"));
   n->g_pending = true;
@@ -598,7 +636,7 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   for (int d = 0; d < 2; d++) rc |= dev_alloc(&n->Rt[d], (size_t)4 * no * no);
   rc |= dev_alloc(&n->status, 1);
   // split-K workspace: enough for ~2 waves of 64x64 tiles plus the largest derivative matrix a few times over
-  n->ws_floats = std::max<size_t>((size_t)4 * n->num_sms * 64 * 64, (size_t)8 * 4 * no * std::max(no, ni));
+  n->ws_floats = std::max<size_t>((size_t)4 * n->num_sms * 64 * 64, (size_t)40 * 4 * no * (1 + ni + no));
   rc |= dev_alloc(&n->ws, n->ws_floats);
   if (rc) { clstm_b200_destroy(n); return 1; }
   cudaMemsetAsync(n->v, 0, n->P * sizeof(float), n->st);
@@ -607,7 +645,11 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   cudaMemsetAsync(n->Rt[0], 0, (size_t)4 * no * no * sizeof(float), n->st);
   cudaMemsetAsync(n->Rt[1], 0, (size_t)4 * no * no * sizeof(float), n->st);
   cudaMemsetAsync(n->status, 0, sizeof(int), n->st);
-  if (lstm_configure() != 0 || ctc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
+  {
+    const char* e = getenv("CLSTM_B200_GEMM");   // "simt" selects the fp32 SIMT tiles (A/B testing against tcgen05)
+    n->use_tc = !(e && strcmp(e, "simt") == 0);
+  }
+  if (lstm_configure() != 0 || ctc_configure() != 0 || gemm_tc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   n->variant = lstm_variant_for(no);
   if (cudaStreamSynchronize(n->st) != cudaSuccess) { clstm_b200_destroy(n); return fail("device initialisation failed"); }
   *out = n;
@@ -898,6 +940,67 @@ int clstm_b200_phase_stats(clstm_b200_net* n, float* ms, long long* launches, in
 }
 void* clstm_b200_stream(clstm_b200_net* n) { return n ? (void*)n->st : nullptr; }
 const char* clstm_b200_lstm_variant(const clstm_b200_net* n) { return n ? n->variant : ""; }
+
+// Self-test of the tcgen05 (3xTF32) dense products against the fp32 SIMT tiles on random data, same shapes/strides
+// as the products of the path.  err[i] = max |tc - simt| / max|simt| for case i.  Returns the number of cases.
+int clstm_b200_selftest_gemm(clstm_b200_net* n, float* err, int max_cases) {
+  if (!n || !err) return -1;
+  if (cudaSetDevice(n->cfg.device) != cudaSuccess) return -1;
+  const int ni = n->ni, no = n->no, nc = n->nc;
+  const int N = 1000 + 37;   // columns, deliberately not a multiple of the tile sizes
+  struct Case { int kind, M, Nn, K; };   // kind 0: nt (B K-contig), 1: nt (B MN-contig), 2: tn with 2 blocks + ones
+  const Case cases[] = {{0, N, 4 * no, ni}, {0, N, nc, 2 * no}, {1, N, 2 * no, nc}, {1, N, ni, 4 * no},
+                        {2, 4 * no, ni + no + 1, N}, {2, nc, 2 * no + 1, N}};
+  const int ncases = (int)(sizeof(cases) / sizeof(cases[0]));
+  const bool saved = n->use_tc;
+  int done = 0;
+  for (int ci = 0; ci < ncases && ci < max_cases; ci++) {
+    const Case& c = cases[ci];
+    size_t na, nb, ncout;
+    if (c.kind == 2) { na = (size_t)c.K * c.M; nb = (size_t)c.K * (c.Nn - 1); ncout = (size_t)c.M * c.Nn; }
+    else { na = (size_t)c.M * c.K; nb = (size_t)c.Nn * c.K; ncout = (size_t)c.M * c.Nn; }
+    std::vector<float> ha(na), hb(nb), hbias(c.Nn);
+    unsigned lcg = 12345u + ci;
+    auto rnd = [&]() { lcg = lcg * 1664525u + 1013904223u; return ((lcg >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+    for (auto& v : ha) v = rnd();
+    for (auto& v : hb) v = rnd();
+    for (auto& v : hbias) v = rnd();
+    float *dA = nullptr, *dB = nullptr, *dbias = nullptr, *dC[2] = {nullptr, nullptr};
+    if (dev_alloc(&dA, na) || dev_alloc(&dB, nb) || dev_alloc(&dbias, (size_t)c.Nn) || dev_alloc(&dC[0], ncout) ||
+        dev_alloc(&dC[1], ncout))
+      return -1;
+    cudaMemcpyAsync(dA, ha.data(), na * 4, cudaMemcpyHostToDevice, n->st);
+    cudaMemcpyAsync(dB, hb.data(), nb * 4, cudaMemcpyHostToDevice, n->st);
+    cudaMemcpyAsync(dbias, hbias.data(), (size_t)c.Nn * 4, cudaMemcpyHostToDevice, n->st);
+    std::vector<float> res[2];
+    for (int pass = 0; pass < 2; pass++) {
+      n->use_tc = (pass == 1);
+      cudaMemsetAsync(dC[pass], 0, ncout * 4, n->st);
+      if (c.kind == 0) dense_nt(n, c.M, c.Nn, c.K, dA, c.K, dB, c.K, false, dC[pass], c.Nn, dbias, 0.f);
+      else if (c.kind == 1) dense_nt(n, c.M, c.Nn, c.K, dA, c.K, dB, c.Nn, true, dC[pass], c.Nn, nullptr, 0.f);
+      else {
+        const int n0 = (c.Nn - 1) / 3, n1 = c.Nn - 1 - n0;      // two column blocks + bias column
+        // B0 = hb[0 .. K*n0), B1 = following K*n1 ; outputs packed [M*n0 | M*n1 | M]
+        dense_tn(n, c.M, c.K, dA, c.M, dB, n0, dB + (size_t)c.K * n0, n1, dC[pass], dC[pass] + (size_t)c.M * n0,
+                 dC[pass] + (size_t)c.M * (n0 + n1));
+      }
+      res[pass].resize(ncout);
+      cudaMemcpyAsync(res[pass].data(), dC[pass], ncout * 4, cudaMemcpyDeviceToHost, n->st);
+      if (cudaStreamSynchronize(n->st) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        n->use_tc = saved;
+        fail("selftest_gemm case %d pass %d: device error", ci, pass);
+        return -1;
+      }
+    }
+    float mx = 0.f, md = 0.f;
+    for (size_t i = 0; i < ncout; i++) { mx = std::max(mx, std::fabs(res[0][i])); md = std::max(md, std::fabs(res[0][i] - res[1][i])); }
+    err[ci] = md / std::max(mx, 1e-20f);
+    cudaFree(dA); cudaFree(dB); cudaFree(dbias); cudaFree(dC[0]); cudaFree(dC[1]);
+    done++;
+  }
+  n->use_tc = saved;
+  return done;
+}
 
 void* clstm_b200_alloc_pinned(size_t bytes) {
   void* p = nullptr;

@@ -37,6 +37,28 @@ int gemm_f32(cudaStream_t st, int M, int N, int K, const float* A, long long sam
 int colsum_f32(cudaStream_t st, int M, int N, const float* A, long long lda, float* out, float beta, float* ws,
                 size_t ws_floats, int num_sms);
 
+// ---------------------------------------------------------------- gemm_tc.cu (tcgen05, 3xTF32)
+struct TcSeg { const float* p; long long ld; int len; };
+struct TcOut {            // destinations of a split-K product: up to 3 row-major column blocks + a per-row vector
+  float* p[3]; long long ld[3]; int len[3]; int nseg; float* bias;
+};
+struct TcArgs {
+  int M, N;
+  int a_mode, b_mode;     // 0: K-contiguous (elem (r,k) = p[r*ld + k]) ; 1: MN-contiguous (elem (r,k) = p[k*ld + r])
+  TcSeg a_k[2], b_k[2];   // mode 0: one source per K segment (segments are padded to multiples of 32 in the k loop)
+  TcSeg a_mn[1], b_mn[3]; // mode 1: A single source; B up to 3 column blocks (len = columns of the block)
+  int k_nseg, k_len[2];   // K segments (mode 0) or the single reduction length (mode 1 x mode 1)
+  int a_vec, b_vec;       // 16-byte loads allowed (ld % 4 == 0 and 16-byte aligned base)
+  int b_nseg, b_ones;     // mode-1 B: number of blocks, index of the all-ones column (-1: none)
+  float* C; long long ldc; const float* bias; float beta;   // direct epilogue: C = beta*C + D + bias[col]
+  float* ws; size_t ws_floats;                              // split-K partials (used when a scatter target is given)
+  int BN, nkb, kb_per_split;                                // filled by the launcher
+};
+// returns kernels launched.  scatter != null: split-K over the reduction, partials reduced deterministically into
+// the scatter targets with `beta`.
+int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms);
+int gemm_tc_configure();
+
 // ---------------------------------------------------------------- lstm.cu
 struct LstmFwdArgs {
   int no;                 // hidden units per direction

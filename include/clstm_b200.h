@@ -127,6 +127,10 @@ void* clstm_b200_stream(clstm_b200_net* net);
 /* which LSTM kernel variant the handle selected: "regs" (weights register-resident) or "generic" */
 const char* clstm_b200_lstm_variant(const clstm_b200_net* net);
 
+/* device self-test: tcgen05 (3xTF32) dense products vs the fp32 SIMT tiles on random data with the shapes of
+ * this net; err[i] = max|difference| / max|reference| per case; returns the number of cases (<0 on error). */
+int clstm_b200_selftest_gemm(clstm_b200_net* net, float* err, int max_cases);
+
 /* page-locked host memory for batches that are copied every step (cudaHostAlloc) */
 void* clstm_b200_alloc_pinned(size_t bytes);
 void clstm_b200_free_pinned(void* p);

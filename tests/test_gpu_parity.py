@@ -181,3 +181,12 @@ def test_error_behaviour(ffi):
         net.ctc_align(np.array([12], np.int32), [1])                  # label out of range
     with pytest.raises(ffi.Error):
         net.forward(x[:0], [0])                                       # empty line
+
+
+@pytest.mark.parametrize("nh", [100, 24])
+def test_tcgen05_dense_products_match_simt(ffi, nh):
+    # 3xTF32 on the 5th-gen tensor cores must reproduce the fp32 SIMT products to fp32-level accuracy
+    net = ffi.Net(48, nh, 83)
+    err = net.selftest_gemm()
+    assert len(err) == 6
+    assert err.max() < 1e-5, err
