@@ -426,7 +426,7 @@ int dense_nt(clstm_b200_net* n, int M, int N, int K, const float* A, long long l
   g.M = M; g.N = N;
   g.a_mode = 0; g.a_k[0] = {A, lda, K}; g.a_vec = vec_ok(A, lda);
   g.k_nseg = 1; g.k_len[0] = K;
-  if (b_mn) { g.b_mode = 1; g.b_mn[0] = {B, ldb, N}; g.b_nseg = 1; g.b_ones = -1; }
+  if (b_mn) { g.b_mode = 1; g.b_mn[0] = {B, ldb, N}; g.b_nseg = 1; g.b_ones = -1; g.b_vec = vec_ok(B, ldb); }
   else { g.b_mode = 0; g.b_k[0] = {B, ldb, K}; g.b_vec = vec_ok(B, ldb); }
   g.C = C; g.ldc = ldc; g.bias = bias; g.beta = beta;
   return gemm_tc(n->st, g, nullptr, n->num_sms);
@@ -443,9 +443,10 @@ int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, con
   }
   TcArgs g{};
   g.M = M; g.N = n0 + n1 + 1;
-  g.a_mode = 1; g.a_mn[0] = {A, lda, M};
+  g.a_mode = 1; g.a_mn[0] = {A, lda, M}; g.a_vec = vec_ok(A, lda);
   g.b_mode = 1; g.b_mn[0] = {B0, n0, n0}; g.b_nseg = 1;
-  if (B1) { g.b_mn[1] = {B1, n1, n1}; g.b_nseg = 2; }
+  g.b_vec = vec_ok(B0, n0) && (n0 % 4 == 0);
+  if (B1) { g.b_mn[1] = {B1, n1, n1}; g.b_nseg = 2; g.b_vec = g.b_vec && vec_ok(B1, n1); }
   g.b_ones = n0 + n1;
   g.k_nseg = 1; g.k_len[0] = K;
   g.beta = 1.f; g.ws = n->ws; g.ws_floats = n->ws_floats;

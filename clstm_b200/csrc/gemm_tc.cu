@@ -5,12 +5,15 @@
 //
 //   D[128 x BN] (fp32, TMEM) += A[128 x 32] * B[BN x 32]^T     per k-block, UMMA M=128, N=BN, K=8 (kind::tf32)
 //
-// Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B layout (rows of 128 bytes = 32 tf32,
-// 16-byte chunk c of row r stored at chunk c ^ (r & 7), 8-row groups 1024 bytes apart), written by the CTA's own
-// threads because the hi/lo split has to happen between global memory and shared memory anyway.  Either operand may
-// be K-contiguous in global memory (activations x weights^T products) or MN-contiguous (the weight-derivative
-// products that reduce over all columns); the loader transposes into the same K-major tile, so one descriptor
-// format serves every product.  Two smem stages; MMA completion is tracked with tcgen05.commit -> mbarrier.
+// Operand tiles live in shared memory in the canonical SWIZZLE_128B layouts, written by the CTA's own threads because
+// the hi/lo split has to happen between global memory and shared memory anyway:
+//   K-major tile: rows of 128 bytes = 32 k, chunk c of row r at c ^ (r & 7), 8-row groups 1024 bytes apart.
+//   K-contiguous sources (activations x weights^T) move as 16-byte chunks; MN-contiguous sources (the derivative
+//   products that reduce over all columns; W1 / Wx used untransposed) are transposed on the way in, lane = k, which
+//   makes the scattered 4-byte stores bank-conflict free.
+// Two smem stages; MMA completion is tracked with tcgen05.commit -> mbarrier.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace cb200 {
@@ -86,63 +89,115 @@ __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) 
 __device__ __forceinline__ void sts16(unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void sts4(unsigned addr, unsigned a) {
-  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
-}
 
-// Tile of R rows x 32 k from a K-contiguous source: element (r, k) = p[(r0 + r) * ld + k0 + k]
-__device__ __forceinline__ void load_kcontig(unsigned hi_base, unsigned lo_base, const float* __restrict__ p,
-                                             long long ld, int R, int rows_valid, int k_valid, bool vec) {
+// ---- K-major tile (mode 0): R rows x 32 k from a K-contiguous source, element (r, k) = p[(r0 + r) * ld + k0 + k].
+// All global loads of the tile are issued before the first conversion (R <= 256 => at most 8 passes).
+__device__ __forceinline__ void load_kmajor(unsigned hi_base, unsigned lo_base, const float* __restrict__ p,
+                                            long long ld, int R, int rows_valid, int k_valid, bool vec) {
   const int tid = threadIdx.x;
-  const int chunk = tid & 7;
-  for (int row = tid >> 3; row < R; row += TCT / 8) {
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < rows_valid) {
+  const int chunk = tid & 7, rsub = tid >> 3;
+  float v[8][4];
+#pragma unroll
+  for (int ps = 0; ps < 8; ps++) {
+    const int row = ps * 32 + rsub;
+    v[ps][0] = v[ps][1] = v[ps][2] = v[ps][3] = 0.f;
+    if (row < R && row < rows_valid) {
       const float* src = p + row * ld + chunk * 4;
       if (vec && chunk * 4 + 3 < k_valid) {
         const float4 f = *reinterpret_cast<const float4*>(src);
-        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        v[ps][0] = f.x; v[ps][1] = f.y; v[ps][2] = f.z; v[ps][3] = f.w;
       } else {
 #pragma unroll
         for (int e = 0; e < 4; e++)
-          if (chunk * 4 + e < k_valid) v[e] = src[e];
+          if (chunk * 4 + e < k_valid) v[ps][e] = src[e];
       }
     }
-    unsigned h[4], l[4];
+  }
 #pragma unroll
-    for (int e = 0; e < 4; e++) split_tf32(v[e], h[e], l[e]);
-    const unsigned off = row * 128 + ((chunk ^ (row & 7)) << 4);
-    sts16(hi_base + off, h[0], h[1], h[2], h[3]);
-    sts16(lo_base + off, l[0], l[1], l[2], l[3]);
+  for (int ps = 0; ps < 8; ps++) {
+    const int row = ps * 32 + rsub;
+    if (row < R) {
+      unsigned h[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) split_tf32(v[ps][e], h[e], l[e]);
+      const unsigned off = row * 128 + ((chunk ^ (row & 7)) << 4);
+      sts16(hi_base + off, h[0], h[1], h[2], h[3]);
+      sts16(lo_base + off, l[0], l[1], l[2], l[3]);
+    }
   }
 }
 
-// Tile of R rows x 32 k from MN-contiguous sources: element (r, k) = seg.p[(k0 + k) * seg.ld + (c - seg.c0)], where
-// c = r0 + r is the global row/column index, looked up in up to 3 segments; c == ones_col yields 1.0.
-__device__ __forceinline__ void load_mncontig(unsigned hi_base, unsigned lo_base, const TcSeg* seg, int nseg,
-                                              int ones_col, int r0, int R, int c_total, int k0, int k_valid) {
-  for (int idx = threadIdx.x; idx < R * BK; idx += TCT) {
-    const int r = idx % R, k = idx / R;          // consecutive threads -> consecutive rows: coalesced global reads
-    const int c = r0 + r;
-    float v = 0.f;
-    if (k < k_valid && c < c_total) {
-      if (c == ones_col) v = 1.f;
-      else {
-        int cl = c;
+// ---- MN-contiguous sources (mode 1): element (k, c) = seg.p[(k0 + k) * seg.ld + c_local], c = r0 + r looked up in up
+// to 3 column blocks; c == ones_col yields 1.0.
+__device__ __forceinline__ float mn_elem(const TcSeg* seg, int nseg, int ones_col, int c, int c_total, long long krow) {
+  if (c >= c_total) return 0.f;
+  if (c == ones_col) return 1.f;
+  float v = 0.f;
+  int cl = c;
 #pragma unroll
-        for (int s = 0; s < 3; s++) {
-          if (s < nseg) {
-            if (cl >= 0 && cl < seg[s].len) v = seg[s].p[(long long)(k0 + k) * seg[s].ld + cl];
-            cl -= seg[s].len;
+  for (int s = 0; s < 3; s++) {
+    if (s < nseg) {
+      if (cl >= 0 && cl < seg[s].len) v = seg[s].p[krow * seg[s].ld + cl];
+      cl -= seg[s].len;
+    }
+  }
+  return v;
+}
+// ---- MN-contiguous source into a K-major tile (in-kernel transpose): a warp takes 4 consecutive mn x 32 k, lane = k.
+// Each lane reads 16 bytes (4 mn) of its k row and scatters them to 4 tile rows; for a fixed component all 32 lanes hit
+// 32 distinct banks (bank = 4*((k>>2)^(mn&7)) + (k&3)), so the transposing stores are conflict-free.
+__device__ __forceinline__ void load_mn_to_kmajor(unsigned hi_base, unsigned lo_base, const TcSeg* seg, int nseg,
+                                                  int ones_col, int r0, int R, int c_total, int k0, int k_valid,
+                                                  bool vec) {
+  const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
+  const int nquad = (R + 3) >> 2;
+  const long long krow = k0 + k;
+  for (int q0 = warp; q0 < nquad; q0 += 4 * (TCT / 32)) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {             // 4 quads in flight per thread
+      const int q = q0 + u * (TCT / 32);
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (q < nquad && k < k_valid) {
+        const int c = r0 + q * 4;
+        bool done = false;
+        if (vec) {
+          int cl = c;
+#pragma unroll
+          for (int s = 0; s < 3; s++) {
+            if (s < nseg) {
+              if (!done && cl >= 0 && cl + 3 < seg[s].len) {
+                const float4 f = *reinterpret_cast<const float4*>(seg[s].p + krow * seg[s].ld + cl);
+                v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
+                done = true;
+              }
+              cl -= seg[s].len;
+            }
+          }
+        }
+        if (!done) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) v[u][e] = mn_elem(seg, nseg, ones_col, c + e, c_total, krow);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int q = q0 + u * (TCT / 32);
+      if (q < nquad) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int r = q * 4 + e;
+          if (r < R) {
+            unsigned h, l;
+            split_tf32(v[u][e], h, l);
+            const unsigned off = r * 128 + (((k >> 2) ^ (r & 7)) << 4) + ((k & 3) << 2);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(hi_base + off), "r"(h) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(lo_base + off), "r"(l) : "memory");
           }
         }
       }
     }
-    unsigned h, l;
-    split_tf32(v, h, l);
-    const unsigned off = r * 128 + (((k >> 2) ^ (r & 7)) << 4) + ((k & 3) << 2);
-    sts4(hi_base + off, h);
-    sts4(lo_base + off, l);
   }
 }
 
@@ -152,7 +207,7 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   __shared__ unsigned tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = g.BN;
-  const unsigned a_bytes = BM * 128, b_bytes = BN * 128;
+  const unsigned a_bytes = BM * 128, b_bytes = (unsigned)((BN + 31) & ~31) * 128;
   const unsigned stage_bytes = 2 * a_bytes + 2 * b_bytes;
   const unsigned smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;      // swizzle atoms need 1024-byte alignment
   const unsigned bar0 = smem_u32(&mbar_s[0]), bar1 = smem_u32(&mbar_s[1]);
@@ -175,11 +230,14 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   const unsigned tmem_d = tmem_base_s;
 
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  // k-block range of this CTA (split-K over blockIdx.z)
-  const int nkb_total = g.nkb;
   const int kb0 = blockIdx.z * g.kb_per_split;
-  const int kb1 = min(nkb_total, kb0 + g.kb_per_split);
+  const int kb1 = min(g.nkb, kb0 + g.kb_per_split);
+  // instruction descriptor: bit 15 / 16 = A / B is MN-major
+  // Both smem tiles are always K-major.  (kind::tf32 with MN-major descriptors -- idesc bits 15/16 -- was tried for
+  // the MN-contiguous sources and returned all-zero accumulators on B200, for either LBO/SBO role assignment, so
+  // those sources are transposed by the loader instead.)
   const unsigned idesc = make_idesc(BN);
+  const bool kseg = (g.a_mode == 0 || g.b_mode == 0);
 
   int it = 0;
   for (int kb = kb0; kb < kb1; kb++, it++) {
@@ -190,31 +248,31 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
     const unsigned b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
     // locate the k-block inside the K segments (each K-contiguous segment is padded to a multiple of 32)
     int seg = 0, kloc = kb * BK;
-    if (g.a_mode == 0 || g.b_mode == 0) {
+    if (kseg) {
       while (seg + 1 < g.k_nseg && kloc >= ((g.k_len[seg] + BK - 1) / BK) * BK) {
         kloc -= ((g.k_len[seg] + BK - 1) / BK) * BK;
         seg++;
       }
     }
-    const int k_valid = (g.a_mode == 0 || g.b_mode == 0) ? (g.k_len[seg] - kloc) : (g.k_len[0] - kb * BK);
+    const int k_valid = g.k_len[seg] - kloc;
     if (g.a_mode == 0)
-      load_kcontig(a_hi, a_lo, g.a_k[seg].p + (long long)m0 * g.a_k[seg].ld + kloc, g.a_k[seg].ld, BM, g.M - m0, k_valid,
-                   g.a_vec != 0);
+      load_kmajor(a_hi, a_lo, g.a_k[seg].p + (long long)m0 * g.a_k[seg].ld + kloc, g.a_k[seg].ld, BM, g.M - m0, k_valid,
+                  g.a_vec != 0);
     else
-      load_mncontig(a_hi, a_lo, g.a_mn, 1, -1, m0, BM, g.M, kb * BK, k_valid);
+      load_mn_to_kmajor(a_hi, a_lo, g.a_mn, 1, -1, m0, BM, g.M, kloc, k_valid, g.a_vec != 0);
     if (g.b_mode == 0)
-      load_kcontig(b_hi, b_lo, g.b_k[seg].p + (long long)n0 * g.b_k[seg].ld + kloc, g.b_k[seg].ld, BN, g.N - n0, k_valid,
-                   g.b_vec != 0);
+      load_kmajor(b_hi, b_lo, g.b_k[seg].p + (long long)n0 * g.b_k[seg].ld + kloc, g.b_k[seg].ld, BN, g.N - n0, k_valid,
+                  g.b_vec != 0);
     else
-      load_mncontig(b_hi, b_lo, g.b_mn, g.b_nseg, g.b_ones, n0, BN, g.N, (g.a_mode == 0) ? kloc : kb * BK, k_valid);
+      load_mn_to_kmajor(b_hi, b_lo, g.b_mn, g.b_nseg, g.b_ones, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
     fence_proxy_async();                                     // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < BK / 8; ks++) {
-        const unsigned long long ah = make_desc(a_hi + ks * 32), al = make_desc(a_lo + ks * 32);
-        const unsigned long long bh = make_desc(b_hi + ks * 32), bl = make_desc(b_lo + ks * 32);
+        const unsigned long long ah = make_desc(a_hi + ks * 32), al = make_desc(a_lo + ks * 32);   // 32 bytes = 8 tf32 along
+        const unsigned long long bh = make_desc(b_hi + ks * 32), bl = make_desc(b_lo + ks * 32);   // the swizzled row
         mma_tf32(tmem_d, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);   // small terms first
         mma_tf32(tmem_d, ah, bl, idesc, 1u);
         mma_tf32(tmem_d, ah, bh, idesc, 1u);
@@ -233,6 +291,8 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   const int lq = warp & 3, ch = warp >> 2;
   const int row = m0 + 32 * lq + lane;
   const int half = BN / 2;
+  const bool st_vec = !g.ws && g.beta == 0.f && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+                      ((n0 + ch * half) % 4 == 0) && (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
   for (int c = 0; c < half; c += 8) {
     float v[8];
     if (it > 0) tmem_ld8(tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * half + c), v);
@@ -241,17 +301,30 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
       for (int e = 0; e < 8; e++) v[e] = 0.f;
     }
     if (row < g.M) {
+      const int col0 = n0 + ch * half + c;
+      if (st_vec && col0 + 7 < g.N) {
+        if (g.bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(g.bias + col0);
+          const float4 b1 = *reinterpret_cast<const float4*>(g.bias + col0 + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        float4* dst = reinterpret_cast<float4*>(g.C + (long long)row * g.ldc + col0);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const int col = n0 + ch * half + c + e;
-        if (col < g.N) {
-          if (g.ws) {
-            g.ws[((size_t)blockIdx.z * g.M + row) * g.N + col] = v[e];
-          } else {
-            float o = v[e];
-            if (g.bias) o += g.bias[col];
-            float* dst = g.C + (long long)row * g.ldc + col;
-            *dst = (g.beta != 0.f) ? fmaf(g.beta, *dst, o) : o;
+        for (int e = 0; e < 8; e++) {
+          const int col = col0 + e;
+          if (col < g.N) {
+            if (g.ws) {
+              g.ws[((size_t)blockIdx.z * g.M + row) * g.N + col] = v[e];
+            } else {
+              float o = v[e];
+              if (g.bias) o += g.bias[col];
+              float* dst = g.C + (long long)row * g.ldc + col;
+              *dst = (g.beta != 0.f) ? fmaf(g.beta, *dst, o) : o;
+            }
           }
         }
       }
@@ -286,7 +359,7 @@ __global__ void tc_reduce_scatter_kernel(int M, int N, int splits, const float* 
   }
 }
 
-size_t tc_smem_bytes(int BN) { return (size_t)2 * (2 * BM * 128 + 2 * BN * 128) + 1024; }
+size_t tc_smem_bytes(int BN) { return (size_t)2 * (2 * BM * 128 + 2 * ((BN + 31) & ~31) * 128) + 1024; }
 
 }  // namespace
 
