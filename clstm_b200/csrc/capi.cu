@@ -321,9 +321,11 @@ int ensure_lattice(clstm_b200_net* n, long long elems) {
   CU(cudaStreamSynchronize(n->st));
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl);
   const long long cap = elems + elems / 8 + 1024;
-  TRY(dev_alloc(&n->lm, (size_t)cap));
-  TRY(dev_alloc(&n->lr, (size_t)cap));
-  TRY(dev_alloc(&n->rl, (size_t)cap));
+  const size_t alloc = (size_t)cap + 2 * (size_t)kLatPad;      // the lattice warps prefetch past the line's rows
+  TRY(dev_alloc(&n->lm, alloc));
+  TRY(dev_alloc(&n->lr, alloc));
+  TRY(dev_alloc(&n->rl, alloc));
+  CU(cudaMemsetAsync(n->lm, 0, alloc * sizeof(float), n->st));
   n->capLat = cap;
   return 0;
 }
@@ -365,7 +367,7 @@ int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const
     const int Sb = raw ? n->hL[b] : 2 * n->hL[b] + 1;
     n->hStOff[b] = so;
     so += Sb;
-    n->h_lat[b] = lat;
+    n->h_lat[b] = lat + kLatPad;
     lat += (long long)T[b] * Sb;
     for (int t0 = 0; t0 < T[b]; t0 += 32) {
       n->h_tiles[ntiles] = b;
@@ -525,8 +527,24 @@ int run_backward(clstm_b200_net* n) {
   }
   {
     Scope s(n, PH_DX);      // inputs.d = sum over both directions of Wx^T delta (clstm.cc:537-541)
-    for (int d = 0; d < 2; d++)
-      s.launches(dense_nt(n, N, ni, 4 * no, n->DG[d], 4 * no, n->v + n->oWx[d], ni, true, n->dx, ni, nullptr, d ? 1.f : 0.f));
+    if (n->use_tc) {   // one product over both directions: K = [DG0 | DG1], B = [Wx0 ; Wx1]
+      TcArgs g{};
+      g.M = N; g.N = ni;
+      g.a_mode = 0; g.b_mode = 1; g.k_nseg = 2; g.b_nseg = 1; g.b_ones = -1;
+      g.a_vec = 1; g.b_vec = 1;
+      for (int d = 0; d < 2; d++) {
+        g.a_k[d] = {n->DG[d], 4 * no, 4 * no};
+        g.b_mn[d] = {n->v + n->oWx[d], ni, ni};
+        g.k_len[d] = 4 * no;
+        g.a_vec = g.a_vec && vec_ok(n->DG[d], 4 * no);
+        g.b_vec = g.b_vec && vec_ok(n->v + n->oWx[d], ni);
+      }
+      g.C = n->dx; g.ldc = ni; g.bias = nullptr; g.beta = 0.f;
+      s.launches(gemm_tc(n->st, g, nullptr, n->num_sms));
+    } else {
+      for (int d = 0; d < 2; d++)
+        s.launches(dense_nt(n, N, ni, 4 * no, n->DG[d], 4 * no, n->v + n->oWx[d], ni, true, n->dx, ni, nullptr, d ? 1.f : 0.f));
+    }
   }
   TRY(check_launch("backward"));
   n->g_pending = true;

@@ -84,57 +84,60 @@ __global__ void __launch_bounds__(TILE_THREADS) ctc_lmatch_kernel(Lines ln, CtcA
 // ------------------------------------------------------------------------------------------------ lattice
 // One lattice pass by one warp.  rev=0: lr(t,s).  rev=1: processes i-th step on column T-1-i and state index jj
 // on real state S-1-jj, result stored at rl(T-1-i, S-1-jj)  (forwardbackward, ctc.cc:42-55).
-// Lane l owns KS consecutive states; a time step is one shuffle plus KS log_adds.  The lmatch rows are
-// software-prefetched PF steps ahead into a register ring.
+// Lane l owns KS consecutive states; a time step is one shuffle plus KS log_adds.  A single warp has nothing to
+// hide latency with, so the loop body is straight-line: running row pointers, a running -5*i, and lmatch rows
+// prefetched PF steps ahead into a register ring without bounds checks (the lattice buffers are padded by
+// kLatPad floats on both sides, so the prefetch may run past the line's rows).
 template <int KS, int PF>
 __device__ void lattice_pass(const float* __restrict__ lm, float* __restrict__ out, int T, int S, bool rev) {
   const int lane = threadIdx.x & 31;
-  float v[KS];
-  float mq[PF][KS];
+  const int j0 = lane * KS;
+  const int dirk = rev ? -1 : 1;
+  const long long rowstep = rev ? -(long long)S : (long long)S;
+  const long long first = (rev ? (long long)(T - 1) * S + (S - 1 - j0) : (long long)j0);
+  const float* lp = lm + first;
+  float* op = out + first;
+  bool ok[KS];
+  float v[KS], mq[PF][KS];
 #pragma unroll
-  for (int k = 0; k < KS; k++) v[k] = (float)(-5.0 * (lane * KS + k));      // ctc.cc:30
-  auto load_row = [&](int i, float* dst) {
-    const int t = rev ? T - 1 - i : i;
-    const float* row = lm + (size_t)t * S;
-#pragma unroll
-    for (int k = 0; k < KS; k++) {
-      const int jj = lane * KS + k;
-      dst[k] = (jj < S) ? row[rev ? S - 1 - jj : jj] : 0.f;
-    }
-  };
-#pragma unroll
-  for (int u = 0; u < PF; u++) {
-    if (u < T) load_row(u, mq[u]);
-    else {
-#pragma unroll
-      for (int k = 0; k < KS; k++) mq[u][k] = 0.f;
-    }
+  for (int k = 0; k < KS; k++) {
+    ok[k] = (j0 + k) < S;
+    v[k] = -5.f * (float)(j0 + k);                                        // ctc.cc:30 (exact in Float)
   }
-  for (int i0 = 0; i0 < T; i0 += PF) {
+#pragma unroll
+  for (int u = 0; u < PF; u++)
+#pragma unroll
+    for (int k = 0; k < KS; k++) mq[u][k] = ok[k] ? lp[u * rowstep + k * dirk] : 0.f;
+  const float* lpn = lp + PF * rowstep;
+  float skipv = 0.f;                                                      // w(0) = skip*i   ctc.cc:32
+  auto step = [&](float* m) {
+    float below = __shfl_up_sync(0xffffffffu, v[KS - 1], 1);              // old v(jj-1) of this lane's first state
+    below = (lane == 0) ? skipv : below;
+    skipv -= 5.f;
+#pragma unroll
+    for (int k = KS - 1; k >= 0; k--) {
+      const float w = (k == 0) ? below : v[k - 1];                        // w(j) = v(j-1) before the update  ctc.cc:33
+      v[k] = log_add_fast(v[k] + m[k], w + m[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < KS; k++)
+      if (ok[k]) op[k * dirk] = v[k];
+    op += rowstep;
+  };
+  const int nfull = T / PF;
+  for (int g = 0; g < nfull; g++) {
 #pragma unroll
     for (int u = 0; u < PF; u++) {
-      const int i = i0 + u;
-      if (i < T) {
-        float below = __shfl_up_sync(0xffffffffu, v[KS - 1], 1);   // old v(jj-1) of the first state of this lane
-        if (lane == 0) below = -5.f * (float)i;                    // w(0) = skip*i   ctc.cc:32 (exact in Float)
+      step(mq[u]);
 #pragma unroll
-        for (int k = KS - 1; k >= 0; k--) {
-          const float w = (k == 0) ? below : v[k - 1];             // w(j) = v(j-1) before the update  ctc.cc:33
-          const float same = v[k] + mq[u][k];
-          const float next = w + mq[u][k];
-          v[k] = log_add_fast(same, next);
-        }
-        const int t = rev ? T - 1 - i : i;
-        float* orow = out + (size_t)t * S;
-#pragma unroll
-        for (int k = 0; k < KS; k++) {
-          const int jj = lane * KS + k;
-          if (jj < S) orow[rev ? S - 1 - jj : jj] = v[k];
-        }
-        if (i + PF < T) load_row(i + PF, mq[u]);
-      }
+      for (int k = 0; k < KS; k++) mq[u][k] = ok[k] ? lpn[k * dirk] : 0.f;   // row of step (g+1)*PF + u
+      lpn += rowstep;
     }
   }
+  const int rem = T - nfull * PF;
+#pragma unroll
+  for (int u = 0; u < PF; u++)
+    if (u < rem) step(mq[u]);
 }
 
 __device__ void lattice_dispatch(const float* lm, float* out, int T, int S, bool rev) {

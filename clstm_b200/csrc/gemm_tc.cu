@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
     if (g.b_mode == 0)
       load_kmajor(b_hi, b_lo, g.b_k[seg].p + (long long)n0 * g.b_k[seg].ld + kloc, g.b_k[seg].ld, BN, g.N - n0, k_valid,
                   g.b_vec != 0);
+    else if (g.k_nseg > 1)   // one MN-contiguous source per K segment (both directions of the input-delta product)
+      load_mn_to_kmajor(b_hi, b_lo, &g.b_mn[seg], 1, -1, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
     else
       load_mn_to_kmajor(b_hi, b_lo, g.b_mn, g.b_nseg, g.b_ones, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
     fence_proxy_async();                                     // generic-proxy smem writes -> visible to the tensor core

@@ -101,6 +101,7 @@ struct CtcArgs {
 };
 int ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a);   // returns kernels launched
 int ctc_configure();
+constexpr int kLatPad = 8192;        // floats of padding before and after the lattice scratch (prefetch overrun)
 constexpr int kCtcMaxStates = 1024;  // S = 2L+1 must not exceed this
 constexpr int kCtcMaxClasses = 512;  // nclasses limit of the per-warp class accumulators
 
