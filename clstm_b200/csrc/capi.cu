@@ -802,7 +802,10 @@ int clstm_b200_ctc_align_states(clstm_b200_net* n, const float* outputs, const i
                                 const int* S, float* aligned) {
   if (!n || !outputs || !T || !states || !S || !aligned) return fail("null argument");
   CU(cudaSetDevice(n->cfg.device));
+  // a free-standing alignment on the geometry of the last forward keeps that forward usable for backward()
+  const bool same_geometry = n->have_forward && (int)n->hT.size() == B && std::equal(T, T + B, n->hT.begin());
   TRY(stage_lines(n, T, B, states, S, /*raw=*/true));
+  n->have_forward = same_geometry;
   CU(cudaMemcpyAsync(n->out, outputs, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyHostToDevice, n->st));
   CU(cudaMemsetAsync(n->status, 0, sizeof(int), n->st));
   TRY(run_ctc(n));
