@@ -104,7 +104,9 @@ struct clstm_b200_net {
   size_t P = 0;
   size_t oWx[2], oB[2], oR[2], oW1, oB1;
   float *v = nullptr, *d = nullptr, *g = nullptr;   // weights, Params.d (derivative+momentum), this step's derivatives
-  float* Rt[2] = {nullptr, nullptr};
+  float* Rt[2] = {nullptr, nullptr};       // derived layouts, refreshed by prepare_weights(): R^T,
+  float* WxT[2] = {nullptr, nullptr};      // Wx^T [ni][4no],
+  float* W1T = nullptr;                    // W1^T [2no][nc]
   bool g_pending = false;
   bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
 
@@ -413,6 +415,16 @@ int check_launch(const char* what) {
   return 0;
 }
 
+void prepare_weights(clstm_b200_net* n) {   // after every change of v
+  TransposeJobs j{};
+  for (int d = 0; d < 2; d++) {
+    j.job[j.n++] = {n->v + n->oR[d], n->Rt[d], 4 * n->no, n->no};
+    j.job[j.n++] = {n->v + n->oWx[d], n->WxT[d], 4 * n->no, n->ni};
+  }
+  j.job[j.n++] = {n->v + n->oW1, n->W1T, n->nc, 2 * n->no};
+  transpose_batch(n->st, j);
+}
+
 // ------------------------------------------------------------------------------------------------ dense products
 bool vec_ok(const float* p, long long ld) { return (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0); }
 
@@ -508,7 +520,8 @@ int run_backward(clstm_b200_net* n) {
   const int N = ln.N, ni = n->ni, no = n->no, nc = n->nc;
   {
     Scope s(n, PH_SOFTMAX_BWD);   // backward_softmax clstm_compute.cc:346-356
-    s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->v + n->oW1, 2 * no, true, n->dH, 2 * no, nullptr, 0.f));
+    if (n->use_tc) s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->W1T, nc, false, n->dH, 2 * no, nullptr, 0.f));
+    else s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->v + n->oW1, 2 * no, true, n->dH, 2 * no, nullptr, 0.f));
     s.launches(dense_tn(n, nc, N, n->delta, nc, n->H, 2 * no, nullptr, 0, n->g + n->oW1, nullptr, n->g + n->oB1));
   }
   {
@@ -530,14 +543,14 @@ int run_backward(clstm_b200_net* n) {
     if (n->use_tc) {   // one product over both directions: K = [DG0 | DG1], B = [Wx0 ; Wx1]
       TcArgs g{};
       g.M = N; g.N = ni;
-      g.a_mode = 0; g.b_mode = 1; g.k_nseg = 2; g.b_nseg = 1; g.b_ones = -1;
+      g.a_mode = 0; g.b_mode = 0; g.k_nseg = 2;
       g.a_vec = 1; g.b_vec = 1;
       for (int d = 0; d < 2; d++) {
         g.a_k[d] = {n->DG[d], 4 * no, 4 * no};
-        g.b_mn[d] = {n->v + n->oWx[d], ni, ni};
+        g.b_k[d] = {n->WxT[d], 4 * no, 4 * no};         // Wx^T [ni][4no]: K-contiguous B operand
         g.k_len[d] = 4 * no;
         g.a_vec = g.a_vec && vec_ok(n->DG[d], 4 * no);
-        g.b_vec = g.b_vec && vec_ok(n->v + n->oWx[d], ni);
+        g.b_vec = g.b_vec && vec_ok(n->WxT[d], 4 * no);
       }
       g.C = n->dx; g.ldc = ni; g.bias = nullptr; g.beta = 0.f;
       s.launches(gemm_tc(n->st, g, nullptr, n->num_sms));
@@ -571,7 +584,7 @@ int run_update(clstm_b200_net* n, float lr, float mom, float clip) {
   Scope s(n, PH_UPDATE);
   sgd_update(n->st, n->v, n->d, n->g, n->P, lr, mom, clip, 0);
   n->g_pending = false;
-  transpose_R(n->st, n->v + n->oR[0], n->Rt[0], n->v + n->oR[1], n->Rt[1], n->no);
+  prepare_weights(n);
   s.launches(2);
   return check_launch("sgd_update");
 }
@@ -652,7 +665,11 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   if (cudaStreamCreateWithFlags(&n->st, cudaStreamNonBlocking) != cudaSuccess) { delete n; return fail("cudaStreamCreate failed"); }
   int rc = 0;
   rc |= dev_alloc(&n->v, n->P); rc |= dev_alloc(&n->d, n->P); rc |= dev_alloc(&n->g, n->P);
-  for (int d = 0; d < 2; d++) rc |= dev_alloc(&n->Rt[d], (size_t)4 * no * no);
+  for (int d = 0; d < 2; d++) {
+    rc |= dev_alloc(&n->Rt[d], (size_t)4 * no * no);
+    rc |= dev_alloc(&n->WxT[d], (size_t)4 * no * ni);
+  }
+  rc |= dev_alloc(&n->W1T, (size_t)2 * no * nc);
   rc |= dev_alloc(&n->status, 1);
   // split-K workspace: enough for ~2 waves of 64x64 tiles plus the largest derivative matrix a few times over
   n->ws_floats = std::max<size_t>((size_t)4 * n->num_sms * 64 * 64, (size_t)40 * 4 * no * (1 + ni + no));
@@ -663,6 +680,9 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   cudaMemsetAsync(n->g, 0, n->P * sizeof(float), n->st);
   cudaMemsetAsync(n->Rt[0], 0, (size_t)4 * no * no * sizeof(float), n->st);
   cudaMemsetAsync(n->Rt[1], 0, (size_t)4 * no * no * sizeof(float), n->st);
+  cudaMemsetAsync(n->WxT[0], 0, (size_t)4 * no * ni * sizeof(float), n->st);
+  cudaMemsetAsync(n->WxT[1], 0, (size_t)4 * no * ni * sizeof(float), n->st);
+  cudaMemsetAsync(n->W1T, 0, (size_t)2 * no * nc * sizeof(float), n->st);
   cudaMemsetAsync(n->status, 0, sizeof(int), n->st);
   {
     const char* e = getenv("CLSTM_B200_GEMM");   // "simt" selects the fp32 SIMT tiles (A/B testing against tcgen05)
@@ -682,6 +702,7 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   if (n->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n->comm);
   free_batch(n);
   dev_free(n->v); dev_free(n->d); dev_free(n->g); dev_free(n->Rt[0]); dev_free(n->Rt[1]);
+  dev_free(n->WxT[0]); dev_free(n->WxT[1]); dev_free(n->W1T);
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->status);
   dev_free(n->ws); dev_free(n->tiles); dev_free(n->tot);
   if (n->h_tiles) cudaFreeHost(n->h_tiles);
@@ -705,7 +726,7 @@ int clstm_b200_set_params(clstm_b200_net* n, const float* flat, size_t cnt) {
   std::vector<float> dev(n->P);
   ref_to_dev(n, flat, dev.data());
   CU(cudaMemcpyAsync(n->v, dev.data(), n->P * sizeof(float), cudaMemcpyHostToDevice, n->st));
-  transpose_R(n->st, n->v + n->oR[0], n->Rt[0], n->v + n->oR[1], n->Rt[1], n->no);
+  prepare_weights(n);
   CU(cudaStreamSynchronize(n->st));
   return check_launch("set_params");
 }

@@ -90,45 +90,52 @@ __device__ __forceinline__ void sts16(unsigned addr, unsigned a, unsigned b, uns
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// ---- K-major tile (mode 0): R rows x 32 k from a K-contiguous source, element (r, k) = p[(r0 + r) * ld + k0 + k].
-// All global loads of the tile are issued before the first conversion (R <= 256 => at most 8 passes).
-__device__ __forceinline__ void load_kmajor(unsigned hi_base, unsigned lo_base, const float* __restrict__ p,
-                                            long long ld, int R, int rows_valid, int k_valid, bool vec) {
+// ---- operand staging.  A k-block of an operand is moved in two phases so that every global load of the k-block (and
+// of the NEXT k-block while the tensor core works on this one) is in flight before the first conversion:
+//   issue_*  : global -> registers (float4 slots, zero filled outside the matrix)
+//   commit_* : registers -> TF32 hi/lo -> shared memory tile (K-major SWIZZLE_128B)
+// Slot maps (TCT = 256 threads):
+//   K-contiguous source (mode 0): slot ps <-> row ps*32 + tid/8, 16-byte chunk tid%8 (4 consecutive k)
+//   MN-contiguous source (mode 1): slot u <-> warp task (tid/32) + 8u = (32-mn group, 4-k group), see issue_mncontig.
+template <int NS>
+__device__ __forceinline__ void issue_kcontig(float4 (&v)[NS], const float* __restrict__ p, long long ld, int R,
+                                              int rows_valid, int k_valid, bool vec) {
   const int tid = threadIdx.x;
   const int chunk = tid & 7, rsub = tid >> 3;
-  float v[8][4];
 #pragma unroll
-  for (int ps = 0; ps < 8; ps++) {
+  for (int ps = 0; ps < NS; ps++) {
     const int row = ps * 32 + rsub;
-    v[ps][0] = v[ps][1] = v[ps][2] = v[ps][3] = 0.f;
+    v[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < R && row < rows_valid) {
       const float* src = p + row * ld + chunk * 4;
-      if (vec && chunk * 4 + 3 < k_valid) {
-        const float4 f = *reinterpret_cast<const float4*>(src);
-        v[ps][0] = f.x; v[ps][1] = f.y; v[ps][2] = f.z; v[ps][3] = f.w;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; e++)
-          if (chunk * 4 + e < k_valid) v[ps][e] = src[e];
+      if (vec && chunk * 4 + 3 < k_valid) v[ps] = *reinterpret_cast<const float4*>(src);
+      else {
+        if (chunk * 4 + 0 < k_valid) v[ps].x = src[0];
+        if (chunk * 4 + 1 < k_valid) v[ps].y = src[1];
+        if (chunk * 4 + 2 < k_valid) v[ps].z = src[2];
+        if (chunk * 4 + 3 < k_valid) v[ps].w = src[3];
       }
     }
   }
+}
+template <int NS>
+__device__ __forceinline__ void commit_kcontig(const float4 (&v)[NS], unsigned hi_base, unsigned lo_base, int R) {
+  const int tid = threadIdx.x;
+  const int chunk = tid & 7, rsub = tid >> 3;
 #pragma unroll
-  for (int ps = 0; ps < 8; ps++) {
+  for (int ps = 0; ps < NS; ps++) {
     const int row = ps * 32 + rsub;
     if (row < R) {
       unsigned h[4], l[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) split_tf32(v[ps][e], h[e], l[e]);
+      split_tf32(v[ps].x, h[0], l[0]); split_tf32(v[ps].y, h[1], l[1]);
+      split_tf32(v[ps].z, h[2], l[2]); split_tf32(v[ps].w, h[3], l[3]);
       const unsigned off = row * 128 + ((chunk ^ (row & 7)) << 4);
       sts16(hi_base + off, h[0], h[1], h[2], h[3]);
       sts16(lo_base + off, l[0], l[1], l[2], l[3]);
     }
   }
 }
-
-// ---- MN-contiguous sources (mode 1): element (k, c) = seg.p[(k0 + k) * seg.ld + c_local], c = r0 + r looked up in up
-// to 3 column blocks; c == ones_col yields 1.0.
+// element (k, c) of MN-contiguous sources: c looked up in up to 3 column blocks; c == ones_col yields 1.0
 __device__ __forceinline__ float mn_elem(const TcSeg* seg, int nseg, int ones_col, int c, int c_total, long long krow) {
   if (c >= c_total) return 0.f;
   if (c == ones_col) return 1.f;
@@ -143,68 +150,84 @@ __device__ __forceinline__ float mn_elem(const TcSeg* seg, int nseg, int ones_co
   }
   return v;
 }
-// ---- MN-contiguous source into a K-major tile (in-kernel transpose): a warp takes 4 consecutive mn x 32 k, lane = k.
-// Each lane reads 16 bytes (4 mn) of its k row and scatters them to 4 tile rows; for a fixed component all 32 lanes hit
-// 32 distinct banks (bank = 4*((k>>2)^(mn&7)) + (k&3)), so the transposing stores are conflict-free.
-__device__ __forceinline__ void load_mn_to_kmajor(unsigned hi_base, unsigned lo_base, const TcSeg* seg, int nseg,
-                                                  int ones_col, int r0, int R, int c_total, int k0, int k_valid,
-                                                  bool vec) {
-  const int warp = threadIdx.x >> 5, k = threadIdx.x & 31;
-  const int nquad = (R + 3) >> 2;
-  const long long krow = k0 + k;
-  for (int q0 = warp; q0 < nquad; q0 += 4 * (TCT / 32)) {
-    float v[4][4];
+// MN-contiguous source: a warp task is (4 consecutive k) x (32 consecutive mn): lane = (kk = lane>>3, ml = lane&7), each
+// lane reads 16 bytes (mn 4*ml .. 4*ml+3 of row k) => every 8 lanes read one contiguous 128-byte line.  To make the
+// transposing 4-byte stores conflict free the tile rows of every 32-row block are PERMUTED: matrix row 4*ml + e lives
+// in tile row 8*e + ml, so for a fixed component e the 32 lanes hit banks 4*(kg ^ ml) + kk = 32 distinct banks.
+// The epilogue undoes the permutation (rows for A, columns for B).
+template <int NS>
+__device__ __forceinline__ void issue_mncontig(float4 (&v)[NS], const TcSeg* seg, int nseg, int ones_col, int r0, int R,
+                                               int c_total, int k0, int k_valid, bool vec) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ml = lane & 7, kk = lane >> 3;
+  const int G = (R + 31) >> 5;                 // 32-mn groups
+  const int ntask = 8 * G;                     // (mg, kg), kg = 0..7
 #pragma unroll
-    for (int u = 0; u < 4; u++) {             // 4 quads in flight per thread
-      const int q = q0 + u * (TCT / 32);
-      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-      if (q < nquad && k < k_valid) {
-        const int c = r0 + q * 4;
+  for (int u = 0; u < NS; u++) {
+    const int t = warp + u * (TCT / 32);
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < ntask) {
+      const int mg = t % G, kg = t / G;
+      const int k = kg * 4 + kk;
+      const int c = r0 + mg * 32 + 4 * ml;
+      if (k < k_valid && mg * 32 + 4 * ml < R) {
+        const long long krow = k0 + k;
         bool done = false;
-        if (vec) {
+        if (vec) {                            // whole quad inside one column block?
           int cl = c;
 #pragma unroll
-          for (int s = 0; s < 3; s++) {
-            if (s < nseg) {
-              if (!done && cl >= 0 && cl + 3 < seg[s].len) {
-                const float4 f = *reinterpret_cast<const float4*>(seg[s].p + krow * seg[s].ld + cl);
-                v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
+          for (int s2 = 0; s2 < 3; s2++) {
+            if (s2 < nseg) {
+              if (!done && cl >= 0 && cl + 3 < seg[s2].len) {
+                v[u] = *reinterpret_cast<const float4*>(seg[s2].p + krow * seg[s2].ld + cl);
                 done = true;
               }
-              cl -= seg[s].len;
+              cl -= seg[s2].len;
             }
           }
         }
         if (!done) {
-#pragma unroll
-          for (int e = 0; e < 4; e++) v[u][e] = mn_elem(seg, nseg, ones_col, c + e, c_total, krow);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int q = q0 + u * (TCT / 32);
-      if (q < nquad) {
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int r = q * 4 + e;
-          if (r < R) {
-            unsigned h, l;
-            split_tf32(v[u][e], h, l);
-            const unsigned off = r * 128 + (((k >> 2) ^ (r & 7)) << 4) + ((k & 3) << 2);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(hi_base + off), "r"(h) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(lo_base + off), "r"(l) : "memory");
-          }
+          v[u].x = mn_elem(seg, nseg, ones_col, c + 0, c_total, krow);
+          v[u].y = mn_elem(seg, nseg, ones_col, c + 1, c_total, krow);
+          v[u].z = mn_elem(seg, nseg, ones_col, c + 2, c_total, krow);
+          v[u].w = mn_elem(seg, nseg, ones_col, c + 3, c_total, krow);
         }
       }
     }
   }
 }
+template <int NS>
+__device__ __forceinline__ void commit_mncontig(const float4 (&v)[NS], unsigned hi_base, unsigned lo_base, int R) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ml = lane & 7, kk = lane >> 3;
+  const int G = (R + 31) >> 5;
+  const int ntask = 8 * G;
+#pragma unroll
+  for (int u = 0; u < NS; u++) {
+    const int t = warp + u * (TCT / 32);
+    if (t < ntask) {
+      const int mg = t % G, kg = t / G;
+      const float e4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int rho = mg * 32 + 8 * e + ml;                  // permuted tile row of matrix row mg*32 + 4*ml + e
+        unsigned h, l;
+        split_tf32(e4[e], h, l);
+        const unsigned off = rho * 128 + ((kg ^ ml) << 4) + (kk << 2);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(hi_base + off), "r"(h) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(lo_base + off), "r"(l) : "memory");
+      }
+    }
+  }
+}
+// inverse of the row permutation inside a 32-block: tile row (or TMEM lane / column) rho -> matrix index
+__device__ __forceinline__ int unpermute32(int rho) { return (rho & ~31) + 4 * (rho & 7) + ((rho & 31) >> 3); }
 
 __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   __shared__ __align__(8) unsigned long long mbar_s[2];
   __shared__ unsigned tmem_base_s;
+  __shared__ __align__(16) float bias_s[256];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int BN = g.BN;
   const unsigned a_bytes = BM * 128, b_bytes = (unsigned)((BN + 31) & ~31) * 128;
@@ -239,34 +262,47 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   const unsigned idesc = make_idesc(BN);
   const bool kseg = (g.a_mode == 0 || g.b_mode == 0);
 
-  int it = 0;
-  for (int kb = kb0; kb < kb1; kb++, it++) {
-    const int s = it & 1;
-    const unsigned bar = s ? bar1 : bar0;
-    if (it >= 2) mbar_wait(bar, ((it >> 1) - 1) & 1);        // the MMAs that read this stage two iterations ago are done
-    const unsigned a_hi = smem0 + s * stage_bytes, a_lo = a_hi + a_bytes;
-    const unsigned b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
-    // locate the k-block inside the K segments (each K-contiguous segment is padded to a multiple of 32)
-    int seg = 0, kloc = kb * BK;
+  // k-block -> (K segment, offset inside the segment); K-contiguous segments are padded to multiples of 32
+  auto locate = [&](int kb, int& seg, int& kloc) {
+    seg = 0; kloc = kb * BK;
     if (kseg) {
       while (seg + 1 < g.k_nseg && kloc >= ((g.k_len[seg] + BK - 1) / BK) * BK) {
         kloc -= ((g.k_len[seg] + BK - 1) / BK) * BK;
         seg++;
       }
     }
+  };
+  float4 ra[4], rb[8];                                       // register staging of one k-block of A (128 rows) and B (<=256)
+  auto issue = [&](int kb) {
+    int seg, kloc;
+    locate(kb, seg, kloc);
     const int k_valid = g.k_len[seg] - kloc;
     if (g.a_mode == 0)
-      load_kmajor(a_hi, a_lo, g.a_k[seg].p + (long long)m0 * g.a_k[seg].ld + kloc, g.a_k[seg].ld, BM, g.M - m0, k_valid,
-                  g.a_vec != 0);
+      issue_kcontig(ra, g.a_k[seg].p + (long long)m0 * g.a_k[seg].ld + kloc, g.a_k[seg].ld, BM, g.M - m0, k_valid, g.a_vec != 0);
     else
-      load_mn_to_kmajor(a_hi, a_lo, g.a_mn, 1, -1, m0, BM, g.M, kloc, k_valid, g.a_vec != 0);
+      issue_mncontig(ra, g.a_mn, 1, -1, m0, BM, g.M, kloc, k_valid, g.a_vec != 0);
     if (g.b_mode == 0)
-      load_kmajor(b_hi, b_lo, g.b_k[seg].p + (long long)n0 * g.b_k[seg].ld + kloc, g.b_k[seg].ld, BN, g.N - n0, k_valid,
-                  g.b_vec != 0);
+      issue_kcontig(rb, g.b_k[seg].p + (long long)n0 * g.b_k[seg].ld + kloc, g.b_k[seg].ld, BN, g.N - n0, k_valid, g.b_vec != 0);
     else if (g.k_nseg > 1)   // one MN-contiguous source per K segment (both directions of the input-delta product)
-      load_mn_to_kmajor(b_hi, b_lo, &g.b_mn[seg], 1, -1, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
+      issue_mncontig(rb, &g.b_mn[seg], 1, -1, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
     else
-      load_mn_to_kmajor(b_hi, b_lo, g.b_mn, g.b_nseg, g.b_ones, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
+      issue_mncontig(rb, g.b_mn, g.b_nseg, g.b_ones, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
+  };
+
+  // bias tile -> shared memory once (the epilogue must not wait on global loads)
+  for (int c = tid; c < BN; c += TCT) bias_s[c] = (g.bias && n0 + c < g.N) ? g.bias[n0 + c] : 0.f;
+  __syncthreads();
+
+  int it = 0;
+  if (kb0 < kb1) issue(kb0);
+  for (int kb = kb0; kb < kb1; kb++, it++) {
+    const int s = it & 1;
+    const unsigned bar = s ? bar1 : bar0;
+    if (it >= 2) mbar_wait(bar, ((it >> 1) - 1) & 1);        // the MMAs that read this stage two iterations ago are done
+    const unsigned a_hi = smem0 + s * stage_bytes, a_lo = a_hi + a_bytes;
+    const unsigned b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
+    if (g.a_mode == 0) commit_kcontig(ra, a_hi, a_lo, BM); else commit_mncontig(ra, a_hi, a_lo, BM);
+    if (g.b_mode == 0) commit_kcontig(rb, b_hi, b_lo, BN); else commit_mncontig(rb, b_hi, b_lo, BN);
     fence_proxy_async();                                     // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -281,6 +317,7 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
       }
       mma_commit(bar);
     }
+    if (kb + 1 < kb1) issue(kb + 1);                         // next k-block's loads fly while the tensor core works
   }
   // all MMAs retire in order: the last commit covers everything
   if (it > 0) {
@@ -289,12 +326,14 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   }
   tc_fence_after();
 
-  // ---- epilogue: TMEM -> registers -> global.  warp w reads lanes 32*(w&3).., column half (w>>2)
+  // ---- epilogue: TMEM -> registers -> global.  warp w reads lanes 32*(w&3).., column half (w>>2).
+  // Operands staged from MN-contiguous sources carry the 32-block permutation: undo it here.
   const int lq = warp & 3, ch = warp >> 2;
-  const int row = m0 + 32 * lq + lane;
+  const int trow = 32 * lq + lane;                                   // TMEM lane = tile row
+  const int row = m0 + (g.a_mode ? unpermute32(trow) : trow);
   const int half = BN / 2;
-  const bool st_vec = !g.ws && g.beta == 0.f && (g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
-                      ((n0 + ch * half) % 4 == 0) && (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+  const bool st_vec = !g.ws && g.b_mode == 0 && g.beta == 0.f && (g.ldc % 4 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((n0 + ch * half) % 4 == 0);
   for (int c = 0; c < half; c += 8) {
     float v[8];
     if (it > 0) tmem_ld8(tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * half + c), v);
@@ -303,32 +342,211 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
       for (int e = 0; e < 8; e++) v[e] = 0.f;
     }
     if (row < g.M) {
-      const int col0 = n0 + ch * half + c;
-      if (st_vec && col0 + 7 < g.N) {
-        if (g.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(g.bias + col0);
-          const float4 b1 = *reinterpret_cast<const float4*>(g.bias + col0 + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        float4* dst = reinterpret_cast<float4*>(g.C + (long long)row * g.ldc + col0);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      const int tc0 = ch * half + c;                                 // first tile column of this group of 8
+      if (st_vec && n0 + tc0 + 7 < g.N) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[tc0]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[tc0 + 4]);
+        float4* dst = reinterpret_cast<float4*>(g.C + (long long)row * g.ldc + n0 + tc0);
+        dst[0] = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
+        dst[1] = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-          const int col = col0 + e;
+          const int lc = g.b_mode ? unpermute32(tc0 + e) : tc0 + e;  // column inside the N tile
+          const int col = n0 + lc;
           if (col < g.N) {
             if (g.ws) {
               g.ws[((size_t)blockIdx.z * g.M + row) * g.N + col] = v[e];
             } else {
-              float o = v[e];
-              if (g.bias) o += g.bias[col];
+              const float o = v[e] + bias_s[lc];
               float* dst = g.C + (long long)row * g.ldc + col;
               *dst = (g.beta != 0.f) ? fmaf(g.beta, *dst, o) : o;
             }
           }
         }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Dedicated kernel for the derivative products  P[M x N] = A^T [B0 | B1 | 1]  (A: [K x M], B blocks: [K x len], all
+// row-major, reduction over the K = N_columns rows), split over K.  Same tiles / MMAs / permutation as above, but every
+// per-slot quantity that does not depend on k (source pointer, leading dimension, smem offset, special-quad flag) is
+// computed once before the k loop, so a k-block costs one LDG.128, 12 conversion and 8 store instructions per slot.
+template <int NSB>
+__global__ void __launch_bounds__(TCT, 1) gemm_tn_kernel(TcArgs g) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  __shared__ __align__(8) unsigned long long mbar_s[2];
+  __shared__ unsigned tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ml = lane & 7, kk = lane >> 3;
+  constexpr int BN = NSB * 32;
+  constexpr unsigned a_bytes = BM * 128, b_bytes = BN * 128, stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const unsigned smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const unsigned bar0 = smem_u32(&mbar_s[0]), bar1 = smem_u32(&mbar_s[1]);
+  if (tid == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_d = tmem_base_s;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * g.kb_per_split;
+  const int kb1 = min(g.nkb, kb0 + g.kb_per_split);
+  const int K = g.k_len[0];
+  const unsigned idesc = make_idesc(BN);
+
+  // ---- per-slot invariants.  A: task t = warp + 8u -> (mg = warp & 3, kg = (warp >> 2) + 2u)
+  const float* pA;            // row (kg0*4 + kk), column m0 + mg*32 + 4*ml ; slot u adds 8*u rows
+  bool a_fast;                // whole quad inside the matrix and 16-byte loadable
+  unsigned offA[4];
+  {
+    const int mg = warp & 3, c = m0 + mg * 32 + 4 * ml;
+    a_fast = g.a_vec && (c + 3 < g.M);
+    pA = g.a_mn[0].p + (long long)(((warp >> 2)) * 4 + kk) * g.a_mn[0].ld + c;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int kg = (warp >> 2) + 2 * u;
+      offA[u] = (unsigned)((mg * 32 + ml) * 128 + ((kg ^ ml) << 4) + (kk << 2));
+    }
+  }
+  // B: task t = warp + 8u -> (mg = t % NSB, kg = t / NSB); the quad's 4 columns usually sit inside one column block
+  const float* pB[NSB];
+  int ldB[NSB], cB[NSB];
+  unsigned offB[NSB];
+  bool b_fast[NSB];
+#pragma unroll
+  for (int u = 0; u < NSB; u++) {
+    const int t = warp + 8 * u, mg = t % NSB, kg = t / NSB;
+    const int c = n0 + mg * 32 + 4 * ml;
+    cB[u] = c;
+    offB[u] = (unsigned)((mg * 32 + ml) * 128 + ((kg ^ ml) << 4) + (kk << 2));
+    pB[u] = nullptr; ldB[u] = 0; b_fast[u] = false;
+    int cl = c;
+#pragma unroll
+    for (int s2 = 0; s2 < 3; s2++) {
+      if (s2 < g.b_nseg) {
+        if (g.b_vec && !b_fast[u] && cl >= 0 && cl + 3 < g.b_mn[s2].len) {
+          pB[u] = g.b_mn[s2].p + (long long)(kg * 4 + kk) * g.b_mn[s2].ld + cl;
+          ldB[u] = (int)g.b_mn[s2].ld;
+          b_fast[u] = true;
+        }
+        cl -= g.b_mn[s2].len;
+      }
+    }
+  }
+
+  float4 ra[4], rb[NSB];
+  auto issue = [&](int kb) {
+    const int k0 = kb * BK;
+    const bool full = (k0 + BK <= K);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int k = ((warp >> 2) + 2 * u) * 4 + kk;
+      ra[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (full || k0 + k < K) {
+        if (a_fast) ra[u] = *reinterpret_cast<const float4*>(pA + (long long)(k0 + 8 * u) * g.a_mn[0].ld);
+        else {
+          const int c = m0 + (warp & 3) * 32 + 4 * ml;
+          const long long krow = k0 + k;
+          ra[u].x = mn_elem(g.a_mn, 1, -1, c + 0, g.M, krow); ra[u].y = mn_elem(g.a_mn, 1, -1, c + 1, g.M, krow);
+          ra[u].z = mn_elem(g.a_mn, 1, -1, c + 2, g.M, krow); ra[u].w = mn_elem(g.a_mn, 1, -1, c + 3, g.M, krow);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NSB; u++) {
+      const int k = ((warp + 8 * u) / NSB) * 4 + kk;
+      rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (full || k0 + k < K) {
+        if (b_fast[u]) rb[u] = *reinterpret_cast<const float4*>(pB[u] + (long long)k0 * ldB[u]);
+        else {
+          const long long krow = k0 + k;
+          rb[u].x = mn_elem(g.b_mn, g.b_nseg, g.b_ones, cB[u] + 0, g.N, krow);
+          rb[u].y = mn_elem(g.b_mn, g.b_nseg, g.b_ones, cB[u] + 1, g.N, krow);
+          rb[u].z = mn_elem(g.b_mn, g.b_nseg, g.b_ones, cB[u] + 2, g.N, krow);
+          rb[u].w = mn_elem(g.b_mn, g.b_nseg, g.b_ones, cB[u] + 3, g.N, krow);
+        }
+      }
+    }
+  };
+  auto put4 = [&](const float4& v, unsigned hi_base, unsigned lo_base, unsigned off) {
+    const float e4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {             // matrix row 4*ml + e -> tile row 8*e + ml: +1024 bytes per e
+      unsigned h, l;
+      split_tf32(e4[e], h, l);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(hi_base + off + e * 1024), "r"(h) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(lo_base + off + e * 1024), "r"(l) : "memory");
+    }
+  };
+
+  int it = 0;
+  if (kb0 < kb1) issue(kb0);
+  for (int kb = kb0; kb < kb1; kb++, it++) {
+    const int s = it & 1;
+    const unsigned bar = s ? bar1 : bar0;
+    if (it >= 2) mbar_wait(bar, ((it >> 1) - 1) & 1);
+    const unsigned a_hi = smem0 + s * stage_bytes, a_lo = a_hi + a_bytes;
+    const unsigned b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
+#pragma unroll
+    for (int u = 0; u < 4; u++) put4(ra[u], a_hi, a_lo, offA[u]);
+#pragma unroll
+    for (int u = 0; u < NSB; u++) put4(rb[u], b_hi, b_lo, offB[u]);
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < BK / 8; ks++) {
+        const unsigned long long ah = make_desc(a_hi + ks * 32), al = make_desc(a_lo + ks * 32);
+        const unsigned long long bh = make_desc(b_hi + ks * 32), bl = make_desc(b_lo + ks * 32);
+        mma_tf32(tmem_d, al, bh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        mma_tf32(tmem_d, ah, bl, idesc, 1u);
+        mma_tf32(tmem_d, ah, bh, idesc, 1u);
+      }
+      mma_commit(bar);
+    }
+    if (kb + 1 < kb1) issue(kb + 1);
+  }
+  if (it > 0) {
+    const int last = it - 1;
+    mbar_wait((last & 1) ? bar1 : bar0, (last >> 1) & 1);
+  }
+  tc_fence_after();
+  // ---- epilogue: partial tile -> workspace slice of this split, undoing the row and column permutations
+  const int lq = warp & 3, ch = warp >> 2;
+  const int row = m0 + unpermute32(32 * lq + lane);
+  constexpr int half = BN / 2;
+  float* __restrict__ wsz = g.ws + (size_t)blockIdx.z * g.M * g.N;
+  for (int c = 0; c < half; c += 8) {
+    float v[8];
+    if (it > 0) tmem_ld8(tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * half + c), v);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = 0.f;
+    }
+    if (row < g.M) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int col = n0 + unpermute32(ch * half + c + e);
+        if (col < g.N) wsz[(size_t)row * g.N + col] = v[e];
       }
     }
   }
@@ -366,7 +584,14 @@ size_t tc_smem_bytes(int BN) { return (size_t)2 * (2 * BM * 128 + 2 * ((BN + 31)
 }  // namespace
 
 int gemm_tc_configure() {
-  return (int)cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256));
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256));
+#define CB200_TN_ATTR(N_)                                                                                          \
+  if (e == cudaSuccess)                                                                                            \
+    e = cudaFuncSetAttribute(gemm_tn_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(32 * N_));
+  CB200_TN_ATTR(1) CB200_TN_ATTR(2) CB200_TN_ATTR(3) CB200_TN_ATTR(4) CB200_TN_ATTR(5) CB200_TN_ATTR(6) CB200_TN_ATTR(7)
+  CB200_TN_ATTR(8)
+#undef CB200_TN_ATTR
+  return (int)e;
 }
 
 int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
@@ -374,6 +599,7 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
   // N tile: multiple of 16, <= 256, as few tiles as possible
   const int ntiles = (g.N + 255) / 256;
   int BN = (((g.N + ntiles - 1) / ntiles) + 15) & ~15;
+  if (g.b_mode == 1) BN = (BN + 31) & ~31;    // permuted 32-row blocks must be complete (see issue_mncontig)
   if (BN < 16) BN = 16;
   g.BN = BN;
   const int mtiles = (g.M + BM - 1) / BM;
@@ -395,7 +621,20 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
   splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
   if (!scatter) g.ws = nullptr;
   dim3 grid(ntiles, mtiles, splits);
-  gemm_tc_kernel<<<grid, TCT, tc_smem_bytes(BN), st>>>(g);
+  if (g.a_mode == 1 && g.b_mode == 1 && scatter) {
+    switch (BN / 32) {
+      case 1: gemm_tn_kernel<1><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      case 2: gemm_tn_kernel<2><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      case 3: gemm_tn_kernel<3><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      case 4: gemm_tn_kernel<4><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      case 5: gemm_tn_kernel<5><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      case 6: gemm_tn_kernel<6><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      case 7: gemm_tn_kernel<7><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      default: gemm_tn_kernel<8><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+    }
+  } else {
+    gemm_tc_kernel<<<grid, TCT, tc_smem_bytes(BN), st>>>(g);
+  }
   if (scatter) {
     const size_t total = (size_t)g.M * g.N;
     size_t nb = (total + 255) / 256;

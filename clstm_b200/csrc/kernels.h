@@ -111,8 +111,10 @@ void softmax_rows(cudaStream_t st, float* z, int N, int nc, int* amax, float* am
 // d += g; g = 0; d = clamp(d); v += lr*d; d *= mom      (clstm_compute.cc:553-563)
 void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,
                 int fold_only);
-// Rt[k][r] = R[r][k] for both directions
-void transpose_R(cudaStream_t st, const float* R0, float* Rt0, const float* R1, float* Rt1, int no);
+// dst[c][r] = src[r][c] for up to 6 small matrices in one launch (derived weight layouts)
+struct TransposeJob { const float* src; float* dst; int rows, cols; };
+struct TransposeJobs { TransposeJob job[6]; int n; };
+void transpose_batch(cudaStream_t st, const TransposeJobs& jobs);
 // trivial_decode per line (ctc.cc:159-194) from the per-column argmax arrays written by softmax_rows / ctc_posterior
 void decode_lines(cudaStream_t st, const Lines& ln, const int* argmax_idx, const float* argmax_val, int* classes,
                   int* locs, int* counts, int max_per_line);

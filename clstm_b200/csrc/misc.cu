@@ -65,21 +65,22 @@ __global__ void sgd_update_kernel(float* __restrict__ v, float* __restrict__ d, 
   }
 }
 
-__global__ void transpose_R_kernel(const float* __restrict__ R0, float* __restrict__ Rt0,
-                                   const float* __restrict__ R1, float* __restrict__ Rt1, int no) {
+// dst[c][r] = src[r][c] for a handful of small weight matrices in one launch (derived layouts, refreshed after
+// every parameter change): R^T for the generic recurrent kernel, W1^T and Wx^T as K-contiguous B operands of the
+// dH / dx products.
+__global__ void transpose_batch_kernel(TransposeJobs jobs) {
   __shared__ float tile[32][33];
-  const float* R = blockIdx.z ? R1 : R0;
-  float* Rt = blockIdx.z ? Rt1 : Rt0;
-  const int rows = 4 * no, cols = no;          // R is rows x cols, Rt is cols x rows
+  const TransposeJob j = jobs.job[blockIdx.z];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (c0 >= j.cols || r0 >= j.rows) return;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < rows && c < cols) ? R[(size_t)r * cols + c] : 0.f;
+    tile[i][threadIdx.x] = (r < j.rows && c < j.cols) ? j.src[(size_t)r * j.cols + c] : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) Rt[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    if (r < j.rows && c < j.cols) j.dst[(size_t)c * j.rows + r] = tile[threadIdx.x][i];
   }
 }
 
@@ -146,9 +147,12 @@ void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float l
   sgd_update_kernel<<<blocks, 256, 0, st>>>(v, d, g, n, lr, mom, clip, fold_only);
 }
 
-void transpose_R(cudaStream_t st, const float* R0, float* Rt0, const float* R1, float* Rt1, int no) {
-  dim3 grid((no + 31) / 32, (4 * no + 31) / 32, 2);
-  transpose_R_kernel<<<grid, dim3(32, 8), 0, st>>>(R0, Rt0, R1, Rt1, no);
+void transpose_batch(cudaStream_t st, const TransposeJobs& jobs) {
+  int mr = 0, mc = 0;
+  for (int i = 0; i < jobs.n; i++) { mr = max(mr, jobs.job[i].rows); mc = max(mc, jobs.job[i].cols); }
+  if (jobs.n <= 0 || mr <= 0 || mc <= 0) return;
+  dim3 grid((mc + 31) / 32, (mr + 31) / 32, jobs.n);
+  transpose_batch_kernel<<<grid, dim3(32, 8), 0, st>>>(jobs);
 }
 
 void decode_lines(cudaStream_t st, const Lines& ln, const int* argmax_idx, const float* argmax_val, int* classes,

@@ -2,7 +2,10 @@
 usage: ncu -i X.ncu-rep --page source --csv --kernel-name regex:K | python tools/ncu_src.py [topN] [loop_only]"""
 import csv, sys
 rows = list(csv.reader(sys.stdin))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+import os
+inst = int(os.environ.get("NCU_INSTANCE", "0"))        # which kernel instance of the dump to summarise
+his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+hi = his[inst]
 hdr = rows[hi]
 col = {h: i for i, h in enumerate(hdr)}
 data = []
