@@ -1,5 +1,5 @@
 // gemm_tc.cu -- tcgen05 (5th-gen tensor core) GEMM with fp32-grade accuracy for the batched dense products of the
-// path (see gemm.cu for the list).  fp32 operands are split on the fly into TF32 hi + TF32 lo parts and each
+// path (see gemm.cu for the list).  fp32 operands are split on the fly into TF32 hi + TF32 lo parts (truncation split, see split_tf32) and each
 // K=8 step issues three MMAs (hi*hi + hi*lo + lo*hi, "3xTF32"): ~2^-21 relative error per product, inside the 1e-4
 // parity bar that plain TF32 (2^-11) would break.
 //
@@ -80,11 +80,13 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
   v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
-// fp32 -> (tf32 hi, tf32 lo)
+// fp32 -> (tf32 hi, tf32 lo).  hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi
+// (exact in fp32; the tensor core reads only the TF32 bits of it).  |x - hi - tf32(lo)| <= 2^-20 |x|.  `cvt.rna.tf32`
+// would round instead of truncate (2^-22) but is emulated with ~8 instructions on sm_100a and this split sits in the
+// innermost load path of every product.
 __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float rem = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(rem));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void sts16(unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
