@@ -286,6 +286,18 @@ def run_b200(a):
                              "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     roof = dict(kernels[dom]); roof["kernel"] = dom; roof["traffic"] = None
+    try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r1_summary.json)
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json")))
+        if (a.nhidden, a.batch, a.T) == (100, 32, 500):
+            for cap in summ.get("full_capture", []):
+                if cap["Kernel Name"].startswith(dom):
+                    def mb(x):
+                        v, u = x.split()[:2]
+                        return float(v) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}[u]
+                    roof["traffic"] = mb(cap["dram__bytes_read.sum"]) + mb(cap["dram__bytes_write.sum"])
+                    roof["traffic_unit"] = "bytes per launch (ncu --set full, profiles/r1_summary.json)"
+    except Exception:
+        pass
     roof["peak_source"] = pk["src"]
     roof.pop("ms_per_step"); roof.pop("launches_per_step")
     roof["kernel_ms"] = kernels[dom]["ms_per_step"]
