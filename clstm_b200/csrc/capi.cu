@@ -98,6 +98,10 @@ struct clstm_b200_net {
   int ni, no, nc, nf;
   int num_sms = 148;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;              // side stream: the W1 derivative product overlaps the backward recurrence
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* ws2 = nullptr;                    // its private split-K workspace
+  size_t ws2_floats = 0;
 
   // ---- parameters, DEVICE layout: [dir0: Wx(4no x ni) | bias(4no) | R(4no x no)] [dir1: ...] [W1(nc x 2no) | b1(nc)]
   // rows of the LSTM blocks are gate-interleaved: r = 4*j + g, g: 0=gi(WGI) 1=gf(WGF) 2=go(WGO) 3=ci(WCI)
@@ -120,7 +124,8 @@ struct clstm_b200_net {
   int* tiles = nullptr;         // device: tile_line | tile_t0
   int* h_tiles = nullptr;
   int capTiles = 0;
-  double* tot = nullptr;        // CTC per-state totals
+  double* tot = nullptr;        // CTC per-state totals (8 time-slice partials)
+  float* mx_part = nullptr;     // CTC slice maxima
   int capStates = 0;
   long long* lat_off = nullptr;
   int* status = nullptr;
@@ -284,7 +289,9 @@ int ensure_lines(clstm_b200_net* n, int B, int nlab) {
     TRY(dev_alloc(&n->meta, (size_t)6 * cb + cl));
     dev_free(n->tot);
     n->capStates = 2 * cl + cb;
-    TRY(dev_alloc(&n->tot, (size_t)n->capStates));
+    TRY(dev_alloc(&n->tot, (size_t)n->capStates * 8));
+    dev_free(n->mx_part);
+    TRY(dev_alloc(&n->mx_part, (size_t)cb * 8));
     TRY(dev_alloc(&n->lat_off, (size_t)cb));
     CU(cudaHostAlloc((void**)&n->h_meta, ((size_t)6 * cb + cl) * sizeof(int), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&n->h_lat, (size_t)cb * sizeof(long long), cudaHostAllocDefault));
@@ -448,11 +455,14 @@ int dense_nt(clstm_b200_net* n, int M, int N, int K, const float* A, long long l
 
 // derivative product reduced over all columns: out += A^T [B0 | B1 | 1], A [K x M] and B blocks [K x len] row-major
 int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, const float* B0, int n0, const float* B1,
-             int n1, float* out0, float* out1, float* out_bias) {
+             int n1, float* out0, float* out1, float* out_bias, bool side = false) {
+  cudaStream_t stream = side ? n->st2 : n->st;
+  float* ws = side ? n->ws2 : n->ws;
+  const size_t wsf = side ? n->ws2_floats : n->ws_floats;
   if (!n->use_tc) {
-    int k = gemm_f32(n->st, M, n0, K, A, 1, lda, B0, n0, 1, out0, n0, nullptr, 1.f, n->ws, n->ws_floats, n->num_sms);
-    if (B1) k += gemm_f32(n->st, M, n1, K, A, 1, lda, B1, n1, 1, out1, n1, nullptr, 1.f, n->ws, n->ws_floats, n->num_sms);
-    k += colsum_f32(n->st, K, M, A, lda, out_bias, 1.f, n->ws, n->ws_floats, n->num_sms);
+    int k = gemm_f32(stream, M, n0, K, A, 1, lda, B0, n0, 1, out0, n0, nullptr, 1.f, ws, wsf, n->num_sms);
+    if (B1) k += gemm_f32(stream, M, n1, K, A, 1, lda, B1, n1, 1, out1, n1, nullptr, 1.f, ws, wsf, n->num_sms);
+    k += colsum_f32(stream, K, M, A, lda, out_bias, 1.f, ws, wsf, n->num_sms);
     return k;
   }
   TcArgs g{};
@@ -463,12 +473,12 @@ int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, con
   if (B1) { g.b_mn[1] = {B1, n1, n1}; g.b_nseg = 2; g.b_vec = g.b_vec && vec_ok(B1, n1); }
   g.b_ones = n0 + n1;
   g.k_nseg = 1; g.k_len[0] = K;
-  g.beta = 1.f; g.ws = n->ws; g.ws_floats = n->ws_floats;
+  g.beta = 1.f; g.ws = ws; g.ws_floats = wsf;
   TcOut o{};
   o.p[0] = out0; o.ld[0] = n0; o.len[0] = n0; o.nseg = 1;
   if (B1) { o.p[1] = out1; o.ld[1] = n1; o.len[1] = n1; o.nseg = 2; }
   o.bias = out_bias;
-  return gemm_tc(n->st, g, &o, n->num_sms);
+  return gemm_tc(stream, g, &o, n->num_sms);
 }
 
 // ------------------------------------------------------------------------------------------------ device passes
@@ -508,7 +518,7 @@ int run_ctc(clstm_b200_net* n) {
   Scope s(n, PH_CTC);
   CtcArgs a;
   a.nc = n->nc; a.out = n->out; a.aligned = n->aligned; a.delta = n->delta;
-  a.lmatch = n->lm; a.lr = n->lr; a.rl = n->rl; a.tot = n->tot; a.amax = n->amax[1]; a.amaxv = n->amaxv[1]; a.status = n->status; a.raw = n->raw_targets ? 1 : 0;
+  a.lmatch = n->lm; a.lr = n->lr; a.rl = n->rl; a.tot = n->tot; a.mx_part = n->mx_part; a.amax = n->amax[1]; a.amaxv = n->amaxv[1]; a.status = n->status; a.raw = n->raw_targets ? 1 : 0;
   s.launches(ctc_align(n->st, n->ln, a));
   TRY(check_launch("ctc_align"));
   n->have_ctc = true;
@@ -522,7 +532,12 @@ int run_backward(clstm_b200_net* n) {
     Scope s(n, PH_SOFTMAX_BWD);   // backward_softmax clstm_compute.cc:346-356
     if (n->use_tc) s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->W1T, nc, false, n->dH, 2 * no, nullptr, 0.f));
     else s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->v + n->oW1, 2 * no, true, n->dH, 2 * no, nullptr, 0.f));
-    s.launches(dense_tn(n, nc, N, n->delta, nc, n->H, 2 * no, nullptr, 0, n->g + n->oW1, nullptr, n->g + n->oB1));
+    // the W1 derivative product needs only delta and H: run it on the side stream, concurrently with the backward
+    // recurrence (which occupies 2B of the 148 SMs), and join before anything consumes g
+    cudaEventRecord(n->ev_fork, n->st);
+    cudaStreamWaitEvent(n->st2, n->ev_fork, 0);
+    s.launches(dense_tn(n, nc, N, n->delta, nc, n->H, 2 * no, nullptr, 0, n->g + n->oW1, nullptr, n->g + n->oB1, true));
+    cudaEventRecord(n->ev_join, n->st2);
   }
   {
     Scope s(n, PH_LSTM_BWD);
@@ -559,6 +574,7 @@ int run_backward(clstm_b200_net* n) {
         s.launches(dense_nt(n, N, ni, 4 * no, n->DG[d], 4 * no, n->v + n->oWx[d], ni, true, n->dx, ni, nullptr, d ? 1.f : 0.f));
     }
   }
+  cudaStreamWaitEvent(n->st, n->ev_join, 0);
   TRY(check_launch("backward"));
   n->g_pending = true;
   return 0;
@@ -662,7 +678,13 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   n->oW1 = o; o += (size_t)nc * 2 * no;
   n->oB1 = o; o += nc;
   n->P = o;
-  if (cudaStreamCreateWithFlags(&n->st, cudaStreamNonBlocking) != cudaSuccess) { delete n; return fail("cudaStreamCreate failed"); }
+  if (cudaStreamCreateWithFlags(&n->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&n->st2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    clstm_b200_destroy(n);
+    return fail("cudaStreamCreate failed");
+  }
   int rc = 0;
   rc |= dev_alloc(&n->v, n->P); rc |= dev_alloc(&n->d, n->P); rc |= dev_alloc(&n->g, n->P);
   for (int d = 0; d < 2; d++) {
@@ -674,6 +696,8 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   // split-K workspace: enough for ~2 waves of 64x64 tiles plus the largest derivative matrix a few times over
   n->ws_floats = std::max<size_t>((size_t)4 * n->num_sms * 64 * 64, (size_t)40 * 4 * no * (1 + ni + no));
   rc |= dev_alloc(&n->ws, n->ws_floats);
+  n->ws2_floats = (size_t)64 * nc * (2 * no + 1);
+  rc |= dev_alloc(&n->ws2, n->ws2_floats);
   if (rc) { clstm_b200_destroy(n); return 1; }
   cudaMemsetAsync(n->v, 0, n->P * sizeof(float), n->st);
   cudaMemsetAsync(n->d, 0, n->P * sizeof(float), n->st);
@@ -699,12 +723,16 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   if (!n) return;
   cudaSetDevice(n->cfg.device);
   if (n->st) cudaStreamSynchronize(n->st);
+  if (n->st2) cudaStreamSynchronize(n->st2);
   if (n->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n->comm);
   free_batch(n);
   dev_free(n->v); dev_free(n->d); dev_free(n->g); dev_free(n->Rt[0]); dev_free(n->Rt[1]);
   dev_free(n->WxT[0]); dev_free(n->WxT[1]); dev_free(n->W1T);
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->status);
-  dev_free(n->ws); dev_free(n->tiles); dev_free(n->tot);
+  dev_free(n->ws); dev_free(n->tiles); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
+  if (n->st2) cudaStreamDestroy(n->st2);
+  if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+  if (n->ev_join) cudaEventDestroy(n->ev_join);
   if (n->h_tiles) cudaFreeHost(n->h_tiles);
   for (int w = 0; w < 2; w++) { dev_free(n->dcls[w]); dev_free(n->dlocs[w]); dev_free(n->dcnt[w]); }
   if (n->h_meta) cudaFreeHost(n->h_meta);

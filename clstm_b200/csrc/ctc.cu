@@ -7,7 +7,7 @@
 //   ctc_lmatch     (grid: 32-column tiles)  o' = max(1e-5,o)/sum ; lmatch(t,s) = log o'(t, class_s)      ctc.cc:68-77
 //   ctc_lattice    (grid: lines, 2 warps)   forward lattice lr and backward lattice rl, skip=-5 soft start,
 //                                           log_add with the |x-y|>10 cutoff                           ctc.cc:24-55
-//   ctc_stats      (grid: lines)            both = lr+rl ; max ; epath = limexp(both-max) ; per-STATE totals over TIME
+//   ctc_max/ctc_sum (grid: lines x 8 slices) both = lr+rl ; max ; epath = limexp(both-max) ; per-STATE totals over TIME
 //                                                                                                       ctc.cc:83-89
 //   ctc_posterior  (grid: 32-column tiles)  epath /= total_s ; aligned(t,c) = sum_{s: class_s=c} epath(t,s) ;
 //                                           aligned /= row total ; delta = aligned - out   ctc.cc:84-109, clstmhl.h:211
@@ -160,22 +160,24 @@ __global__ void __launch_bounds__(64) ctc_lattice_kernel(Lines ln, CtcArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ stats
-// per line: lmatch <- epath = limexp(lr + rl - max) ; tot[s] = max(1e-9, sum_t epath(t,s))  (double)
-__global__ void __launch_bounds__(256) ctc_stats_kernel(Lines ln, CtcArgs a) {
+// Two kernels, grid (lines, kStatSlices): each CTA takes a slice of the line's time axis.
+//   ctc_max:  slice maximum of both = lr + rl                                   (ctc.cc:54, amax2 :83)
+//   ctc_sum:  lmatch <- epath = limexp(both - max) ; per-state partial sums over the slice's time range (double)
+// The posterior kernel adds the kStatSlices partials in a fixed order: tot[s] = max(1e-9, sum_t epath(t,s)) (:84-87).
+constexpr int kStatSlices = 8;
+__global__ void __launch_bounds__(256) ctc_max_kernel(Lines ln, CtcArgs a) {
   __shared__ float red_s[8];
-  __shared__ float mx_s;
-  __shared__ double part_s[4][64];
-  const int b = ln.order[blockIdx.x];
+  const int b = ln.order[blockIdx.x], z = blockIdx.y;
   const int T = ln.T[b], L = ln.L[b];
   const int S = a.raw ? L : 2 * L + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* __restrict__ lr = a.lr + ln.lat_off[b];
   const float* __restrict__ rl = a.rl + ln.lat_off[b];
-  float* __restrict__ ep = a.lmatch + ln.lat_off[b];      // lmatch is dead after the lattice passes
-  const int TS = T * S;
+  const int rows = (T + kStatSlices - 1) / kStatSlices;
+  const int i0 = min(T, z * rows) * S, i1 = min(T, (z + 1) * rows) * S;
   float mx = -INFINITY;
 #pragma unroll 4
-  for (int i = tid; i < TS; i += 256) mx = fmaxf(mx, lr[i] + rl[i]);   // both = lr + rl ctc.cc:54 ; amax2 :83
+  for (int i = i0 + tid; i < i1; i += 256) mx = fmaxf(mx, lr[i] + rl[i]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) red_s[warp] = mx;
@@ -183,27 +185,40 @@ __global__ void __launch_bounds__(256) ctc_stats_kernel(Lines ln, CtcArgs a) {
   if (tid == 0) {
     float m = red_s[0];
     for (int i = 1; i < 8; i++) m = fmaxf(m, red_s[i]);
-    mx_s = m;
+    a.mx_part[(size_t)b * kStatSlices + z] = m;
   }
-  __syncthreads();
-  mx = mx_s;
-  double* __restrict__ tot = a.tot + ln.st_off[b];
+}
+__global__ void __launch_bounds__(256) ctc_sum_kernel(Lines ln, CtcArgs a) {
+  __shared__ double part_s[4][64];
+  const int b = ln.order[blockIdx.x], z = blockIdx.y;
+  const int T = ln.T[b], L = ln.L[b];
+  const int S = a.raw ? L : 2 * L + 1;
+  const int tid = threadIdx.x;
+  const float* __restrict__ lr = a.lr + ln.lat_off[b];
+  const float* __restrict__ rl = a.rl + ln.lat_off[b];
+  float* __restrict__ ep = a.lmatch + ln.lat_off[b];      // lmatch is dead after the lattice passes
+  float mx = a.mx_part[(size_t)b * kStatSlices];
+#pragma unroll
+  for (int i = 1; i < kStatSlices; i++) mx = fmaxf(mx, a.mx_part[(size_t)b * kStatSlices + i]);
+  const int rows = (T + kStatSlices - 1) / kStatSlices;
+  const int t0 = min(T, z * rows), t1 = min(T, (z + 1) * rows);
+  double* __restrict__ tot = a.tot + ((size_t)ln.st_off[b]) * kStatSlices + (size_t)z * S;
   const int sl = tid & 63, tr = tid >> 6;                 // 64 states x 4 time phases per sweep
   for (int s0 = 0; s0 < S; s0 += 64) {
     const int s = s0 + sl;
     double acc = 0.0;
     if (s < S) {
 #pragma unroll 4
-      for (int t = tr; t < T; t += 4) {
+      for (int t = t0 + tr; t < t1; t += 4) {
         const int i = t * S + s;
-        const float e = limexp_((lr[i] + rl[i]) - mx);    // epath  ctc.cc:83 (kept in the lmatch buffer)
+        const float e = limexp_((lr[i] + rl[i]) - mx);    // epath  ctc.cc:83
         ep[i] = e;
         acc += (double)e;
       }
     }
     part_s[tr][sl] = acc;
     __syncthreads();
-    if (tr == 0 && s < S) tot[s] = fmax(1e-9, (part_s[0][sl] + part_s[1][sl]) + (part_s[2][sl] + part_s[3][sl]));
+    if (tr == 0 && s < S) tot[s] = (part_s[0][sl] + part_s[1][sl]) + (part_s[2][sl] + part_s[3][sl]);
     __syncthreads();
   }
 }
@@ -223,8 +238,14 @@ __global__ void __launch_bounds__(TILE_THREADS) ctc_posterior_kernel(Lines ln, C
   double* tot_s = dsm + 8 * nc;
   int* cls_s = reinterpret_cast<int*>(tot_s + S);
   const int* lab = ln.labels + ln.lab_off[b];
-  const double* __restrict__ tot = a.tot + ln.st_off[b];
-  for (int s = tid; s < S; s += TILE_THREADS) { cls_s[s] = state_class(lab, s, raw); tot_s[s] = tot[s]; }
+  const double* __restrict__ tot = a.tot + ((size_t)ln.st_off[b]) * kStatSlices;
+  for (int s = tid; s < S; s += TILE_THREADS) {
+    cls_s[s] = state_class(lab, s, raw);
+    double acc = 0.0;
+#pragma unroll
+    for (int z = 0; z < kStatSlices; z++) acc += tot[(size_t)z * S + s];   // fixed order: deterministic
+    tot_s[s] = fmax(1e-9, acc);
+  }
   __syncthreads();
   const float* __restrict__ ep_l = a.lmatch + ln.lat_off[b];
   for (int c = warp; c < ncols; c += TILE_THREADS / 32) {
@@ -279,9 +300,10 @@ int ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a) {
   const size_t sm_d = (size_t)(8 * a.nc + kCtcMaxStates) * sizeof(double) + (size_t)kCtcMaxStates * sizeof(int);
   ctc_lmatch_kernel<<<ln.ntiles, TILE_THREADS, sm_a, st>>>(ln, a);
   ctc_lattice_kernel<<<ln.B, 64, 0, st>>>(ln, a);
-  ctc_stats_kernel<<<ln.B, 256, 0, st>>>(ln, a);
+  ctc_max_kernel<<<dim3(ln.B, kStatSlices), 256, 0, st>>>(ln, a);
+  ctc_sum_kernel<<<dim3(ln.B, kStatSlices), 256, 0, st>>>(ln, a);
   ctc_posterior_kernel<<<ln.ntiles, TILE_THREADS, sm_d, st>>>(ln, a);
-  return 4;
+  return 5;
 }
 
 int ctc_configure() {

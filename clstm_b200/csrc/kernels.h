@@ -93,7 +93,8 @@ struct CtcArgs {
   float* lmatch;          // lattice scratch, per line T x S
   float* lr;              // forward lattice
   float* rl;              // backward lattice
-  double* tot;            // per-state totals over time (packed, Lines::st_off)
+  double* tot;            // per-state partial totals over time: [st_off*8 + slice*S + s] (8 time slices per line)
+  float* mx_part;         // [B][8] slice maxima of lr + rl
   int* amax;              // [N] argmax of aligned per column (tensor.h:357-366 tie rule)
   float* amaxv;           // [N] its value
   int* status;            // device int (reserved)
