@@ -312,7 +312,8 @@ def run_b200(a):
                       "lstm_kernel": net.lstm_variant, "parallelism": "dp%d" % world},
            "e2e": {"value": e2e, "unit": "px/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h},
-           "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels}
+           "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
+           "allreduce_ms_per_step": (stats.get("allreduce", (0.0, 0))[0] / a.steps) if world > 1 else 0.0}
     if world == 1 and not a.no_cpu_baseline:
         cb = cpu_reference(a, a.cpu_seconds, 1)
         cb.pop("seconds")

@@ -190,3 +190,30 @@ def test_tcgen05_dense_products_match_simt(ffi, nh):
     err = net.selftest_gemm()
     assert len(err) == 6
     assert err.max() < 1e-5, err
+
+
+def test_long_lines_wide_net_generic_path(ffi, oracle):
+    # BASELINE config 3 shape in miniature: nhidden=200 (generic recurrent kernels), ragged lines up to T=1500,
+    # transcripts up to 75 labels (lattice lanes own 5 states each); alignment indices must be bit-exact.
+    ni, nh, nc = 48, 200, 83
+    x, Ts, labels, L = synth.make_lines(3, (600, 1500), ni, nc, seed=9)
+    onet, gnet = make_pair(ffi, oracle, ni, nh, nc, "init")
+    out = gnet.forward(x, Ts)
+    aligned = gnet.ctc_align(labels, L)
+    gnet.backward()
+    amax = gnet.argmax(1)
+    dec_al = gnet.decode(1)
+    gd = gnet.get_derivs()
+    onet.clear_derivs()
+    for b, (xx, oo, aa, ll, am) in enumerate(zip(split(x, Ts), split(out, Ts), split(aligned, Ts), split(labels, L), split(amax, Ts))):
+        o_out, _ = onet.fwdbwd(xx, ll)
+        assert np.abs(o_out - oo).max() < TOL
+        o_al = oracle.ctc_align_labels(oo, ll)
+        # with untrained (near-uniform) outputs the lattice values reach ~ -4.4*T ~ -6000 here; one Float ulp at that
+        # magnitude is 4.9e-4, so the reference's own Float recursion is only defined to a few 1e-4 in the posteriors
+        assert np.abs(o_al - aa).max() < 5e-4
+        assert np.array_equal(oracle.argmax_rows(o_al), am)
+        cs, locs = oracle.trivial_decode(o_al)
+        assert np.array_equal(cs, dec_al[b][0]) and np.array_equal(locs, dec_al[b][1])
+    od = onet.get_derivs()
+    assert np.abs(od - gd).max() < 5e-3 * max(1.0, np.abs(od).max())
