@@ -180,6 +180,7 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    dp_mode = "none"
     net = clstm_b200.Net(48, a.nhidden, a.nclasses, device=local)
     net.set_params(synth.reference_init(48, a.nhidden, a.nclasses, seed=0.222))
     if world > 1:
@@ -188,6 +189,15 @@ def run_b200(a):
             idt.copy_(torch.frombuffer(bytearray(clstm_b200.Net.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         net.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        if os.environ.get("CLSTM_B200_DP", "p2p") != "nccl" and world <= 8:
+            # NVLink peer-memory path: one fused kernel reads every rank's derivatives and applies the update
+            mine = torch.frombuffer(bytearray(net.p2p_handle()), dtype=torch.uint8).cuda()
+            allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            net.p2p_connect([bytes(h.cpu().numpy().tobytes()) for h in allh], rank, world)
+            dp_mode = "p2p-fused"
+        else:
+            dp_mode = "nccl"
 
     x, T, labels, L = make_batch(a, rank)
     N = int(T.sum())
@@ -309,7 +319,8 @@ def run_b200(a):
            "config": {"workload": workload_name(a), "lines_per_gpu": a.batch, "global_lines": a.batch * world,
                       "columns_per_gpu": N, "l2": "flushed between timed steps (256 MiB memset)",
                       "weights": "reference LCG init (negbiased, 0.01), seed 0.222", "lr": LR, "momentum": MOM,
-                      "lstm_kernel": net.lstm_variant, "parallelism": "dp%d" % world},
+                      "lstm_kernel": net.lstm_variant, "parallelism": "dp%d" % world,
+                      "grad_exchange": dp_mode},
            "e2e": {"value": e2e, "unit": "px/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,

@@ -42,6 +42,8 @@ EXPORTS = {
     "clstm_b200_comm_unique_id": (C.c_int, [C.c_void_p]),
     "clstm_b200_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "clstm_b200_allreduce_derivs": (C.c_int, [C.c_void_p]),
+    "clstm_b200_p2p_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "clstm_b200_p2p_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "clstm_b200_train_step": (C.c_int, [C.c_void_p, f32p, i32p, C.c_int, i32p, i32p, C.c_float, C.c_float, C.c_float,
                                         f32p, f32p, i32p, i32p, i32p, C.c_int]),
     "clstm_b200_upload_batch": (C.c_int, [C.c_void_p, f32p, i32p, C.c_int, i32p, i32p]),
@@ -278,6 +280,17 @@ class Net:
     def comm_init(self, id_bytes, rank, world):
         buf = (C.c_char * 128).from_buffer_copy(id_bytes)
         _chk(lib().clstm_b200_comm_init(self.h, C.cast(buf, C.c_void_p), rank, world))
+
+    def p2p_handle(self):
+        buf = (C.c_char * 64)()
+        _chk(lib().clstm_b200_p2p_handle(self.h, C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
+    def p2p_connect(self, handles, rank, world):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        _chk(lib().clstm_b200_p2p_connect(self.h, C.cast(buf, C.c_void_p), rank, world))
 
     def allreduce_derivs(self):
         _chk(lib().clstm_b200_allreduce_derivs(self.h))

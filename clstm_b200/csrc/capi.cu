@@ -157,6 +157,11 @@ struct clstm_b200_net {
   // ---- communicator
   void* comm = nullptr;
   int rank = 0, world = 1;
+  // ---- NVLink peer path: g lives inside a peer-mappable comm buffer [1 KiB header | g]
+  float* comm_buf = nullptr;
+  float* peer_buf[kMaxPeers] = {};
+  bool p2p = false;
+  unsigned epoch = 0;
 };
 
 namespace {
@@ -605,6 +610,20 @@ int run_update(clstm_b200_net* n, float lr, float mom, float clip) {
   return check_launch("sgd_update");
 }
 
+// share_deltas + sgd_update fused over NVLink peer memory (all ranks must call this the same number of times)
+int run_peer_update(clstm_b200_net* n, float lr, float mom, float clip) {
+  Scope s(n, PH_ALLREDUCE);
+  PeerArgs a{};
+  for (int r = 0; r < n->world; r++) a.comm[r] = n->peer_buf[r];
+  a.rank = n->rank; a.world = n->world; a.epoch = ++n->epoch;
+  a.v = n->v; a.d = n->d; a.n = n->P; a.lr = lr; a.mom = mom; a.clip = clip;
+  peer_allreduce_update(n->st, a);
+  n->g_pending = false;
+  prepare_weights(n);
+  s.launches(3);
+  return check_launch("peer_allreduce_update");
+}
+
 int run_decode(clstm_b200_net* n, int which, int max_per_line) {
   TRY(ensure_decode(n, max_per_line));
   Scope s(n, PH_DECODE);
@@ -686,7 +705,9 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
     return fail("cudaStreamCreate failed");
   }
   int rc = 0;
-  rc |= dev_alloc(&n->v, n->P); rc |= dev_alloc(&n->d, n->P); rc |= dev_alloc(&n->g, n->P);
+  rc |= dev_alloc(&n->v, n->P); rc |= dev_alloc(&n->d, n->P);
+  rc |= dev_alloc(&n->comm_buf, n->P + kPeerHeaderFloats);
+  n->g = n->comm_buf ? n->comm_buf + kPeerHeaderFloats : nullptr;
   for (int d = 0; d < 2; d++) {
     rc |= dev_alloc(&n->Rt[d], (size_t)4 * no * no);
     rc |= dev_alloc(&n->WxT[d], (size_t)4 * no * ni);
@@ -701,7 +722,7 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   if (rc) { clstm_b200_destroy(n); return 1; }
   cudaMemsetAsync(n->v, 0, n->P * sizeof(float), n->st);
   cudaMemsetAsync(n->d, 0, n->P * sizeof(float), n->st);
-  cudaMemsetAsync(n->g, 0, n->P * sizeof(float), n->st);
+  cudaMemsetAsync(n->comm_buf, 0, (n->P + kPeerHeaderFloats) * sizeof(float), n->st);
   cudaMemsetAsync(n->Rt[0], 0, (size_t)4 * no * no * sizeof(float), n->st);
   cudaMemsetAsync(n->Rt[1], 0, (size_t)4 * no * no * sizeof(float), n->st);
   cudaMemsetAsync(n->WxT[0], 0, (size_t)4 * no * ni * sizeof(float), n->st);
@@ -726,7 +747,9 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   if (n->st2) cudaStreamSynchronize(n->st2);
   if (n->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n->comm);
   free_batch(n);
-  dev_free(n->v); dev_free(n->d); dev_free(n->g); dev_free(n->Rt[0]); dev_free(n->Rt[1]);
+  for (int r = 0; r < kMaxPeers; r++)
+    if (n->peer_buf[r] && r != n->rank) cudaIpcCloseMemHandle(n->peer_buf[r]);
+  dev_free(n->v); dev_free(n->d); dev_free(n->comm_buf); n->g = nullptr; dev_free(n->Rt[0]); dev_free(n->Rt[1]);
   dev_free(n->WxT[0]); dev_free(n->WxT[1]); dev_free(n->W1T);
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->status);
   dev_free(n->ws); dev_free(n->tiles); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
@@ -931,6 +954,34 @@ int clstm_b200_comm_init(clstm_b200_net* n, const void* id128, int rank, int wor
   n->world = world;
   return 0;
 }
+// Peer-memory path: export this rank's comm buffer, import everybody's.  handle64: 64-byte cudaIpcMemHandle_t.
+int clstm_b200_p2p_handle(clstm_b200_net* n, void* handle64) {
+  if (!n || !handle64) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, n->comm_buf));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, sizeof h);
+  return 0;
+}
+int clstm_b200_p2p_connect(clstm_b200_net* n, const void* handles, int rank, int world) {
+  if (!n || !handles) return fail("null argument");
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail("bad rank/world (at most %d peers)", kMaxPeers);
+  if (n->P % 4 != 0 && false) return fail("unreachable");
+  CU(cudaSetDevice(n->cfg.device));
+  CU(cudaStreamSynchronize(n->st));
+  for (int r = 0; r < world; r++) {
+    if (r == rank) { n->peer_buf[r] = n->comm_buf; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * 64, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    n->peer_buf[r] = (float*)p;
+  }
+  n->rank = rank; n->world = world; n->p2p = true; n->epoch = 0;
+  return 0;
+}
+
 int clstm_b200_allreduce_derivs(clstm_b200_net* n) {
   if (!n) return fail("null argument");
   if (!n->comm) return fail("no communicator attached (clstm_b200_comm_init)");
@@ -947,8 +998,12 @@ int clstm_b200_step_resident(clstm_b200_net* n, float lr, float momentum, float 
   TRY(run_forward(n));
   TRY(run_ctc(n));
   TRY(run_backward(n));
-  TRY(run_allreduce(n));
-  TRY(run_update(n, lr, momentum, clip));
+  if (n->p2p && n->world > 1) {
+    TRY(run_peer_update(n, lr, momentum, clip));
+  } else {
+    TRY(run_allreduce(n));
+    TRY(run_update(n, lr, momentum, clip));
+  }
   TRY(run_decode(n, 0, std::max(n->capDec, n->ln.Tmax / 2 + 1)));
   return 0;
 }

@@ -112,6 +112,20 @@ void softmax_rows(cudaStream_t st, float* z, int N, int nc, int* amax, float* am
 // d += g; g = 0; d = clamp(d); v += lr*d; d *= mom      (clstm_compute.cc:553-563)
 void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,
                 int fold_only);
+// fused share_deltas + sgd_update over NVLink peer memory (misc.cu)
+constexpr int kPeerHeaderFloats = 256;            // 1 KiB header in front of g inside the comm buffer
+constexpr int kPeerArrive = 0, kPeerDepart = 16, kPeerCounter = 32;   // header slots (32-bit words)
+constexpr int kMaxPeers = 8;
+struct PeerArgs {
+  float* comm[kMaxPeers];   // comm buffer of every rank (own one included), peer-mapped
+  int rank, world;
+  unsigned epoch;
+  float *v, *d;
+  size_t n;
+  float lr, mom, clip;
+};
+void peer_allreduce_update(cudaStream_t st, const PeerArgs& a);   // 2 launches
+
 // dst[c][r] = src[r][c] for up to 6 small matrices in one launch (derived weight layouts)
 struct TransposeJob { const float* src; float* dst; int rows, cols; };
 struct TransposeJobs { TransposeJob job[6]; int n; };

@@ -129,7 +129,96 @@ __global__ void decode_kernel(Lines ln, const int* __restrict__ amax, const floa
   }
   if (threadIdx.x == 0) counts[b] = base_s;
 }
+// ------------------------------------------------------------------------------------------------------------------
+// share_deltas (clstm.cc:731-744) + sgd_update (clstm.cc:201-217) in ONE kernel over NVLink peer memory.
+// Every rank's step derivatives g live in a peer-mapped "comm buffer" [header 1 KiB | g].  Each rank reads ALL ranks'
+// g directly over NVLink/NVSwitch (one-shot all-reduce: world-1 remote reads of P floats, 544 KB..6 MB, latency bound,
+// no intermediate buffer), adds them in rank order (identical result on every rank), folds the sum into Params.d and
+// applies clip + update.  Flag protocol in the header (32-bit epochs, one slot per writer rank):
+//   arrive[r] : rank r's g for this epoch is complete          (written remotely by r into every rank's header)
+//   depart[r] : rank r has finished reading everybody's g       (ditto) -> the owner may zero / overwrite its g
+// Spins are bounded (~8 s) and trap, so a lost peer becomes an error instead of a hang.
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned* p, unsigned epoch) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(p) != epoch) {
+    if (clock64() - t0 > 16000000000ll) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_allreduce_update_kernel(PeerArgs a) {
+  unsigned* hdr = reinterpret_cast<unsigned*>(a.comm[a.rank]);
+  // ---- all ranks' g complete?
+  if (blockIdx.x == 0 && threadIdx.x < a.world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned*>(a.comm[threadIdx.x]) + kPeerArrive + a.rank, a.epoch);
+  }
+  if (threadIdx.x < a.world) spin_until(hdr + kPeerArrive + threadIdx.x, a.epoch);
+  __syncthreads();
+  // ---- sum over ranks in rank order, fold, clip, update (clstm_compute.cc:553-563)
+  const size_t n4 = a.n / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < a.world; r++) {
+      const float4 g = reinterpret_cast<const float4*>(a.comm[r] + kPeerHeaderFloats)[i];
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    float4 d = reinterpret_cast<float4*>(a.d)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    float dd[4] = {d.x + s.x, d.y + s.y, d.z + s.z, d.w + s.w};
+    float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      if (a.clip < 1e6f) { dd[e] = fminf(dd[e], a.clip); dd[e] = fmaxf(dd[e], -a.clip); }
+      vv[e] = __fadd_rn(vv[e], __fmul_rn(dd[e], a.lr));
+      dd[e] = dd[e] * a.mom;
+    }
+    reinterpret_cast<float4*>(a.v)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    reinterpret_cast<float4*>(a.d)[i] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+  }
+  if (blockIdx.x == 0)   // tail (n % 4) elements
+    for (size_t i = n4 * 4 + threadIdx.x; i < a.n; i += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < a.world; r++) s += (a.comm[r] + kPeerHeaderFloats)[i];
+      float di = a.d[i] + s;
+      if (a.clip < 1e6f) { di = fminf(di, a.clip); di = fmaxf(di, -a.clip); }
+      a.v[i] = __fadd_rn(a.v[i], __fmul_rn(di, a.lr));
+      a.d[i] = di * a.mom;
+    }
+  // ---- last block of this rank announces "done reading" to every rank
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned last_s;
+  if (threadIdx.x == 0) last_s = (atomicAdd(hdr + kPeerCounter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (last_s && threadIdx.x < a.world) {
+    if (threadIdx.x == 0) hdr[kPeerCounter] = 0;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<unsigned*>(a.comm[threadIdx.x]) + kPeerDepart + a.rank, a.epoch);
+  }
+}
+// zero the local g once every rank has finished reading it
+__global__ void __launch_bounds__(256) peer_zero_kernel(PeerArgs a) {
+  const unsigned* hdr = reinterpret_cast<const unsigned*>(a.comm[a.rank]);
+  if (threadIdx.x < a.world) spin_until(hdr + kPeerDepart + threadIdx.x, a.epoch);
+  __syncthreads();
+  float* g = a.comm[a.rank] + kPeerHeaderFloats;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x) g[i] = 0.f;
+}
+
 }  // namespace
+
+void peer_allreduce_update(cudaStream_t st, const PeerArgs& a) {
+  peer_allreduce_update_kernel<<<64, 256, 0, st>>>(a);
+  peer_zero_kernel<<<32, 256, 0, st>>>(a);
+}
 
 void softmax_rows(cudaStream_t st, float* z, int N, int nc, int* amax, float* amaxv) {
   if (N <= 0) return;

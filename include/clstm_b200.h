@@ -99,6 +99,14 @@ int clstm_b200_comm_unique_id(void* id128);
 int clstm_b200_comm_init(clstm_b200_net* net, const void* id128, int rank, int world);
 int clstm_b200_allreduce_derivs(clstm_b200_net* net);
 
+/* NVLink peer-memory variant of the same exchange, fused with the update: every rank exports its derivative buffer
+ * (64-byte cudaIpcMemHandle_t), the launcher gathers the handles of all ranks, and after clstm_b200_p2p_connect the
+ * fused training step (clstm_b200_train_step / clstm_b200_step_resident) replaces "NCCL all-reduce + sgd_update" by ONE
+ * kernel that reads all ranks' derivatives directly over NVLink/NVSwitch, sums them in rank order and applies
+ * clip + update (at most 8 ranks of one node). */
+int clstm_b200_p2p_handle(clstm_b200_net* net, void* handle64);
+int clstm_b200_p2p_connect(clstm_b200_net* net, const void* handles /* world x 64 bytes */, int rank, int world);
+
 /* CLSTMOCR::train for a minibatch (clstmhl.h:201-223): forward, CTC align, backward, [all-reduce when a
  * communicator is attached], sgd_update, decode of the outputs.  Host buffers as above; out/aligned/classes/
  * locs/counts nullable.  One stream, no host synchronisation between the kernels. */

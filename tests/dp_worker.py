@@ -2,7 +2,8 @@
 
 mode "gloo": CPU. Each rank runs the reference step (oracle fwdbwd per line) on its shard, derivatives are summed with
 a gloo all_reduce (share_deltas semantics), every rank applies the same update; rank 0 writes the parameters.
-mode "nccl": GPU. Same with the CUDA path; the all-reduce is issued from inside libclstm_b200.so over NCCL."""
+mode "nccl": GPU. Same with the CUDA path; the all-reduce is issued from inside libclstm_b200.so over NCCL.
+mode "p2p":  GPU. The fused NVLink peer-memory kernel (all-reduce + clip + update in one launch)."""
 import os
 import sys
 
@@ -50,6 +51,11 @@ else:
         idt.copy_(torch.frombuffer(bytearray(clstm_b200.Net.comm_unique_id()), dtype=torch.uint8))
     dist.broadcast(idt, 0)
     net.comm_init(idt.cpu().numpy().tobytes(), rank, world)
+    if mode == "p2p":
+        mine = torch.frombuffer(bytearray(net.p2p_handle()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        net.p2p_connect([h.cpu().numpy().tobytes() for h in allh], rank, world)
     for _ in range(steps):
         net.train_step(xs, Ts, ls, Ls, lr, mom)
     params = net.get_params()

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_equals_one_gpu(tmp_path):
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
+def test_two_gpu_equals_one_gpu(tmp_path, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -20,7 +21,7 @@ def test_two_gpu_equals_one_gpu(tmp_path):
     out = str(tmp_path / "dp_gpu.npy")
     subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                            "--master-addr", "127.0.0.1", "--master-port", "29544",
-                           os.path.join(ROOT, "tests", "dp_worker.py"), "nccl", out, "100"], timeout=600)
+                           os.path.join(ROOT, "tests", "dp_worker.py"), mode, out, "100"], timeout=600)
     got = np.load(out)
     ni, nh, nc, B, steps = 48, 100, 20, 6, 2
     x, T, labels, L = synth.make_lines(B, (25, 45), ni, nc, seed=17)
