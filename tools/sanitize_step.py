@@ -1,0 +1,16 @@
+"""Tiny training steps through every kernel family (regs + generic LSTM, tcgen05 + SIMT GEMM, CTC, decode, update) for
+compute-sanitizer runs:  compute-sanitizer --tool memcheck|racecheck python tools/sanitize_step.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import clstm_b200
+from clstm_b200 import synth
+for nh in (16, 5):
+    x, T, labels, L = synth.make_lines(3, (9, 21), 48, 11, seed=2)
+    net = clstm_b200.Net(48, nh, 11)
+    net.set_params(synth.trained_like(net.nparams, 0.3))
+    for _ in range(2):
+        dec, out, al = net.train_step(x, T, labels, L, 1e-3, 0.9, want_out=True, want_aligned=True)
+    assert np.isfinite(out).all() and np.isfinite(al).all()
+    net.forward(x, T); net.ctc_align(labels, L); net.backward(); net.decode(1); net.argmax(0)
+    print("ok", nh, net.lstm_variant)
