@@ -84,6 +84,12 @@ const char* lstm_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a
 const char* lstm_variant_for(int no);
 int lstm_configure();   // opt in to large dynamic smem etc.; returns cudaError_t as int
 
+// ---------------------------------------------------------------- lstm_cluster.cu (thread-block clusters + DSMEM)
+bool lstm_cluster_supported(int no);
+int lstm_cluster_configure();
+int lstm_cluster_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a);    // cudaError_t as int, -1: size n/a
+int lstm_cluster_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
+
 // ---------------------------------------------------------------- ctc.cu
 struct CtcArgs {
   int nc;

@@ -510,7 +510,9 @@ int generic_threads(int no) {
 }
 }  // namespace
 
-const char* lstm_variant_for(int no) { return has_regs_variant(no) ? "regs" : "generic"; }
+const char* lstm_variant_for(int no) {
+  return has_regs_variant(no) ? "regs" : (lstm_cluster_supported(no) ? "cluster" : "generic");
+}
 
 int lstm_configure() {
   cudaError_t e = cudaFuncSetAttribute(lstm_fwd_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -522,7 +524,8 @@ int lstm_configure() {
   if (e != cudaSuccess) return (int)e;
   CB200_BWD_SMEM(16) CB200_BWD_SMEM(32) CB200_BWD_SMEM(50) CB200_BWD_SMEM(64) CB200_BWD_SMEM(100)
 #undef CB200_BWD_SMEM
-  return (int)e;
+  if (e != cudaSuccess) return (int)e;
+  return lstm_cluster_configure();
 }
 
 const char* lstm_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
@@ -533,6 +536,10 @@ const char* lstm_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a)
     case 64: launch_fwd_regs<64>(st, ln, a); return "regs";
     case 100: launch_fwd_regs<100>(st, ln, a); return "regs";
     default: break;
+  }
+  if (lstm_cluster_supported(a.no)) {   // register-resident over a thread-block cluster (DSMEM exchange of h)
+    if (lstm_cluster_forward(st, ln, a) == 0) return "cluster";
+    cudaGetLastError();                 // cluster not schedulable on this device: stream the weights instead
   }
   const size_t smem = (size_t)6 * a.no * sizeof(float);
   lstm_fwd_generic<<<dim3(ln.B, 2), generic_threads(a.no), smem, st>>>(ln, a);
@@ -547,6 +554,10 @@ const char* lstm_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a
     case 64: launch_bwd_regs<64>(st, ln, a); return "regs";
     case 100: launch_bwd_regs<100>(st, ln, a); return "regs";
     default: break;
+  }
+  if (lstm_cluster_supported(a.no)) {
+    if (lstm_cluster_backward(st, ln, a) == 0) return "cluster";
+    cudaGetLastError();
   }
   const size_t smem = (size_t)9 * a.no * sizeof(float);
   lstm_bwd_generic<<<dim3(ln.B, 2), generic_threads(a.no), smem, st>>>(ln, a);

@@ -1,0 +1,426 @@
+// lstm_cluster.cu -- register-resident recurrence for hidden sizes whose recurrent matrix does not fit one SM:
+// a thread-block CLUSTER of CS CTAs per (line, direction).  CTA c owns UC = NO/CS hidden units, i.e. the 4*UC gate
+// rows of those units times all NO columns = 40 000 weights = 100 per thread x 400 threads, exactly the register
+// budget of the single-CTA kernel (lstm.cu).  NO = 200 -> CS = 4, NO = 400 -> CS = 16 (non-portable cluster size).
+//
+// forward : every CTA keeps a full copy of h (NO floats, double buffered) in its shared memory.  Per step a group of
+//           LU = NO/25 lanes per unit splits K into slices of 25, reduce-scatters the four gate sums, applies the
+//           gates / cell update, and lane i of the group stores the new h of the unit into CTA i's copy through
+//           distributed shared memory (st.shared::cluster).  One cluster barrier per step.
+// backward: each CTA multiplies ITS rows of R (own units) with its own deltas for ALL NO outputs -- no delta exchange --
+//           and scatters the partial sums to the CTA that owns the output unit (DSMEM); the owner adds the CS partials.
+//           One CTA barrier + one cluster barrier per step.
+// Same math, gate-interleaved row order, fast gate functions and staging scheme as lstm.cu (see there for the
+// reference citations).
+#include <cooperative_groups.h>
+
+#include "kernels.h"
+
+namespace cb200 {
+namespace {
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float x, float y) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+  return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& x, float& y) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(u64& acc, u64 a, u64 b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ ulonglong2 lds_v2u64(unsigned addr) {
+  ulonglong2 v;
+  asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// store into the shared memory of CTA `rank` of the cluster (distributed shared memory)
+__device__ __forceinline__ void st_dsmem_f32(unsigned local_addr, unsigned rank, float v) {
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank_() {
+  unsigned r;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cp_async4(unsigned saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kStage = 4;
+
+template <int NO> struct ClCfg {
+  static constexpr int SL = 25, NPF = 12;              // k-slice per lane: 12 packed pairs + 1 tail
+  static constexpr int SSTR = 28;                      // slice stride in smem (16-byte aligned, conflict-free)
+  static constexpr int LU = NO / SL;                   // lanes per unit (8 or 16)
+  static constexpr int CS = (NO * NO) / 10000;         // CTAs per cluster (4 or 16)
+  static constexpr int UC = NO / CS;                   // units per CTA (50 or 25)
+  static constexpr int THREADS = UC * LU;              // 400
+  static constexpr int TPAD = (THREADS + 31) & ~31;    // 416
+  static constexpr int LB = (LU == 8) ? 3 : 4;         // log2(LU)
+  static_assert(NO % SL == 0 && (LU == 8 || LU == 16) && UC * CS == NO && THREADS == 400, "unsupported size");
+};
+
+// reduce-scatter four partials over the top two bits of the lane-in-group index, all-reduce over the remaining bits:
+// afterwards every lane holds the group total of gate q = 2*bit(LB-1) + bit(LB-2).
+template <int LB>
+__device__ __forceinline__ float group_reduce4(float p0, float p1, float p2, float p3, bool hi, bool lo) {
+  constexpr int X1 = 1 << (LB - 1), X2 = 1 << (LB - 2);
+  float k0 = hi ? p2 : p0, k1 = hi ? p3 : p1;
+  const float s0 = hi ? p0 : p2, s1 = hi ? p1 : p3;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, X1);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, X1);
+  float r = lo ? k1 : k0;
+  const float s2 = lo ? k0 : k1;
+  r += __shfl_xor_sync(0xffffffffu, s2, X2);
+#pragma unroll
+  for (int x = X2 >> 1; x > 0; x >>= 1) r += __shfl_xor_sync(0xffffffffu, r, x);
+  return r;
+}
+
+// ----------------------------------------------------------------------------------------------------- forward
+template <int NO>
+__global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_fwd_cluster(Lines ln, LstmFwdArgs a) {
+  typedef ClCfg<NO> Cfg;
+  constexpr int SL = Cfg::SL, NPF = Cfg::NPF, SSTR = Cfg::SSTR, LU = Cfg::LU, CS = Cfg::CS, UC = Cfg::UC, LB = Cfg::LB;
+  constexpr int ROWS = 4 * NO, TPAD = Cfg::TPAD;
+  __shared__ __align__(16) float h_s[2][LU * SSTR];
+  __shared__ float xp_s[kStage][TPAD];
+  const int tid0 = threadIdx.x;
+  const unsigned crank = cluster_rank_();
+  const int b = ln.order[blockIdx.x / CS], d = blockIdx.y;
+  const int T = ln.T[b], off = ln.off[b];
+  const int tid = (tid0 < Cfg::THREADS) ? tid0 : Cfg::THREADS - LU + (tid0 % LU);   // padding lanes clone the last unit group
+  const int ul = tid / LU, lg = tid % LU;                          // unit inside the CTA, lane inside the unit group
+  const int unit = (int)crank * UC + ul;                           // global hidden unit
+  const bool hi = (lg >> (LB - 1)) & 1, lo = (lg >> (LB - 2)) & 1;
+  const int q = 2 * (int)hi + (int)lo;                             // gate this lane ends up with
+  const bool lead = (lg & ((1 << (LB - 2)) - 1)) == 0;             // one lane per (unit, gate)
+  const int row = 4 * unit + q;
+  const float* __restrict__ XPb = d ? a.XP[1] : a.XP[0];
+  float* __restrict__ Gb = d ? a.G[1] : a.G[0];
+  float* __restrict__ Cb = d ? a.C[1] : a.C[0];
+  float* __restrict__ Hpb = d ? a.Hprev[1] : a.Hprev[0];
+  float* __restrict__ Hb = a.H + d * NO;
+
+  u64 w[4][NPF];
+  float wt[4];
+  {
+    const float* Rd = d ? a.R[1] : a.R[0];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const float* Rr = Rd + (size_t)(4 * unit + g) * NO + lg * SL;
+#pragma unroll
+      for (int p = 0; p < NPF; p++) w[g][p] = pack2(Rr[2 * p], Rr[2 * p + 1]);
+      wt[g] = Rr[SL - 1];
+    }
+  }
+  for (int k = tid0; k < 2 * LU * SSTR; k += blockDim.x) (&h_s[0][0])[k] = 0.f;
+
+  const unsigned hs_base = (unsigned)__cvta_generic_to_shared(&h_s[0][0]);
+  constexpr unsigned BUFB = LU * SSTR * 4;
+  unsigned rd_addr = hs_base + lg * (SSTR * 4);
+  unsigned wr_addr = hs_base + BUFB + ((unit / SL) * SSTR + (unit % SL)) * 4;   // h[unit] in buffer 1 (any CTA)
+  const unsigned xs_addr = (unsigned)__cvta_generic_to_shared(&xp_s[0][tid0]);
+
+  const int dt = d ? -1 : 1;
+  unsigned ncol = off + (d ? T - 1 : 0);
+  // output stream of the lead lanes: q=0 -> H, q=1 -> C, q=2 -> Hprev (h of the previous step), q=3 -> nothing extra
+  float* __restrict__ obase = (q == 0) ? Hb : (q == 1) ? Cb : Hpb;
+  const unsigned ostride = (q == 0) ? 2 * NO : NO;
+
+#pragma unroll
+  for (int u = 0; u < kStage - 1; u++) {
+    if (u < T) cp_async4(xs_addr + u * (TPAD * 4), XPb + (size_t)(ncol + u * dt) * ROWS + row);
+    cp_async_commit();
+  }
+  cluster_sync_();        // every CTA's h buffers are zeroed before anybody writes into them remotely
+
+  float c = 0.f, hprev = 0.f;
+  const float sc = (q == 3) ? -2.f * kLog2e : -kLog2e;
+  int tog = (int)BUFB;
+  for (int s = 0; s < T; s++) {
+    {
+      const int sn = s + kStage - 1;
+      if (sn < T) cp_async4(xs_addr + (sn & (kStage - 1)) * (TPAD * 4), XPb + (size_t)(ncol + (kStage - 1) * dt) * ROWS + row);
+      cp_async_commit();
+      cp_async_wait<kStage - 1>();
+    }
+    u64 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+    float htail = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      const ulonglong2 h2 = lds_v2u64(rd_addr + 16 * i);
+      if (i < 6) {
+        ffma2(acc0, w[0][2 * i], h2.x); ffma2(acc1, w[1][2 * i], h2.x);
+        ffma2(acc2, w[2][2 * i], h2.x); ffma2(acc3, w[3][2 * i], h2.x);
+        ffma2(acc0, w[0][2 * i + 1], h2.y); ffma2(acc1, w[1][2 * i + 1], h2.y);
+        ffma2(acc2, w[2][2 * i + 1], h2.y); ffma2(acc3, w[3][2 * i + 1], h2.y);
+      } else {
+        float dummy; unpack2(h2.x, htail, dummy);
+      }
+    }
+    const float xp = lds_f32(xs_addr + (s & (kStage - 1)) * (TPAD * 4));
+    float l0, l1;
+    unpack2(acc0, l0, l1); const float p0 = fmaf(wt[0], htail, l0 + l1);
+    unpack2(acc1, l0, l1); const float p1 = fmaf(wt[1], htail, l0 + l1);
+    unpack2(acc2, l0, l1); const float p2 = fmaf(wt[2], htail, l0 + l1);
+    unpack2(acc3, l0, l1); const float p3 = fmaf(wt[3], htail, l0 + l1);
+    const float pre = group_reduce4<LB>(p0, p1, p2, p3, hi, lo) + xp;
+    const float sg = rcp_approx(1.0f + ex2_approx(sc * pre));
+    const float act = (q == 3) ? fmaf(2.f, sg, -1.f) : sg;
+    if (lead) Gb[ncol * ROWS + row] = act;
+    const float gi = __shfl_sync(0xffffffffu, act, 0 << (LB - 2), LU);
+    const float gf = __shfl_sync(0xffffffffu, act, 1 << (LB - 2), LU);
+    const float go = __shfl_sync(0xffffffffu, act, 2 << (LB - 2), LU);
+    const float ci = __shfl_sync(0xffffffffu, act, 3 << (LB - 2), LU);
+    c = fmaf(gf, c, ci * gi);
+    const float th = fmaf(2.f, rcp_approx(1.0f + ex2_approx(-2.f * kLog2e * c)), -1.f);
+    const float hh = th * go;
+    if (lg < CS) st_dsmem_f32(wr_addr, (unsigned)lg, hh);           // lane i of the group feeds CTA i's copy of h
+    if (lead && q < 3) obase[(size_t)ncol * ostride + unit] = (q == 1) ? c : (q == 2) ? hprev : hh;
+    hprev = hh;
+    ncol += dt;
+    cluster_sync_();
+    rd_addr += tog; wr_addr -= tog; tog = -tog;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------- backward
+// thread = (k-group kgp of 4 outputs, row slice rs of 25 own rows): 100 weights R[own row][k].  KG = NO/4 groups,
+// RSL = 4*UC/25 row slices per group (8 for NO=200, 4 for NO=400): KG*RSL = 400 threads.
+template <int NO>
+__global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln, LstmBwdArgs a) {
+  typedef ClCfg<NO> Cfg;
+  constexpr int SL = Cfg::SL, NPF = Cfg::NPF, SSTR = Cfg::SSTR, CS = Cfg::CS, UC = Cfg::UC;
+  constexpr int ROWS = 4 * NO, TPAD = Cfg::TPAD, OWN = 4 * UC;     // own delta rows per CTA (200 or 100)
+  constexpr int RSL = OWN / SL;                                    // 8 or 4 row slices
+  constexpr int RB = (RSL == 8) ? 3 : 2;
+  extern __shared__ __align__(16) float bsm[];
+  float* dg_s = bsm;                         // [2][RSL * SSTR]   own deltas, sliced
+  float* part_s = bsm + 2 * RSL * SSTR;      // [2][CS][UC]       partial dh of my units from every CTA (double buffered)
+  float* st_s = part_s + 2 * CS * UC;        // [kStage][TPAD][8] per-thread staging ring
+  const int tid0 = threadIdx.x;
+  const unsigned crank = cluster_rank_();
+  const int b = ln.order[blockIdx.x / CS], d = blockIdx.y;
+  const int T = ln.T[b], off = ln.off[b];
+  const unsigned st_addr0 = (unsigned)__cvta_generic_to_shared(st_s + (size_t)tid0 * 8);
+  const int tid = (tid0 < Cfg::THREADS) ? tid0 : Cfg::THREADS - RSL + (tid0 % RSL);   // padding lanes clone the last k-group
+  // ---- matvec role: outputs kg4..kg4+3 (global unit indices), own-row slice rs
+  const int kgp = tid / RSL, rs = tid % RSL;
+  const int kg4 = kgp * 4;
+  const bool hi = (rs >> (RB - 1)) & 1, lo = (rs >> (RB - 2)) & 1;
+  const int kout = kg4 + 2 * (int)hi + (int)lo;                    // output unit this lane holds after the reduce
+  // ---- pointwise role: thread -> (own unit pu, gate pg), 4*UC <= 400 threads take part
+  const bool pw = tid0 < OWN;
+  const int pu = pw ? tid0 >> 2 : 0, pg = tid0 & 3;
+  const int punit = (int)crank * UC + pu;
+  const float* __restrict__ Gb = d ? a.G[1] : a.G[0];
+  const float* __restrict__ Cb = d ? a.C[1] : a.C[0];
+  const float* __restrict__ dHb = a.dH + d * NO;
+  float* __restrict__ DGb = d ? a.DG[1] : a.DG[0];
+
+  u64 w[4][NPF];
+  float wt[4];
+  {
+    const float* R = d ? a.R[1] : a.R[0];
+    const int r0 = 4 * (int)crank * UC + rs * SL;                  // first own row of the slice (global row index)
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+#pragma unroll
+      for (int p = 0; p < NPF; p++)
+        w[kk][p] = pack2(R[(size_t)(r0 + 2 * p) * NO + kg4 + kk], R[(size_t)(r0 + 2 * p + 1) * NO + kg4 + kk]);
+      wt[kk] = R[(size_t)(r0 + SL - 1) * NO + kg4 + kk];
+    }
+  }
+  for (int i = tid0; i < 2 * RSL * SSTR + 2 * CS * UC; i += blockDim.x) bsm[i] = 0.f;
+
+  const unsigned ds_base = (unsigned)__cvta_generic_to_shared(dg_s);
+  constexpr unsigned DBUF = RSL * SSTR * 4;
+  unsigned rd_addr = ds_base + rs * (SSTR * 4);
+  const int prow = 4 * pu + pg;                                    // own delta row published by the pointwise thread
+  unsigned wr_addr = ds_base + ((prow / SL) * SSTR + (prow % SL)) * 4;
+  const unsigned ps_base = (unsigned)__cvta_generic_to_shared(part_s);
+  constexpr unsigned PBUF = CS * UC * 4;
+  // where this lane's reduced partial goes: CTA kout/UC, slot [crank][kout % UC]
+  const unsigned dst_rank = (unsigned)(kout / UC);
+  unsigned pdst = ps_base + ((int)crank * UC + (kout % UC)) * 4;   // buffer 0
+  unsigned psrc = ps_base + pu * 4;                                // + c*UC*4 per source CTA, buffer 1 first (zeros)
+  const bool send = (rs & ((1 << (RB - 2)) - 1)) == 0 || RB == 2;  // one lane per output after the all-reduce
+  constexpr unsigned STG = TPAD * 32;
+
+  const int dt = d ? 1 : -1;
+  unsigned ncol = off + (d ? 0 : T - 1);
+  auto stage = [&](int u, unsigned col) {
+    const unsigned sa = st_addr0 + (u & (kStage - 1)) * STG;
+    cp_async16(sa, Gb + (size_t)col * ROWS + 4 * punit);
+    cp_async4(sa + 16, Cb + (size_t)col * NO + punit);
+    if (u + 1 < T) cp_async4(sa + 20, Cb + (size_t)(col + dt) * NO + punit);
+    cp_async4(sa + 24, dHb + (size_t)col * (2 * NO) + punit);
+  };
+#pragma unroll
+  for (int u = 0; u < kStage - 1; u++) {
+    if (u < T && pw) stage(u, ncol + u * dt);
+    cp_async_commit();
+  }
+  cluster_sync_();
+
+  float dcc = 0.f;
+  const bool p_lo = (pg & 1) != 0, p_hi = (pg & 2) != 0;
+  int dtog = (int)DBUF, ptog = (int)PBUF;
+  unsigned pread = psrc + PBUF;                                    // read buffer 1 (zero) at the first step
+  for (int u = 0; u < T; u++) {
+    {
+      const int un = u + kStage - 1;
+      if (un < T && pw) stage(un, ncol + (kStage - 1) * dt);
+      cp_async_commit();
+      cp_async_wait<kStage - 1>();
+    }
+    const bool first = (u + 1 == T);
+    if (pw) {
+      const unsigned sa = st_addr0 + (u & (kStage - 1)) * STG;
+      const ulonglong2 gq = lds_v2u64(sa);
+      const ulonglong2 cq = lds_v2u64(sa + 16);
+      float gi, gf, go, ci, c, cprev, dhu, unused;
+      unpack2(gq.x, gi, gf); unpack2(gq.y, go, ci);
+      unpack2(cq.x, c, cprev); unpack2(cq.y, dhu, unused);
+      if (first) cprev = 0.f;
+      float dhrec = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < CS; cc++) dhrec += lds_f32(pread + cc * (UC * 4));   // partials from every CTA, fixed order
+      const float dh = dhu + dhrec;
+      const float th = fmaf(2.f, rcp_approx(1.0f + ex2_approx(-2.f * kLog2e * c)), -1.f);
+      const float dc = fmaf(1.f - th * th, go * dh, dcc);
+      dcc = first ? 0.f : dc * gf;
+      const float y0 = p_lo ? gf : gi, y1 = p_lo ? ci : go;
+      const float y = p_hi ? y1 : y0;
+      const float B0 = p_lo ? cprev : ci, B1 = p_lo ? gi : dh;
+      const float Bv = p_hi ? B1 : B0;
+      const float Av = (pg == 2) ? th : dc;
+      const float fp = (1.f - y) * ((pg == 3) ? (1.f + y) : y);
+      const float dl = fp * (Av * Bv);
+      sts_f32(wr_addr, dl);
+      DGb[ncol * ROWS + 4 * punit + pg] = dl;
+    }
+    __syncthreads();
+    u64 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+    float dtail = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      const ulonglong2 d2 = lds_v2u64(rd_addr + 16 * i);
+      if (i < 6) {
+        ffma2(acc0, w[0][2 * i], d2.x); ffma2(acc1, w[1][2 * i], d2.x);
+        ffma2(acc2, w[2][2 * i], d2.x); ffma2(acc3, w[3][2 * i], d2.x);
+        ffma2(acc0, w[0][2 * i + 1], d2.y); ffma2(acc1, w[1][2 * i + 1], d2.y);
+        ffma2(acc2, w[2][2 * i + 1], d2.y); ffma2(acc3, w[3][2 * i + 1], d2.y);
+      } else {
+        float dummy; unpack2(d2.x, dtail, dummy);
+      }
+    }
+    float l0, l1;
+    unpack2(acc0, l0, l1); const float p0 = fmaf(wt[0], dtail, l0 + l1);
+    unpack2(acc1, l0, l1); const float p1 = fmaf(wt[1], dtail, l0 + l1);
+    unpack2(acc2, l0, l1); const float p2 = fmaf(wt[2], dtail, l0 + l1);
+    unpack2(acc3, l0, l1); const float p3 = fmaf(wt[3], dtail, l0 + l1);
+    const float part = group_reduce4<RB>(p0, p1, p2, p3, hi, lo);
+    if (send && tid0 < Cfg::THREADS) st_dsmem_f32(pdst, dst_rank, part);       // my rows' share of dh_prev[kout]
+    ncol += dt;
+    cluster_sync_();
+    rd_addr += dtog; wr_addr += dtog; dtog = -dtog;
+    pread = psrc + ((ptog > 0) ? 0u : PBUF);                                    // the buffer that was just filled
+    pdst += ptog; ptog = -ptog;
+  }
+}
+
+template <int NO> constexpr size_t bwd_cluster_smem() {
+  typedef ClCfg<NO> Cfg;
+  return (size_t)(2 * (4 * Cfg::UC / Cfg::SL) * Cfg::SSTR + 2 * Cfg::CS * Cfg::UC + kStage * Cfg::TPAD * 8) * sizeof(float);
+}
+
+template <int NO>
+cudaError_t launch_cluster(bool fwd, cudaStream_t st, const Lines& ln, const void* args) {
+  typedef ClCfg<NO> Cfg;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ln.B * Cfg::CS, 2, 1);
+  cfg.blockDim = dim3(Cfg::TPAD, 1, 1);
+  cfg.dynamicSmemBytes = fwd ? 0 : bwd_cluster_smem<NO>();
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = Cfg::CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (fwd) return cudaLaunchKernelEx(&cfg, lstm_fwd_cluster<NO>, ln, *static_cast<const LstmFwdArgs*>(args));
+  return cudaLaunchKernelEx(&cfg, lstm_bwd_cluster<NO>, ln, *static_cast<const LstmBwdArgs*>(args));
+}
+
+template <int NO>
+cudaError_t configure_one() {
+  cudaError_t e = cudaFuncSetAttribute(lstm_bwd_cluster<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)bwd_cluster_smem<NO>());
+  if (e != cudaSuccess) return e;
+  if (ClCfg<NO>::CS > 8) {
+    e = cudaFuncSetAttribute(lstm_fwd_cluster<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(lstm_bwd_cluster<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  }
+  return e;
+}
+
+}  // namespace
+
+bool lstm_cluster_supported(int no) { return no == 200 || no == 400; }
+
+int lstm_cluster_configure() {
+  cudaError_t e = configure_one<200>();
+  if (e == cudaSuccess) e = configure_one<400>();
+  return (int)e;
+}
+
+int lstm_cluster_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
+  if (a.no == 200) return (int)launch_cluster<200>(true, st, ln, &a);
+  if (a.no == 400) return (int)launch_cluster<400>(true, st, ln, &a);
+  return -1;
+}
+int lstm_cluster_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a) {
+  if (a.no == 200) return (int)launch_cluster<200>(false, st, ln, &a);
+  if (a.no == 400) return (int)launch_cluster<400>(false, st, ln, &a);
+  return -1;
+}
+
+}  // namespace cb200

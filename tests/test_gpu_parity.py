@@ -45,6 +45,8 @@ CASES = [
     (48, 50, 83, 2, (30, 50), "trained"),     # regs, K padded to a multiple of 4
     (7, 5, 4, 2, (9, 14), "trained"),         # generic kernels, test-deriv.cc-sized net
     (48, 24, 30, 4, (1, 40), "trained"),      # generic, ragged incl. very short lines
+    (48, 200, 83, 3, (1, 60), "trained"),     # 4-CTA cluster kernels (BASELINE config 3 width)
+    (48, 400, 83, 2, (20, 45), "trained"),    # 16-CTA cluster kernels (BASELINE config 4 width)
 ]
 
 
@@ -192,8 +194,8 @@ def test_tcgen05_dense_products_match_simt(ffi, nh):
     assert err.max() < 1e-5, err
 
 
-def test_long_lines_wide_net_generic_path(ffi, oracle):
-    # BASELINE config 3 shape in miniature: nhidden=200 (generic recurrent kernels), ragged lines up to T=1500,
+def test_long_lines_wide_net(ffi, oracle):
+    # BASELINE config 3 shape in miniature: nhidden=200 (cluster recurrent kernels), ragged lines up to T=1500,
     # transcripts up to 75 labels (lattice lanes own 5 states each); alignment indices must be bit-exact.
     ni, nh, nc = 48, 200, 83
     x, Ts, labels, L = synth.make_lines(3, (600, 1500), ni, nc, seed=9)
