@@ -11,7 +11,9 @@
 //   K-contiguous sources (activations x weights^T) move as 16-byte chunks; MN-contiguous sources (the derivative
 //   products that reduce over all columns; W1 / Wx used untransposed) are transposed on the way in, lane = k, which
 //   makes the scattered 4-byte stores bank-conflict free.
-// Two smem stages; MMA completion is tracked with tcgen05.commit -> mbarrier.
+// One smem stage per CTA and two CTAs per SM by default (the CTAs overlap each other's load / MMA / epilogue phases; the
+// next k-block is prefetched into registers during the MMAs); CLSTM_B200_TC_STAGES=2 selects two stages and one CTA per SM.
+// MMA completion is tracked with tcgen05.commit -> mbarrier.
 #include <cstdlib>
 
 #include "kernels.h"
@@ -225,7 +227,7 @@ __device__ __forceinline__ void commit_mncontig(const float4 (&v)[NS], unsigned 
 // inverse of the row permutation inside a 32-block: tile row (or TMEM lane / column) rho -> matrix index
 __device__ __forceinline__ int unpermute32(int rho) { return (rho & ~31) + 4 * (rho & 7) + ((rho & 31) >> 3); }
 
-__global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
+__global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(TcArgs g) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   __shared__ __align__(8) unsigned long long mbar_s[2];
   __shared__ unsigned tmem_base_s;
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   // the MN-contiguous sources and returned all-zero accumulators on B200, for either LBO/SBO role assignment, so
   // those sources are transposed by the loader instead.)
   const unsigned idesc = make_idesc(BN);
+  const bool two_stage = g.stages == 2;
   const bool kseg = (g.a_mode == 0 || g.b_mode == 0);
 
   // k-block -> (K segment, offset inside the segment); K-contiguous segments are padded to multiples of 32
@@ -298,9 +301,10 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   int it = 0;
   if (kb0 < kb1) issue(kb0);
   for (int kb = kb0; kb < kb1; kb++, it++) {
-    const int s = it & 1;
+    const int s = two_stage ? (it & 1) : 0;
     const unsigned bar = s ? bar1 : bar0;
-    if (it >= 2) mbar_wait(bar, ((it >> 1) - 1) & 1);        // the MMAs that read this stage two iterations ago are done
+    if (two_stage) { if (it >= 2) mbar_wait(bar, ((it >> 1) - 1) & 1); }   // the MMAs that last read this stage are done
+    else if (it >= 1) mbar_wait(bar, (it - 1) & 1);
     const unsigned a_hi = smem0 + s * stage_bytes, a_lo = a_hi + a_bytes;
     const unsigned b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
     if (g.a_mode == 0) commit_kcontig(ra, a_hi, a_lo, BM); else commit_mncontig(ra, a_hi, a_lo, BM);
@@ -324,7 +328,8 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
   // all MMAs retire in order: the last commit covers everything
   if (it > 0) {
     const int last = it - 1;
-    mbar_wait((last & 1) ? bar1 : bar0, (last >> 1) & 1);
+    if (two_stage) mbar_wait((last & 1) ? bar1 : bar0, (last >> 1) & 1);
+    else mbar_wait(bar0, last & 1);
   }
   tc_fence_after();
 
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(TcArgs g) {
 // per-slot quantity that does not depend on k (source pointer, leading dimension, smem offset, special-quad flag) is
 // computed once before the k loop, so a k-block costs one LDG.128, 12 conversion and 8 store instructions per slot.
 template <int NSB>
-__global__ void __launch_bounds__(TCT, 1) gemm_tn_kernel(TcArgs g) {
+__global__ void __launch_bounds__(TCT, 2) gemm_tn_kernel(TcArgs g) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   __shared__ __align__(8) unsigned long long mbar_s[2];
   __shared__ unsigned tmem_base_s;
@@ -413,6 +418,7 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tn_kernel(TcArgs g) {
   const int kb1 = min(g.nkb, kb0 + g.kb_per_split);
   const int K = g.k_len[0];
   const unsigned idesc = make_idesc(BN);
+  const bool two_stage = g.stages == 2;
 
   // ---- per-slot invariants.  A: task t = warp + 8u -> (mg = warp & 3, kg = (warp >> 2) + 2u)
   const float* pA;            // row (kg0*4 + kk), column m0 + mg*32 + 4*ml ; slot u adds 8*u rows
@@ -502,9 +508,10 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tn_kernel(TcArgs g) {
   int it = 0;
   if (kb0 < kb1) issue(kb0);
   for (int kb = kb0; kb < kb1; kb++, it++) {
-    const int s = it & 1;
+    const int s = two_stage ? (it & 1) : 0;
     const unsigned bar = s ? bar1 : bar0;
-    if (it >= 2) mbar_wait(bar, ((it >> 1) - 1) & 1);
+    if (two_stage) { if (it >= 2) mbar_wait(bar, ((it >> 1) - 1) & 1); }
+    else if (it >= 1) mbar_wait(bar, (it - 1) & 1);
     const unsigned a_hi = smem0 + s * stage_bytes, a_lo = a_hi + a_bytes;
     const unsigned b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
 #pragma unroll
@@ -529,7 +536,8 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tn_kernel(TcArgs g) {
   }
   if (it > 0) {
     const int last = it - 1;
-    mbar_wait((last & 1) ? bar1 : bar0, (last >> 1) & 1);
+    if (two_stage) mbar_wait((last & 1) ? bar1 : bar0, (last >> 1) & 1);
+    else mbar_wait(bar0, last & 1);
   }
   tc_fence_after();
   // ---- epilogue: partial tile -> workspace slice of this split, undoing the row and column permutations
@@ -581,11 +589,13 @@ __global__ void tc_reduce_scatter_kernel(int M, int N, int splits, const float* 
   }
 }
 
-size_t tc_smem_bytes(int BN) { return (size_t)2 * (2 * BM * 128 + 2 * ((BN + 31) & ~31) * 128) + 1024; }
+size_t tc_smem_bytes(int BN, int stages = 2) { return (size_t)stages * (2 * BM * 128 + 2 * ((BN + 31) & ~31) * 128) + 1024; }
+int g_tc_stages = 1;   // 1: one smem stage, two CTAs per SM overlap each other's load / MMA / epilogue phases; 2: two stages, one CTA
 
 }  // namespace
 
 int gemm_tc_configure() {
+  if (const char* e = getenv("CLSTM_B200_TC_STAGES")) g_tc_stages = (atoi(e) == 2) ? 2 : 1;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256));
 #define CB200_TN_ATTR(N_)                                                                                          \
   if (e == cudaSuccess)                                                                                            \
@@ -613,7 +623,7 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
   g.nkb = nkb;
   int splits = 1;
   if (scatter) {  // split-K until ~1 wave, at least 4 k-blocks per CTA
-    splits = num_sms / (mtiles * ntiles);
+    splits = (num_sms * (g_tc_stages == 1 ? 2 : 1)) / (mtiles * ntiles);
     if (splits > nkb / 4) splits = nkb / 4;
     if (splits > 64) splits = 64;
     if (splits < 1) splits = 1;
@@ -622,20 +632,21 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
   g.kb_per_split = (nkb + splits - 1) / splits;
   splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
   if (!scatter) g.ws = nullptr;
+  g.stages = g_tc_stages;
   dim3 grid(ntiles, mtiles, splits);
   if (g.a_mode == 1 && g.b_mode == 1 && scatter) {
     switch (BN / 32) {
-      case 1: gemm_tn_kernel<1><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
-      case 2: gemm_tn_kernel<2><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
-      case 3: gemm_tn_kernel<3><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
-      case 4: gemm_tn_kernel<4><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
-      case 5: gemm_tn_kernel<5><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
-      case 6: gemm_tn_kernel<6><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
-      case 7: gemm_tn_kernel<7><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
-      default: gemm_tn_kernel<8><<<grid, TCT, tc_smem_bytes(BN), st>>>(g); break;
+      case 1: gemm_tn_kernel<1><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
+      case 2: gemm_tn_kernel<2><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
+      case 3: gemm_tn_kernel<3><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
+      case 4: gemm_tn_kernel<4><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
+      case 5: gemm_tn_kernel<5><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
+      case 6: gemm_tn_kernel<6><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
+      case 7: gemm_tn_kernel<7><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
+      default: gemm_tn_kernel<8><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
     }
   } else {
-    gemm_tc_kernel<<<grid, TCT, tc_smem_bytes(BN), st>>>(g);
+    gemm_tc_kernel<<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g);
   }
   if (scatter) {
     const size_t total = (size_t)g.M * g.N;

@@ -52,7 +52,7 @@ struct TcArgs {
   int b_nseg, b_ones;     // mode-1 B: number of blocks, index of the all-ones column (-1: none)
   float* C; long long ldc; const float* bias; float beta;   // direct epilogue: C = beta*C + D + bias[col]
   float* ws; size_t ws_floats;                              // split-K partials (used when a scatter target is given)
-  int BN, nkb, kb_per_split;                       // filled by the launcher
+  int BN, nkb, kb_per_split, stages;               // filled by the launcher (stages: smem stages, 1 or 2)
 };
 // returns kernels launched.  scatter != null: split-K over the reduction, partials reduced deterministically into
 // the scatter targets with `beta`.
