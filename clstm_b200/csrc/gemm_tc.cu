@@ -11,8 +11,8 @@
 //   K-contiguous sources (activations x weights^T) move as 16-byte chunks; MN-contiguous sources (the derivative
 //   products that reduce over all columns; W1 / Wx used untransposed) are transposed on the way in, lane = k, which
 //   makes the scattered 4-byte stores bank-conflict free.
-// One smem stage per CTA and two CTAs per SM by default (the CTAs overlap each other's load / MMA / epilogue phases; the
-// next k-block is prefetched into registers during the MMAs); CLSTM_B200_TC_STAGES=2 selects two stages and one CTA per SM.
+// Direct products: one smem stage per CTA and two CTAs per SM (the CTAs overlap each other's load / MMA / epilogue
+// phases; the next k-block is prefetched into registers during the MMAs).  Split-K derivative products: two stages, one CTA.
 // MMA completion is tracked with tcgen05.commit -> mbarrier.
 #include <cstdlib>
 
@@ -590,12 +590,16 @@ __global__ void tc_reduce_scatter_kernel(int M, int N, int splits, const float* 
 }
 
 size_t tc_smem_bytes(int BN, int stages = 2) { return (size_t)stages * (2 * BM * 128 + 2 * ((BN + 31) & ~31) * 128) + 1024; }
-int g_tc_stages = 1;   // 1: one smem stage, two CTAs per SM overlap each other's load / MMA / epilogue phases; 2: two stages, one CTA
+// smem stages of the direct products / of the split-K derivative products.  1: one stage, two CTAs per SM overlap each
+// other's load / MMA / epilogue phases (measured better for the few-k-block direct products: xproj 52.6 -> 44.3 us);
+// 2: two stages, one CTA per SM (better for the long split-K loops: wgrad 109 vs 132 us).
+int g_tc_stages = 1, g_tn_stages = 2;
 
 }  // namespace
 
 int gemm_tc_configure() {
   if (const char* e = getenv("CLSTM_B200_TC_STAGES")) g_tc_stages = (atoi(e) == 2) ? 2 : 1;
+  if (const char* e = getenv("CLSTM_B200_TN_STAGES")) g_tn_stages = (atoi(e) == 2) ? 2 : 1;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256));
 #define CB200_TN_ATTR(N_)                                                                                          \
   if (e == cudaSuccess)                                                                                            \
@@ -623,7 +627,7 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
   g.nkb = nkb;
   int splits = 1;
   if (scatter) {  // split-K until ~1 wave, at least 4 k-blocks per CTA
-    splits = (num_sms * (g_tc_stages == 1 ? 2 : 1)) / (mtiles * ntiles);
+    splits = (num_sms * (g_tn_stages == 1 ? 2 : 1)) / (mtiles * ntiles);
     if (splits > nkb / 4) splits = nkb / 4;
     if (splits > 64) splits = 64;
     if (splits < 1) splits = 1;
@@ -632,7 +636,7 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
   g.kb_per_split = (nkb + splits - 1) / splits;
   splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
   if (!scatter) g.ws = nullptr;
-  g.stages = g_tc_stages;
+  g.stages = scatter ? g_tn_stages : g_tc_stages;
   dim3 grid(ntiles, mtiles, splits);
   if (g.a_mode == 1 && g.b_mode == 1 && scatter) {
     switch (BN / 32) {
