@@ -50,6 +50,10 @@ EXPORTS = {
     "clstm_b200_step_resident": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "clstm_b200_fetch_decoded": (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, C.c_int]),
     "clstm_b200_synchronize": (C.c_int, [C.c_void_p]),
+    "clstm_b200_normalize_batch": (C.c_int, [C.c_void_p, f32p, i32p, i32p, C.c_int, C.c_int, f32p, i32p, i32p, i32p]),
+    "clstm_b200_normalizer_state": (C.c_int, [C.c_void_p, f32p, f32p]),
+    "clstm_b200_get_inputs": (C.c_int, [C.c_void_p, f32p]),
+    "clstm_b200_forward_resident": (C.c_int, [C.c_void_p, f32p]),
     "clstm_b200_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "clstm_b200_num_phases": (C.c_int, []),
     "clstm_b200_phase_name": (C.c_char_p, [C.c_int]),
@@ -237,6 +241,45 @@ class Net:
         La, Lp = _i32(L)
         self.N, self.B = int(Ta.sum()), Ta.size
         _chk(lib().clstm_b200_upload_batch(self.h, xp, Tp, self.B, lp, Lp))
+
+    # ---- raw line images -> normalised resident batch (extras.cc normalizers on the device)
+    KINDS = {"none": 0, "mean": 1, "center": 2}
+
+    def normalize_batch(self, images, kind="center", params=None, labels=None, L=None):
+        """images: list of [h][w] float arrays (row j, column i; ink = 1).  Returns the normalised widths T."""
+        W = np.array([im.shape[1] for im in images], np.int32)
+        H = np.array([im.shape[0] for im in images], np.int32)
+        raw = np.concatenate([np.ascontiguousarray(im, np.float32).ravel() for im in images])
+        ra, rp = _f32(raw)
+        T = np.zeros(len(images), np.int32)
+        pp = None
+        if params is not None:
+            pa, pp = _f32(params)
+        lp = Lp = None
+        if L is not None:
+            la, lp = _i32(labels)
+            La, Lp = _i32(L)
+        _chk(lib().clstm_b200_normalize_batch(self.h, rp, W.ctypes.data_as(i32p), H.ctypes.data_as(i32p), len(images),
+                                              self.KINDS[kind], pp, lp, Lp, T.ctypes.data_as(i32p)))
+        self.N, self.B = int(T.sum()), T.size
+        self._rawW = W
+        return T
+
+    def normalizer_state(self):
+        center = np.zeros(int(self._rawW.sum()), np.float32)
+        r = np.zeros(self.B, np.float32)
+        _chk(lib().clstm_b200_normalizer_state(self.h, center.ctypes.data_as(f32p), r.ctypes.data_as(f32p)))
+        return center, r
+
+    def get_inputs(self):
+        x = np.zeros((self.N, self.ni), np.float32)
+        _chk(lib().clstm_b200_get_inputs(self.h, x.ctypes.data_as(f32p)))
+        return x
+
+    def forward_resident(self):
+        out = np.zeros((self.N, self.nc), np.float32)
+        _chk(lib().clstm_b200_forward_resident(self.h, out.ctypes.data_as(f32p)))
+        return out
 
     def step_resident(self, lr, momentum, clip=100.0):
         _chk(lib().clstm_b200_step_resident(self.h, lr, momentum, clip))

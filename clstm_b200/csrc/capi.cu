@@ -12,6 +12,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <map>
 #include <vector>
 
 #include "../../include/clstm_b200.h"
@@ -42,9 +43,9 @@ int fail(const char* fmt, ...) {
     if (r_) return r_;       \
   } while (0)
 
-enum Phase { PH_H2D, PH_XPROJ, PH_LSTM_FWD, PH_SOFTMAX_FWD, PH_CTC, PH_SOFTMAX_BWD, PH_LSTM_BWD, PH_WGRAD, PH_DX,
+enum Phase { PH_H2D, PH_NORMALIZE, PH_XPROJ, PH_LSTM_FWD, PH_SOFTMAX_FWD, PH_CTC, PH_SOFTMAX_BWD, PH_LSTM_BWD, PH_WGRAD, PH_DX,
              PH_ALLREDUCE, PH_UPDATE, PH_DECODE, PH_D2H, PH_COUNT };
-const char* kPhaseNames[PH_COUNT] = {"h2d", "xproj_gemm", "lstm_fwd", "softmax_fwd", "ctc_align", "softmax_bwd",
+const char* kPhaseNames[PH_COUNT] = {"h2d", "normalize", "xproj_gemm", "lstm_fwd", "softmax_fwd", "ctc_align", "softmax_bwd",
                                      "lstm_bwd", "wgrad_gemm", "dx_gemm", "allreduce", "sgd_update", "decode", "d2h"};
 
 // ---- minimal NCCL surface, resolved at run time (the library under torch is reused when already loaded) ----
@@ -145,6 +146,15 @@ struct clstm_b200_net {
   Lines ln{};
   bool have_batch = false, have_forward = false, have_labels = false, have_ctc = false, raw_targets = false;
   const char* variant = "generic";
+
+  // ---- line normalizer scratch (normalize.cu)
+  float *n_raw = nullptr, *n_tmp = nullptr, *n_smooth = nullptr, *n_a = nullptr, *n_center = nullptr, *n_r = nullptr,
+        *n_scale = nullptr, *n_masks = nullptr;
+  double *n_ym = nullptr, *n_yd = nullptr;
+  int* n_meta = nullptr;        // W | H | poff | coff | moff[3B] | mrange[3B]
+  size_t n_capPix = 0, n_capCols = 0, n_capMask = 0;
+  int n_capB = 0, n_B = 0, n_cols = 0;
+  std::vector<float> n_hr;      // r (centre) of the last normalised batch
 
   // ---- measurement
   bool prof = false;
@@ -418,6 +428,38 @@ int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const
   n->raw_targets = raw;
   n->have_forward = false;
   n->have_ctc = false;
+  return 0;
+}
+
+// ---- normalizers -------------------------------------------------------------------------------------------------
+// gauss1d's mask (extras.cc:60-69), built with the host libm so that the device pass reproduces the reference bit for bit
+void host_gauss_mask(float sigma, std::vector<float>& mask, int& range) {
+  range = 1 + int(3.0 * sigma);
+  mask.assign(2 * range + 1, 0.f);
+  for (int i = 0; i <= range; i++) {
+    double y = exp(-i * i / 2.0 / sigma / sigma);
+    mask[range + i] = mask[range - i] = (float)y;
+  }
+  float total = 0.0;
+  for (size_t i = 0; i < mask.size(); i++) total += mask[i];
+  for (size_t i = 0; i < mask.size(); i++) mask[i] /= total;
+}
+int ensure_norm(clstm_b200_net* n, size_t pix, size_t cols, int B, size_t nmask) {
+  if (pix > n->n_capPix || cols > n->n_capCols || B > n->n_capB || nmask > n->n_capMask) {
+    CU(cudaStreamSynchronize(n->st));
+    dev_free(n->n_raw); dev_free(n->n_tmp); dev_free(n->n_smooth); dev_free(n->n_a); dev_free(n->n_center);
+    dev_free(n->n_r); dev_free(n->n_scale); dev_free(n->n_masks); dev_free(n->n_ym); dev_free(n->n_yd); dev_free(n->n_meta);
+    n->n_capPix = std::max(pix + pix / 8 + 1024, n->n_capPix);
+    n->n_capCols = std::max(cols + cols / 8 + 256, n->n_capCols);
+    n->n_capB = std::max(B + B / 4 + 8, n->n_capB);
+    n->n_capMask = std::max(nmask + nmask / 4 + 1024, n->n_capMask);
+    TRY(dev_alloc(&n->n_raw, n->n_capPix)); TRY(dev_alloc(&n->n_tmp, n->n_capPix)); TRY(dev_alloc(&n->n_smooth, n->n_capPix));
+    TRY(dev_alloc(&n->n_a, n->n_capCols)); TRY(dev_alloc(&n->n_center, n->n_capCols));
+    TRY(dev_alloc(&n->n_r, (size_t)n->n_capB)); TRY(dev_alloc(&n->n_scale, (size_t)n->n_capB));
+    TRY(dev_alloc(&n->n_ym, (size_t)n->n_capB)); TRY(dev_alloc(&n->n_yd, (size_t)n->n_capB));
+    TRY(dev_alloc(&n->n_masks, n->n_capMask));
+    TRY(dev_alloc(&n->n_meta, (size_t)10 * n->n_capB));
+  }
   return 0;
 }
 
@@ -733,7 +775,7 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
     const char* e = getenv("CLSTM_B200_GEMM");   // "simt" selects the fp32 SIMT tiles (A/B testing against tcgen05)
     n->use_tc = !(e && strcmp(e, "simt") == 0);
   }
-  if (lstm_configure() != 0 || ctc_configure() != 0 || gemm_tc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
+  if (lstm_configure() != 0 || ctc_configure() != 0 || gemm_tc_configure() != 0 || norm_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   n->variant = lstm_variant_for(no);
   if (cudaStreamSynchronize(n->st) != cudaSuccess) { clstm_b200_destroy(n); return fail("device initialisation failed"); }
   *out = n;
@@ -753,6 +795,8 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   dev_free(n->WxT[0]); dev_free(n->WxT[1]); dev_free(n->W1T);
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->status);
   dev_free(n->ws); dev_free(n->tiles); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
+  dev_free(n->n_raw); dev_free(n->n_tmp); dev_free(n->n_smooth); dev_free(n->n_a); dev_free(n->n_center);
+  dev_free(n->n_r); dev_free(n->n_scale); dev_free(n->n_masks); dev_free(n->n_ym); dev_free(n->n_yd); dev_free(n->n_meta);
   if (n->st2) cudaStreamDestroy(n->st2);
   if (n->ev_fork) cudaEventDestroy(n->ev_fork);
   if (n->ev_join) cudaEventDestroy(n->ev_join);
@@ -835,6 +879,141 @@ int clstm_b200_upload_batch(clstm_b200_net* n, const float* x, const int* T, int
 
 int clstm_b200_forward(clstm_b200_net* n, const float* x, const int* T, int B, float* out) {
   TRY(clstm_b200_upload_batch(n, x, T, B, nullptr, nullptr));
+  TRY(run_forward(n));
+  if (out) {
+    Scope s(n, PH_D2H);
+    CU(cudaMemcpyAsync(out, n->out, (size_t)n->ln.N * n->nc * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  }
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+
+int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W, const int* H, int B, int kind,
+                               const float* params, const int* labels, const int* L, int* T_out) {
+  if (!n || !raw || !W || !H) return fail("null argument");
+  if (B <= 0) return fail("batch must contain at least one line");
+  if (kind < 0 || kind > 2) return fail("unknown normalizer name");      // extras.cc:299
+  if (L != nullptr && labels == nullptr) return fail("labels missing");
+  CU(cudaSetDevice(n->cfg.device));
+  const int th = n->ni;                                                  // target_height = ninput (clstmhl.h:164)
+  const float range = params ? params[0] : (kind == 1 ? 1.0f : 4.0f);    // extras.h:36, extras.cc:159,233
+  const float smooth2d = params ? params[1] : 1.0f, smooth1d = params ? params[2] : 0.3f;
+  const float vscale = params ? params[3] : 1.0f;
+  std::vector<int> meta((size_t)10 * B);
+  int* mW = meta.data(); int* mH = mW + B; int* mP = mH + B; int* mC = mP + B; int* mO = mC + B; int* mR = mO + 3 * B;
+  size_t pix = 0, cols = 0;
+  int maxpix = 0, maxh = 0;
+  for (int b = 0; b < B; b++) {
+    if (W[b] <= 0 || H[b] <= 0) return fail("line %d has an empty image (%d x %d)", b, W[b], H[b]);
+    if (H[b] > kNormMaxHeight) return fail("line %d is %d rows high (max %d)", b, H[b], kNormMaxHeight);
+    if (kind == 0 && H[b] != th) return fail("line %d: height %d != target_height %d (NoNormalizer, extras.cc:149)", b, H[b], th);
+    mW[b] = W[b]; mH[b] = H[b]; mP[b] = (int)pix; mC[b] = (int)cols;
+    pix += (size_t)W[b] * H[b]; cols += W[b];
+    if (pix > 0x7fffffff) return fail("raw batch too large");
+    maxpix = std::max(maxpix, W[b] * H[b]); maxh = std::max(maxh, H[b]);
+  }
+  std::vector<float> masks;
+  if (kind == 2) {
+    std::map<float, std::pair<int, int>> cache;   // sigma -> (offset, range)
+    std::vector<float> m;
+    for (int b = 0; b < B; b++) {
+      const int h = H[b];
+      const float sig[3] = {(float)(h * 0.5), h * smooth2d, h * smooth1d};   // gauss2d(h*smooth2d, h*0.5); gauss1d(h*smooth1d)
+      for (int k = 0; k < 3; k++) {
+        auto it = cache.find(sig[k]);
+        if (it == cache.end()) {
+          int r;
+          host_gauss_mask(sig[k], m, r);
+          it = cache.emplace(sig[k], std::make_pair((int)masks.size(), r)).first;
+          masks.insert(masks.end(), m.begin(), m.end());
+        }
+        mO[3 * b + k] = it->second.first; mR[3 * b + k] = it->second.second;
+      }
+    }
+  }
+  TRY(ensure_norm(n, pix, cols, B, masks.size()));
+  NormLines nl;
+  nl.W = n->n_meta; nl.H = nl.W + B; nl.poff = nl.H + B; nl.coff = nl.poff + B; nl.moff = nl.coff + B; nl.mrange = nl.moff + 3 * B;
+  nl.masks = n->n_masks; nl.range = range;
+  std::vector<int> tw(B);
+  std::vector<float> scale(B, 0.f);
+  std::vector<double> ym(B, 0.0), yd(B, 0.0);
+  {
+    Scope s(n, PH_H2D);
+    CU(cudaMemcpyAsync(n->n_raw, raw, pix * sizeof(float), cudaMemcpyHostToDevice, n->st));
+    CU(cudaMemcpyAsync(n->n_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, n->st));
+    if (!masks.empty()) CU(cudaMemcpyAsync(n->n_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice, n->st));
+  }
+  n->n_hr.assign(B, 0.f);
+  if (kind == 2) {
+    {
+      Scope s(n, PH_NORMALIZE);
+      s.launches(norm_center_measure(n->st, nl, B, maxpix, maxh, n->n_raw, n->n_tmp, n->n_smooth, n->n_a, n->n_center, n->n_r));
+      TRY(check_launch("normalizer measure"));
+    }
+    CU(cudaMemcpyAsync(n->n_hr.data(), n->n_r, B * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+    CU(cudaStreamSynchronize(n->st));
+    for (int b = 0; b < B; b++) {                         // CenterNormalizer::normalize, extras.cc:275-276
+      const float r = n->n_hr[b];
+      scale[b] = (2.0 * r) / th;
+      tw[b] = std::max(int(W[b] / scale[b]), 1);
+    }
+  } else if (kind == 1) {
+    {
+      Scope s(n, PH_NORMALIZE);
+      s.launches(norm_mean_measure(n->st, nl, B, maxh, n->n_raw, n->n_ym, n->n_yd));
+      TRY(check_launch("normalizer measure"));
+    }
+    CU(cudaMemcpyAsync(ym.data(), n->n_ym, B * sizeof(double), cudaMemcpyDeviceToHost, n->st));
+    CU(cudaMemcpyAsync(yd.data(), n->n_yd, B * sizeof(double), cudaMemcpyDeviceToHost, n->st));
+    CU(cudaStreamSynchronize(n->st));
+    for (int b = 0; b < B; b++) {                         // MeanNormalizer::normalize, extras.cc:185-188
+      float actual = vscale * 2 * range * yd[b];
+      scale[b] = actual / th;
+      tw[b] = int(W[b] / scale[b]);
+      if (tw[b] <= 0) return fail("line %d: normalised width %d", b, tw[b]);
+    }
+  } else {
+    for (int b = 0; b < B; b++) tw[b] = W[b];
+  }
+  for (int b = 0; b < B; b++)
+    if ((long long)tw[b] > 64LL * 1024 * 1024) return fail("line %d: normalised width %d is not plausible", b, tw[b]);
+  TRY(stage_lines(n, tw.data(), B, labels, L));
+  {
+    Scope s(n, PH_NORMALIZE);
+    CU(cudaMemcpyAsync(n->n_scale, scale.data(), B * sizeof(float), cudaMemcpyHostToDevice, n->st));
+    s.launches(norm_resample(n->st, nl, B, n->ln.Tmax, n->n_raw, n->n_center, n->n_scale, n->n_ym, n->ln.T, n->ln.off, n->x, th, kind));
+    TRY(check_launch("normalizer resample"));
+  }
+  n->n_B = B; n->n_cols = (int)cols;
+  if (T_out) memcpy(T_out, tw.data(), B * sizeof(int));
+  CU(cudaStreamSynchronize(n->st));     // `scale` and `meta` are stack/heap temporaries of this call
+  return 0;
+}
+
+int clstm_b200_normalizer_state(clstm_b200_net* n, float* center, float* r) {
+  if (!n) return fail("null argument");
+  if (n->n_B <= 0) return fail("normalizer_state called before normalize_batch");
+  CU(cudaSetDevice(n->cfg.device));
+  if (center) CU(cudaMemcpyAsync(center, n->n_center, (size_t)n->n_cols * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  if (r) memcpy(r, n->n_hr.data(), (size_t)n->n_B * sizeof(float));
+  return 0;
+}
+
+int clstm_b200_get_inputs(clstm_b200_net* n, float* x) {
+  if (!n || !x) return fail("null argument");
+  if (!n->have_batch) return fail("get_inputs called without a resident batch");
+  CU(cudaSetDevice(n->cfg.device));
+  CU(cudaMemcpyAsync(x, n->x, (size_t)n->ln.N * n->ni * sizeof(float), cudaMemcpyDeviceToHost, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  return 0;
+}
+
+int clstm_b200_forward_resident(clstm_b200_net* n, float* out) {
+  if (!n) return fail("null argument");
+  if (!n->have_batch) return fail("forward_resident called without a resident batch");
+  CU(cudaSetDevice(n->cfg.device));
   TRY(run_forward(n));
   if (out) {
     Scope s(n, PH_D2H);

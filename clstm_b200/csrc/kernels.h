@@ -90,6 +90,22 @@ int lstm_cluster_configure();
 int lstm_cluster_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a);    // cudaError_t as int, -1: size n/a
 int lstm_cluster_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
 
+// ---------------------------------------------------------------- normalize.cu (text-line normalizers, extras.cc)
+constexpr int kNormMaxHeight = 1024;   // rows of a raw line image
+struct NormLines {
+  const int *W, *H;          // raw width (columns) / height (rows) per line
+  const int *poff, *coff;    // offset of the line's pixels / columns inside the concatenated buffers
+  const float* masks;        // Gaussian masks, built on the host exactly like gauss1d does
+  const int *moff, *mrange;  // [3*b + k]: offset / half width of mask k (0: along y, 1: along x, 2: centre line)
+  float range;               // CenterNormalizer::range
+};
+int norm_configure();
+int norm_center_measure(cudaStream_t st, const NormLines& nl, int B, int maxpix, int maxh, const float* raw, float* tmp,
+                        float* smooth, float* a, float* center, float* r_out);
+int norm_mean_measure(cudaStream_t st, const NormLines& nl, int B, int maxh, const float* raw, double* ymean, double* ymad);
+int norm_resample(cudaStream_t st, const NormLines& nl, int B, int maxT, const float* raw, const float* center,
+                  const float* scale, const double* ymean, const int* T, const int* off, float* x, int ni, int kind);
+
 // ---------------------------------------------------------------- ctc.cu
 struct CtcArgs {
   int nc;

@@ -69,3 +69,25 @@ def reference_init(ninput, nhidden, nclasses, seed=0.1, scale=0.01):
         blocks += [wci, wgf, wgi, wgo]            # std::map order of the parameter names
     blocks.append(draw(nclasses, 2 * nhidden + 1))
     return np.concatenate([b.T.ravel() for b in blocks]).astype(np.float32)   # col-major flatten
+
+
+def make_raw_line(w, h, seed=0, nglyph=None):
+    """Synthetic RAW text-line image [h][w] (row j, column i), ink = 1 on background 0, like a scanned line after the
+    `raw = 1 - raw` of clstmocrtrain.cc:75: blobs ("glyphs") of varying height along a slowly drifting baseline plus
+    a little noise.  Used by the normalizer parity tests and the CLI tests."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w), np.float32)
+    jj = np.arange(h, dtype=np.float32)[:, None]
+    ii = np.arange(w, dtype=np.float32)[None, :]
+    base = 0.55 * h + 0.08 * h * np.sin(ii / max(w, 1) * 3.1 + rng.uniform(0, 3))
+    xh = 0.22 * h
+    n = nglyph if nglyph is not None else max(1, w // max(4, int(0.6 * h)))
+    xs = np.sort(rng.uniform(0, w, n))
+    for x0 in xs:
+        gh = xh * rng.uniform(0.8, 2.0)
+        gw = 0.25 * h * rng.uniform(0.5, 1.2)
+        cy = base[0, int(min(max(x0, 0), w - 1))] - gh / 2 + rng.uniform(-0.05, 0.05) * h
+        d = ((ii - x0) / gw) ** 2 + ((jj - cy) / (gh / 2)) ** 2
+        img = np.maximum(img, np.clip(1.5 - d, 0, 1).astype(np.float32))
+    img += rng.uniform(0, 0.02, img.shape).astype(np.float32)
+    return np.clip(img, 0, 1).astype(np.float32)

@@ -123,6 +123,25 @@ int clstm_b200_fetch_decoded(clstm_b200_net* net, int which, int* classes, int* 
                              int max_per_line);
 int clstm_b200_synchronize(clstm_b200_net* net);
 
+/* Text-line normalizers on the device (extras.h:31-47, extras.cc:146-301): measure() + normalize() of B raw line
+ * images, written straight into the resident input batch (the place clstm_b200_upload_batch fills), so that
+ * CLSTMOCR::fwdbwd / predict (clstmhl.h:201-205, 233-237) never materialise the normalised image on the host.
+ *   raw     concatenated images, line b is W[b] x H[b] floats with pixel (i = column, j = row) at i + j*W[b]
+ *           (the reference's Tensor2 image(i, j), already inverted: ink = 1, as clstmocrtrain.cc:74-75 does)
+ *   kind    0 "none" (NoNormalizer; H[b] must equal ninput), 1 "mean" (MeanNormalizer), 2 "center" (CenterNormalizer)
+ *   params  {range, smooth2d, smooth1d, vscale} or NULL for the reference defaults (extras.h:36-39; mean: range 1)
+ *   labels/L nullable transcripts staged with the batch (as in upload_batch);  T_out[b] = normalised width
+ * target_height is the net's ninput (clstmhl.h:164).  Results are bit-identical to the reference's float/double
+ * arithmetic (same operations in the same order; Gaussian masks from the host libm). */
+int clstm_b200_normalize_batch(clstm_b200_net* net, const float* raw, const int* W, const int* H, int B, int kind,
+                               const float* params, const int* labels, const int* L, int* T_out);
+/* CenterNormalizer state of the last normalize_batch: `center` (sum of W floats, extras.cc:229) and `r` (B floats, :230) */
+int clstm_b200_normalizer_state(clstm_b200_net* net, float* center, float* r);
+/* the resident input batch, [N][ninput] (what set_inputs would hold, clstm.cc:684-690) */
+int clstm_b200_get_inputs(clstm_b200_net* net, float* x);
+/* INetwork::forward on the resident batch (after upload_batch / normalize_batch); out nullable */
+int clstm_b200_forward_resident(clstm_b200_net* net, float* out);
+
 /* Measurement hooks (bench.py): per-phase CUDA-event timing on the handle's own stream.
  * phases: see clstm_b200_phase_name(i), i < clstm_b200_num_phases().  ms[i] = accumulated milliseconds and
  * launches[i] = kernel launches since the last reset. */

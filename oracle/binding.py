@@ -66,6 +66,18 @@ def lib():
         L.oracle_train_lines.restype = C.c_double
         L.oracle_train_lines.argtypes = [C.c_void_p, f32p, i32p, C.c_int, i32p, i32p, C.c_float,
                                          C.c_float, C.c_int, C.c_int]
+        L.oracle_gauss_mask.restype = C.c_int
+        L.oracle_gauss_mask.argtypes = [C.c_float, f32p, C.c_int]
+        L.oracle_center_measure.restype = C.c_float
+        L.oracle_center_measure.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, f32p, f32p]
+        L.oracle_center_width.restype = C.c_int
+        L.oracle_center_width.argtypes = [C.c_int, C.c_float, C.c_int]
+        L.oracle_center_normalize.argtypes = [f32p, C.c_int, C.c_int, f32p, C.c_float, C.c_int, f32p]
+        L.oracle_mean_measure.argtypes = [f32p, C.c_int, C.c_int, f64p, f64p]
+        L.oracle_mean_width.restype = C.c_int
+        L.oracle_mean_width.argtypes = [C.c_int, C.c_double, C.c_float, C.c_float, C.c_int]
+        L.oracle_mean_normalize.argtypes = [f32p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_float, C.c_float,
+                                            C.c_int, f32p]
         _LIB = L
     return _LIB
 
@@ -236,3 +248,50 @@ class Net64:
         dp = np.empty(self.nparams, np.float64)
         lib().oracle64_backward(self.h, p, din.ctypes.data_as(f64p), dp.ctypes.data_as(f64p))
         return din, dp
+
+
+# ---- text-line normalizers (oracle/normalizer_oracle.cc).  Images are numpy [h][w] (row j, column i) = Tensor2 (i, j).
+def gauss_mask(sigma):
+    cap = 2 * (1 + int(3.0 * sigma)) + 8
+    m = np.zeros(cap, np.float32)
+    r = lib().oracle_gauss_mask(float(np.float32(sigma)), m.ctypes.data_as(f32p), cap)
+    assert r >= 0
+    return m[:2 * r + 1].copy(), r
+
+
+def center_measure(img, range_=4.0, smooth2d=1.0, smooth1d=0.3):
+    a, pa = _f32(img)
+    h, w = a.shape
+    center = np.zeros(w, np.float32)
+    smooth = np.zeros((h, w), np.float32)
+    r = lib().oracle_center_measure(pa, w, h, range_, smooth2d, smooth1d, center.ctypes.data_as(f32p),
+                                    smooth.ctypes.data_as(f32p))
+    return center, float(r), smooth
+
+
+def center_normalize(img, center, r, target_height=48):
+    a, pa = _f32(img)
+    h, w = a.shape
+    c, pc = _f32(center)
+    tw = lib().oracle_center_width(w, r, target_height)
+    out = np.zeros((target_height, tw), np.float32)
+    lib().oracle_center_normalize(pa, w, h, pc, r, target_height, out.ctypes.data_as(f32p))
+    return out
+
+
+def center_line(img, target_height=48, range_=4.0, smooth2d=1.0, smooth1d=0.3):
+    """measure + normalize; returns the network input [T][target_height] (x[t][j] = out(t, j))."""
+    center, r, _ = center_measure(img, range_, smooth2d, smooth1d)
+    return np.ascontiguousarray(center_normalize(img, center, r, target_height).T)
+
+
+def mean_line(img, target_height=48, range_=1.0, vscale=1.0):
+    a, pa = _f32(img)
+    h, w = a.shape
+    ym, yd = C.c_double(), C.c_double()
+    lib().oracle_mean_measure(pa, w, h, C.byref(ym), C.byref(yd))
+    tw = lib().oracle_mean_width(w, yd.value, vscale, range_, target_height)
+    out = np.zeros((target_height, max(tw, 0)), np.float32)
+    if tw > 0:
+        lib().oracle_mean_normalize(pa, w, h, ym.value, yd.value, vscale, range_, target_height, out.ctypes.data_as(f32p))
+    return np.ascontiguousarray(out.T), ym.value, yd.value
