@@ -1,5 +1,6 @@
 // clstm_host.cc -- see clstm_host.h.  Host plumbing only; all arithmetic of the path runs behind the C ABI.
 #include "clstm_host.h"
+#include "clstm_extras.h"
 
 #include <algorithm>
 #include <cmath>
@@ -9,6 +10,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <set>
 #include <sstream>
 
 namespace ocropus {
@@ -73,6 +75,21 @@ void Codec::encode(Classes& cs, const std::wstring& s) const {
     if (it->second == 0) THROW("class 0 (blank) cannot be part of a transcript");
     cs.push_back(it->second);
   }
+}
+
+void Codec::build(const vector<string>& fnames, const std::wstring& extra) {   // clstm.cc:247-267
+  std::set<int> codes;
+  codes.insert(0);
+  for (auto c : extra) codes.insert(int(c));
+  for (const string& fname : fnames) {
+    std::ifstream stream(fname);
+    string line;
+    while (getline(stream, line)) {
+      if (line.empty() || line[0] == '#') continue;   // blank lines and comment lines carry no characters
+      for (auto c : utf8_to_utf32(line)) codes.insert(int(c));
+    }
+  }
+  set(vector<int>(codes.begin(), codes.end()));       // std::set iterates in increasing code order
 }
 
 // ------------------------------------------------------------------------------------------------ UTF-8
@@ -251,6 +268,27 @@ struct Stacked : INetwork {      // clstm.cc:421-456
       for (int t = 0; t < T; t++)
         for (int c = 0; c < nc; c++) outputs[t].v(c, b) = out[((size_t)b * T + t) * nc + c];
     lastB = B; lastT = T;
+  }
+  // CLSTMOCR::fwdbwd/predict prologue (clstmhl.h:201-205): normalizer->measure + normalize + set_inputs + forward with
+  // the normalised line produced on the device; inputs/outputs are mirrored to the host Sequences afterwards.
+  void forward_raw(Tensor2& raw, INormalizer& nm) {
+    upload();
+    const int ni = ninput(), nc = noutput();
+    if (nm.target_height != ni) throwf("normalizer target_height %d does not match the network (%d)", nm.target_height, ni);
+    int W = raw.dimension(0), H = raw.dimension(1), T = 0;
+    float p[4];
+    nm.abi_params(p);
+    check(clstm_b200_normalize_batch(h, raw.ptr(), &W, &H, 1, nm.kind(), p, nullptr, nullptr, &T));
+    vector<float> x((size_t)T * ni), out((size_t)T * nc);
+    check(clstm_b200_forward_resident(h, out.data()));
+    check(clstm_b200_get_inputs(h, x.data()));
+    inputs.resize(T, ni, 1);
+    outputs.resize(T, nc, 1);
+    for (int t = 0; t < T; t++) {
+      for (int i = 0; i < ni; i++) inputs[t].v(i, 0) = x[(size_t)t * ni + i];
+      for (int c = 0; c < nc; c++) outputs[t].v(c, 0) = out[(size_t)t * nc + c];
+    }
+    lastB = 1; lastT = T;
   }
   void backward() override {       // Stacked::backward clstm.cc:440-454; outputs[t].d set by the caller
     if (!h || outputs.size() != lastT || outputs.cols() != lastB) THROW("backward called without a matching forward");
@@ -636,10 +674,16 @@ Network load_net(const string& file) {
 
 // ------------------------------------------------------------------------------------------------ CLSTMOCR
 namespace {
-void run_forward(Network& net, Tensor2& image) {
-  set_inputs(net, image);
-  net->forward();
-  g_last_forward = as_device_root(net.get());
+void run_forward(CLSTMOCR& ocr, Tensor2& raw) {   // measure + normalize + set_inputs + forward (clstmhl.h:202-206)
+  Stacked* s = as_device_root(ocr.net.get());
+  if (!s) THROW("CLSTMOCR: the network root is not a device network");
+  if (!ocr.normalizer) THROW("CLSTMOCR: no normalizer (createBidi or load first)");
+  ocr.normalizer->target_height = ocr.target_height;
+  s->forward_raw(raw, *ocr.normalizer);
+  ocr.image.resize(s->lastT, s->ninput());
+  for (int t = 0; t < s->lastT; t++)
+    for (int i = 0; i < s->ninput(); i++) ocr.image(t, i) = s->inputs[t].v(i, 0);
+  g_last_forward = s;
 }
 void device_decode(Network& net, int which, Classes& cs, vector<int>* where) {  // trivial_decode ctc.cc:159-194 on the device
   Stacked* s = as_device_root(net.get());
@@ -660,6 +704,8 @@ bool CLSTMOCR::maybe_load(const string& fname) {
   }
   nclasses = net->codec.size();
   target_height = net->ninput();
+  normalizer.reset(make_CenterNormalizer());
+  normalizer->target_height = target_height;
   return true;
 }
 void CLSTMOCR::load(const string& fname) {
@@ -673,9 +719,11 @@ void CLSTMOCR::createBidi(const vector<int> codec, int nhidden) {
   net = make_net("bidi", {{"ninput", target_height}, {"noutput", nclasses}, {"nhidden", nhidden}});
   net->initialize();   // no-op on the root, as upstream (clstmhl.h:196)
   net->codec.set(codec);
+  normalizer.reset(make_CenterNormalizer());
+  normalizer->target_height = target_height;
 }
-std::wstring CLSTMOCR::fwdbwd(Tensor2& image, const std::wstring& target) {  // clstmhl.h:201-217, step by step
-  run_forward(net, image);
+std::wstring CLSTMOCR::fwdbwd(Tensor2& raw, const std::wstring& target) {  // clstmhl.h:201-217, step by step
+  run_forward(*this, raw);
   Classes transcript;
   net->codec.encode(transcript, target);
   mktargets(targets, transcript, nclasses);
@@ -687,8 +735,8 @@ std::wstring CLSTMOCR::fwdbwd(Tensor2& image, const std::wstring& target) {  // 
   device_decode(net, 0, outputs, nullptr);
   return net->codec.decode(outputs);
 }
-std::wstring CLSTMOCR::train(Tensor2& image, const std::wstring& target) {
-  std::wstring result = fwdbwd(image, target);
+std::wstring CLSTMOCR::train(Tensor2& raw, const std::wstring& target) {
+  std::wstring result = fwdbwd(raw, target);
   update();
   return result;
 }
@@ -703,14 +751,14 @@ std::string CLSTMOCR::aligned_utf8() {   // clstmhl.h:224-229: decode of the ali
   Classes cs(cls.begin(), cls.begin() + count);
   return utf32_to_utf8(net->codec.decode(cs));
 }
-std::wstring CLSTMOCR::predict(Tensor2& image, vector<int>* where) {  // clstmhl.h:233-242
-  run_forward(net, image);
+std::wstring CLSTMOCR::predict(Tensor2& raw, vector<int>* where) {  // clstmhl.h:233-242
+  run_forward(*this, raw);
   Classes outputs;
   device_decode(net, 0, outputs, where);
   return net->codec.decode(outputs);
 }
-void CLSTMOCR::predict(vector<CharPrediction>& preds, Tensor2& image) {  // clstmhl.h:243-261
-  run_forward(net, image);
+void CLSTMOCR::predict(vector<CharPrediction>& preds, Tensor2& raw) {  // clstmhl.h:243-261
+  run_forward(*this, raw);
   Classes outputs;
   vector<int> where;
   device_decode(net, 0, outputs, &where);
@@ -728,35 +776,39 @@ void CLSTMOCR::get_outputs(Tensor2& outputs) {  // clstmhl.h:265-271
 }
 std::vector<std::wstring> CLSTMOCR::train_batch(std::vector<Tensor2>& images, const std::vector<std::wstring>& tg) {
   if (images.size() != tg.size() || images.empty()) THROW("train_batch: need one transcript per image");
-  clstm_b200_net* h = device_handle(net);
-  const int B = (int)images.size(), ni = target_height;
-  vector<int> T(B), L(B), labels;
-  size_t ncol = 0;
-  int tmax = 0;
+  if (!normalizer) THROW("CLSTMOCR: no normalizer (createBidi or load first)");
+  Stacked* s = as_device_root(net.get());
+  if (!s) THROW("CLSTMOCR: the network root is not a device network");
+  s->upload();
+  clstm_b200_net* h = s->h;
+  const int B = (int)images.size();
+  vector<int> W(B), H(B), T(B), L(B), labels;
+  size_t npix = 0;
   for (int b = 0; b < B; b++) {
-    if (images[b].dimension(1) != ni) THROW("train_batch: image height does not match the network");
-    T[b] = images[b].dimension(0);
-    ncol += T[b];
-    tmax = std::max(tmax, T[b]);
+    W[b] = images[b].dimension(0); H[b] = images[b].dimension(1);
+    npix += (size_t)W[b] * H[b];
     Classes cs;
     net->codec.encode(cs, tg[b]);
     L[b] = (int)cs.size();
     labels.insert(labels.end(), cs.begin(), cs.end());
   }
-  vector<float> x(ncol * ni);
-  size_t off = 0;
-  for (int b = 0; b < B; b++) {
-    for (int t = 0; t < T[b]; t++)
-      for (int i = 0; i < ni; i++) x[(off + t) * ni + i] = images[b](t, i);
-    off += T[b];
-  }
-  const int cap = tmax / 2 + 1;
-  vector<int> cls((size_t)B * cap), locs((size_t)B * cap), cnt(B);
+  vector<float> raw;
+  raw.reserve(npix);
+  for (int b = 0; b < B; b++) raw.insert(raw.end(), images[b].data.begin(), images[b].data.end());
+  normalizer->target_height = target_height;
+  float p[4];
+  normalizer->abi_params(p);
+  check(clstm_b200_normalize_batch(h, raw.data(), W.data(), H.data(), B, normalizer->kind(), p,
+                                   labels.empty() ? L.data() : labels.data(), L.data(), T.data()));
   const Float lr = net->effective_lr();
   const Float momentum = (double)net->attr.get("momentum", 0.9), gc = (double)net->attr.get("gradient_clip", 100.0);
-  check(clstm_b200_train_step(h, x.data(), T.data(), B, labels.empty() ? L.data() : labels.data(), L.data(), lr, momentum,
-                              gc, nullptr, nullptr, cls.data(), locs.data(), cnt.data(), cap));
-  if (auto* s = as_device_root(net.get())) s->host_stale = true;
+  check(clstm_b200_step_resident(h, lr, momentum, gc));
+  int tmax = 0;
+  for (int b = 0; b < B; b++) tmax = std::max(tmax, T[b]);
+  const int cap = tmax / 2 + 1;
+  vector<int> cls((size_t)B * cap), locs((size_t)B * cap), cnt(B);
+  check(clstm_b200_fetch_decoded(h, 0, cls.data(), locs.data(), cnt.data(), cap));
+  s->host_stale = true;
   std::vector<std::wstring> out(B);
   for (int b = 0; b < B; b++) {
     Classes cs(cls.begin() + (size_t)b * cap, cls.begin() + (size_t)b * cap + cnt[b]);

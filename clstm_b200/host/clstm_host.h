@@ -101,6 +101,7 @@ class Codec {  // clstm.h:82-92, clstm.cc:219-267
   wchar_t decode(int cls) const;
   std::wstring decode(const Classes& cs) const;
   void encode(Classes& cs, const std::wstring& s) const;
+  void build(const std::vector<std::string>& fnames, const std::wstring& extra);   // clstm.cc:247-267
 };
 
 // ---- networks --------------------------------------------------------------------------------------------------
@@ -178,13 +179,18 @@ clstm_b200_net* device_handle(Network net);
 
 struct CharPrediction { int i; int x; wchar_t c; float p; };                 // clstmhl.h:18-23
 
-// clstmhl.h:146-272.  The line normalizer / PNG reader are outside this round's scope: images
-// passed here are already normalised to target_height rows, image(t,i), t = column.
+struct INormalizer;                                                          // clstm_extras.h (extras.h:31-43)
+
+// clstmhl.h:146-272.  `raw` images are Tensor2 raw(i, j), i = column, j = row, ink = 1 (clstmocrtrain.cc:74-75); they
+// are measured and normalised ON THE DEVICE by `normalizer` (CenterNormalizer by default, like the reference) straight
+// into the network's input batch.  With a NoNormalizer the image must already be target_height rows high.
 struct CLSTMOCR {
+  std::shared_ptr<INormalizer> normalizer;
   Network net;
   int target_height = 48;
   int nclasses = -1;
   Sequence aligned, targets;
+  Tensor2 image;                                                             // the normalised line of the last call
   void setLearningRate(float lr, float mom) { net->setLearningRate(lr, mom); }
   bool maybe_load(const std::string& fname);
   void load(const std::string& fname);
@@ -200,7 +206,8 @@ struct CLSTMOCR {
   void predict(std::vector<CharPrediction>& preds, Tensor2& image);
   std::string predict_utf8(Tensor2& image) { return utf32_to_utf8(predict(image)); }
   void get_outputs(Tensor2& outputs);
-  // minibatch extension: B lines, one fused device step (clstm_b200_train_step); returns the decoded strings
+  // minibatch extension: B raw lines -> normalise + forward + CTC + backward + update in one device step
+  // (clstm_b200_normalize_batch + clstm_b200_step_resident); returns the decoded strings
   std::vector<std::wstring> train_batch(std::vector<Tensor2>& images, const std::vector<std::wstring>& targets);
 };
 

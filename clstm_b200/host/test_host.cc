@@ -6,10 +6,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "clstm_host.h"
+#include "clstm_extras.h"
 
 using namespace ocropus;
 using std::string;
@@ -82,13 +84,82 @@ static int run_cpu(const char* fname) {
   Tensor2 img = render(L"ab", 48);
   try { ocr.predict(img); } catch (const char* msg) { threw = string(msg).find("no CPU fallback") != string::npos || string(msg).find("device") != string::npos; }
   if (getenv("EXPECT_NO_GPU")) CHECK(threw);
+  // ---- utils.h / clstm.h helpers
+  std::wstring k1 = L"kitten", k2 = L"sitting", e0 = L"";
+  CHECK(levenshtein(k1, k2) == 3 && levenshtein(k2, k1) == 3 && levenshtein(k1, e0) == 6 && levenshtein(k1, k1) == 0);
+  CHECK(ocropus::basename(string("/a/b.c/line-01.bin.png")) == "/a/b.c/line-01" && ocropus::basename(string("x")) == "x");
+  {
+    Trigger t(10, 35, 0);                    // every 10, forced at upto-1 = 34
+    vector<int> fired;
+    for (int i = 0; i < 35; i++) if (t(i)) fired.push_back(i);
+    CHECK((fired == vector<int>{0, 10, 20, 30, 34}));
+    Trigger u(10, -1, 0);
+    u.skip0();
+    CHECK(!u(0) && !u(9) && u(10) && u.since() == 10 && !u(11));
+    Trigger z(0, 100, 0);
+    CHECK(!z(5));
+  }
+  {
+    const string gt = string(fname) + ".gt.txt";
+    write_text(gt, string("# comment\nhello\n\nw\xc3\xb6rld"));
+    Codec c;
+    c.build({gt}, L"~");
+    CHECK(c.codec.front() == 0 && c.size() == 10 && c.encoder.count(0xf6) && c.encoder.count('~'));   // 0 ~ d e h l o r w ö
+    CHECK(read_text32(gt) == utf8_to_utf32("# comment\nhello\n\nw\xc3\xb6rld"));
+    vector<string> lines;
+    read_lines(lines, gt);
+    CHECK(lines.size() == 4 && lines[1] == "hello");
+  }
+  threw = false;
+  try { make_Normalizer("fancy"); } catch (const char* msg) { threw = string(msg) == "unknown normalizer name"; }
+  CHECK(threw);
+  {
+    std::unique_ptr<INormalizer> nm(make_Normalizer("center"));
+    CHECK(nm->kind() == 2 && nm->target_height == 48 && nm->range == 4.0f && nm->smooth1d == 0.3f);
+    std::unique_ptr<INormalizer> mm(make_Normalizer("mean"));
+    CHECK(mm->kind() == 1 && mm->range == 1.0f);
+  }
+  // ---- PNG codec round trip (extras.cc:537-560): write quantises with floor(v*256), read returns (r+g+b)/(3*255.0)
+  {
+    Tensor2 im;
+    im.resize(37, 11);
+    for (int i = 0; i < 37; i++)
+      for (int j = 0; j < 11; j++) im(i, j) = (float)((i * 7 + j * 13) % 101) / 100.0f;
+    const string pn = string(fname) + ".png";
+    write_png(pn.c_str(), im);
+    Tensor2 back;
+    read_png(back, pn.c_str());
+    CHECK(back.dimension(0) == 37 && back.dimension(1) == 11);
+    for (int i = 0; i < 37; i++)
+      for (int j = 0; j < 11; j++) {
+        double v = im(i, j) * 256;
+        v = v > 255.999999 ? 255.999999 : v;
+        const int q = (int)std::floor(v);
+        CHECK(back(i, j) == (Float)((q + q + q) / (3 * 255.0)));
+      }
+    threw = false;
+    try { read_png(back, "/nonexistent/x.png"); } catch (const char* msg) { threw = string(msg) == "error on open"; }
+    CHECK(threw);
+  }
   printf("host cpu ok: %d params saved to %s\n", P, fname);
   return 0;
+}
+
+// a RAW scanned-looking line (ink = 1): the bands of render() drawn 60 rows high with a margin, so that the
+// CenterNormalizer has something to measure
+static Tensor2 render_raw(const std::wstring& text) {
+  Tensor2 small = render(text, 48), raw;
+  const int T = small.dimension(0);
+  raw.resize(T + 10, 60);
+  for (int t = 0; t < T; t++)
+    for (int i = 0; i < 48; i++) raw(t + 5, i + 7) = small(t, i);
+  return raw;
 }
 
 static int run_gpu() {
   CLSTMOCR ocr;
   ocr.createBidi(demo_codec(), 16);
+  ocr.normalizer.reset(make_NoNormalizer());   // render() draws lines that are already target_height rows high
   ocr.setLearningRate(1e-2, 0.9);
   const std::wstring text = L"abc de";
   Tensor2 img = render(text, 48);
@@ -115,6 +186,8 @@ static int run_gpu() {
   ocr.save("/tmp/clstm_b200_host_test.clstm");
   CLSTMOCR ocr2;
   ocr2.load("/tmp/clstm_b200_host_test.clstm");
+  CHECK(ocr2.normalizer && ocr2.normalizer->kind() == 2);   // load installs a CenterNormalizer (clstmhl.h:165)
+  ocr2.normalizer.reset(make_NoNormalizer());
   CHECK(ocr2.predict(img) == text);
   // derivatives and the momentum buffer are not saved (clstm_proto.cc:51): a step after reload works from zero
   ocr2.setLearningRate(1e-2, 0.9);
@@ -133,6 +206,43 @@ static int run_gpu() {
   for (int k = 0; k < 300; k++) ocr.train_batch(imgs, tgs);
   auto res = ocr.train_batch(imgs, tgs);
   CHECK(res[0] == tgs[0] && res[1] == tgs[1] && res[2] == tgs[2]);
+  // ---- raw lines through PNG files and the CenterNormalizer (the clstmocrtrain data path, clstmocrtrain.cc:68-76)
+  {
+    CLSTMOCR o3;
+    o3.createBidi(demo_codec(), 16);
+    CHECK(o3.normalizer->kind() == 2);
+    o3.setLearningRate(1e-2, 0.9);
+    Tensor2 raw0 = render_raw(text), page, raw;
+    page.resize(raw0.dimension(0), raw0.dimension(1));
+    for (size_t k = 0; k < page.data.size(); k++) page.data[k] = 1.0f - raw0.data[k];   // paper is white on disk
+    write_png("/tmp/clstm_b200_host_line.png", page);
+    read_png(raw, "/tmp/clstm_b200_host_line.png");
+    for (Float& v : raw.data) v = -v + Float(1);
+    std::wstring g3;
+    int it3 = 0;
+    for (; it3 < 800; it3++) {
+      g3 = o3.train(raw, text);
+      if (g3 == text && it3 > 20) break;
+    }
+    printf("raw line: trained %d steps, reads: %s, normalised to %d x %d\n", it3, utf32_to_utf8(g3).c_str(),
+           o3.image.dimension(0), o3.image.dimension(1));
+    CHECK(o3.predict(raw) == text);
+    CHECK(o3.image.dimension(1) == 48 && o3.image.dimension(0) > 10);
+    // the stand-alone normalizer returns the very image the OCR wrapper fed to the network
+    std::unique_ptr<INormalizer> nm(make_CenterNormalizer());
+    Tensor2 nimg;
+    nm->measure(raw);
+    nm->normalize(nimg, raw);
+    CHECK(nimg.dimension(0) == o3.image.dimension(0) && nimg.data == o3.image.data);
+    bool threw = false;
+    Tensor2 other = render_raw(L"ab");
+    try { nm->normalize(nimg, other); } catch (const char* msg) { threw = string(msg) == "measure doesn't match normalize"; }
+    CHECK(threw);
+    vector<Tensor2> raws = {render_raw(L"ab"), render_raw(L"cde a"), raw};
+    for (int k = 0; k < 200; k++) o3.train_batch(raws, tgs);
+    auto r3 = o3.train_batch(raws, tgs);
+    CHECK(r3[0] == tgs[0] && r3[1] == tgs[1] && r3[2] == tgs[2]);
+  }
   printf("host gpu ok\n");
   return 0;
 }
@@ -151,8 +261,21 @@ static int run_load(const char* fname) {
   return 0;
 }
 
+// decodes a PNG written by anybody (tests/golden/png, made with PIL) and prints r+g+b per pixel for cross-checking
+static int run_png(const char* fname) {
+  Tensor2 im;
+  read_png(im, fname);
+  printf("%d %d\n", im.dimension(0), im.dimension(1));
+  for (int j = 0; j < im.dimension(1); j++) {
+    for (int i = 0; i < im.dimension(0); i++) printf("%d ", (int)std::lround(im(i, j) * 3 * 255.0));
+    printf("\n");
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   try {
+    if (argc >= 3 && !strcmp(argv[1], "png")) return run_png(argv[2]);
     if (argc >= 3 && !strcmp(argv[1], "load")) return run_load(argv[2]);
     if (argc >= 3 && !strcmp(argv[1], "cpu")) return run_cpu(argv[2]);
     if (argc >= 2 && !strcmp(argv[1], "gpu")) return run_gpu();
