@@ -133,6 +133,35 @@ def cpu_reference(a, budget_s, threads):
             "seconds": t}
 
 
+def normalizer_leg(net, a):
+    """Side measurement (not part of `value`): the step in front of the path, CenterNormalizer measure + normalize of
+    one batch of raw 60-row line images from host memory into the resident input batch (clstm_b200_normalize_batch),
+    next to the CPU restatement of extras.cc on one line."""
+    import time
+    from clstm_b200 import synth
+    B, h, w = a.batch, 60, 640
+    imgs = [synth.make_raw_line(w, h, seed=900 + b) for b in range(B)]
+    net.normalize_batch(imgs, "center")
+    net.profile(True)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        T = net.normalize_batch(imgs, "center")
+    dt = (time.perf_counter() - t0) / reps
+    stats = net.phase_stats()
+    net.profile(False)
+    dev_ms = stats.get("normalize", (0.0, 0))[0] / reps
+    res = {"kind": "center", "lines": B, "raw_shape": [h, w], "normalized_columns": int(T.sum()),
+           "ms_per_batch_host_to_resident": dt * 1e3, "device_ms_per_batch": dev_ms,
+           "value": B * w * h / dt, "unit": "raw px/s", "launches_per_batch": stats.get("normalize", (0.0, 0))[1] / reps}
+    if not a.no_cpu_baseline:
+        from oracle import binding as ob
+        t0 = time.perf_counter()
+        ob.center_line(imgs[0])
+        res["cpu_port_px_per_s"] = w * h / (time.perf_counter() - t0)
+    return res
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -325,6 +354,8 @@ def run_b200(a):
                    "d2h_bytes_per_step": d2h},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
            "allreduce_ms_per_step": (stats.get("allreduce", (0.0, 0))[0] / a.steps) if world > 1 else 0.0}
+    if world == 1:
+        out["normalizer"] = normalizer_leg(net, a)
     if world == 1 and not a.no_cpu_baseline:
         cb = cpu_reference(a, a.cpu_seconds, 1)
         cb.pop("seconds")
