@@ -50,6 +50,8 @@ EXPORTS = {
     "clstm_b200_step_resident": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "clstm_b200_fetch_decoded": (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, C.c_int]),
     "clstm_b200_synchronize": (C.c_int, [C.c_void_p]),
+    "clstm_b200_prefetch_batch": (C.c_int, [C.c_void_p, f32p, i32p, C.c_int, i32p, i32p]),
+    "clstm_b200_step_prefetched": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "clstm_b200_normalize_batch": (C.c_int, [C.c_void_p, f32p, i32p, i32p, C.c_int, C.c_int, f32p, i32p, i32p, i32p]),
     "clstm_b200_normalizer_state": (C.c_int, [C.c_void_p, f32p, f32p]),
     "clstm_b200_get_inputs": (C.c_int, [C.c_void_p, f32p]),
@@ -280,6 +282,31 @@ class Net:
         out = np.zeros((self.N, self.nc), np.float32)
         _chk(lib().clstm_b200_forward_resident(self.h, out.ctypes.data_as(f32p)))
         return out
+
+    def prefetch_batch(self, x, T, labels, L):
+        """stage the next batch on the copy stream; the arrays are kept alive until the matching step_prefetched"""
+        xa, xp = _f32(x)
+        Ta, Tp = _i32(T)
+        la, lp = _i32(labels)
+        La, Lp = _i32(L)
+        self._prefetch_keep = (xa, Ta, la, La)
+        self._prefetch_geom = (int(Ta.sum()), Ta.size)
+        _chk(lib().clstm_b200_prefetch_batch(self.h, xp, Tp, Ta.size, lp, Lp))
+
+    def step_prefetched(self, lr, momentum, clip=100.0):
+        _chk(lib().clstm_b200_step_prefetched(self.h, lr, momentum, clip))
+        self.N, self.B = self._prefetch_geom
+
+    def fetch_decoded(self, max_per_line, which=0):
+        """decoded classes / locations of the last step (synchronises the handle's stream)"""
+        m = int(max_per_line)
+        if getattr(self, "_dec_bufs", None) is None or self._dec_bufs[0].shape != (self.B, m):
+            self._dec_bufs = (pinned_array((self.B, m), np.int32), pinned_array((self.B, m), np.int32),
+                              pinned_array((self.B,), np.int32))
+        cls, locs, cnt = self._dec_bufs
+        _chk(lib().clstm_b200_fetch_decoded(self.h, which, cls.ctypes.data_as(i32p), locs.ctypes.data_as(i32p),
+                                            cnt.ctypes.data_as(i32p), m))
+        return [(cls[b, :cnt[b]].copy(), locs[b, :cnt[b]].copy()) for b in range(self.B)]
 
     def step_resident(self, lr, momentum, clip=100.0):
         _chk(lib().clstm_b200_step_resident(self.h, lr, momentum, clip))

@@ -100,7 +100,8 @@ struct clstm_b200_net {
   int num_sms = 148;
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;              // side stream: the W1 derivative product overlaps the backward recurrence
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_dx = nullptr;
+  bool dx_pending = false;                 // the input-delta product is still running on the side stream
   float* ws2 = nullptr;                    // its private split-K workspace
   size_t ws2_floats = 0;
 
@@ -115,8 +116,17 @@ struct clstm_b200_net {
   bool g_pending = false;
   bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
 
-  // ---- batch capacity and buffers
+  // ---- batch capacity and buffers.  The INPUT SET (x, metadata, tiles, their pinned staging, host geometry, Lines view)
+  // exists twice: the members below are the current set, `spare` holds the other one, swap_sets() exchanges them.
+  // clstm_b200_prefetch_batch fills the spare set on the copy stream while a step that was launched on the current
+  // set is still running (kernels captured its pointers by value).
   int capN = 0, capB = 0, capLab = 0;
+  size_t capX = 0;                         // floats in x (per set; capN sizes the compute buffers shared by both sets)
+  int capB2 = 0, capLab2 = 0;              // capacity of the shared per-line compute buffers (tot, mx_part, dcnt, h_small)
+  cudaStream_t stc = nullptr;              // copy stream of the input pipeline
+  cudaEvent_t ev_ready = nullptr, ev_consumed = nullptr;   // per set: staging finished / last step on the set finished
+  bool consumed_recorded = false, prefetched = false;
+  int dec_B = 0;                           // lines of the batch the decode buffers refer to
   long long capLat = 0;
   float *x = nullptr, *XP[2] = {}, *G[2] = {}, *C[2] = {}, *H = nullptr, *Hprev[2] = {}, *out = nullptr,
         *aligned = nullptr, *delta = nullptr, *dH = nullptr, *DG[2] = {}, *dx = nullptr;
@@ -145,6 +155,17 @@ struct clstm_b200_net {
   std::vector<int> hT, hOff, hL, hLabOff, hOrder, hStOff;
   Lines ln{};
   bool have_batch = false, have_forward = false, have_labels = false, have_ctc = false, raw_targets = false;
+  struct InputSet {                        // storage of the set that is not current (same meaning as the members above)
+    float* x = nullptr; size_t capX = 0;
+    int* meta = nullptr; long long* lat_off = nullptr; int* h_meta = nullptr; long long* h_lat = nullptr;
+    int capB = 0, capLab = 0;
+    int* tiles = nullptr; int* h_tiles = nullptr; int capTiles = 0;
+    cudaEvent_t meta_done = nullptr, ev_ready = nullptr, ev_consumed = nullptr;
+    bool consumed_recorded = false;
+    std::vector<int> hT, hOff, hL, hLabOff, hOrder, hStOff;
+    Lines ln{};
+    bool have_batch = false, have_labels = false, raw_targets = false;
+  } spare;
   const char* variant = "generic";
 
   // ---- line normalizer scratch (normalize.cu)
@@ -259,8 +280,21 @@ void dev_to_ref(const clstm_b200_net* n, const float* dev, float* ref) {
   }
 }
 
+void swap_sets(clstm_b200_net* n) {
+  auto& o = n->spare;
+  std::swap(n->x, o.x); std::swap(n->capX, o.capX);
+  std::swap(n->meta, o.meta); std::swap(n->lat_off, o.lat_off); std::swap(n->h_meta, o.h_meta); std::swap(n->h_lat, o.h_lat);
+  std::swap(n->capB, o.capB); std::swap(n->capLab, o.capLab);
+  std::swap(n->tiles, o.tiles); std::swap(n->h_tiles, o.h_tiles); std::swap(n->capTiles, o.capTiles);
+  std::swap(n->meta_done, o.meta_done); std::swap(n->ev_ready, o.ev_ready); std::swap(n->ev_consumed, o.ev_consumed);
+  std::swap(n->consumed_recorded, o.consumed_recorded);
+  n->hT.swap(o.hT); n->hOff.swap(o.hOff); n->hL.swap(o.hL); n->hLabOff.swap(o.hLabOff); n->hOrder.swap(o.hOrder);
+  n->hStOff.swap(o.hStOff);
+  std::swap(n->ln, o.ln);
+  std::swap(n->have_batch, o.have_batch); std::swap(n->have_labels, o.have_labels); std::swap(n->raw_targets, o.raw_targets);
+}
 void free_batch(clstm_b200_net* n) {
-  dev_free(n->x); dev_free(n->H); dev_free(n->out); dev_free(n->aligned); dev_free(n->delta); dev_free(n->dH);
+  dev_free(n->H); dev_free(n->out); dev_free(n->aligned); dev_free(n->delta); dev_free(n->dH);
   dev_free(n->dx);
   for (int d = 0; d < 2; d++) {
     dev_free(n->XP[d]); dev_free(n->G[d]); dev_free(n->C[d]); dev_free(n->Hprev[d]); dev_free(n->DG[d]);
@@ -274,7 +308,6 @@ int ensure_columns(clstm_b200_net* n, int N) {
   free_batch(n);
   const size_t cap = (size_t)N + N / 8 + 64;
   const int no = n->no, ni = n->ni, nc = n->nc;
-  TRY(dev_alloc(&n->x, cap * ni));
   TRY(dev_alloc(&n->H, cap * 2 * no));
   TRY(dev_alloc(&n->out, cap * nc));
   TRY(dev_alloc(&n->aligned, cap * nc));
@@ -293,34 +326,51 @@ int ensure_columns(clstm_b200_net* n, int N) {
   n->capN = (int)cap;
   return 0;
 }
+int ensure_x(clstm_b200_net* n, size_t floats) {      // per input set
+  if (floats <= n->capX) return 0;
+  CU(cudaStreamSynchronize(n->st));
+  CU(cudaStreamSynchronize(n->stc));
+  dev_free(n->x);
+  n->capX = floats + floats / 8 + 64 * (size_t)n->ni;
+  TRY(dev_alloc(&n->x, n->capX));
+  return 0;
+}
 int ensure_lines(clstm_b200_net* n, int B, int nlab) {
-  if (B > n->capB || nlab > n->capLab) {
+  if (B > n->capB || nlab > n->capLab) {              // per input set: metadata and its pinned staging
     CU(cudaStreamSynchronize(n->st));
+    CU(cudaStreamSynchronize(n->stc));
     const int cb = std::max(B + B / 4 + 8, n->capB), cl = std::max(nlab + nlab / 4 + 64, n->capLab);
     dev_free(n->meta); dev_free(n->lat_off);
     if (n->h_meta) cudaFreeHost(n->h_meta);
     if (n->h_lat) cudaFreeHost(n->h_lat);
-    if (n->h_small) cudaFreeHost(n->h_small);
     TRY(dev_alloc(&n->meta, (size_t)6 * cb + cl));
+    TRY(dev_alloc(&n->lat_off, (size_t)cb));
+    CU(cudaHostAlloc((void**)&n->h_meta, ((size_t)6 * cb + cl) * sizeof(int), cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&n->h_lat, (size_t)cb * sizeof(long long), cudaHostAllocDefault));
+    n->capB = cb;
+    n->capLab = cl;
+  }
+  if (B > n->capB2 || nlab > n->capLab2) {            // shared by both sets: per-line compute scratch
+    CU(cudaStreamSynchronize(n->st));
+    const int cb = std::max(B + B / 4 + 8, n->capB2), cl = std::max(nlab + nlab / 4 + 64, n->capLab2);
+    if (n->h_small) cudaFreeHost(n->h_small);
     dev_free(n->tot);
     n->capStates = 2 * cl + cb;
     TRY(dev_alloc(&n->tot, (size_t)n->capStates * 8));
     dev_free(n->mx_part);
     TRY(dev_alloc(&n->mx_part, (size_t)cb * 8));
-    TRY(dev_alloc(&n->lat_off, (size_t)cb));
-    CU(cudaHostAlloc((void**)&n->h_meta, ((size_t)6 * cb + cl) * sizeof(int), cudaHostAllocDefault));
-    CU(cudaHostAlloc((void**)&n->h_lat, (size_t)cb * sizeof(long long), cudaHostAllocDefault));
     CU(cudaHostAlloc((void**)&n->h_small, ((size_t)2 * cb + 8) * sizeof(int), cudaHostAllocDefault));
     for (int w = 0; w < 2; w++) { dev_free(n->dcnt[w]); TRY(dev_alloc(&n->dcnt[w], (size_t)cb)); }
-    n->capB = cb;
-    n->capLab = cl;
-    n->capDec = 0;  // decode buffers depend on capB
+    n->capB2 = cb;
+    n->capLab2 = cl;
+    n->capDec = 0;  // decode buffers depend on capB2
   }
   return 0;
 }
 int ensure_tiles(clstm_b200_net* n, int ntiles) {
   if (ntiles <= n->capTiles) return 0;
   CU(cudaStreamSynchronize(n->st));
+  CU(cudaStreamSynchronize(n->stc));
   dev_free(n->tiles);
   if (n->h_tiles) cudaFreeHost(n->h_tiles);
   const int cap = ntiles + ntiles / 4 + 64;
@@ -334,8 +384,8 @@ int ensure_decode(clstm_b200_net* n, int max_per_line) {
   CU(cudaStreamSynchronize(n->st));
   for (int w = 0; w < 2; w++) {
     dev_free(n->dcls[w]); dev_free(n->dlocs[w]);
-    TRY(dev_alloc(&n->dcls[w], (size_t)n->capB * max_per_line));
-    TRY(dev_alloc(&n->dlocs[w], (size_t)n->capB * max_per_line));
+    TRY(dev_alloc(&n->dcls[w], (size_t)n->capB2 * max_per_line));
+    TRY(dev_alloc(&n->dlocs[w], (size_t)n->capB2 * max_per_line));
   }
   n->capDec = max_per_line;
   return 0;
@@ -355,7 +405,9 @@ int ensure_lattice(clstm_b200_net* n, long long elems) {
 }
 
 // Stage line lengths (and optionally transcripts) and publish the Lines view.
-int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const int* L, bool raw = false) {
+int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const int* L, bool raw = false,
+                cudaStream_t cs = nullptr) {
+  if (!cs) cs = n->st;
   if (B <= 0) return fail("batch must contain at least one line");
   long long N = 0;
   for (int b = 0; b < B; b++) {
@@ -371,6 +423,7 @@ int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const
     nlab += L[b];
   }
   TRY(ensure_columns(n, (int)N));
+  TRY(ensure_x(n, (size_t)N * n->ni));
   TRY(ensure_lines(n, B, nlab));
   if (n->meta_done) CU(cudaEventSynchronize(n->meta_done));   // pinned staging buffers free again?
   n->hT.assign(T, T + B);
@@ -413,11 +466,11 @@ int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const
   memcpy(hm + 4 * cb, n->hOrder.data(), B * sizeof(int));
   memcpy(hm + 5 * cb, n->hStOff.data(), B * sizeof(int));
   if (L && nlab) memcpy(hm + 6 * cb, labels, nlab * sizeof(int));
-  CU(cudaMemcpyAsync(n->meta, hm, ((size_t)6 * cb + nlab) * sizeof(int), cudaMemcpyHostToDevice, n->st));
-  CU(cudaMemcpyAsync(n->tiles, n->h_tiles, ((size_t)n->capTiles + ntiles) * sizeof(int), cudaMemcpyHostToDevice, n->st));
-  CU(cudaMemcpyAsync(n->lat_off, n->h_lat, (size_t)B * sizeof(long long), cudaMemcpyHostToDevice, n->st));
+  CU(cudaMemcpyAsync(n->meta, hm, ((size_t)6 * cb + nlab) * sizeof(int), cudaMemcpyHostToDevice, cs));
+  CU(cudaMemcpyAsync(n->tiles, n->h_tiles, ((size_t)n->capTiles + ntiles) * sizeof(int), cudaMemcpyHostToDevice, cs));
+  CU(cudaMemcpyAsync(n->lat_off, n->h_lat, (size_t)B * sizeof(long long), cudaMemcpyHostToDevice, cs));
   if (!n->meta_done) CU(cudaEventCreateWithFlags(&n->meta_done, cudaEventDisableTiming));
-  CU(cudaEventRecord(n->meta_done, n->st));
+  CU(cudaEventRecord(n->meta_done, cs));
   Lines& ln = n->ln;
   ln.B = B; ln.N = (int)N; ln.Tmax = tmax;
   ln.T = n->meta; ln.off = n->meta + cb; ln.L = n->meta + 2 * cb; ln.lab_off = n->meta + 3 * cb;
@@ -572,7 +625,14 @@ int run_ctc(clstm_b200_net* n) {
   return 0;
 }
 
-int run_backward(clstm_b200_net* n) {
+// defer_dx: the input-delta product (nobody downstream of the step needs it) goes to the side stream and is joined by
+// join_dx() at the end of the step, so it overlaps the weight-derivative tail, the gradient exchange and the update.
+void join_dx(clstm_b200_net* n) {
+  if (!n->dx_pending) return;
+  cudaStreamWaitEvent(n->st, n->ev_dx, 0);
+  n->dx_pending = false;
+}
+int run_backward(clstm_b200_net* n, bool defer_dx = false) {
   const Lines& ln = n->ln;
   const int N = ln.N, ni = n->ni, no = n->no, nc = n->nc;
   {
@@ -593,6 +653,12 @@ int run_backward(clstm_b200_net* n) {
     for (int d = 0; d < 2; d++) { a.R[d] = n->v + n->oR[d]; a.G[d] = n->G[d]; a.C[d] = n->C[d]; a.DG[d] = n->DG[d]; }
     lstm_backward(n->st, ln, a);
     s.launches(1);
+  }
+  cudaStream_t dxs = n->st;
+  if (defer_dx && n->use_tc && !n->prof) {   // (phase profiling keeps everything on one stream)
+    cudaEventRecord(n->ev_fork2, n->st);
+    cudaStreamWaitEvent(n->st2, n->ev_fork2, 0);
+    dxs = n->st2;
   }
   {
     Scope s(n, PH_WGRAD);   // W.d += delta * src^T over all columns (backward_lin1 clstm_compute.cc:297-298)
@@ -615,7 +681,11 @@ int run_backward(clstm_b200_net* n) {
         g.b_vec = g.b_vec && vec_ok(n->WxT[d], 4 * no);
       }
       g.C = n->dx; g.ldc = ni; g.bias = nullptr; g.beta = 0.f;
-      s.launches(gemm_tc(n->st, g, nullptr, n->num_sms));
+      s.launches(gemm_tc(dxs, g, nullptr, n->num_sms));
+      if (dxs != n->st) {
+        cudaEventRecord(n->ev_dx, n->st2);
+        n->dx_pending = true;
+      }
     } else {
       for (int d = 0; d < 2; d++)
         s.launches(dense_nt(n, N, ni, 4 * no, n->DG[d], 4 * no, n->v + n->oWx[d], ni, true, n->dx, ni, nullptr, d ? 1.f : 0.f));
@@ -647,6 +717,7 @@ int run_update(clstm_b200_net* n, float lr, float mom, float clip) {
   Scope s(n, PH_UPDATE);
   sgd_update(n->st, n->v, n->d, n->g, n->P, lr, mom, clip, 0);
   n->g_pending = false;
+  join_dx(n);              // the deferred input-delta product reads Wx^T, which prepare_weights is about to rewrite
   prepare_weights(n);
   s.launches(2);
   return check_launch("sgd_update");
@@ -661,6 +732,7 @@ int run_peer_update(clstm_b200_net* n, float lr, float mom, float clip) {
   a.v = n->v; a.d = n->d; a.n = n->P; a.lr = lr; a.mom = mom; a.clip = clip;
   peer_allreduce_update(n->st, a);
   n->g_pending = false;
+  join_dx(n);              // see run_update
   prepare_weights(n);
   s.launches(3);
   return check_launch("peer_allreduce_update");
@@ -671,12 +743,13 @@ int run_decode(clstm_b200_net* n, int which, int max_per_line) {
   Scope s(n, PH_DECODE);
   decode_lines(n->st, n->ln, n->amax[which], n->amaxv[which], n->dcls[which], n->dlocs[which], n->dcnt[which],
                n->capDec);
+  n->dec_B = n->ln.B;
   s.launches(1);
   return check_launch("decode");
 }
 
 int fetch_decode(clstm_b200_net* n, int which, int* classes, int* locs, int* counts, int max_per_line) {
-  const int B = n->ln.B;
+  const int B = n->dec_B;                 // the batch that was decoded (a prefetched batch may be current by now)
   {
     Scope s(n, PH_D2H);
     CU(cudaMemcpyAsync(counts, n->dcnt[which], (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, n->st));
@@ -741,8 +814,15 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   n->P = o;
   if (cudaStreamCreateWithFlags(&n->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&n->st2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&n->stc, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_consumed, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->spare.ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->spare.ev_consumed, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&n->ev_dx, cudaEventDisableTiming) != cudaSuccess) {
     clstm_b200_destroy(n);
     return fail("cudaStreamCreate failed");
   }
@@ -787,27 +867,39 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   cudaSetDevice(n->cfg.device);
   if (n->st) cudaStreamSynchronize(n->st);
   if (n->st2) cudaStreamSynchronize(n->st2);
+  if (n->stc) cudaStreamSynchronize(n->stc);
   if (n->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(n->comm);
   free_batch(n);
+  for (int k = 0; k < 2; k++) {            // both input sets
+    dev_free(n->x); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->tiles);
+    if (n->h_tiles) cudaFreeHost(n->h_tiles);
+    if (n->h_meta) cudaFreeHost(n->h_meta);
+    if (n->h_lat) cudaFreeHost(n->h_lat);
+    n->h_tiles = nullptr; n->h_meta = nullptr; n->h_lat = nullptr;
+    if (n->meta_done) cudaEventDestroy(n->meta_done);
+    if (n->ev_ready) cudaEventDestroy(n->ev_ready);
+    if (n->ev_consumed) cudaEventDestroy(n->ev_consumed);
+    n->meta_done = nullptr; n->ev_ready = nullptr; n->ev_consumed = nullptr;
+    swap_sets(n);
+  }
+  if (n->stc) cudaStreamDestroy(n->stc);
   for (int r = 0; r < kMaxPeers; r++)
     if (n->peer_buf[r] && r != n->rank) cudaIpcCloseMemHandle(n->peer_buf[r]);
   dev_free(n->v); dev_free(n->d); dev_free(n->comm_buf); n->g = nullptr; dev_free(n->Rt[0]); dev_free(n->Rt[1]);
   dev_free(n->WxT[0]); dev_free(n->WxT[1]); dev_free(n->W1T);
-  dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->meta); dev_free(n->lat_off); dev_free(n->status);
-  dev_free(n->ws); dev_free(n->tiles); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
+  dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->status);
+  dev_free(n->ws); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
   dev_free(n->n_raw); dev_free(n->n_tmp); dev_free(n->n_smooth); dev_free(n->n_a); dev_free(n->n_center);
   dev_free(n->n_r); dev_free(n->n_scale); dev_free(n->n_masks); dev_free(n->n_ym); dev_free(n->n_yd); dev_free(n->n_meta);
   if (n->st2) cudaStreamDestroy(n->st2);
   if (n->ev_fork) cudaEventDestroy(n->ev_fork);
   if (n->ev_join) cudaEventDestroy(n->ev_join);
-  if (n->h_tiles) cudaFreeHost(n->h_tiles);
+  if (n->ev_fork2) cudaEventDestroy(n->ev_fork2);
+  if (n->ev_dx) cudaEventDestroy(n->ev_dx);
   for (int w = 0; w < 2; w++) { dev_free(n->dcls[w]); dev_free(n->dlocs[w]); dev_free(n->dcnt[w]); }
-  if (n->h_meta) cudaFreeHost(n->h_meta);
-  if (n->h_lat) cudaFreeHost(n->h_lat);
   if (n->h_small) cudaFreeHost(n->h_small);
   for (auto& r : n->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : n->pool) cudaEventDestroy(e);
-  if (n->meta_done) cudaEventDestroy(n->meta_done);
   if (n->st) cudaStreamDestroy(n->st);
   delete n;
 }
@@ -902,7 +994,7 @@ int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W
   std::vector<int> meta((size_t)10 * B);
   int* mW = meta.data(); int* mH = mW + B; int* mP = mH + B; int* mC = mP + B; int* mO = mC + B; int* mR = mO + 3 * B;
   size_t pix = 0, cols = 0;
-  int maxpix = 0, maxh = 0;
+  int maxpix = 0, maxh = 0, maxw = 0, maxrange = 0;
   for (int b = 0; b < B; b++) {
     if (W[b] <= 0 || H[b] <= 0) return fail("line %d has an empty image (%d x %d)", b, W[b], H[b]);
     if (H[b] > kNormMaxHeight) return fail("line %d is %d rows high (max %d)", b, H[b], kNormMaxHeight);
@@ -910,7 +1002,7 @@ int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W
     mW[b] = W[b]; mH[b] = H[b]; mP[b] = (int)pix; mC[b] = (int)cols;
     pix += (size_t)W[b] * H[b]; cols += W[b];
     if (pix > 0x7fffffff) return fail("raw batch too large");
-    maxpix = std::max(maxpix, W[b] * H[b]); maxh = std::max(maxh, H[b]);
+    maxpix = std::max(maxpix, W[b] * H[b]); maxh = std::max(maxh, H[b]); maxw = std::max(maxw, W[b]);
   }
   std::vector<float> masks;
   if (kind == 2) {
@@ -928,6 +1020,7 @@ int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W
           masks.insert(masks.end(), m.begin(), m.end());
         }
         mO[3 * b + k] = it->second.first; mR[3 * b + k] = it->second.second;
+        maxrange = std::max(maxrange, it->second.second);
       }
     }
   }
@@ -948,7 +1041,8 @@ int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W
   if (kind == 2) {
     {
       Scope s(n, PH_NORMALIZE);
-      s.launches(norm_center_measure(n->st, nl, B, maxpix, maxh, n->n_raw, n->n_tmp, n->n_smooth, n->n_a, n->n_center, n->n_r));
+      if (maxrange > kNormMaxRange) return fail("normalizer smoothing width %d exceeds the supported %d", maxrange, kNormMaxRange);
+      s.launches(norm_center_measure(n->st, nl, B, maxw, maxh, maxrange, n->n_raw, n->n_tmp, n->n_smooth, n->n_a, n->n_center, n->n_r));
       TRY(check_launch("normalizer measure"));
     }
     CU(cudaMemcpyAsync(n->n_hr.data(), n->n_r, B * sizeof(float), cudaMemcpyDeviceToHost, n->st));
@@ -1176,7 +1270,7 @@ int clstm_b200_step_resident(clstm_b200_net* n, float lr, float momentum, float 
   CU(cudaSetDevice(n->cfg.device));
   TRY(run_forward(n));
   TRY(run_ctc(n));
-  TRY(run_backward(n));
+  TRY(run_backward(n, /*defer_dx=*/true));
   if (n->p2p && n->world > 1) {
     TRY(run_peer_update(n, lr, momentum, clip));
   } else {
@@ -1184,7 +1278,42 @@ int clstm_b200_step_resident(clstm_b200_net* n, float lr, float momentum, float 
     TRY(run_update(n, lr, momentum, clip));
   }
   TRY(run_decode(n, 0, std::max(n->capDec, n->ln.Tmax / 2 + 1)));
+  join_dx(n);
   return 0;
+}
+
+// ---- input pipeline: stage batch i+1 on the copy stream into the spare input set while step i runs
+int clstm_b200_prefetch_batch(clstm_b200_net* n, const float* x, const int* T, int B, const int* labels, const int* L) {
+  if (!n || !x || !T || !labels || !L) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  const bool keep_fwd = n->have_forward, keep_ctc = n->have_ctc;   // flags of the CURRENT batch (stage_lines resets them)
+  swap_sets(n);                            // work on the spare set under the usual member names
+  int rc = 0;
+  do {
+    if (n->consumed_recorded) {            // the step that last ran on this set must be done before it is overwritten
+      if (cudaStreamWaitEvent(n->stc, n->ev_consumed, 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
+    }
+    if ((rc = stage_lines(n, T, B, labels, L, false, n->stc)) != 0) break;
+    if (cudaMemcpyAsync(n->x, x, (size_t)n->ln.N * n->ni * sizeof(float), cudaMemcpyHostToDevice, n->stc) != cudaSuccess ||
+        cudaEventRecord(n->ev_ready, n->stc) != cudaSuccess) { rc = fail("prefetch copy failed"); break; }
+  } while (0);
+  swap_sets(n);
+  n->have_forward = keep_fwd; n->have_ctc = keep_ctc;
+  n->prefetched = (rc == 0);
+  return rc;
+}
+
+int clstm_b200_step_prefetched(clstm_b200_net* n, float lr, float momentum, float clip) {
+  if (!n) return fail("null argument");
+  if (!n->prefetched) return fail("step_prefetched: no prefetched batch");
+  CU(cudaSetDevice(n->cfg.device));
+  CU(cudaEventRecord(n->ev_consumed, n->st));   // everything enqueued so far on the current set
+  n->consumed_recorded = true;
+  swap_sets(n);
+  n->prefetched = false;
+  n->have_forward = false; n->have_ctc = false;
+  CU(cudaStreamWaitEvent(n->st, n->ev_ready, 0));
+  return clstm_b200_step_resident(n, lr, momentum, clip);
 }
 
 int clstm_b200_fetch_decoded(clstm_b200_net* n, int which, int* classes, int* locs, int* counts, int max_per_line) {

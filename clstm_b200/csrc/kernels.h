@@ -100,8 +100,9 @@ struct NormLines {
   float range;               // CenterNormalizer::range
 };
 int norm_configure();
-int norm_center_measure(cudaStream_t st, const NormLines& nl, int B, int maxpix, int maxh, const float* raw, float* tmp,
-                        float* smooth, float* a, float* center, float* r_out);
+int norm_center_measure(cudaStream_t st, const NormLines& nl, int B, int maxw, int maxh, int maxrange, const float* raw,
+                        float* tmp, float* smooth, float* a, float* center, float* r_out);
+constexpr int kNormMaxRange = 1 + 3 * 3 * kNormMaxHeight / 2;   // Gaussian masks up to sigma = 1.5 * kNormMaxHeight
 int norm_mean_measure(cudaStream_t st, const NormLines& nl, int B, int maxh, const float* raw, double* ymean, double* ymad);
 int norm_resample(cudaStream_t st, const NormLines& nl, int B, int maxT, const float* raw, const float* center,
                   const float* scale, const double* ymean, const int* T, const int* off, float* x, int ni, int kind);

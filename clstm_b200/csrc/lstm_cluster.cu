@@ -64,6 +64,10 @@ __device__ __forceinline__ void cluster_sync_() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// split form: global stores issued between arrive and wait are not covered by this step's release, so the barrier
+// does not have to wait for them to drain (they have a whole step until the next arrive)
+__device__ __forceinline__ void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ unsigned cluster_rank_() {
   unsigned r;
   asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -202,7 +206,6 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_fwd_cluster(Lines ln,
     const float pre = group_reduce4<LB>(p0, p1, p2, p3, hi, lo) + xp;
     const float sg = rcp_approx(1.0f + ex2_approx(sc * pre));
     const float act = (q == 3) ? fmaf(2.f, sg, -1.f) : sg;
-    if (lead) Gb[ncol * ROWS + row] = act;
     const float gi = __shfl_sync(0xffffffffu, act, 0 << (LB - 2), LU);
     const float gf = __shfl_sync(0xffffffffu, act, 1 << (LB - 2), LU);
     const float go = __shfl_sync(0xffffffffu, act, 2 << (LB - 2), LU);
@@ -211,10 +214,12 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_fwd_cluster(Lines ln,
     const float th = fmaf(2.f, rcp_approx(1.0f + ex2_approx(-2.f * kLog2e * c)), -1.f);
     const float hh = th * go;
     if (lg < CS) st_dsmem_f32(wr_addr, (unsigned)lg, hh);           // lane i of the group feeds CTA i's copy of h
+    cluster_arrive_();
+    if (lead) Gb[ncol * ROWS + row] = act;                          // stash stores: after the arrive (see cluster_arrive_)
     if (lead && q < 3) obase[(size_t)ncol * ostride + unit] = (q == 1) ? c : (q == 2) ? hprev : hh;
     hprev = hh;
     ncol += dt;
-    cluster_sync_();
+    cluster_wait_();
     rd_addr += tog; wr_addr -= tog; tog = -tog;
   }
 }
@@ -310,6 +315,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln,
       cp_async_wait<kStage - 1>();
     }
     const bool first = (u + 1 == T);
+    float dl_keep = 0.f;
     if (pw) {
       const unsigned sa = st_addr0 + (u & (kStage - 1)) * STG;
       const ulonglong2 gq = lds_v2u64(sa);
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln,
       const float fp = (1.f - y) * ((pg == 3) ? (1.f + y) : y);
       const float dl = fp * (Av * Bv);
       sts_f32(wr_addr, dl);
-      DGb[ncol * ROWS + 4 * punit + pg] = dl;
+      dl_keep = dl;
     }
     __syncthreads();
     u64 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
@@ -357,8 +363,10 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln,
     unpack2(acc3, l0, l1); const float p3 = fmaf(wt[3], dtail, l0 + l1);
     const float part = group_reduce4<RB>(p0, p1, p2, p3, hi, lo);
     if (send && tid0 < Cfg::THREADS) st_dsmem_f32(pdst, dst_rank, part);       // my rows' share of dh_prev[kout]
+    cluster_arrive_();
+    if (pw) DGb[ncol * ROWS + 4 * punit + pg] = dl_keep;                        // after the arrive (see cluster_arrive_)
     ncol += dt;
-    cluster_sync_();
+    cluster_wait_();
     rd_addr += dtog; wr_addr += dtog; dtog = -dtog;
     pread = psrc + ((ptog > 0) ? 0u : PBUF);                                    // the buffer that was just filled
     pdst += ptog; ptog = -ptog;

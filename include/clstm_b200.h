@@ -123,6 +123,17 @@ int clstm_b200_fetch_decoded(clstm_b200_net* net, int which, int* classes, int* 
                              int max_per_line);
 int clstm_b200_synchronize(clstm_b200_net* net);
 
+/* Input pipeline for a training loop (the data-loader side of clstmocrtrain.cc:172-177): stage the NEXT batch into a
+ * second input set on a copy stream while the step on the current batch is still running, then run the step on it.
+ *   prefetch_batch(i+1) may be called as soon as step i has been launched (step_resident / step_prefetched return
+ *   without waiting); the host buffers must stay valid until the following step_prefetched has been called and
+ *   should be pinned (clstm_b200_alloc_pinned) for the copy to overlap.  step_prefetched makes the prefetched batch
+ *   current and runs clstm_b200_step_resident on it.  fetch_decoded afterwards returns the results of that step.
+ * If the prefetched batch needs larger device buffers than any batch before, the call waits for the running step and
+ * re-allocates (device-resident activations of the current batch are lost; decoded results are kept). */
+int clstm_b200_prefetch_batch(clstm_b200_net* net, const float* x, const int* T, int B, const int* labels, const int* L);
+int clstm_b200_step_prefetched(clstm_b200_net* net, float lr, float momentum, float clip);
+
 /* Text-line normalizers on the device (extras.h:31-47, extras.cc:146-301): measure() + normalize() of B raw line
  * images, written straight into the resident input batch (the place clstm_b200_upload_batch fills), so that
  * CLSTMOCR::fwdbwd / predict (clstmhl.h:201-205, 233-237) never materialise the normalised image on the host.

@@ -219,3 +219,30 @@ def test_long_lines_wide_net(ffi, oracle):
         assert np.array_equal(cs, dec_al[b][0]) and np.array_equal(locs, dec_al[b][1])
     od = onet.get_derivs()
     assert np.abs(od - gd).max() < 5e-3 * max(1.0, np.abs(od).max())
+
+
+def test_input_pipeline_matches_sequential_steps(ffi):
+    # prefetch_batch(i+1) on the copy stream while step i runs, second input set; batches of changing geometry
+    # (growing and shrinking) must give bit-identical decodes and parameters to one train_step per batch
+    ni, nh, nc = 48, 100, 30
+    batches = [synth.make_lines(B, T, ni, nc, seed=40 + k) for k, (B, T) in
+               enumerate([(4, (30, 60)), (6, (50, 90)), (2, (10, 20)), (8, (80, 120)), (5, (40, 70))])]
+    p0 = synth.reference_init(ni, nh, nc, seed=0.4)
+    seq = ffi.Net(ni, nh, nc); seq.set_params(p0)
+    ref_dec = []
+    for x, T, labels, L in batches:
+        dec, _, _ = seq.train_step(x, T, labels, L, 1e-3, 0.9)
+        ref_dec.append(dec)
+    pipe = ffi.Net(ni, nh, nc); pipe.set_params(p0)
+    pipe.prefetch_batch(*batches[0])
+    for k in range(len(batches)):
+        pipe.step_prefetched(1e-3, 0.9)
+        if k + 1 < len(batches):
+            pipe.prefetch_batch(*batches[k + 1])
+        dec = pipe.fetch_decoded(int(batches[k][1].max()) // 2 + 1)
+        assert len(dec) == len(ref_dec[k])
+        for (c0, l0), (c1, l1) in zip(ref_dec[k], dec):
+            assert np.array_equal(c0, c1) and np.array_equal(l0, l1)
+    assert np.array_equal(seq.get_params(), pipe.get_params())
+    with pytest.raises(ffi.Error, match="no prefetched batch"):
+        pipe.step_prefetched(1e-3, 0.9)

@@ -1,11 +1,12 @@
-"""Tiny training steps through every kernel family (regs + generic LSTM, tcgen05 + SIMT GEMM, CTC, decode, update) for
+"""Tiny training steps through every kernel family (regs + cluster + generic LSTM, tcgen05 + SIMT GEMM, CTC, decode, update,
+normalizers) for
 compute-sanitizer runs:  compute-sanitizer --tool memcheck|racecheck python tools/sanitize_step.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import clstm_b200
 from clstm_b200 import synth
-for nh in (16, 5):
+for nh in (16, 5, 200):
     x, T, labels, L = synth.make_lines(3, (9, 21), 48, 11, seed=2)
     net = clstm_b200.Net(48, nh, 11)
     net.set_params(synth.trained_like(net.nparams, 0.3))
@@ -14,3 +15,12 @@ for nh in (16, 5):
     assert np.isfinite(out).all() and np.isfinite(al).all()
     net.forward(x, T); net.ctc_align(labels, L); net.backward(); net.decode(1); net.argmax(0)
     print("ok", nh, net.lstm_variant)
+imgs = [synth.make_raw_line(w, h, seed=k) for k, (w, h) in enumerate([(40, 30), (17, 48), (70, 52)])]
+net = clstm_b200.Net(48, 16, 11)
+net.set_params(synth.trained_like(net.nparams, 0.3))
+for kind in ("center", "mean"):
+    T = net.normalize_batch(imgs, kind, labels=np.array([1, 2, 3], np.int32), L=[1, 1, 1])
+    net.step_resident(1e-3, 0.9)
+    net.synchronize()
+    assert np.isfinite(net.get_inputs()).all()
+    print("ok normalizer", kind, list(T))
