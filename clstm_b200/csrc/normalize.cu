@@ -177,35 +177,35 @@ __global__ void __launch_bounds__(NT) norm_center_sums_kernel(NormLines nl, cons
   const float* __restrict__ raw = raw_all + nl.poff[b];
   const float* __restrict__ center = center_all + nl.coff[b];
   // s1 = sum line(i,j), sy = sum line(i,j) * |j - center(i)|, both float, strictly in (i outer, j inner) order.
-  // The block stages 32 columns at a time as ONE LINEAR STREAM in summation order (seq[di*h + j]); lane 0 of warp 0
-  // carries s1 and lane 0 of warp 1 carries sy, each reading the stream with wide, address-independent loads so that
-  // only the 4-cycle FADD chain is serial.
-  __shared__ float cen_s[TILE_I];
+  // The block stages TI columns at a time as LINEAR STREAMS in summation order (index di*h + j): `tile` holds the pixels,
+  // `prod` the products pixel * |j - center| (computed by all threads, they are independent).  Lane 0 of warp 0 then
+  // chains s1 over `tile`, lane 0 of warp 1 chains sy over `prod`, both with 128-bit loads: only the FADD chains are serial.
+  const int TI = (h <= 384) ? TILE_I : (h <= 768 ? TILE_I / 2 : TILE_I / 4);   // two streams must fit shared memory
+  float* prod = tile + TI * h;
   float s1 = 0.f, sy = 0.f;
-  for (int i0 = 0; i0 < w; i0 += TILE_I) {
-    const int ni = min(TILE_I, w - i0);
-    for (int e = tid; e < h * TILE_I; e += NT) {
-      const int j = e / TILE_I, di = e % TILE_I;
-      if (di < ni) tile[di * h + j] = raw[i0 + di + j * w];
+  for (int i0 = 0; i0 < w; i0 += TI) {
+    const int ni = min(TI, w - i0);
+    for (int e = tid; e < h * TI; e += NT) {
+      const int j = e / TI, di = e % TI;
+      if (di < ni) {
+        const float v = raw[i0 + di + j * w];
+        tile[di * h + j] = v;
+        prod[di * h + j] = __fmul_rn(v, fabsf(__fsub_rn((float)j, center[i0 + di])));
+      }
     }
-    if (tid < TILE_I) cen_s[tid] = (tid < ni) ? center[i0 + tid] : 0.f;
     __syncthreads();
     const int cnt = ni * h;
-    if (tid == 0) {
+    if (tid == 0 || tid == 32) {
+      const float* __restrict__ seq = tid ? prod : tile;
+      float acc = tid ? sy : s1;
       int k = 0;
 #pragma unroll 4
       for (; k + 4 <= cnt; k += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(&tile[k]);
-        s1 = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s1, v.x), v.y), v.z), v.w);
+        const float4 v = *reinterpret_cast<const float4*>(&seq[k]);
+        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
       }
-      for (; k < cnt; k++) s1 = __fadd_rn(s1, tile[k]);
-    } else if (tid == 32) {
-      for (int di = 0; di < ni; di++) {        // counted inner loop: the loads and |j - c| run ahead of the FADD chain
-        const float c = cen_s[di];
-        const float* __restrict__ col = tile + di * h;
-#pragma unroll 8
-        for (int j = 0; j < h; j++) sy = __fadd_rn(sy, __fmul_rn(col[j], fabsf(__fsub_rn((float)j, c))));
-      }
+      for (; k < cnt; k++) acc = __fadd_rn(acc, seq[k]);
+      if (tid) sy = acc; else s1 = acc;
     }
     __syncthreads();
   }
@@ -311,7 +311,7 @@ int norm_center_measure(cudaStream_t st, const NormLines& nl, int B, int maxw, i
   const size_t smem_m = (size_t)((2 * maxrange + 1 + 3) & ~3) * sizeof(float);
   norm_gauss_y_kernel<<<dim3((maxw + GT - 1) / GT, (maxh + 3) / 4, B), GT, smem_m, st>>>(nl, raw, tmp);
   norm_gauss_x_kernel<<<dim3((maxw + 4 * GT - 1) / (4 * GT), maxh, B), GT, smem_m + (size_t)(4 * GT + 2 * maxrange) * sizeof(float), st>>>(nl, tmp, smooth);
-  const size_t smem = (size_t)maxh * TILE_I * sizeof(float);
+  const size_t smem = (size_t)2 * maxh * ((maxh <= 384) ? TILE_I : (maxh <= 768 ? TILE_I / 2 : TILE_I / 4)) * sizeof(float);
   norm_center_line_kernel<<<B, NT, 0, st>>>(nl, raw, smooth, a, center);
   norm_center_sums_kernel<<<B, NT, smem, st>>>(nl, raw, center, r_out);
   return 4;
@@ -335,7 +335,7 @@ int norm_configure() {
   if (e0 == cudaSuccess)
     e0 = cudaFuncSetAttribute(norm_gauss_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((2 * kMaxRange + 8) * sizeof(float)));
   if (e0 != cudaSuccess) return (int)e0;
-  cudaError_t e = cudaFuncSetAttribute(norm_center_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormMaxHeight * TILE_I * 4);
+  cudaError_t e = cudaFuncSetAttribute(norm_center_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 768 * (TILE_I / 2) * 4);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(norm_mean_measure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNormMaxHeight * TILE_I * 4);
   return (int)e;
