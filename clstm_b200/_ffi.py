@@ -22,9 +22,21 @@ class Cfg(C.Structure):
     _fields_ = [("ninput", C.c_int), ("nhidden", C.c_int), ("nclasses", C.c_int), ("device", C.c_int)]
 
 
+class CfgEx(C.Structure):
+    _fields_ = [("ninput", C.c_int), ("noutput", C.c_int), ("device", C.c_int), ("nblocks", C.c_int),
+                ("nhidden", C.c_int * 2), ("direction", C.c_int * 2), ("cell", C.c_int), ("output", C.c_int)]
+
+
+CELLS = {"NPLSTM": 0, "LINNPLSTM": 1, "RELUTANHNPLSTM": 2, "RELUNPLSTM": 3, "RELU2NPLSTM": 4}
+OUTPUTS = {"SoftmaxLayer": 0, "SigmoidLayer": 1, "LinearLayer": 2, "TanhLayer": 3, "ReluLayer": 4, None: -1}
+# prefab name (clstm_prefab.cc:152-160) -> (nblocks, directions)
+PREFABS = {"lstm1": (1, (0, 0)), "revlstm1": (1, (1, 0)), "bidi": (1, (2, 0)), "bidi0": (1, (2, 0)), "bidi2": (2, (2, 2))}
+
+
 # every symbol include/clstm_b200.h declares: (restype, argtypes)
 EXPORTS = {
     "clstm_b200_create": (C.c_int, [C.POINTER(Cfg), C.POINTER(C.c_void_p)]),
+    "clstm_b200_create_ex": (C.c_int, [C.POINTER(CfgEx), C.POINTER(C.c_void_p)]),
     "clstm_b200_destroy": (None, [C.c_void_p]),
     "clstm_b200_nparams": (C.c_size_t, [C.c_void_p]),
     "clstm_b200_set_params": (C.c_int, [C.c_void_p, f32p, C.c_size_t]),
@@ -119,12 +131,22 @@ def pinned_array(shape, dtype):
 class Net:
     """Device-resident bidi net: Stacked{Parallel{NPLSTM, Reversed{NPLSTM}}, SoftmaxLayer}."""
 
-    def __init__(self, ninput, nhidden, nclasses, device=0):
+    def __init__(self, ninput, nhidden, nclasses, device=0, prefab="bidi", nhidden2=0, cell="NPLSTM",
+                 output="SoftmaxLayer"):
         L = lib()
         self.ni, self.nh, self.nc = ninput, nhidden, nclasses
-        cfg = Cfg(ninput, nhidden, nclasses, device)
         h = C.c_void_p()
-        _chk(L.clstm_b200_create(C.byref(cfg), C.byref(h)))
+        if prefab == "bidi" and cell == "NPLSTM" and output == "SoftmaxLayer":
+            cfg = Cfg(ninput, nhidden, nclasses, device)
+            _chk(L.clstm_b200_create(C.byref(cfg), C.byref(h)))
+        else:   # the other prefabs / layer variants of clstm_prefab.cc, clstm.cc:382-389, 655-668
+            nblocks, dirs = PREFABS[prefab]
+            if prefab == "bidi0":
+                output = None
+                self.nc = 2 * nhidden
+            ex = CfgEx(ninput, nclasses, device, nblocks, (C.c_int * 2)(nhidden, nhidden2), (C.c_int * 2)(*dirs),
+                       CELLS[cell], OUTPUTS[output])
+            _chk(L.clstm_b200_create_ex(C.byref(ex), C.byref(h)))
         self.h = h
         self.nparams = L.clstm_b200_nparams(h)
         self.N = 0

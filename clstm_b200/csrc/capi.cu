@@ -105,14 +105,28 @@ struct clstm_b200_net {
   float* ws2 = nullptr;                    // its private split-K workspace
   size_t ws2_floats = 0;
 
-  // ---- parameters, DEVICE layout: [dir0: Wx(4no x ni) | bias(4no) | R(4no x no)] [dir1: ...] [W1(nc x 2no) | b1(nc)]
-  // rows of the LSTM blocks are gate-interleaved: r = 4*j + g, g: 0=gi(WGI) 1=gf(WGF) 2=go(WGO) 3=ci(WCI)
+  // ---- topology: nblk stacked recurrent blocks (each 1 or 2 LSTMs over the same input), then an output layer.
+  //   bidi   : 1 block {fwd, reversed}          lstm1 : 1 block {fwd}        revlstm1 : 1 block {reversed}
+  //   bidi2  : 2 blocks {fwd, reversed}         bidi0 : 1 block, no output layer          (clstm_prefab.cc:22-129)
+  struct Block {
+    int ni = 0, no = 0, ndir = 2, d0 = 0;  // directions d0 .. d0+ndir-1 (index 0: forward in time, 1: reversed)
+    int hoff[2] = {0, 0};                  // column offset of direction d inside H / dH rows
+    size_t oWx[2] = {}, oB[2] = {}, oR[2] = {};
+    float *Rt[2] = {}, *WxT[2] = {};       // derived layouts, refreshed by prepare_weights(): R^T, Wx^T [ni][4no]
+    float *XP[2] = {}, *G[2] = {}, *C[2] = {}, *Hprev[2] = {}, *DG[2] = {};
+    float *H = nullptr, *dH = nullptr;     // [N][ndir*no]
+    int nout() const { return ndir * no; }
+  } blk[2];
+  int nblk = 1;
+  int cell = 0;                            // LSTM variant, see kernels.h
+  int out_kind = 0;                        // 0 SoftmaxLayer, 1 SigmoidLayer, 2 LinearLayer, 3 TanhLayer, 4 ReluLayer, -1 none
+  int nfeat = 0;                           // inputs of the output layer = outputs of the last block
+  // ---- parameters, DEVICE layout per block and direction [Wx(4no x ni) | bias(4no) | R(4no x no)], then [W1(nc x nfeat) | b1(nc)]
+  // rows of the LSTM matrices are gate-interleaved: r = 4*j + g, g: 0=gi(WGI) 1=gf(WGF) 2=go(WGO) 3=ci(WCI)
   size_t P = 0;
-  size_t oWx[2], oB[2], oR[2], oW1, oB1;
+  size_t oW1 = 0, oB1 = 0;
   float *v = nullptr, *d = nullptr, *g = nullptr;   // weights, Params.d (derivative+momentum), this step's derivatives
-  float* Rt[2] = {nullptr, nullptr};       // derived layouts, refreshed by prepare_weights(): R^T,
-  float* WxT[2] = {nullptr, nullptr};      // Wx^T [ni][4no],
-  float* W1T = nullptr;                    // W1^T [2no][nc]
+  float* W1T = nullptr;                    // W1^T [nfeat][nc]
   bool g_pending = false;
   bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
 
@@ -128,8 +142,7 @@ struct clstm_b200_net {
   bool consumed_recorded = false, prefetched = false;
   int dec_B = 0;                           // lines of the batch the decode buffers refer to
   long long capLat = 0;
-  float *x = nullptr, *XP[2] = {}, *G[2] = {}, *C[2] = {}, *H = nullptr, *Hprev[2] = {}, *out = nullptr,
-        *aligned = nullptr, *delta = nullptr, *dH = nullptr, *DG[2] = {}, *dx = nullptr;
+  float *x = nullptr, *out = nullptr, *aligned = nullptr, *delta = nullptr, *dx = nullptr;
   float *lm = nullptr, *lr = nullptr, *rl = nullptr;
   int* meta = nullptr;          // device: T | off | L | lab_off | order | st_off | labels
   int* tiles = nullptr;         // device: tile_line | tile_t0
@@ -236,49 +249,50 @@ int gate_ref_index(int g) {  // position of gate g's matrix inside a direction's
   return m[g];
 }
 
-// reference flat (walk_params order, col-major, bias column first) <-> device layout
-void ref_to_dev(const clstm_b200_net* n, const float* ref, float* dev) {
-  const int ni = n->ni, no = n->no, nc = n->nc, nf = n->nf;
-  const size_t msz = (size_t)no * (1 + nf);
-  for (int d = 0; d < 2; d++) {
-    const float* blk = ref + (size_t)d * 4 * msz;
-    for (int g = 0; g < 4; g++) {
-      const float* W = blk + (size_t)gate_ref_index(g) * msz;
-      for (int j = 0; j < no; j++) {
-        const int r = 4 * j + g;
-        dev[n->oB[d] + r] = W[j];
-        for (int i = 0; i < ni; i++) dev[n->oWx[d] + (size_t)r * ni + i] = W[j + (size_t)(1 + i) * no];
-        for (int k = 0; k < no; k++) dev[n->oR[d] + (size_t)r * no + k] = W[j + (size_t)(1 + ni + k) * no];
+// reference flat (walk_params order: blocks in stacking order, forward LSTM before the reversed one, matrices sorted by
+// name WCI,WGF,WGI,WGO, each col-major with the bias column first; then W1) <-> device layout
+template <bool TO_DEV, class A, class B>
+void convert_params(const clstm_b200_net* n, A* ref, B* dev) {
+  size_t pos = 0;
+  for (int k = 0; k < n->nblk; k++) {
+    const auto& bk = n->blk[k];
+    const int ni = bk.ni, no = bk.no, nf = ni + no;
+    const size_t msz = (size_t)no * (1 + nf);
+    for (int d = bk.d0; d < bk.d0 + bk.ndir; d++) {
+      for (int g = 0; g < 4; g++) {
+        A* W = ref + pos + (size_t)gate_ref_index(g) * msz;
+        for (int j = 0; j < no; j++) {
+          const int r = 4 * j + g;
+          if (TO_DEV) {
+            const_cast<float&>(dev[bk.oB[d] + r]) = W[j];
+            for (int i = 0; i < ni; i++) const_cast<float&>(dev[bk.oWx[d] + (size_t)r * ni + i]) = W[j + (size_t)(1 + i) * no];
+            for (int q = 0; q < no; q++) const_cast<float&>(dev[bk.oR[d] + (size_t)r * no + q]) = W[j + (size_t)(1 + ni + q) * no];
+          } else {
+            const_cast<float&>(W[j]) = dev[bk.oB[d] + r];
+            for (int i = 0; i < ni; i++) const_cast<float&>(W[j + (size_t)(1 + i) * no]) = dev[bk.oWx[d] + (size_t)r * ni + i];
+            for (int q = 0; q < no; q++) const_cast<float&>(W[j + (size_t)(1 + ni + q) * no]) = dev[bk.oR[d] + (size_t)r * no + q];
+          }
+        }
+      }
+      pos += 4 * msz;
+    }
+  }
+  if (n->out_kind >= 0) {
+    const int nc = n->nc, nfeat = n->nfeat;
+    A* W1 = ref + pos;
+    for (int c = 0; c < nc; c++) {
+      if (TO_DEV) {
+        const_cast<float&>(dev[n->oB1 + c]) = W1[c];
+        for (int q = 0; q < nfeat; q++) const_cast<float&>(dev[n->oW1 + (size_t)c * nfeat + q]) = W1[c + (size_t)(1 + q) * nc];
+      } else {
+        const_cast<float&>(W1[c]) = dev[n->oB1 + c];
+        for (int q = 0; q < nfeat; q++) const_cast<float&>(W1[c + (size_t)(1 + q) * nc]) = dev[n->oW1 + (size_t)c * nfeat + q];
       }
     }
   }
-  const float* W1 = ref + 8 * msz;
-  for (int c = 0; c < nc; c++) {
-    dev[n->oB1 + c] = W1[c];
-    for (int k = 0; k < 2 * no; k++) dev[n->oW1 + (size_t)c * 2 * no + k] = W1[c + (size_t)(1 + k) * nc];
-  }
 }
-void dev_to_ref(const clstm_b200_net* n, const float* dev, float* ref) {
-  const int ni = n->ni, no = n->no, nc = n->nc, nf = n->nf;
-  const size_t msz = (size_t)no * (1 + nf);
-  for (int d = 0; d < 2; d++) {
-    float* blk = ref + (size_t)d * 4 * msz;
-    for (int g = 0; g < 4; g++) {
-      float* W = blk + (size_t)gate_ref_index(g) * msz;
-      for (int j = 0; j < no; j++) {
-        const int r = 4 * j + g;
-        W[j] = dev[n->oB[d] + r];
-        for (int i = 0; i < ni; i++) W[j + (size_t)(1 + i) * no] = dev[n->oWx[d] + (size_t)r * ni + i];
-        for (int k = 0; k < no; k++) W[j + (size_t)(1 + ni + k) * no] = dev[n->oR[d] + (size_t)r * no + k];
-      }
-    }
-  }
-  float* W1 = ref + 8 * msz;
-  for (int c = 0; c < nc; c++) {
-    W1[c] = dev[n->oB1 + c];
-    for (int k = 0; k < 2 * no; k++) W1[c + (size_t)(1 + k) * nc] = dev[n->oW1 + (size_t)c * 2 * no + k];
-  }
-}
+void ref_to_dev(const clstm_b200_net* n, const float* ref, float* dev) { convert_params<true>(n, ref, dev); }
+void dev_to_ref(const clstm_b200_net* n, const float* dev, float* ref) { convert_params<false>(n, ref, dev); }
 
 void swap_sets(clstm_b200_net* n) {
   auto& o = n->spare;
@@ -294,12 +308,13 @@ void swap_sets(clstm_b200_net* n) {
   std::swap(n->have_batch, o.have_batch); std::swap(n->have_labels, o.have_labels); std::swap(n->raw_targets, o.raw_targets);
 }
 void free_batch(clstm_b200_net* n) {
-  dev_free(n->H); dev_free(n->out); dev_free(n->aligned); dev_free(n->delta); dev_free(n->dH);
-  dev_free(n->dx);
-  for (int d = 0; d < 2; d++) {
-    dev_free(n->XP[d]); dev_free(n->G[d]); dev_free(n->C[d]); dev_free(n->Hprev[d]); dev_free(n->DG[d]);
-    dev_free(n->amax[d]); dev_free(n->amaxv[d]);
+  dev_free(n->out); dev_free(n->aligned); dev_free(n->delta); dev_free(n->dx);
+  for (int k = 0; k < n->nblk; k++) {
+    auto& bk = n->blk[k];
+    dev_free(bk.H); dev_free(bk.dH);
+    for (int d = 0; d < 2; d++) { dev_free(bk.XP[d]); dev_free(bk.G[d]); dev_free(bk.C[d]); dev_free(bk.Hprev[d]); dev_free(bk.DG[d]); }
   }
+  for (int w = 0; w < 2; w++) { dev_free(n->amax[w]); dev_free(n->amaxv[w]); }
 }
 
 int ensure_columns(clstm_b200_net* n, int N) {
@@ -307,21 +322,26 @@ int ensure_columns(clstm_b200_net* n, int N) {
   CU(cudaStreamSynchronize(n->st));
   free_batch(n);
   const size_t cap = (size_t)N + N / 8 + 64;
-  const int no = n->no, ni = n->ni, nc = n->nc;
-  TRY(dev_alloc(&n->H, cap * 2 * no));
+  const int ni = n->ni, nc = n->nc;
   TRY(dev_alloc(&n->out, cap * nc));
   TRY(dev_alloc(&n->aligned, cap * nc));
   TRY(dev_alloc(&n->delta, cap * nc));
-  TRY(dev_alloc(&n->dH, cap * 2 * no));
   TRY(dev_alloc(&n->dx, cap * ni));
-  for (int d = 0; d < 2; d++) {
-    TRY(dev_alloc(&n->XP[d], cap * 4 * no));
-    TRY(dev_alloc(&n->G[d], cap * 4 * no));
-    TRY(dev_alloc(&n->C[d], cap * no));
-    TRY(dev_alloc(&n->Hprev[d], cap * no));
-    TRY(dev_alloc(&n->DG[d], cap * 4 * no));
-    TRY(dev_alloc(&n->amax[d], cap));
-    TRY(dev_alloc(&n->amaxv[d], cap));
+  for (int k = 0; k < n->nblk; k++) {
+    auto& bk = n->blk[k];
+    TRY(dev_alloc(&bk.H, cap * bk.nout()));
+    TRY(dev_alloc(&bk.dH, cap * bk.nout()));
+    for (int d = bk.d0; d < bk.d0 + bk.ndir; d++) {
+      TRY(dev_alloc(&bk.XP[d], cap * 4 * bk.no));
+      TRY(dev_alloc(&bk.G[d], cap * 4 * bk.no));
+      TRY(dev_alloc(&bk.C[d], cap * bk.no));
+      TRY(dev_alloc(&bk.Hprev[d], cap * bk.no));
+      TRY(dev_alloc(&bk.DG[d], cap * 4 * bk.no));
+    }
+  }
+  for (int w = 0; w < 2; w++) {
+    TRY(dev_alloc(&n->amax[w], cap));
+    TRY(dev_alloc(&n->amaxv[w], cap));
   }
   n->capN = (int)cap;
   return 0;
@@ -414,7 +434,8 @@ int stage_lines(clstm_b200_net* n, const int* T, int B, const int* labels, const
     if (T[b] <= 0) return fail("line %d has non-positive length %d", b, T[b]);
     N += T[b];
   }
-  if (N > 0x7fffffff / (4LL * std::max(n->no, 16))) return fail("batch too large: %lld columns", N);
+  const int widest = std::max(std::max(n->blk[0].no, n->nblk > 1 ? n->blk[1].no : 0), 16);
+  if (N > 0x7fffffff / (4LL * widest)) return fail("batch too large: %lld columns", N);
   int nlab = 0;
   if (L) for (int b = 0; b < B; b++) {
     if (L[b] < 0) return fail("line %d has negative transcript length", b);
@@ -524,14 +545,16 @@ int check_launch(const char* what) {
 
 void prepare_weights(clstm_b200_net* n) {   // after every change of v
   TransposeJobs j{};
-  for (int d = 0; d < 2; d++) {
-    j.job[j.n++] = {n->v + n->oR[d], n->Rt[d], 4 * n->no, n->no};
-    j.job[j.n++] = {n->v + n->oWx[d], n->WxT[d], 4 * n->no, n->ni};
+  for (int k = 0; k < n->nblk; k++) {
+    auto& bk = n->blk[k];
+    for (int d = bk.d0; d < bk.d0 + bk.ndir; d++) {
+      j.job[j.n++] = {n->v + bk.oR[d], bk.Rt[d], 4 * bk.no, bk.no};
+      j.job[j.n++] = {n->v + bk.oWx[d], bk.WxT[d], 4 * bk.no, bk.ni};
+    }
   }
-  j.job[j.n++] = {n->v + n->oW1, n->W1T, n->nc, 2 * n->no};
+  if (n->out_kind >= 0) j.job[j.n++] = {n->v + n->oW1, n->W1T, n->nc, n->nfeat};
   transpose_batch(n->st, j);
 }
-
 // ------------------------------------------------------------------------------------------------ dense products
 bool vec_ok(const float* p, long long ld) { return (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0); }
 
@@ -582,31 +605,46 @@ int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, con
 }
 
 // ------------------------------------------------------------------------------------------------ device passes
+const float* block_input(const clstm_b200_net* n, int k) { return k == 0 ? n->x : n->blk[k - 1].H; }
 int run_forward(clstm_b200_net* n) {
   const Lines& ln = n->ln;
-  const int N = ln.N, ni = n->ni, no = n->no, nc = n->nc;
-  {
-    Scope s(n, PH_XPROJ);
-    for (int d = 0; d < 2; d++)
-      s.launches(dense_nt(n, N, 4 * no, ni, n->x, ni, n->v + n->oWx[d], ni, false, n->XP[d], 4 * no, n->v + n->oB[d], 0.f));
-  }
-  {
-    Scope s(n, PH_LSTM_FWD);
-    LstmFwdArgs a;
-    a.no = no;
-    for (int d = 0; d < 2; d++) {
-      a.XP[d] = n->XP[d]; a.R[d] = n->v + n->oR[d]; a.Rt[d] = n->Rt[d];
-      a.G[d] = n->G[d]; a.C[d] = n->C[d]; a.Hprev[d] = n->Hprev[d];
+  const int N = ln.N, nc = n->nc;
+  for (int k = 0; k < n->nblk; k++) {
+    auto& bk = n->blk[k];
+    const float* in = block_input(n, k);
+    {
+      Scope s(n, PH_XPROJ);
+      for (int d = bk.d0; d < bk.d0 + bk.ndir; d++)
+        s.launches(dense_nt(n, N, 4 * bk.no, bk.ni, in, bk.ni, n->v + bk.oWx[d], bk.ni, false, bk.XP[d], 4 * bk.no, n->v + bk.oB[d], 0.f));
     }
-    a.H = n->H;
-    n->variant = lstm_forward(n->st, ln, a);
-    s.launches(1);
+    {
+      Scope s(n, PH_LSTM_FWD);
+      LstmFwdArgs a;
+      a.no = bk.no; a.d0 = bk.d0; a.ndir = bk.ndir; a.hstride = bk.nout(); a.cell = n->cell;
+      for (int d = 0; d < 2; d++) {
+        a.hoff[d] = bk.hoff[d];
+        a.XP[d] = bk.XP[d]; a.R[d] = n->v + bk.oR[d]; a.Rt[d] = bk.Rt[d];
+        a.G[d] = bk.G[d]; a.C[d] = bk.C[d]; a.Hprev[d] = bk.Hprev[d];
+      }
+      a.H = bk.H;
+      const char* var = lstm_forward(n->st, ln, a);
+      if (k == 0) n->variant = var;
+      s.launches(1);
+    }
   }
   {
     Scope s(n, PH_SOFTMAX_FWD);
-    s.launches(dense_nt(n, N, nc, 2 * no, n->H, 2 * no, n->v + n->oW1, 2 * no, false, n->out, nc, n->v + n->oB1, 0.f));
-    softmax_rows(n->st, n->out, N, nc, n->amax[0], n->amaxv[0]);
-    s.launches(1);
+    const auto& last = n->blk[n->nblk - 1];
+    if (n->out_kind < 0) {          // bidi0: the block's outputs are the network's outputs
+      CU(cudaMemcpyAsync(n->out, last.H, (size_t)N * nc * sizeof(float), cudaMemcpyDeviceToDevice, n->st));
+      full_rows(n->st, n->out, N, nc, 2, n->amax[0], n->amaxv[0]);
+      s.launches(1);
+    } else {
+      s.launches(dense_nt(n, N, nc, n->nfeat, last.H, n->nfeat, n->v + n->oW1, n->nfeat, false, n->out, nc, n->v + n->oB1, 0.f));
+      if (n->out_kind == 0) softmax_rows(n->st, n->out, N, nc, n->amax[0], n->amaxv[0]);
+      else full_rows(n->st, n->out, N, nc, n->out_kind, n->amax[0], n->amaxv[0]);
+      s.launches(1);
+    }
   }
   TRY(check_launch("forward"));
   n->have_forward = true;
@@ -615,6 +653,7 @@ int run_forward(clstm_b200_net* n) {
 }
 
 int run_ctc(clstm_b200_net* n) {
+  if (n->out_kind != 0) return fail("CTC alignment needs a SoftmaxLayer output (this net has output kind %d)", n->out_kind);
   Scope s(n, PH_CTC);
   CtcArgs a;
   a.nc = n->nc; a.out = n->out; a.aligned = n->aligned; a.delta = n->delta;
@@ -634,64 +673,81 @@ void join_dx(clstm_b200_net* n) {
 }
 int run_backward(clstm_b200_net* n, bool defer_dx = false) {
   const Lines& ln = n->ln;
-  const int N = ln.N, ni = n->ni, no = n->no, nc = n->nc;
+  const int N = ln.N, nc = n->nc, nfeat = n->nfeat;
+  auto& last = n->blk[n->nblk - 1];
   {
-    Scope s(n, PH_SOFTMAX_BWD);   // backward_softmax clstm_compute.cc:346-356
-    if (n->use_tc) s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->W1T, nc, false, n->dH, 2 * no, nullptr, 0.f));
-    else s.launches(dense_nt(n, N, 2 * no, nc, n->delta, nc, n->v + n->oW1, 2 * no, true, n->dH, 2 * no, nullptr, 0.f));
-    // the W1 derivative product needs only delta and H: run it on the side stream, concurrently with the backward
-    // recurrence (which occupies 2B of the 148 SMs), and join before anything consumes g
-    cudaEventRecord(n->ev_fork, n->st);
-    cudaStreamWaitEvent(n->st2, n->ev_fork, 0);
-    s.launches(dense_tn(n, nc, N, n->delta, nc, n->H, 2 * no, nullptr, 0, n->g + n->oW1, nullptr, n->g + n->oB1, true));
-    cudaEventRecord(n->ev_join, n->st2);
-  }
-  {
-    Scope s(n, PH_LSTM_BWD);
-    LstmBwdArgs a;
-    a.no = no; a.dH = n->dH;
-    for (int d = 0; d < 2; d++) { a.R[d] = n->v + n->oR[d]; a.G[d] = n->G[d]; a.C[d] = n->C[d]; a.DG[d] = n->DG[d]; }
-    lstm_backward(n->st, ln, a);
-    s.launches(1);
-  }
-  cudaStream_t dxs = n->st;
-  if (defer_dx && n->use_tc && !n->prof) {   // (phase profiling keeps everything on one stream)
-    cudaEventRecord(n->ev_fork2, n->st);
-    cudaStreamWaitEvent(n->st2, n->ev_fork2, 0);
-    dxs = n->st2;
-  }
-  {
-    Scope s(n, PH_WGRAD);   // W.d += delta * src^T over all columns (backward_lin1 clstm_compute.cc:297-298)
-    for (int d = 0; d < 2; d++)
-      s.launches(dense_tn(n, 4 * no, N, n->DG[d], 4 * no, n->x, ni, n->Hprev[d], no, n->g + n->oWx[d], n->g + n->oR[d],
-                          n->g + n->oB[d]));
-  }
-  {
-    Scope s(n, PH_DX);      // inputs.d = sum over both directions of Wx^T delta (clstm.cc:537-541)
-    if (n->use_tc) {   // one product over both directions: K = [DG0 | DG1], B = [Wx0 ; Wx1]
-      TcArgs g{};
-      g.M = N; g.N = ni;
-      g.a_mode = 0; g.b_mode = 0; g.k_nseg = 2;
-      g.a_vec = 1; g.b_vec = 1;
-      for (int d = 0; d < 2; d++) {
-        g.a_k[d] = {n->DG[d], 4 * no, 4 * no};
-        g.b_k[d] = {n->WxT[d], 4 * no, 4 * no};         // Wx^T [ni][4no]: K-contiguous B operand
-        g.k_len[d] = 4 * no;
-        g.a_vec = g.a_vec && vec_ok(n->DG[d], 4 * no);
-        g.b_vec = g.b_vec && vec_ok(n->WxT[d], 4 * no);
-      }
-      g.C = n->dx; g.ldc = ni; g.bias = nullptr; g.beta = 0.f;
-      s.launches(gemm_tc(dxs, g, nullptr, n->num_sms));
-      if (dxs != n->st) {
-        cudaEventRecord(n->ev_dx, n->st2);
-        n->dx_pending = true;
-      }
+    Scope s(n, PH_SOFTMAX_BWD);   // backward_softmax clstm_compute.cc:346-356 / backward_full :316-320
+    if (n->out_kind < 0) {
+      CU(cudaMemcpyAsync(last.dH, n->delta, (size_t)N * nc * sizeof(float), cudaMemcpyDeviceToDevice, n->st));
     } else {
-      for (int d = 0; d < 2; d++)
-        s.launches(dense_nt(n, N, ni, 4 * no, n->DG[d], 4 * no, n->v + n->oWx[d], ni, true, n->dx, ni, nullptr, d ? 1.f : 0.f));
+      if (n->out_kind > 0) { full_backward(n->st, n->delta, n->out, (size_t)N * nc, n->out_kind); s.launches(1); }
+      if (n->use_tc) s.launches(dense_nt(n, N, nfeat, nc, n->delta, nc, n->W1T, nc, false, last.dH, nfeat, nullptr, 0.f));
+      else s.launches(dense_nt(n, N, nfeat, nc, n->delta, nc, n->v + n->oW1, nfeat, true, last.dH, nfeat, nullptr, 0.f));
+      // the W1 derivative product needs only delta and H: run it on the side stream, concurrently with the backward
+      // recurrence (which occupies 2B of the 148 SMs), and join before anything consumes g
+      cudaEventRecord(n->ev_fork, n->st);
+      cudaStreamWaitEvent(n->st2, n->ev_fork, 0);
+      s.launches(dense_tn(n, nc, N, n->delta, nc, last.H, nfeat, nullptr, 0, n->g + n->oW1, nullptr, n->g + n->oB1, true));
+      cudaEventRecord(n->ev_join, n->st2);
     }
   }
-  cudaStreamWaitEvent(n->st, n->ev_join, 0);
+  for (int k = n->nblk - 1; k >= 0; k--) {
+    auto& bk = n->blk[k];
+    const int ni = bk.ni, no = bk.no;
+    {
+      Scope s(n, PH_LSTM_BWD);
+      LstmBwdArgs a;
+      a.no = no; a.d0 = bk.d0; a.ndir = bk.ndir; a.hstride = bk.nout(); a.cell = n->cell; a.dH = bk.dH;
+      for (int d = 0; d < 2; d++) {
+        a.hoff[d] = bk.hoff[d];
+        a.R[d] = n->v + bk.oR[d]; a.G[d] = bk.G[d]; a.C[d] = bk.C[d]; a.DG[d] = bk.DG[d];
+      }
+      lstm_backward(n->st, ln, a);
+      s.launches(1);
+    }
+    cudaStream_t dxs = n->st;
+    if (k == 0 && defer_dx && n->use_tc && !n->prof) {   // (phase profiling keeps everything on one stream)
+      cudaEventRecord(n->ev_fork2, n->st);
+      cudaStreamWaitEvent(n->st2, n->ev_fork2, 0);
+      dxs = n->st2;
+    }
+    {
+      Scope s(n, PH_WGRAD);   // W.d += delta * src^T over all columns (backward_lin1 clstm_compute.cc:297-298)
+      for (int d = bk.d0; d < bk.d0 + bk.ndir; d++)
+        s.launches(dense_tn(n, 4 * no, N, bk.DG[d], 4 * no, block_input(n, k), ni, bk.Hprev[d], no, n->g + bk.oWx[d],
+                            n->g + bk.oR[d], n->g + bk.oB[d]));
+    }
+    {
+      Scope s(n, PH_DX);      // deltas of the block's input = sum over its directions of Wx^T delta (clstm.cc:537-541)
+      float* din = (k == 0) ? n->dx : n->blk[k - 1].dH;
+      if (n->use_tc) {   // one product over the directions: K = [DG(d0) | DG(d0+1)], B = [Wx ; Wx']
+        TcArgs g{};
+        g.M = N; g.N = ni;
+        g.a_mode = 0; g.b_mode = 0; g.k_nseg = bk.ndir;
+        g.a_vec = 1; g.b_vec = 1;
+        for (int q = 0; q < bk.ndir; q++) {
+          const int d = bk.d0 + q;
+          g.a_k[q] = {bk.DG[d], 4 * no, 4 * no};
+          g.b_k[q] = {bk.WxT[d], 4 * no, 4 * no};       // Wx^T [ni][4no]: K-contiguous B operand
+          g.k_len[q] = 4 * no;
+          g.a_vec = g.a_vec && vec_ok(bk.DG[d], 4 * no);
+          g.b_vec = g.b_vec && vec_ok(bk.WxT[d], 4 * no);
+        }
+        g.C = din; g.ldc = ni; g.bias = nullptr; g.beta = 0.f;
+        s.launches(gemm_tc(dxs, g, nullptr, n->num_sms));
+        if (dxs != n->st) {
+          cudaEventRecord(n->ev_dx, n->st2);
+          n->dx_pending = true;
+        }
+      } else {
+        for (int q = 0; q < bk.ndir; q++) {
+          const int d = bk.d0 + q;
+          s.launches(dense_nt(n, N, ni, 4 * no, bk.DG[d], 4 * no, n->v + bk.oWx[d], ni, true, din, ni, nullptr, q ? 1.f : 0.f));
+        }
+      }
+    }
+  }
+  if (n->out_kind >= 0) cudaStreamWaitEvent(n->st, n->ev_join, 0);
   TRY(check_launch("backward"));
   n->g_pending = true;
   return 0;
@@ -786,9 +842,28 @@ const char* clstm_b200_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPh
 
 int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   if (!cfg || !out) return fail("null argument");
+  clstm_b200_cfg_ex ex;
+  memset(&ex, 0, sizeof ex);
+  ex.ninput = cfg->ninput; ex.noutput = cfg->nclasses; ex.device = cfg->device;
+  ex.nblocks = 1; ex.nhidden[0] = cfg->nhidden; ex.direction[0] = 2; ex.cell = 0; ex.output = 0;
+  return clstm_b200_create_ex(&ex, out);
+}
+
+int clstm_b200_create_ex(const clstm_b200_cfg_ex* cfg, clstm_b200_net** out) {
+  if (!cfg || !out) return fail("null argument");
   *out = nullptr;
-  if (cfg->ninput <= 0 || cfg->nhidden <= 0 || cfg->nclasses < 2) return fail("bad dimensions (Softmax requires nclasses>=2, clstm.cc:400)");
-  if (cfg->nclasses > kCtcMaxClasses) return fail("nclasses %d > %d not supported", cfg->nclasses, kCtcMaxClasses);
+  if (cfg->nblocks < 1 || cfg->nblocks > 2) return fail("nblocks must be 1 or 2 (got %d)", cfg->nblocks);
+  if (cfg->cell < 0 || cfg->cell > 4) return fail("unknown LSTM cell variant %d", cfg->cell);
+  if (cfg->output < -1 || cfg->output > 4) return fail("unknown output layer kind %d", cfg->output);
+  for (int k = 0; k < cfg->nblocks; k++) {
+    if (cfg->nhidden[k] <= 0) return fail("bad dimensions (nhidden[%d] = %d)", k, cfg->nhidden[k]);
+    if (cfg->direction[k] < 0 || cfg->direction[k] > 2) return fail("direction[%d] must be 0 (forward), 1 (reversed) or 2 (both)", k);
+  }
+  const int last_out = cfg->nhidden[cfg->nblocks - 1] * (cfg->direction[cfg->nblocks - 1] == 2 ? 2 : 1);
+  const int nclasses = cfg->output < 0 ? last_out : cfg->noutput;
+  if (cfg->ninput <= 0 || nclasses < 1) return fail("bad dimensions");
+  if (cfg->output == 0 && nclasses < 2) return fail("bad dimensions (Softmax requires nclasses>=2, clstm.cc:400)");
+  if (nclasses > kCtcMaxClasses) return fail("nclasses %d > %d not supported", nclasses, kCtcMaxClasses);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -799,18 +874,31 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   CU(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail("device %d is sm_%d%d; this library contains sm_100a code only", cfg->device, prop.major, prop.minor);
   auto* n = new clstm_b200_net;
-  n->cfg = *cfg;
-  n->ni = cfg->ninput; n->no = cfg->nhidden; n->nc = cfg->nclasses; n->nf = n->ni + n->no;
+  n->cfg.ninput = cfg->ninput; n->cfg.nhidden = cfg->nhidden[0]; n->cfg.nclasses = nclasses; n->cfg.device = cfg->device;
+  n->ni = cfg->ninput; n->no = cfg->nhidden[0]; n->nc = nclasses; n->nf = n->ni + n->no;
+  n->nblk = cfg->nblocks; n->cell = cfg->cell; n->out_kind = cfg->output;
   n->num_sms = prop.multiProcessorCount;
-  const int ni = n->ni, no = n->no, nc = n->nc;
+  const int nc = n->nc;
   size_t o = 0;
-  for (int d = 0; d < 2; d++) {
-    n->oWx[d] = o; o += (size_t)4 * no * ni;
-    n->oB[d] = o;  o += (size_t)4 * no;
-    n->oR[d] = o;  o += (size_t)4 * no * no;
+  int nin = cfg->ninput;
+  for (int k = 0; k < n->nblk; k++) {
+    auto& bk = n->blk[k];
+    bk.ni = nin; bk.no = cfg->nhidden[k];
+    bk.ndir = cfg->direction[k] == 2 ? 2 : 1;
+    bk.d0 = cfg->direction[k] == 1 ? 1 : 0;
+    bk.hoff[0] = 0; bk.hoff[1] = (bk.ndir == 2) ? bk.no : 0;
+    for (int d = bk.d0; d < bk.d0 + bk.ndir; d++) {
+      bk.oWx[d] = o; o += (size_t)4 * bk.no * bk.ni;
+      bk.oB[d] = o;  o += (size_t)4 * bk.no;
+      bk.oR[d] = o;  o += (size_t)4 * bk.no * bk.no;
+    }
+    nin = bk.nout();
   }
-  n->oW1 = o; o += (size_t)nc * 2 * no;
-  n->oB1 = o; o += nc;
+  n->nfeat = nin;
+  if (n->out_kind >= 0) {
+    n->oW1 = o; o += (size_t)nc * n->nfeat;
+    n->oB1 = o; o += nc;
+  }
   n->P = o;
   if (cudaStreamCreateWithFlags(&n->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&n->st2, cudaStreamNonBlocking) != cudaSuccess ||
@@ -830,33 +918,38 @@ int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out) {
   rc |= dev_alloc(&n->v, n->P); rc |= dev_alloc(&n->d, n->P);
   rc |= dev_alloc(&n->comm_buf, n->P + kPeerHeaderFloats);
   n->g = n->comm_buf ? n->comm_buf + kPeerHeaderFloats : nullptr;
-  for (int d = 0; d < 2; d++) {
-    rc |= dev_alloc(&n->Rt[d], (size_t)4 * no * no);
-    rc |= dev_alloc(&n->WxT[d], (size_t)4 * no * ni);
+  size_t wmax = 0;                       // largest per-direction LSTM parameter block (split-K workspace sizing)
+  for (int k = 0; k < n->nblk; k++) {
+    auto& bk = n->blk[k];
+    wmax = std::max(wmax, (size_t)4 * bk.no * (1 + bk.ni + bk.no));
+    for (int d = bk.d0; d < bk.d0 + bk.ndir; d++) {
+      rc |= dev_alloc(&bk.Rt[d], (size_t)4 * bk.no * bk.no);
+      rc |= dev_alloc(&bk.WxT[d], (size_t)4 * bk.no * bk.ni);
+      if (!rc) {
+        cudaMemsetAsync(bk.Rt[d], 0, (size_t)4 * bk.no * bk.no * sizeof(float), n->st);
+        cudaMemsetAsync(bk.WxT[d], 0, (size_t)4 * bk.no * bk.ni * sizeof(float), n->st);
+      }
+    }
   }
-  rc |= dev_alloc(&n->W1T, (size_t)2 * no * nc);
+  rc |= dev_alloc(&n->W1T, (size_t)std::max(1, n->nfeat) * nc);
   rc |= dev_alloc(&n->status, 1);
   // split-K workspace: enough for ~2 waves of 64x64 tiles plus the largest derivative matrix a few times over
-  n->ws_floats = std::max<size_t>((size_t)4 * n->num_sms * 64 * 64, (size_t)40 * 4 * no * (1 + ni + no));
+  n->ws_floats = std::max<size_t>((size_t)4 * n->num_sms * 64 * 64, (size_t)40 * wmax);
   rc |= dev_alloc(&n->ws, n->ws_floats);
-  n->ws2_floats = (size_t)64 * nc * (2 * no + 1);
+  n->ws2_floats = (size_t)64 * nc * (n->nfeat + 1);
   rc |= dev_alloc(&n->ws2, n->ws2_floats);
   if (rc) { clstm_b200_destroy(n); return 1; }
   cudaMemsetAsync(n->v, 0, n->P * sizeof(float), n->st);
   cudaMemsetAsync(n->d, 0, n->P * sizeof(float), n->st);
   cudaMemsetAsync(n->comm_buf, 0, (n->P + kPeerHeaderFloats) * sizeof(float), n->st);
-  cudaMemsetAsync(n->Rt[0], 0, (size_t)4 * no * no * sizeof(float), n->st);
-  cudaMemsetAsync(n->Rt[1], 0, (size_t)4 * no * no * sizeof(float), n->st);
-  cudaMemsetAsync(n->WxT[0], 0, (size_t)4 * no * ni * sizeof(float), n->st);
-  cudaMemsetAsync(n->WxT[1], 0, (size_t)4 * no * ni * sizeof(float), n->st);
-  cudaMemsetAsync(n->W1T, 0, (size_t)2 * no * nc * sizeof(float), n->st);
+  cudaMemsetAsync(n->W1T, 0, (size_t)std::max(1, n->nfeat) * nc * sizeof(float), n->st);
   cudaMemsetAsync(n->status, 0, sizeof(int), n->st);
   {
     const char* e = getenv("CLSTM_B200_GEMM");   // "simt" selects the fp32 SIMT tiles (A/B testing against tcgen05)
     n->use_tc = !(e && strcmp(e, "simt") == 0);
   }
   if (lstm_configure() != 0 || ctc_configure() != 0 || gemm_tc_configure() != 0 || norm_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
-  n->variant = lstm_variant_for(no);
+  n->variant = n->cell == 0 ? lstm_variant_for(n->no) : "generic";
   if (cudaStreamSynchronize(n->st) != cudaSuccess) { clstm_b200_destroy(n); return fail("device initialisation failed"); }
   *out = n;
   return 0;
@@ -885,8 +978,9 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   if (n->stc) cudaStreamDestroy(n->stc);
   for (int r = 0; r < kMaxPeers; r++)
     if (n->peer_buf[r] && r != n->rank) cudaIpcCloseMemHandle(n->peer_buf[r]);
-  dev_free(n->v); dev_free(n->d); dev_free(n->comm_buf); n->g = nullptr; dev_free(n->Rt[0]); dev_free(n->Rt[1]);
-  dev_free(n->WxT[0]); dev_free(n->WxT[1]); dev_free(n->W1T);
+  dev_free(n->v); dev_free(n->d); dev_free(n->comm_buf); n->g = nullptr; dev_free(n->W1T);
+  for (int k = 0; k < 2; k++)
+    for (int d = 0; d < 2; d++) { dev_free(n->blk[k].Rt[d]); dev_free(n->blk[k].WxT[d]); }
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->status);
   dev_free(n->ws); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
   dev_free(n->n_raw); dev_free(n->n_tmp); dev_free(n->n_smooth); dev_free(n->n_a); dev_free(n->n_center);

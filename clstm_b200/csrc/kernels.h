@@ -60,22 +60,30 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms);
 int gemm_tc_configure();
 
 // ---------------------------------------------------------------- lstm.cu
+// One recurrent block = up to two LSTMs over the same input: slot index d = 0 runs forward in time, d = 1 reversed
+// (Reversed{}, clstm.cc:458-479).  A launch covers the `ndir` directions d0 .. d0+ndir-1 (bidirectional: d0=0, ndir=2;
+// lstm1: d0=0, ndir=1; revlstm1: d0=1, ndir=1).  H / dH rows hold the directions side by side: direction d occupies
+// columns [hoff[d], hoff[d]+no) of rows with `hstride` floats (Parallel's concat, clstm.cc:525-527).
+// cell: 0 NPLSTM (SIG,TANH,TANH), 1 LINNPLSTM (SIG,TANH,LIN), 2 RELUTANHNPLSTM (SIG,RELU,TANH), 3 RELUNPLSTM (SIG,RELU,LIN),
+// 4 RELU2NPLSTM (SIG,RELU,RELU)  (clstm.cc:655-668); the register / cluster kernels implement cell 0 only.
 struct LstmFwdArgs {
   int no;                 // hidden units per direction
+  int d0 = 0, ndir = 2, hstride = 0, hoff[2] = {0, 0}, cell = 0;
   const float* XP[2];     // [N][4no] input projection + bias, gate-interleaved rows r = 4*j + g
   const float* R[2];      // [4no][no] recurrent weights, row-major, rows gate-interleaved
   const float* Rt[2];     // [no][4no] transposed copy
   float* G[2];            // [N][4no] gate activations (gi,gf,go,ci)
   float* C[2];            // [N][no] cell states
-  float* H;               // [N][2no] outputs of both directions (Parallel concat)
+  float* H;               // [N][hstride] outputs of the block's directions (Parallel concat)
   float* Hprev[2];        // [N][no] output of the previous step in the direction's own time order
 };
 struct LstmBwdArgs {
   int no;
+  int d0 = 0, ndir = 2, hstride = 0, hoff[2] = {0, 0}, cell = 0;
   const float* R[2];
   const float* G[2];
   const float* C[2];
-  const float* dH;        // [N][2no] d(loss)/d(H) from the softmax layer
+  const float* dH;        // [N][hstride] d(loss)/d(H) from the layer above
   float* DG[2];           // [N][4no] deltas of the gate pre-activations
 };
 // returns the variant name actually used
@@ -132,6 +140,9 @@ constexpr int kCtcMaxClasses = 512;  // nclasses limit of the per-warp class acc
 // ---------------------------------------------------------------- misc.cu
 // out[n][:] = limexp(z[n][:]) / sum  in place (clstm_compute.cc:324-345)
 void softmax_rows(cudaStream_t st, float* z, int N, int nc, int* amax, float* amaxv);
+// Full<F> output layers (kind 1 SIG, 2 LIN, 3 TANH, 4 RELU): activation in place (+ per-column argmax) and delta <- f'(y) delta
+void full_rows(cudaStream_t st, float* z, int N, int nc, int kind, int* amax, float* amaxv);
+void full_backward(cudaStream_t st, float* delta, const float* y, size_t n, int kind);
 // d += g; g = 0; d = clamp(d); v += lr*d; d *= mom      (clstm_compute.cc:553-563)
 void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,
                 int fold_only);
@@ -149,9 +160,9 @@ struct PeerArgs {
 };
 void peer_allreduce_update(cudaStream_t st, const PeerArgs& a);   // 2 launches
 
-// dst[c][r] = src[r][c] for up to 6 small matrices in one launch (derived weight layouts)
+// dst[c][r] = src[r][c] for up to 10 small matrices in one launch (derived weight layouts)
 struct TransposeJob { const float* src; float* dst; int rows, cols; };
-struct TransposeJobs { TransposeJob job[6]; int n; };
+struct TransposeJobs { TransposeJob job[10]; int n; };
 void transpose_batch(cudaStream_t st, const TransposeJobs& jobs);
 // trivial_decode per line (ctc.cc:159-194) from the per-column argmax arrays written by softmax_rows / ctc_posterior
 void decode_lines(cudaStream_t st, const Lines& ln, const int* argmax_idx, const float* argmax_val, int* classes,

@@ -42,6 +42,13 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 // tanh via the same exponential: 2*sigmoid(2x) - 1 (abs. error ~1e-7, well inside the 1e-4 parity bar)
 __device__ __forceinline__ float tanhf_(float x) { return 2.0f / (1.0f + expf(-2.0f * x)) - 1.0f; }
 
+// cell variants (GenericNPLSTM<F,G,H>, clstm.cc:546-668): G = nonlinearity of the cell input ci, H = of the cell output
+__device__ __forceinline__ bool cell_g_relu(int cell) { return cell >= 2; }
+__device__ __forceinline__ int cell_h_kind(int cell) { return (cell == 0 || cell == 2) ? 2 : (cell == 4 ? 3 : 0); }   // 2 TANH, 3 RELU, 0 LIN
+__device__ __forceinline__ float cell_h(int kind, float c) { return kind == 2 ? tanhf_(c) : (kind == 3 ? fmaxf(c, 0.f) : c); }
+// derivative in terms of the OUTPUT y of the nonlinearity (backward_nonlin0, clstm_compute.cc:231-267)
+__device__ __forceinline__ float cell_h_deriv(int kind, float y) { return kind == 2 ? 1.f - y * y : (kind == 3 ? (y > 0.f ? 1.f : 0.f) : 1.f); }
+
 // --------------------------------------------------------------------------------------------------------
 // generic kernels
 // --------------------------------------------------------------------------------------------------------
@@ -52,8 +59,10 @@ __global__ void lstm_fwd_generic(Lines ln, LstmFwdArgs a) {
   float* h_s = sm;
   float* c_s = sm + no;
   float* act_s = sm + 2 * no;
-  const int b = ln.order[blockIdx.x], d = blockIdx.y;
+  const int b = ln.order[blockIdx.x], d = a.d0 + blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
+  const bool g_relu = cell_g_relu(a.cell);
+  const int hk = cell_h_kind(a.cell);
   const float* __restrict__ XP = a.XP[d];
   const float* __restrict__ Rt = a.Rt[d];
   float* __restrict__ G = a.G[d];
@@ -67,7 +76,7 @@ __global__ void lstm_fwd_generic(Lines ln, LstmFwdArgs a) {
     for (int r = threadIdx.x; r < no4; r += blockDim.x) {
       float acc = XP[n * no4 + r];
       for (int k = 0; k < no; k++) acc = fmaf(Rt[(size_t)k * no4 + r], h_s[k], acc);
-      const float act = ((r & 3) == 3) ? tanhf_(acc) : sigmoidf_(acc);
+      const float act = ((r & 3) == 3) ? (g_relu ? fmaxf(acc, 0.f) : tanhf_(acc)) : sigmoidf_(acc);
       act_s[r] = act;
       G[n * no4 + r] = act;
     }
@@ -77,10 +86,10 @@ __global__ void lstm_fwd_generic(Lines ln, LstmFwdArgs a) {
       float c = ci * gi;                       // forward_statemem clstm_compute.cc:504-508
       if (s > 0) c = fmaf(gf, c_s[j], c);
       c_s[j] = c;
-      const float hh = tanhf_(c) * go;         // forward_nonlingate :530-537
+      const float hh = cell_h(hk, c) * go;     // forward_nonlingate :530-537
       h_s[j] = hh;
       C[n * no + j] = c;
-      a.H[n * (2 * no) + d * no + j] = hh;
+      a.H[n * a.hstride + a.hoff[d] + j] = hh;
       if (s == 0) Hp[n * no + j] = 0.f;
       if (s + 1 < T) {
         const size_t n2 = (size_t)off + (d ? t - 1 : t + 1);
@@ -98,8 +107,10 @@ __global__ void lstm_bwd_generic(Lines ln, LstmBwdArgs a) {
   float* dg_s = sm;
   float* part_s = sm + no4;
   float* dcc_s = sm + 2 * no4;
-  const int b = ln.order[blockIdx.x], d = blockIdx.y;
+  const int b = ln.order[blockIdx.x], d = a.d0 + blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
+  const bool g_relu = cell_g_relu(a.cell);
+  const int hk = cell_h_kind(a.cell);
   const float* __restrict__ R = a.R[d];
   const float* __restrict__ G = a.G[d];
   const float* __restrict__ C = a.C[d];
@@ -112,14 +123,14 @@ __global__ void lstm_bwd_generic(Lines ln, LstmBwdArgs a) {
     const size_t n = (size_t)off + t;
     const size_t npv = (size_t)off + (d ? t + 1 : t - 1);  // column of forward step fs-1
     for (int j = threadIdx.x; j < no; j += blockDim.x) {
-      const float dh = a.dH[n * (2 * no) + d * no + j] +
+      const float dh = a.dH[n * a.hstride + a.hoff[d] + j] +
                        (part_s[j] + part_s[no + j] + part_s[2 * no + j] + part_s[3 * no + j]);
       const float4 g4 = *reinterpret_cast<const float4*>(G + n * no4 + 4 * j);
       const float gi = g4.x, gf = g4.y, go = g4.z, ci = g4.w;
       const float c = C[n * no + j];
-      const float th = tanhf_(c);                        // backward_nonlingate clstm_compute.cc:539-547
+      const float th = cell_h(hk, c);                    // backward_nonlingate clstm_compute.cc:539-547
       const float dgo = th * dh;
-      const float dc = dcc_s[j] + (1.f - th * th) * (go * dh);
+      const float dc = dcc_s[j] + cell_h_deriv(hk, th) * (go * dh);
       float dgf = 0.f, carry = 0.f;
       if (fs > 0) {                                      // backward_statemem :509-515
         dgf = dc * C[npv * no + j];
@@ -131,7 +142,7 @@ __global__ void lstm_bwd_generic(Lines ln, LstmBwdArgs a) {
       o.x = gi * (1.f - gi) * dgi;
       o.y = gf * (1.f - gf) * dgf;
       o.z = go * (1.f - go) * dgo;
-      o.w = (1.f - ci * ci) * dci;
+      o.w = (g_relu ? (ci > 0.f ? 1.f : 0.f) : (1.f - ci * ci)) * dci;
       *reinterpret_cast<float4*>(dg_s + 4 * j) = o;
       *reinterpret_cast<float4*>(DG + n * no4 + 4 * j) = o;
     }
@@ -221,7 +232,7 @@ __global__ void __launch_bounds__(RegCfg<NO>::THREADS, 1) lstm_fwd_regs(Lines ln
   __shared__ __align__(16) float h_s[2][4 * SSTR];
   __shared__ float xp_s[kStage][THREADS];                // per-thread ring of staged input projections
   const int tid = threadIdx.x;
-  const int b = ln.order[blockIdx.x], d = blockIdx.y;
+  const int b = ln.order[blockIdx.x], d = a.d0 + blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
   // padding quads (THREADS > ROWS) are exact clones of the last quad: same loads, same stores, same values, so the
   // whole loop is branch-free straight-line code for every thread
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(RegCfg<NO>::THREADS, 1) lstm_fwd_regs(Lines ln
   float* __restrict__ Gb = d ? a.G[1] : a.G[0];
   float* __restrict__ Cb = d ? a.C[1] : a.C[0];
   float* __restrict__ Hpb = d ? a.Hprev[1] : a.Hprev[0];
-  float* __restrict__ Hb = a.H + d * NO;
+  float* __restrict__ Hb = a.H + a.hoff[d];
 
   u64 w[4][NPF > 0 ? NPF : 1];                           // full pairs of the slice
   float wt[4];                                           // odd tail element of the slice (SL odd)
@@ -262,7 +273,7 @@ __global__ void __launch_bounds__(RegCfg<NO>::THREADS, 1) lstm_fwd_regs(Lines ln
   const int dt = d ? -1 : 1;
   const int t0 = d ? T - 1 : 0;
   float* __restrict__ obase = (q == 0 || q == 3) ? Hb : (q == 1) ? Cb : Hpb;
-  const unsigned ostride = (q == 0 || q == 3) ? 2 * NO : NO;
+  const unsigned ostride = (q == 0 || q == 3) ? (unsigned)a.hstride : NO;
   unsigned ncol = off + t0;
 
   // stage the input projection of the first kStage-1 steps
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(RegCfg<NO>::THREADS_B, 1) lstm_bwd_regs(Lines 
   float* dg_s = bsm;                                     // [2][16 * RSTR]  delta double buffer, [row slice][pos]
   float* st_s = bsm + 2 * 16 * RSTR;                     // [kStage][THREADS][8] per-thread staging ring
   int tid = threadIdx.x;
-  const int b = ln.order[blockIdx.x], d = blockIdx.y;
+  const int b = ln.order[blockIdx.x], d = a.d0 + blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
   // padding 16-lane groups (THREADS > 16*KG) are exact clones of the last k-group => straight-line code
   const unsigned st_addr0 = (unsigned)__cvta_generic_to_shared(st_s + (size_t)tid * 8);
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(RegCfg<NO>::THREADS_B, 1) lstm_bwd_regs(Lines 
   const int kg4 = (tid >> 4) * 4, rs = tid & 15;
   const float* __restrict__ Gb = d ? a.G[1] : a.G[0];
   const float* __restrict__ Cb = d ? a.C[1] : a.C[0];
-  const float* __restrict__ dHb = a.dH + d * NO;
+  const float* __restrict__ dHb = a.dH + a.hoff[d];
   float* __restrict__ DGb = d ? a.DG[1] : a.DG[0];
   const int row = 4 * k + p;                             // the delta row this thread publishes
 
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(RegCfg<NO>::THREADS_B, 1) lstm_bwd_regs(Lines 
     cp_async16(sa, Gb + (size_t)col * ROWS + 4 * k);
     cp_async4(sa + 16, Cb + (size_t)col * NO + k);
     if (u + 1 < T) cp_async4(sa + 20, Cb + (size_t)(col + dt) * NO + k);
-    cp_async4(sa + 24, dHb + (size_t)col * (2 * NO) + k);
+    cp_async4(sa + 24, dHb + (size_t)col * a.hstride + k);
   };
 #pragma unroll
   for (int u = 0; u < kStage - 1; u++) {
@@ -495,11 +506,11 @@ template <int NO> constexpr size_t bwd_regs_smem() {
 
 template <int NO>
 void launch_fwd_regs(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
-  lstm_fwd_regs<NO><<<dim3(ln.B, 2), RegCfg<NO>::THREADS, 0, st>>>(ln, a);
+  lstm_fwd_regs<NO><<<dim3(ln.B, a.ndir), RegCfg<NO>::THREADS, 0, st>>>(ln, a);
 }
 template <int NO>
 void launch_bwd_regs(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a) {
-  lstm_bwd_regs<NO><<<dim3(ln.B, 2), RegCfg<NO>::THREADS_B, bwd_regs_smem<NO>(), st>>>(ln, a);
+  lstm_bwd_regs<NO><<<dim3(ln.B, a.ndir), RegCfg<NO>::THREADS_B, bwd_regs_smem<NO>(), st>>>(ln, a);
 }
 
 bool has_regs_variant(int no) { return no == 16 || no == 32 || no == 50 || no == 64 || no == 100; }
@@ -529,7 +540,7 @@ int lstm_configure() {
 }
 
 const char* lstm_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
-  switch (a.no) {
+  switch (a.cell == 0 ? a.no : -1) {        // the register / cluster kernels hard-wire the NPLSTM nonlinearities
     case 16: launch_fwd_regs<16>(st, ln, a); return "regs";
     case 32: launch_fwd_regs<32>(st, ln, a); return "regs";
     case 50: launch_fwd_regs<50>(st, ln, a); return "regs";
@@ -537,17 +548,17 @@ const char* lstm_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a)
     case 100: launch_fwd_regs<100>(st, ln, a); return "regs";
     default: break;
   }
-  if (lstm_cluster_supported(a.no)) {   // register-resident over a thread-block cluster (DSMEM exchange of h)
+  if (a.cell == 0 && lstm_cluster_supported(a.no)) {   // register-resident over a thread-block cluster (DSMEM exchange of h)
     if (lstm_cluster_forward(st, ln, a) == 0) return "cluster";
     cudaGetLastError();                 // cluster not schedulable on this device: stream the weights instead
   }
   const size_t smem = (size_t)6 * a.no * sizeof(float);
-  lstm_fwd_generic<<<dim3(ln.B, 2), generic_threads(a.no), smem, st>>>(ln, a);
+  lstm_fwd_generic<<<dim3(ln.B, a.ndir), generic_threads(a.no), smem, st>>>(ln, a);
   return "generic";
 }
 
 const char* lstm_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a) {
-  switch (a.no) {
+  switch (a.cell == 0 ? a.no : -1) {
     case 16: launch_bwd_regs<16>(st, ln, a); return "regs";
     case 32: launch_bwd_regs<32>(st, ln, a); return "regs";
     case 50: launch_bwd_regs<50>(st, ln, a); return "regs";
@@ -555,12 +566,12 @@ const char* lstm_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a
     case 100: launch_bwd_regs<100>(st, ln, a); return "regs";
     default: break;
   }
-  if (lstm_cluster_supported(a.no)) {
+  if (a.cell == 0 && lstm_cluster_supported(a.no)) {
     if (lstm_cluster_backward(st, ln, a) == 0) return "cluster";
     cudaGetLastError();
   }
   const size_t smem = (size_t)9 * a.no * sizeof(float);
-  lstm_bwd_generic<<<dim3(ln.B, 2), generic_threads(a.no), smem, st>>>(ln, a);
+  lstm_bwd_generic<<<dim3(ln.B, a.ndir), generic_threads(a.no), smem, st>>>(ln, a);
   return "generic";
 }
 

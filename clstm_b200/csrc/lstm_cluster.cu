@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_fwd_cluster(Lines ln,
   __shared__ float xp_s[kStage][TPAD];
   const int tid0 = threadIdx.x;
   const unsigned crank = cluster_rank_();
-  const int b = ln.order[blockIdx.x / CS], d = blockIdx.y;
+  const int b = ln.order[blockIdx.x / CS], d = a.d0 + blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
   const int tid = (tid0 < Cfg::THREADS) ? tid0 : Cfg::THREADS - LU + (tid0 % LU);   // padding lanes clone the last unit group
   const int ul = tid / LU, lg = tid % LU;                          // unit inside the CTA, lane inside the unit group
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_fwd_cluster(Lines ln,
   float* __restrict__ Gb = d ? a.G[1] : a.G[0];
   float* __restrict__ Cb = d ? a.C[1] : a.C[0];
   float* __restrict__ Hpb = d ? a.Hprev[1] : a.Hprev[0];
-  float* __restrict__ Hb = a.H + d * NO;
+  float* __restrict__ Hb = a.H + a.hoff[d];
 
   u64 w[4][NPF];
   float wt[4];
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_fwd_cluster(Lines ln,
   unsigned ncol = off + (d ? T - 1 : 0);
   // output stream of the lead lanes: q=0 -> H, q=1 -> C, q=2 -> Hprev (h of the previous step), q=3 -> nothing extra
   float* __restrict__ obase = (q == 0) ? Hb : (q == 1) ? Cb : Hpb;
-  const unsigned ostride = (q == 0) ? 2 * NO : NO;
+  const unsigned ostride = (q == 0) ? (unsigned)a.hstride : NO;
 
 #pragma unroll
   for (int u = 0; u < kStage - 1; u++) {
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln,
   float* st_s = part_s + 2 * CS * UC;        // [kStage][TPAD][8] per-thread staging ring
   const int tid0 = threadIdx.x;
   const unsigned crank = cluster_rank_();
-  const int b = ln.order[blockIdx.x / CS], d = blockIdx.y;
+  const int b = ln.order[blockIdx.x / CS], d = a.d0 + blockIdx.y;
   const int T = ln.T[b], off = ln.off[b];
   const unsigned st_addr0 = (unsigned)__cvta_generic_to_shared(st_s + (size_t)tid0 * 8);
   const int tid = (tid0 < Cfg::THREADS) ? tid0 : Cfg::THREADS - RSL + (tid0 % RSL);   // padding lanes clone the last k-group
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln,
   const int punit = (int)crank * UC + pu;
   const float* __restrict__ Gb = d ? a.G[1] : a.G[0];
   const float* __restrict__ Cb = d ? a.C[1] : a.C[0];
-  const float* __restrict__ dHb = a.dH + d * NO;
+  const float* __restrict__ dHb = a.dH + a.hoff[d];
   float* __restrict__ DGb = d ? a.DG[1] : a.DG[0];
 
   u64 w[4][NPF];
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln,
     cp_async16(sa, Gb + (size_t)col * ROWS + 4 * punit);
     cp_async4(sa + 16, Cb + (size_t)col * NO + punit);
     if (u + 1 < T) cp_async4(sa + 20, Cb + (size_t)(col + dt) * NO + punit);
-    cp_async4(sa + 24, dHb + (size_t)col * (2 * NO) + punit);
+    cp_async4(sa + 24, dHb + (size_t)col * a.hstride + punit);
   };
 #pragma unroll
   for (int u = 0; u < kStage - 1; u++) {
@@ -382,7 +382,8 @@ template <int NO>
 cudaError_t launch_cluster(bool fwd, cudaStream_t st, const Lines& ln, const void* args) {
   typedef ClCfg<NO> Cfg;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(ln.B * Cfg::CS, 2, 1);
+  const int ndir = fwd ? static_cast<const LstmFwdArgs*>(args)->ndir : static_cast<const LstmBwdArgs*>(args)->ndir;
+  cfg.gridDim = dim3(ln.B * Cfg::CS, ndir, 1);
   cfg.blockDim = dim3(Cfg::TPAD, 1, 1);
   cfg.dynamicSmemBytes = fwd ? 0 : bwd_cluster_smem<NO>();
   cfg.stream = st;

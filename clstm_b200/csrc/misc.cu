@@ -49,6 +49,53 @@ __global__ void softmax_rows_kernel(float* __restrict__ z, int N, int nc, int* _
   }
 }
 
+// Full<F> output layers (clstm.cc:357-389): y = f(z) element-wise, kind 1 SIG, 2 LIN, 3 TANH, 4 RELU, plus the per-column
+// argmax like softmax_rows.  sigmoid is Eigen's unclamped 1/(1+exp(-x)) (clstm_compute.cc:116-118).
+__device__ __forceinline__ float full_act(int kind, float x) {
+  switch (kind) {
+    case 1: return 1.0f / (1.0f + expf(-x));
+    case 3: return tanhf(x);
+    case 4: return fmaxf(x, 0.f);
+    default: return x;
+  }
+}
+__global__ void full_rows_kernel(float* __restrict__ z, int N, int nc, int kind, int* __restrict__ amax,
+                                 float* __restrict__ amaxv) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int n = warp; n < N; n += nwarps) {
+    float* row = z + (size_t)n * nc;
+    float mv = -INFINITY;
+    int mi = -1;
+    for (int c = lane; c < nc; c += 32) {
+      const float o = full_act(kind, row[c]);
+      row[c] = o;
+      if (!(o < mv)) { mv = o; mi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+      if (ov > mv || (ov == mv && oi > mi)) { mv = ov; mi = oi; }
+    }
+    if (lane == 0) { amax[n] = mi; amaxv[n] = mv; }
+  }
+}
+// backward_nonlin0 (clstm_compute.cc:231-267): delta <- f'(y) * delta, f' expressed through the output y
+__global__ void full_backward_kernel(float* __restrict__ delta, const float* __restrict__ y, size_t n, int kind) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = y[i], d = delta[i];
+    float r;
+    switch (kind) {
+      case 1: r = v * (1.f - v) * d; break;
+      case 3: r = (1.f - v * v) * d; break;
+      case 4: r = d * (v > 0.f ? 1.f : 0.f); break;
+      default: r = d;
+    }
+    delta[i] = r;
+  }
+}
+
 // Folds this step's derivatives g into the accumulator d (Params.d) and applies sgd_update(Network)
 // (clstm.cc:201-217): clip_gradient then v += lr*d ; d *= momentum  (clstm_compute.cc:553-563).
 __global__ void sgd_update_kernel(float* __restrict__ v, float* __restrict__ d, float* __restrict__ g, size_t n,
@@ -226,6 +273,19 @@ void softmax_rows(cudaStream_t st, float* z, int N, int nc, int* amax, float* am
   int blocks = (N + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   softmax_rows_kernel<<<blocks, threads, 0, st>>>(z, N, nc, amax, amaxv);
+}
+
+void full_rows(cudaStream_t st, float* z, int N, int nc, int kind, int* amax, float* amaxv) {
+  if (N <= 0) return;
+  int blocks = (N + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  full_rows_kernel<<<blocks, 256, 0, st>>>(z, N, nc, kind, amax, amaxv);
+}
+void full_backward(cudaStream_t st, float* delta, const float* y, size_t n, int kind) {
+  if (n == 0 || kind == 2) return;     // LinearLayer: identity
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  full_backward_kernel<<<(int)blocks, 256, 0, st>>>(delta, y, n, kind);
 }
 
 void sgd_update(cudaStream_t st, float* v, float* d, float* g, size_t n, float lr, float mom, float clip,

@@ -46,6 +46,24 @@ typedef struct clstm_b200_cfg {
 /* replaces make_net("bidi", ...) + initialize() for the device-resident net (clstmhl.h:191-200).
  * Weights are zero until clstm_b200_set_params(); the host mirror fills them with the reference LCG init. */
 int clstm_b200_create(const clstm_b200_cfg* cfg, clstm_b200_net** out);
+
+/* The other prefab topologies of clstm_prefab.cc:22-129 and the layer variants of clstm.cc:382-389, 655-668:
+ * nblocks stacked recurrent blocks (each one LSTM, one Reversed{LSTM}, or Parallel{LSTM, Reversed{LSTM}}) followed by
+ * an output layer.   lstm1: {1, direction 0}   revlstm1: {1, direction 1}   bidi: {1, direction 2}
+ * bidi2: {2 blocks, direction 2, 2}   bidi0: bidi with output -1.   The flat parameter order is walk_params of the
+ * corresponding reference tree (clstm.cc:59-62).  The CTC entry points need a Softmax output; the register / cluster
+ * recurrent kernels serve cell 0 (NPLSTM), the other cells run on the generic kernels. */
+typedef struct {
+  int ninput;        /* features per column                                                              */
+  int noutput;       /* outputs of the output layer (ignored for output -1)                              */
+  int device;
+  int nblocks;       /* 1 or 2                                                                           */
+  int nhidden[2];    /* hidden units per LSTM of block k ("nhidden", "nhidden2")                         */
+  int direction[2];  /* 0 forward only, 1 reversed only, 2 both (Parallel, outputs concatenated)         */
+  int cell;          /* 0 NPLSTM, 1 LINNPLSTM, 2 RELUTANHNPLSTM, 3 RELUNPLSTM, 4 RELU2NPLSTM              */
+  int output;        /* 0 SoftmaxLayer, 1 SigmoidLayer, 2 LinearLayer, 3 TanhLayer, 4 ReluLayer, -1 none */
+} clstm_b200_cfg_ex;
+int clstm_b200_create_ex(const clstm_b200_cfg_ex* cfg, clstm_b200_net** out);
 void clstm_b200_destroy(clstm_b200_net* net);
 
 /* n_params / set_params / get_params / get_derivs / set_derivs / clear_derivs (clstm.cc:838-918) */

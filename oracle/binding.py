@@ -32,6 +32,8 @@ def lib():
         L.oracle_rinit.argtypes = [f32p, C.c_int, C.c_int, C.c_float, C.c_char_p, C.c_float]
         L.oracle_bidi_create.restype = C.c_void_p
         L.oracle_bidi_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.oracle_prefab_create.restype = C.c_void_p
+        L.oracle_prefab_create.argtypes = [C.c_char_p] + [C.c_int] * 6
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_nparams.restype = C.c_size_t
         L.oracle_nparams.argtypes = [C.c_void_p]
@@ -169,6 +171,27 @@ class BidiOracle:
         la, lp = _i32(labels)
         La, Lp = _i32(L)
         return lib().oracle_train_lines(self.h, xp, Tp, Ta.size, lp, Lp, lr, momentum, threads, reps)
+
+
+CELLS = {"NPLSTM": 0, "LINNPLSTM": 1, "RELUTANHNPLSTM": 2, "RELUNPLSTM": 3, "RELU2NPLSTM": 4}
+OUTPUTS = {"SoftmaxLayer": 0, "SigmoidLayer": 1, "LinearLayer": 2, "TanhLayer": 3, "ReluLayer": 4, None: -1}
+
+
+class PrefabOracle(BidiOracle):
+    """the 1-D prefabs of clstm_prefab.cc:22-129 (lstm1, revlstm1, bidi, bidi0, bidi2) with the LSTM cell variants of
+    clstm.cc:655-668 and the Full<F> / Softmax output layers of clstm.cc:382-419"""
+
+    def __init__(self, prefab, ni, nh, nc, nh2=0, cell="NPLSTM", output="SoftmaxLayer", seed=None):
+        L = lib()
+        if seed is not None:
+            L.oracle_seed(float(seed))
+        if prefab == "bidi0":
+            output, nc = None, 2 * nh
+        self.ni, self.nh, self.nc = ni, nh, nc
+        self.h = L.oracle_prefab_create(prefab.encode(), ni, nh, nh2, nc, CELLS[cell], OUTPUTS[output])
+        assert self.h, prefab
+        self.nparams = L.oracle_nparams(self.h)
+        self.T = 0
 
 
 def ctc_align_dense(outputs, targets, double=False):

@@ -91,7 +91,7 @@ template <class F> inline int argmax1(const F* m, int n) {  // tensor.h:357-366 
   return mi;
 }
 
-enum { LIN = 0, SIG = 1, TANH = 2 };
+enum { LIN = 0, SIG = 1, TANH = 2, RELU = 3 };   // clstm_compute.h nonlinearity codes used here
 
 // ------------------------------------------------------------------------------------------
 // compute ops  (clstm_compute.cc)
@@ -147,6 +147,7 @@ void forward_nonlin0(Batch<F>& y, int nl) {
   const size_t N = y.v.a.size();
   if (nl == SIG) for (size_t i = 0; i < N; i++) p[i] = F(1) / (F(1) + std::exp(-p[i]));
   else if (nl == TANH) for (size_t i = 0; i < N; i++) p[i] = std::tanh(p[i]);
+  else if (nl == RELU) for (size_t i = 0; i < N; i++) p[i] = std::max(p[i], F(0));   // forward_relu :123-125
 }
 // backward_nonlin0 (clstm_compute.cc:231-267): in place on d
 template <class F>
@@ -156,6 +157,7 @@ void backward_nonlin0(Batch<F>& y, int nl) {
   const size_t N = y.v.a.size();
   if (nl == SIG) for (size_t i = 0; i < N; i++) d[i] = v[i] * (-v[i] + F(1)) * d[i];
   else if (nl == TANH) for (size_t i = 0; i < N; i++) d[i] = (-v[i] * v[i] + F(1)) * d[i];
+  else if (nl == RELU) for (size_t i = 0; i < N; i++) d[i] = d[i] * (v[i] > F(0) ? F(1) : F(0));   // backward_relu0 :241-244
 }
 template <class F> void forward_full1(Batch<F>& y, const Batch<F>& W, const Batch<F>& x, int nl) {  // :308-314
   forward_lin1(y, W, x);
@@ -238,20 +240,22 @@ void backward_statemem(Batch<F>& state, Batch<F>& ci, Batch<F>& gi, Seq<F>& stat
   for (size_t i = 0; i < N; i++) gi.d.a[i] += state.d.a[i] * ci.v.a[i];
   for (size_t i = 0; i < N; i++) ci.d.a[i] += state.d.a[i] * gi.v.a[i];
 }
-// forward_nonlingate / backward_nonlingate with H = TANH (clstm_compute.cc:519-547)
+// forward_nonlingate / backward_nonlingate (clstm_compute.cc:519-547), H = nl (TANH for NPLSTM; LIN / RELU variants)
+template <class F> inline F nonlin_h(F x, int nl) { return nl == TANH ? std::tanh(x) : (nl == RELU ? std::max(x, F(0)) : x); }
 template <class F>
-void forward_nonlingate(Batch<F>& out, const Batch<F>& state, const Batch<F>& go) {
+void forward_nonlingate(Batch<F>& out, const Batch<F>& state, const Batch<F>& go, int nl = TANH) {
   const size_t N = out.v.a.size();
-  for (size_t i = 0; i < N; i++) out.v.a[i] = std::tanh(state.v.a[i]) * go.v.a[i];
+  for (size_t i = 0; i < N; i++) out.v.a[i] = nonlin_h(state.v.a[i], nl) * go.v.a[i];
 }
 template <class F>
-void backward_nonlingate(const Batch<F>& out, Batch<F>& state, Batch<F>& go) {
+void backward_nonlingate(const Batch<F>& out, Batch<F>& state, Batch<F>& go, int nl = TANH) {
   const size_t N = out.v.a.size();
   for (size_t i = 0; i < N; i++) {
-    const F th = std::tanh(state.v.a[i]);         // temp.v  (recomputed, :543)
+    const F th = nonlin_h(state.v.a[i], nl);      // temp.v  (recomputed, :543)
     go.d.a[i] += th * out.d.a[i];                 // backward_gate :524
     const F td = go.v.a[i] * out.d.a[i];          // temp.d  :525 (temp.d starts at 0)
-    state.d.a[i] += (-th * th + F(1)) * td;       // backward_tanh :172
+    const F dv = nl == TANH ? (-th * th + F(1)) : (nl == RELU ? (th > F(0) ? F(1) : F(0)) : F(1));
+    state.d.a[i] += dv * td;                      // backward_nonlin :172 / relu / identity (additive form)
   }
 }
 // clip_gradient + sgd_update(Params) (clstm_compute.cc:553-563)
@@ -317,12 +321,13 @@ void rinit_params(Batch<F>& p, int r, int c) {  // clstm.cc:30-36 defaults: negb
 }
 
 template <class F>
-struct NPLSTM : Layer<F> {  // GenericNPLSTM<SIG,TANH,TANH>  clstm.cc:546-653
+struct NPLSTM : Layer<F> {  // GenericNPLSTM<F=SIG, G, H>  clstm.cc:546-668 (G = g_nl, H = h_nl; NPLSTM: TANH, TANH)
   using Layer<F>::inputs; using Layer<F>::outputs;
   Seq<F> source, gi, gf, go, ci, state;
   Batch<F> WGI, WGF, WGO, WCI;
   int ni, no, nf;
-  NPLSTM(int ni_, int no_) : ni(ni_), no(no_), nf(ni_ + no_) {
+  int g_nl = TANH, h_nl = TANH;
+  NPLSTM(int ni_, int no_, int g_nl_ = TANH, int h_nl_ = TANH) : ni(ni_), no(no_), nf(ni_ + no_), g_nl(g_nl_), h_nl(h_nl_) {
     this->parameters["WGI"] = &WGI; this->parameters["WGF"] = &WGF;
     this->parameters["WGO"] = &WGO; this->parameters["WCI"] = &WCI;
     rinit_params(WGI, no, nf + 1);  // draw order clstm.cc:588-591
@@ -341,9 +346,9 @@ struct NPLSTM : Layer<F> {  // GenericNPLSTM<SIG,TANH,TANH>  clstm.cc:546-653
       forward_full1(gi[t], WGI, source[t], SIG);
       forward_full1(gf[t], WGF, source[t], SIG);
       forward_full1(go[t], WGO, source[t], SIG);
-      forward_full1(ci[t], WCI, source[t], TANH);
+      forward_full1(ci[t], WCI, source[t], g_nl);
       forward_statemem(state[t], ci[t], gi[t], state, t - 1, gf[t]);
-      forward_nonlingate(outputs[t], state[t], go[t]);
+      forward_nonlingate(outputs[t], state[t], go[t], h_nl);
     }
   }
   void backward() override {  // clstm.cc:622-653 (the O(T^2) anynan asserts are omitted)
@@ -353,9 +358,9 @@ struct NPLSTM : Layer<F> {  // GenericNPLSTM<SIG,TANH,TANH>  clstm.cc:546-653
     Seq<F> out;
     out.copy(outputs);
     for (int t = N - 1; t >= 0; t--) {
-      backward_nonlingate(out[t], state[t], go[t]);
+      backward_nonlingate(out[t], state[t], go[t], h_nl);
       backward_statemem(state[t], ci[t], gi[t], state, t - 1, gf[t]);
-      backward_full1(ci[t], WCI, source[t], TANH);
+      backward_full1(ci[t], WCI, source[t], g_nl);
       backward_full1(go[t], WGO, source[t], SIG);
       backward_full1(gf[t], WGF, source[t], SIG);
       backward_full1(gi[t], WGI, source[t], SIG);
@@ -437,6 +442,25 @@ struct Softmax : Layer<F> {  // SoftmaxLayer clstm.cc:391-419
 };
 
 template <class F>
+struct Full : Layer<F> {  // Full<NONLIN> clstm.cc:354-389: LinearLayer, SigmoidLayer, TanhLayer, ReluLayer
+  using Layer<F>::inputs; using Layer<F>::outputs;
+  Batch<F> W1;
+  int nl;
+  Full(int ni, int no, int nl_) : nl(nl_) {
+    this->parameters["W1"] = &W1;
+    rinit_params(W1, no, ni + 1);
+  }
+  int noutput() override { return W1.rows(); }
+  void forward() override {
+    outputs.resize(inputs.size(), W1.rows(), inputs.cols());
+    for (int t = 0; t < inputs.size(); t++) forward_full1(outputs[t], W1, inputs[t], nl);
+  }
+  void backward() override {
+    for (int t = outputs.size() - 1; t >= 0; t--) backward_full1(outputs[t], W1, inputs[t], nl);
+  }
+};
+
+template <class F>
 struct Stacked : Layer<F> {  // clstm.cc:421-456
   using Layer<F>::inputs; using Layer<F>::outputs; using Layer<F>::sub;
   int noutput() override { return sub.back()->noutput(); }
@@ -471,6 +495,40 @@ std::shared_ptr<Layer<F>> make_bidi(int ni, int nh, int no) {  // clstm_prefab.c
   auto sm = std::make_shared<Softmax<F>>(2 * nh, no);
   auto st = std::make_shared<Stacked<F>>();
   st->sub.push_back(par); st->sub.push_back(sm);
+  return st;
+}
+
+// the 1-D prefabs of clstm_prefab.cc:22-129.  cell: 0 NPLSTM, 1 LINNPLSTM, 2 RELUTANHNPLSTM, 3 RELUNPLSTM, 4 RELU2NPLSTM
+// (clstm.cc:655-668); output: 0 SoftmaxLayer, 1 SigmoidLayer, 2 LinearLayer, 3 TanhLayer, 4 ReluLayer, -1 none (bidi0)
+template <class F>
+std::shared_ptr<Layer<F>> make_prefab(const std::string& kind, int ni, int nh, int nh2, int no, int cell, int output) {
+  const int g_nl = cell >= 2 ? RELU : TANH;
+  const int h_nl = (cell == 0 || cell == 2) ? TANH : (cell == 4 ? RELU : LIN);
+  auto lstm = [&](int i, int o) { return std::make_shared<NPLSTM<F>>(i, o, g_nl, h_nl); };
+  auto bidi_block = [&](int i, int o) {
+    auto fwd = lstm(i, o);
+    auto rev = std::make_shared<Reversed<F>>();
+    rev->sub.push_back(lstm(i, o));
+    auto par = std::make_shared<Parallel<F>>();
+    par->sub.push_back(fwd); par->sub.push_back(rev);
+    return par;
+  };
+  auto out_layer = [&](int i) -> std::shared_ptr<Layer<F>> {
+    if (output == 0) return std::make_shared<Softmax<F>>(i, no);
+    static const int nls[5] = {0, SIG, LIN, TANH, RELU};
+    return std::make_shared<Full<F>>(i, no, nls[output]);
+  };
+  if (kind == "bidi0") return bidi_block(ni, nh);
+  auto st = std::make_shared<Stacked<F>>();
+  if (kind == "lstm1") { st->sub.push_back(lstm(ni, nh)); st->sub.push_back(out_layer(nh)); }
+  else if (kind == "revlstm1") {
+    auto rev = std::make_shared<Reversed<F>>();
+    rev->sub.push_back(lstm(ni, nh));
+    st->sub.push_back(rev); st->sub.push_back(out_layer(nh));
+  } else if (kind == "bidi") { st->sub.push_back(bidi_block(ni, nh)); st->sub.push_back(out_layer(2 * nh)); }
+  else if (kind == "bidi2") {
+    st->sub.push_back(bidi_block(ni, nh)); st->sub.push_back(bidi_block(2 * nh, nh2)); st->sub.push_back(out_layer(2 * nh2));
+  } else return nullptr;
   return st;
 }
 
@@ -665,6 +723,14 @@ oracle_net* oracle_bidi_create(int ninput, int nhidden, int noutput) {
   auto* o = new oracle_net;
   o->ni = ninput; o->nh = nhidden; o->nc = noutput;
   o->net = make_bidi<float>(ninput, nhidden, noutput);
+  return o;
+}
+oracle_net* oracle_prefab_create(const char* prefab, int ninput, int nhidden, int nhidden2, int noutput, int cell, int output) {
+  auto net = make_prefab<float>(prefab, ninput, nhidden, nhidden2, noutput, cell, output);
+  if (!net) return nullptr;
+  auto* o = new oracle_net;
+  o->ni = ninput; o->nh = nhidden; o->nc = net->noutput();
+  o->net = net;
   return o;
 }
 void oracle_destroy(oracle_net* o) { delete o; }

@@ -125,3 +125,36 @@ def test_product_side_init_matches_reference_lcg(oracle):
     from clstm_b200 import synth
     net = oracle.BidiOracle(9, 6, 5, seed=0.222)
     assert np.array_equal(net.get_params(), synth.reference_init(9, 6, 5, seed=0.222))
+
+
+@pytest.mark.parametrize("prefab,cell,output", [
+    ("lstm1", "NPLSTM", "SigmoidLayer"), ("revlstm1", "LINNPLSTM", "SigmoidLayer"), ("bidi", "RELUTANHNPLSTM", "TanhLayer"),
+    ("bidi2", "RELUNPLSTM", "LinearLayer"), ("bidi0", "RELU2NPLSTM", None), ("bidi2", "NPLSTM", "ReluLayer")])
+def test_prefab_variants_gradcheck(oracle, prefab, cell, output):
+    # the reference's gradient-check recipe (test-deriv.cc:103-176) on every prefab / cell / output-layer variant of the
+    # oracle: central differences of sum(out * probe) against backward(), float32 => loose tolerance.  (SoftmaxLayer is
+    # left out on purpose: its backward has no Jacobian upstream, clstm_compute.cc:346-356, so it is not a gradient.)
+    ni, nh, nh2, nc, T = 5, 4, 3, 6, 7
+    rng = np.random.default_rng(11)
+    net = oracle.PrefabOracle(prefab, ni, nh, nc, nh2=nh2, cell=cell, output=output, seed=0.37)
+    p = rng.normal(0, 0.4, net.nparams).astype(np.float32)
+    net.set_params(p)
+    x = rng.uniform(-1, 1, (T, ni)).astype(np.float32)
+    probe = rng.normal(0, 1, (T, net.nc)).astype(np.float32)
+    out = net.forward(x)
+    assert out.shape == (T, net.nc)
+    net.clear_derivs()
+    din = net.backward(probe)
+    g = net.get_derivs()
+    eps = 2e-3
+    for idx in rng.choice(net.nparams, 12, replace=False):
+        q = p.copy(); q[idx] += eps; net.set_params(q); lp = float((net.forward(x) * probe).sum())
+        q[idx] -= 2 * eps; net.set_params(q); lm = float((net.forward(x) * probe).sum())
+        num = (lp - lm) / (2 * eps)
+        assert abs(num - g[idx]) < 3e-2 * max(1.0, abs(num)), (prefab, idx, num, g[idx])
+    net.set_params(p)
+    for t, i in [(0, 0), (T - 1, ni - 1), (3, 2)]:
+        xx = x.copy(); xx[t, i] += eps; lp = float((net.forward(xx) * probe).sum())
+        xx[t, i] -= 2 * eps; lm = float((net.forward(xx) * probe).sum())
+        num = (lp - lm) / (2 * eps)
+        assert abs(num - din[t, i]) < 3e-2 * max(1.0, abs(num)), (prefab, t, i, num, din[t, i])
