@@ -204,7 +204,32 @@ struct SoftmaxLayer : INetwork {  // clstm.cc:391-419
   void backward() override { THROW(kNotStandalone); }
 };
 
-// Stacked{ Parallel{ NPLSTM, Reversed{ NPLSTM } }, SoftmaxLayer }: the whole tree runs as one device net.
+struct FullLayer : INetwork {     // parameter container of Full<NONLIN> clstm.cc:354-389 (Linear/Sigmoid/Tanh/ReluLayer)
+  Params W1;
+  FullLayer() { enroll(W1, "W1"); }
+  void initialize() override {
+    const int no = (int)(double)attr.get("noutput"), ni = (int)(double)attr.get("ninput");
+    rinit_attr(W1, no, ni + 1, attr);
+  }
+  int noutput() override { return W1.rows(); }
+  int ninput() override { return W1.cols() - 1; }
+  void forward() override { THROW(kNotStandalone); }
+  void backward() override { THROW(kNotStandalone); }
+};
+int cell_code(const string& kind) {      // LSTM variants clstm.cc:655-668 -> clstm_b200_cfg_ex.cell, -1: not an LSTM
+  static const char* k[5] = {"NPLSTM", "LINNPLSTM", "RELUTANHNPLSTM", "RELUNPLSTM", "RELU2NPLSTM"};
+  for (int i = 0; i < 5; i++) if (kind == k[i]) return i;
+  return -1;
+}
+int output_code(const string& kind) {    // output layers -> clstm_b200_cfg_ex.output, -2: not an output layer
+  static const char* k[5] = {"SoftmaxLayer", "SigmoidLayer", "LinearLayer", "TanhLayer", "ReluLayer"};
+  for (int i = 0; i < 5; i++) if (kind == k[i]) return i;
+  return -2;
+}
+
+// Stacked{ recurrent block [, recurrent block] [, output layer] }: the whole tree runs as one device net.  A recurrent
+// block is an LSTM, Reversed{LSTM} or Parallel{LSTM, Reversed{LSTM}} (lstm1 / revlstm1 / bidi / bidi2 / perplstm of
+// clstm_prefab.cc:22-129; a Stacked with a single Stacked child is looked through).
 struct Stacked : INetwork {      // clstm.cc:421-456
   clstm_b200_net* h = nullptr;
   bool weights_on_device = false;   // device copy current w.r.t. the host Params.v
@@ -213,23 +238,52 @@ struct Stacked : INetwork {      // clstm.cc:421-456
   ~Stacked() override { clstm_b200_destroy(h); }
   int noutput() override { return sub.back()->noutput(); }
   int ninput() override { return sub[0]->ninput(); }
-  bool is_bidi() const {
-    if (sub.size() != 2 || sub[0]->kind != "Parallel" || sub[1]->kind != "SoftmaxLayer") return false;
-    auto& par = *sub[0];
-    return par.sub.size() == 2 && par.sub[0]->kind == "NPLSTM" && par.sub[1]->kind == "Reversed" &&
-           par.sub[1]->sub.size() == 1 && par.sub[1]->sub[0]->kind == "NPLSTM";
+  // recognise one recurrent block; returns false if `net` is not one
+  static bool parse_block(INetwork* net, int& direction, int& nhidden, int& cell) {
+    auto lstm = [&](INetwork* l) {
+      const int c = cell_code(l->kind);
+      if (c < 0 || (cell >= 0 && c != cell)) return false;   // one cell type per network on the device
+      cell = c;
+      nhidden = l->noutput();
+      return true;
+    };
+    if (cell_code(net->kind) >= 0) { direction = 0; return lstm(net); }
+    if (net->kind == "Reversed" && net->sub.size() == 1) { direction = 1; return lstm(net->sub[0].get()); }
+    if (net->kind == "Parallel" && net->sub.size() == 2 && net->sub[1]->kind == "Reversed" && net->sub[1]->sub.size() == 1) {
+      direction = 2;
+      int nh2 = 0;
+      if (!lstm(net->sub[0].get())) return false;
+      const int nh1 = nhidden;
+      if (!lstm(net->sub[1]->sub[0].get())) return false;
+      nh2 = nhidden;
+      return nh1 == nh2;
+    }
+    return false;
+  }
+  bool describe(clstm_b200_cfg_ex& cfg) {
+    INetwork* root = this;
+    while (root->sub.size() == 1 && root->sub[0]->kind == "Stacked") root = root->sub[0].get();
+    memset(&cfg, 0, sizeof cfg);
+    cfg.ninput = ninput(); cfg.noutput = noutput();
+    cfg.device = (int)(double)attr.get("gpu", 0);
+    int cell = -1;
+    size_t nsub = root->sub.size();
+    cfg.output = -1;
+    if (nsub >= 1 && output_code(root->sub[nsub - 1]->kind) >= 0) { cfg.output = output_code(root->sub[nsub - 1]->kind); nsub--; }
+    if (nsub < 1 || nsub > 2) return false;
+    cfg.nblocks = (int)nsub;
+    for (size_t k = 0; k < nsub; k++)
+      if (!parse_block(root->sub[k].get(), cfg.direction[k], cfg.nhidden[k], cell)) return false;
+    cfg.cell = cell;
+    return true;
   }
   void ensure_device() {
-    if (!is_bidi()) THROW("only the `bidi` topology (clstm_prefab.cc:52-68) runs on the device");
-    if (!h) {
-      clstm_b200_cfg cfg;
-      cfg.ninput = ninput();
-      cfg.nhidden = sub[0]->sub[0]->noutput();
-      cfg.nclasses = noutput();
-      cfg.device = (int)(double)attr.get("gpu", 0);
-      check(clstm_b200_create(&cfg, &h));
-      weights_on_device = false;
-    }
+    if (h) return;
+    clstm_b200_cfg_ex cfg;
+    if (!describe(cfg))
+      THROW("this topology does not run on the device (supported: lstm1, revlstm1, bidi, bidi2, perplstm; clstm_prefab.cc:22-129)");
+    check(clstm_b200_create_ex(&cfg, &h));
+    weights_on_device = false;
   }
   void upload() {
     ensure_device();
@@ -325,7 +379,15 @@ struct Registrar {
     register_layer<Parallel>("Parallel");
     register_layer<Reversed>("Reversed");
     register_layer<NPLSTM>("NPLSTM");
+    register_layer<NPLSTM>("LINNPLSTM");          // same parameter container, other cell nonlinearities on the device
+    register_layer<NPLSTM>("RELUTANHNPLSTM");
+    register_layer<NPLSTM>("RELUNPLSTM");
+    register_layer<NPLSTM>("RELU2NPLSTM");
     register_layer<SoftmaxLayer>("SoftmaxLayer");
+    register_layer<FullLayer>("LinearLayer");
+    register_layer<FullLayer>("SigmoidLayer");
+    register_layer<FullLayer>("TanhLayer");
+    register_layer<FullLayer>("ReluLayer");
   }
 };
 }  // namespace
@@ -356,21 +418,67 @@ Network layer(const string& kind, int ninput, int noutput, const Assoc& args, co
   net->initialize();
   return net;
 }
-static Network make_bidi(const Assoc& params) {  // clstm_prefab.cc:52-68
-  const int ninput = (int)(double)params.get("ninput"), nhidden = (int)(double)params.get("nhidden");
-  const int noutput = (int)(double)params.get("noutput");
-  const string lstm_type = params.get("lstm_type", "NPLSTM"), output_type = params.get("output_type", "SoftmaxLayer");
-  if (lstm_type != "NPLSTM" || output_type != "SoftmaxLayer")
-    THROW("only lstm_type=NPLSTM with output_type=SoftmaxLayer is on the device path");
-  return layer("Stacked", ninput, noutput, {},
-               {layer("Parallel", ninput, 2 * nhidden, {},
-                      {layer(lstm_type, ninput, nhidden, params, {}),
-                       layer("Reversed", ninput, ninput, {}, {layer(lstm_type, ninput, nhidden, params, {})})}),
-                layer(output_type, 2 * nhidden, noutput, params, {})});
+// the 1-D prefabs of clstm_prefab.cc:22-129 (lstm_type / output_type as upstream; noutput == 1 defaults to a sigmoid)
+namespace {
+struct PrefabArgs {
+  int ninput, nhidden, noutput;
+  string lstm_type, output_type;
+  explicit PrefabArgs(const Assoc& p) {
+    ninput = (int)(double)p.get("ninput");
+    noutput = (int)(double)p.get("noutput");
+    nhidden = (int)(double)p.get("nhidden", noutput);
+    lstm_type = p.get("lstm_type", "NPLSTM");
+    output_type = p.get("output_type", noutput == 1 ? "SigmoidLayer" : "SoftmaxLayer");
+  }
+};
+Network bidi_block(const Assoc& params, const string& lstm_type, int ninput, int nhidden) {
+  return layer("Parallel", ninput, 2 * nhidden, {},
+               {layer(lstm_type, ninput, nhidden, params, {}),
+                layer("Reversed", ninput, ninput, {}, {layer(lstm_type, ninput, nhidden, params, {})})});
 }
-Network make_net(const string& kind, const Assoc& args) {
+Network make_lstm1(const Assoc& params) {      // clstm_prefab.cc:22-32
+  PrefabArgs a(params);
+  return layer("Stacked", a.ninput, a.noutput, {},
+               {layer(a.lstm_type, a.ninput, a.nhidden, params, {}), layer(a.output_type, a.nhidden, a.noutput, params, {})});
+}
+Network make_revlstm1(const Assoc& params) {   // clstm_prefab.cc:36-48
+  PrefabArgs a(params);
+  return layer("Stacked", a.ninput, a.noutput, {},
+               {layer("Reversed", a.ninput, a.nhidden, {}, {layer(a.lstm_type, a.ninput, a.nhidden, params, {})}),
+                layer(a.output_type, a.nhidden, a.noutput, params, {})});
+}
+Network make_bidi(const Assoc& params) {       // clstm_prefab.cc:52-68
+  PrefabArgs a(params);
+  return layer("Stacked", a.ninput, a.noutput, {},
+               {bidi_block(params, a.lstm_type, a.ninput, a.nhidden), layer(a.output_type, 2 * a.nhidden, a.noutput, params, {})});
+}
+Network make_bidi0(const Assoc& params) {      // clstm_prefab.cc:72-82: no output layer, `noutput` hidden units per direction
+  PrefabArgs a(params);
+  return bidi_block(params, a.lstm_type, a.ninput, a.noutput);
+}
+Network make_bidi2(const Assoc& params) {      // clstm_prefab.cc:86-109
+  PrefabArgs a(params);
+  const int nhidden2 = (int)(double)params.get("nhidden2");
+  return layer("Stacked", a.ninput, a.noutput, {},
+               {bidi_block(params, a.lstm_type, a.ninput, a.nhidden), bidi_block(params, a.lstm_type, 2 * a.nhidden, nhidden2),
+                layer(a.output_type, 2 * nhidden2, a.noutput, params, {})});
+}
+Network make_perplstm(const Assoc& params) {   // clstm_prefab.cc:111-125: a bidi net with a sigmoid output inside a Stacked
+  PrefabArgs a(params);
+  Assoc inner = {{"ninput", a.ninput}, {"nhidden", a.nhidden}, {"noutput", a.noutput},
+                 {"output_type", String(params.get("output_type", "SigmoidLayer"))}};
+  return layer("Stacked", a.ninput, a.noutput, {}, {make_bidi(inner)});
+}
+}  // namespace
+Network make_net(const string& kind, const Assoc& args) {   // clstm_prefab.cc:163-173
   Network result;
   if (kind == "bidi") result = make_bidi(args);
+  else if (kind == "lstm1") result = make_lstm1(args);
+  else if (kind == "revlstm1") result = make_revlstm1(args);
+  else if (kind == "bidi0") result = make_bidi0(args);
+  else if (kind == "bidi2") result = make_bidi2(args);
+  else if (kind == "perplstm") result = make_perplstm(args);
+  else if (kind == "twod") THROW("the 2-D prefab `twod` is out of scope (SURVEY.md section 8)");
   else result = layer(kind, (int)(double)args.get("ninput"), (int)(double)args.get("noutput"), args, {});
   if (!result) throwf("no such network or layer: %s", kind.c_str());
   result->attr.set("kind", kind);

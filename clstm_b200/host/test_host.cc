@@ -84,6 +84,31 @@ static int run_cpu(const char* fname) {
   Tensor2 img = render(L"ab", 48);
   try { ocr.predict(img); } catch (const char* msg) { threw = string(msg).find("no CPU fallback") != string::npos || string(msg).find("device") != string::npos; }
   if (getenv("EXPECT_NO_GPU")) CHECK(threw);
+  // ---- the other 1-D prefabs and layer variants (clstm_prefab.cc:22-129, clstm.cc:382-389, 655-668)
+  {
+    Network b2 = make_net("bidi2", {{"ninput", 48}, {"nhidden", 5}, {"nhidden2", 7}, {"noutput", 9}});
+    CHECK(b2->kind == "Stacked" && b2->sub.size() == 3 && b2->sub[1]->kind == "Parallel" && b2->sub[2]->kind == "SoftmaxLayer");
+    CHECK(n_params(b2) == 2 * 4 * 5 * (1 + 48 + 5) + 2 * 4 * 7 * (1 + 10 + 7) + 9 * (1 + 14));
+    Network l1 = make_net("lstm1", {{"ninput", 8}, {"nhidden", 4}, {"noutput", 1}});
+    CHECK(l1->sub.size() == 2 && l1->sub[0]->kind == "NPLSTM" && l1->sub[1]->kind == "SigmoidLayer");   // noutput == 1 => sigmoid
+    Network rl = make_net("revlstm1", {{"ninput", 8}, {"nhidden", 4}, {"noutput", 3}, {"lstm_type", "LINNPLSTM"}});
+    CHECK(rl->sub[0]->kind == "Reversed" && rl->sub[0]->sub[0]->kind == "LINNPLSTM" && rl->sub[1]->kind == "SoftmaxLayer");
+    Network b0 = make_net("bidi0", {{"ninput", 8}, {"noutput", 3}});
+    CHECK(b0->kind == "Parallel" && b0->noutput() == 6 && n_params(b0) == 2 * 4 * 3 * (1 + 8 + 3));
+    Network pp = make_net("perplstm", {{"ninput", 8}, {"nhidden", 4}, {"noutput", 2}});
+    CHECK(pp->sub.size() == 1 && pp->sub[0]->kind == "Stacked" && pp->sub[0]->sub[1]->kind == "SigmoidLayer");
+    threw = false;
+    try { make_net("twod", {{"ninput", 8}, {"nhidden", 4}, {"noutput", 2}}); } catch (const char*) { threw = true; }
+    CHECK(threw);
+    const string f2 = string(fname) + ".bidi2";
+    save_net(f2, b2);
+    Network b2l = load_net(f2);
+    CHECK(b2l->sub.size() == 3 && n_params(b2l) == n_params(b2));
+    vector<Float> q0(n_params(b2)), q1(n_params(b2));
+    get_params(b2, q0.data(), (int)q0.size());
+    get_params(b2l, q1.data(), (int)q1.size());
+    CHECK(q0 == q1);
+  }
   // ---- utils.h / clstm.h helpers
   std::wstring k1 = L"kitten", k2 = L"sitting", e0 = L"";
   CHECK(levenshtein(k1, k2) == 3 && levenshtein(k2, k1) == 3 && levenshtein(k1, e0) == 6 && levenshtein(k1, k1) == 0);
@@ -242,6 +267,53 @@ static int run_gpu() {
     for (int k = 0; k < 200; k++) o3.train_batch(raws, tgs);
     auto r3 = o3.train_batch(raws, tgs);
     CHECK(r3[0] == tgs[0] && r3[1] == tgs[1] && r3[2] == tgs[2]);
+  }
+  // ---- rank 4: a two-block net (bidi2) learns the same line; a sigmoid-output lstm1 runs forward/backward/update
+  {
+    CLSTMOCR o4;
+    o4.net = make_net("bidi2", {{"ninput", 48}, {"nhidden", 12}, {"nhidden2", 10}, {"noutput", 7}});
+    o4.net->codec.set(demo_codec());
+    o4.nclasses = 7;
+    o4.normalizer.reset(make_NoNormalizer());
+    o4.setLearningRate(1e-2, 0.9);
+    std::wstring g4;
+    int it4 = 0;
+    for (; it4 < 900; it4++) {
+      g4 = o4.train(img, text);
+      if (g4 == text && it4 > 20) break;
+    }
+    printf("bidi2: trained %d steps, reads: %s\n", it4, utf32_to_utf8(g4).c_str());
+    CHECK(o4.predict(img) == text);
+    o4.save("/tmp/clstm_b200_host_bidi2.clstm");
+    CLSTMOCR o5;
+    o5.load("/tmp/clstm_b200_host_bidi2.clstm");
+    o5.normalizer.reset(make_NoNormalizer());
+    CHECK(o5.predict(img) == text);
+    Network l1 = make_net("lstm1", {{"ninput", 48}, {"nhidden", 6}, {"noutput", 1}, {"lstm_type", "RELUTANHNPLSTM"}});
+    l1->setLearningRate(1e-3, 0.9);
+    set_inputs(l1, img);
+    l1->forward();
+    CHECK(l1->outputs.size() == img.dimension(0) && l1->outputs.rows() == 1);
+    for (int t = 0; t < l1->outputs.size(); t++) {
+      CHECK(l1->outputs[t].v(0, 0) > 0.f && l1->outputs[t].v(0, 0) < 1.f);
+      l1->outputs[t].d(0, 0) = 1.0f - l1->outputs[t].v(0, 0);          // push the sigmoid towards 1
+    }
+    const Float before = l1->outputs[10].v(0, 0);
+    l1->backward();
+    sgd_update(l1);
+    for (int k = 0; k < 20; k++) {
+      l1->forward();
+      for (int t = 0; t < l1->outputs.size(); t++) l1->outputs[t].d(0, 0) = 1.0f - l1->outputs[t].v(0, 0);
+      l1->backward();
+      sgd_update(l1);
+    }
+    l1->forward();
+    CHECK(l1->outputs[10].v(0, 0) > before);
+    Network b0 = make_net("bidi0", {{"ninput", 48}, {"noutput", 3}});
+    bool threw = false;
+    set_inputs(b0, img);
+    try { b0->forward(); } catch (const char*) { threw = true; }   // a bare Parallel is a container; it needs a Stacked root
+    CHECK(threw);
   }
   printf("host gpu ok\n");
   return 0;
