@@ -82,6 +82,20 @@ __device__ __forceinline__ void tmem_ld8(unsigned taddr, float* v) {
   v[4] = __uint_as_float(r4); v[5] = __uint_as_float(r5); v[6] = __uint_as_float(r6); v[7] = __uint_as_float(r7);
 }
 
+// four 32x32b.x8 loads in flight under ONE wait: 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float* v) {
+  unsigned r[32];
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[8 * q + 0]), "=r"(r[8 * q + 1]), "=r"(r[8 * q + 2]), "=r"(r[8 * q + 3]), "=r"(r[8 * q + 4]),
+                   "=r"(r[8 * q + 5]), "=r"(r[8 * q + 6]), "=r"(r[8 * q + 7])
+                 : "r"(taddr + 8 * q));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
 // fp32 -> (tf32 hi, tf32 lo).  hi = x with the 13 low mantissa bits cleared (exactly representable in TF32), lo = x - hi
 // (exact in fp32; the tensor core reads only the TF32 bits of it).  |x - hi - tf32(lo)| <= 2^-20 |x|.  `cvt.rna.tf32`
 // would round instead of truncate (2^-22) but is emulated with ~8 instructions on sm_100a and this split sits in the
@@ -227,7 +241,12 @@ __device__ __forceinline__ void commit_mncontig(const float4 (&v)[NS], unsigned 
 // inverse of the row permutation inside a 32-block: tile row (or TMEM lane / column) rho -> matrix index
 __device__ __forceinline__ int unpermute32(int rho) { return (rho & ~31) + 4 * (rho & 7) + ((rho & 31) >> 3); }
 
+// AMODE / BMODE: operand modes fixed at compile time (0: K-contiguous), -1: taken from g at run time.  The <0,0> instance
+// (every forward product, dH, dx) drops the transposing loaders and column blocks and is a fraction of the code size --
+// the generic instance spent ~30% of its issue slots waiting for instruction fetch.
+template <int AMODE, int BMODE>
 __global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(TcArgs g) {
+  const int a_mode = (AMODE >= 0) ? AMODE : g.a_mode, b_mode = (BMODE >= 0) ? BMODE : g.b_mode;
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   __shared__ __align__(8) unsigned long long mbar_s[2];
   __shared__ unsigned tmem_base_s;
@@ -265,7 +284,7 @@ __global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(TcArgs g) {
   // those sources are transposed by the loader instead.)
   const unsigned idesc = make_idesc(BN);
   const bool two_stage = g.stages == 2;
-  const bool kseg = (g.a_mode == 0 || g.b_mode == 0);
+  const bool kseg = (a_mode == 0 || b_mode == 0);
 
   // k-block -> (K segment, offset inside the segment); K-contiguous segments are padded to multiples of 32
   auto locate = [&](int kb, int& seg, int& kloc) {
@@ -282,11 +301,11 @@ __global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(TcArgs g) {
     int seg, kloc;
     locate(kb, seg, kloc);
     const int k_valid = g.k_len[seg] - kloc;
-    if (g.a_mode == 0)
+    if (a_mode == 0)
       issue_kcontig(ra, g.a_k[seg].p + (long long)m0 * g.a_k[seg].ld + kloc, g.a_k[seg].ld, BM, g.M - m0, k_valid, g.a_vec != 0);
     else
       issue_mncontig(ra, g.a_mn, 1, -1, m0, BM, g.M, kloc, k_valid, g.a_vec != 0);
-    if (g.b_mode == 0)
+    if (b_mode == 0)
       issue_kcontig(rb, g.b_k[seg].p + (long long)n0 * g.b_k[seg].ld + kloc, g.b_k[seg].ld, BN, g.N - n0, k_valid, g.b_vec != 0);
     else if (g.k_nseg > 1)   // one MN-contiguous source per K segment (both directions of the input-delta product)
       issue_mncontig(rb, &g.b_mn[seg], 1, -1, n0, BN, g.N, kloc, k_valid, g.b_vec != 0);
@@ -307,8 +326,8 @@ __global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(TcArgs g) {
     else if (it >= 1) mbar_wait(bar, (it - 1) & 1);
     const unsigned a_hi = smem0 + s * stage_bytes, a_lo = a_hi + a_bytes;
     const unsigned b_hi = a_lo + a_bytes, b_lo = b_hi + b_bytes;
-    if (g.a_mode == 0) commit_kcontig(ra, a_hi, a_lo, BM); else commit_mncontig(ra, a_hi, a_lo, BM);
-    if (g.b_mode == 0) commit_kcontig(rb, b_hi, b_lo, BN); else commit_mncontig(rb, b_hi, b_lo, BN);
+    if (a_mode == 0) commit_kcontig(ra, a_hi, a_lo, BM); else commit_mncontig(ra, a_hi, a_lo, BM);
+    if (b_mode == 0) commit_kcontig(rb, b_hi, b_lo, BN); else commit_mncontig(rb, b_hi, b_lo, BN);
     fence_proxy_async();                                     // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (tid == 0) {
@@ -337,42 +356,56 @@ __global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(TcArgs g) {
   // Operands staged from MN-contiguous sources carry the 32-block permutation: undo it here.
   const int lq = warp & 3, ch = warp >> 2;
   const int trow = 32 * lq + lane;                                   // TMEM lane = tile row
-  const int row = m0 + (g.a_mode ? unpermute32(trow) : trow);
+  const int row = m0 + (a_mode ? unpermute32(trow) : trow);
   const int half = BN / 2;
-  const bool st_vec = !g.ws && g.b_mode == 0 && g.beta == 0.f && (g.ldc % 4 == 0) &&
+  const bool st_vec = !g.ws && b_mode == 0 && g.beta == 0.f && (g.ldc % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && ((n0 + ch * half) % 4 == 0);
-  for (int c = 0; c < half; c += 8) {
-    float v[8];
-    if (it > 0) tmem_ld8(tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * half + c), v);
-    else {
+  // one group of 8 accumulator columns -> global
+  auto emit8 = [&](int tc0, const float* v) {                       // tc0: first tile column of the group
+    if (row >= g.M) return;
+    if (st_vec && n0 + tc0 + 7 < g.N) {
+      const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[tc0]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[tc0 + 4]);
+      float4* dst = reinterpret_cast<float4*>(g.C + (long long)row * g.ldc + n0 + tc0);
+      dst[0] = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
+      dst[1] = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
+    } else {
 #pragma unroll
-      for (int e = 0; e < 8; e++) v[e] = 0.f;
-    }
-    if (row < g.M) {
-      const int tc0 = ch * half + c;                                 // first tile column of this group of 8
-      if (st_vec && n0 + tc0 + 7 < g.N) {
-        const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[tc0]);
-        const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[tc0 + 4]);
-        float4* dst = reinterpret_cast<float4*>(g.C + (long long)row * g.ldc + n0 + tc0);
-        dst[0] = make_float4(v[0] + b0.x, v[1] + b0.y, v[2] + b0.z, v[3] + b0.w);
-        dst[1] = make_float4(v[4] + b1.x, v[5] + b1.y, v[6] + b1.z, v[7] + b1.w);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          const int lc = g.b_mode ? unpermute32(tc0 + e) : tc0 + e;  // column inside the N tile
-          const int col = n0 + lc;
-          if (col < g.N) {
-            if (g.ws) {
-              g.ws[((size_t)blockIdx.z * g.M + row) * g.N + col] = v[e];
-            } else {
-              const float o = v[e] + bias_s[lc];
-              float* dst = g.C + (long long)row * g.ldc + col;
-              *dst = (g.beta != 0.f) ? fmaf(g.beta, *dst, o) : o;
-            }
+      for (int e = 0; e < 8; e++) {
+        const int lc = b_mode ? unpermute32(tc0 + e) : tc0 + e;  // column inside the N tile
+        const int col = n0 + lc;
+        if (col < g.N) {
+          if (g.ws) {
+            g.ws[((size_t)blockIdx.z * g.M + row) * g.N + col] = v[e];
+          } else {
+            const float o = v[e] + bias_s[lc];
+            float* dst = g.C + (long long)row * g.ldc + col;
+            *dst = (g.beta != 0.f) ? fmaf(g.beta, *dst, o) : o;
           }
         }
       }
     }
+  };
+  const unsigned tbase = tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * half);
+  int c = 0;
+  for (; c + 32 <= half; c += 32) {                                  // 32 columns per TMEM round trip
+    float v[32];
+    if (it > 0) tmem_ld32(tbase + (unsigned)c, v);
+    else {
+#pragma unroll
+      for (int e = 0; e < 32; e++) v[e] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) emit8(ch * half + c + 8 * q, v + 8 * q);
+  }
+  for (; c < half; c += 8) {
+    float v[8];
+    if (it > 0) tmem_ld8(tbase + (unsigned)c, v);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = 0.f;
+    }
+    emit8(ch * half + c, v);
   }
   tc_fence_before();
   __syncthreads();
@@ -600,7 +633,9 @@ int g_tc_stages = 1, g_tn_stages = 2;
 int gemm_tc_configure() {
   if (const char* e = getenv("CLSTM_B200_TC_STAGES")) g_tc_stages = (atoi(e) == 2) ? 2 : 1;
   if (const char* e = getenv("CLSTM_B200_TN_STAGES")) g_tn_stages = (atoi(e) == 2) ? 2 : 1;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256));
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<-1, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256));
 #define CB200_TN_ATTR(N_)                                                                                          \
   if (e == cudaSuccess)                                                                                            \
     e = cudaFuncSetAttribute(gemm_tn_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(32 * N_));
@@ -650,7 +685,8 @@ int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
       default: gemm_tn_kernel<8><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g); break;
     }
   } else {
-    gemm_tc_kernel<<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g);
+    if (g.a_mode == 0 && g.b_mode == 0) gemm_tc_kernel<0, 0><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g);
+    else gemm_tc_kernel<-1, -1><<<grid, TCT, tc_smem_bytes(BN, g.stages), st>>>(g);
   }
   if (scatter) {
     const size_t total = (size_t)g.M * g.N;
