@@ -246,3 +246,25 @@ def test_input_pipeline_matches_sequential_steps(ffi):
     assert np.array_equal(seq.get_params(), pipe.get_params())
     with pytest.raises(ffi.Error, match="no prefetched batch"):
         pipe.step_prefetched(1e-3, 0.9)
+
+
+@pytest.mark.parametrize("nh,B,T", [(200, 5, (1, 70)), (400, 3, (20, 45)), (200, 2, (33, 33))])
+def test_cluster_pair_kernels_parity(ffi, oracle, monkeypatch, nh, B, T):
+    # two lines per cluster, software pipelined (lstm_cluster.cu): forced on for small batches, odd line counts and
+    # very different lengths inside a pair included
+    monkeypatch.setenv("CLSTM_B200_CLUSTER_PAIR", "1")
+    ni, nc = 48, 83
+    x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=77)
+    onet, gnet = make_pair(ffi, oracle, ni, nh, nc, "trained")
+    assert gnet.lstm_variant == "cluster"
+    out = gnet.forward(x, Ts)
+    probe = np.random.default_rng(3).normal(0, 1, out.shape).astype(np.float32)
+    gnet.clear_derivs()
+    din = gnet.backward(probe)
+    gd = gnet.get_derivs()
+    onet.clear_derivs()
+    for xx, oo, pp, dd in zip(split(x, Ts), split(out, Ts), split(probe, Ts), split(din, Ts)):
+        assert np.abs(onet.forward(xx) - oo).max() < TOL
+        assert np.abs(onet.backward(pp) - dd).max() < 2e-4 * max(1.0, np.abs(dd).max())
+    od = onet.get_derivs()
+    assert np.abs(od - gd).max() < 3e-4 * max(1.0, np.abs(od).max())
