@@ -64,6 +64,36 @@ __device__ __forceinline__ void cluster_sync_() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- mbarrier + st.async exchange: the store and the signal are one operation, nothing waits on a release fence
+__device__ __forceinline__ void mbar_init_(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arm_(unsigned bar, unsigned bytes) {   // this CTA's single arrival + the bytes to expect
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();       // a lost transfer must surface as an error, never as a hang
+  }
+}
+// 4-byte store into CTA `rank`'s shared memory that also completes 4 bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_f32(unsigned local_addr, unsigned local_bar, unsigned rank, float v) {
+  unsigned raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+               "r"(__float_as_uint(v)), "r"(rbar)
+               : "memory");
+}
+
 // split form: global stores issued between arrive and wait are not covered by this step's release, so the barrier
 // does not have to wait for them to drain (they have a whole step until the next arrive)
 __device__ __forceinline__ void cluster_arrive_() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -371,6 +401,285 @@ __global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster(Lines ln,
     pread = psrc + ((ptog > 0) ? 0u : PBUF);                                    // the buffer that was just filled
     pdst += ptog; ptog = -ptog;
   }
+}
+
+// Backward, exchange through mbarriers (see lstm_fwd_cluster3): the partial sums travel with st.async and complete the
+// owner's barrier; only the pointwise threads wait for them, the CTA barrier that follows orders everybody else.
+template <int NO>
+__global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_bwd_cluster3(Lines ln, LstmBwdArgs a) {
+  typedef ClCfg<NO> Cfg;
+  constexpr int SL = Cfg::SL, NPF = Cfg::NPF, SSTR = Cfg::SSTR, CS = Cfg::CS, UC = Cfg::UC;
+  constexpr int ROWS = 4 * NO, TPAD = Cfg::TPAD, OWN = 4 * UC;     // own delta rows per CTA (200 or 100)
+  constexpr int RSL = OWN / SL;                                    // 8 or 4 row slices
+  constexpr int RB = (RSL == 8) ? 3 : 2;
+  extern __shared__ __align__(16) float bsm[];
+  float* dg_s = bsm;                         // [2][RSL * SSTR]   own deltas, sliced
+  float* part_s = bsm + 2 * RSL * SSTR;      // [2][CS][UC]       partial dh of my units from every CTA (double buffered)
+  float* st_s = part_s + 2 * CS * UC;        // [kStage][TPAD][8] per-thread staging ring
+  __shared__ __align__(8) unsigned long long pbar[2];   // one mbarrier per partial-sum buffer
+  const int tid0 = threadIdx.x;
+  const unsigned crank = cluster_rank_();
+  const int b = ln.order[blockIdx.x / CS], d = a.d0 + blockIdx.y;
+  const int T = ln.T[b], off = ln.off[b];
+  const unsigned st_addr0 = (unsigned)__cvta_generic_to_shared(st_s + (size_t)tid0 * 8);
+  const int tid = (tid0 < Cfg::THREADS) ? tid0 : Cfg::THREADS - RSL + (tid0 % RSL);   // padding lanes clone the last k-group
+  // ---- matvec role: outputs kg4..kg4+3 (global unit indices), own-row slice rs
+  const int kgp = tid / RSL, rs = tid % RSL;
+  const int kg4 = kgp * 4;
+  const bool hi = (rs >> (RB - 1)) & 1, lo = (rs >> (RB - 2)) & 1;
+  const int kout = kg4 + 2 * (int)hi + (int)lo;                    // output unit this lane holds after the reduce
+  // ---- pointwise role: thread -> (own unit pu, gate pg), 4*UC <= 400 threads take part
+  const bool pw = tid0 < OWN;
+  const int pu = pw ? tid0 >> 2 : 0, pg = tid0 & 3;
+  const int punit = (int)crank * UC + pu;
+  const float* __restrict__ Gb = d ? a.G[1] : a.G[0];
+  const float* __restrict__ Cb = d ? a.C[1] : a.C[0];
+  const float* __restrict__ dHb = a.dH + a.hoff[d];
+  float* __restrict__ DGb = d ? a.DG[1] : a.DG[0];
+
+  u64 w[4][NPF];
+  float wt[4];
+  {
+    const float* R = d ? a.R[1] : a.R[0];
+    const int r0 = 4 * (int)crank * UC + rs * SL;                  // first own row of the slice (global row index)
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+#pragma unroll
+      for (int p = 0; p < NPF; p++)
+        w[kk][p] = pack2(R[(size_t)(r0 + 2 * p) * NO + kg4 + kk], R[(size_t)(r0 + 2 * p + 1) * NO + kg4 + kk]);
+      wt[kk] = R[(size_t)(r0 + SL - 1) * NO + kg4 + kk];
+    }
+  }
+  for (int i = tid0; i < 2 * RSL * SSTR + 2 * CS * UC; i += blockDim.x) bsm[i] = 0.f;
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&pbar[0]);
+  if (tid0 == 0) {
+    mbar_init_(bar0, 1);
+    mbar_init_(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  const unsigned ds_base = (unsigned)__cvta_generic_to_shared(dg_s);
+  constexpr unsigned DBUF = RSL * SSTR * 4;
+  unsigned rd_addr = ds_base + rs * (SSTR * 4);
+  const int prow = 4 * pu + pg;                                    // own delta row published by the pointwise thread
+  unsigned wr_addr = ds_base + ((prow / SL) * SSTR + (prow % SL)) * 4;
+  const unsigned ps_base = (unsigned)__cvta_generic_to_shared(part_s);
+  constexpr unsigned PBUF = CS * UC * 4;
+  // where this lane's reduced partial goes: CTA kout/UC, slot [crank][kout % UC]
+  const unsigned dst_rank = (unsigned)(kout / UC);
+  unsigned pdst = ps_base + ((int)crank * UC + (kout % UC)) * 4;   // buffer 0
+  unsigned psrc = ps_base + pu * 4;                                // + c*UC*4 per source CTA, buffer 1 first (zeros)
+  const bool send = (rs & ((1 << (RB - 2)) - 1)) == 0 || RB == 2;  // one lane per output after the all-reduce
+  constexpr unsigned STG = TPAD * 32;
+
+  const int dt = d ? 1 : -1;
+  unsigned ncol = off + (d ? 0 : T - 1);
+  auto stage = [&](int u, unsigned col) {
+    const unsigned sa = st_addr0 + (u & (kStage - 1)) * STG;
+    cp_async16(sa, Gb + (size_t)col * ROWS + 4 * punit);
+    cp_async4(sa + 16, Cb + (size_t)col * NO + punit);
+    if (u + 1 < T) cp_async4(sa + 20, Cb + (size_t)(col + dt) * NO + punit);
+    cp_async4(sa + 24, dHb + (size_t)col * a.hstride + punit);
+  };
+#pragma unroll
+  for (int u = 0; u < kStage - 1; u++) {
+    if (u < T && pw) stage(u, ncol + u * dt);
+    cp_async_commit();
+  }
+  cluster_sync_();
+
+  float dcc = 0.f;
+  const bool p_lo = (pg & 1) != 0, p_hi = (pg & 2) != 0;
+  int dtog = (int)DBUF, ptog = (int)PBUF;
+  unsigned pread = psrc + PBUF;                                    // read buffer 1 (zero) at the first step
+  for (int u = 0; u < T; u++) {
+    {
+      const int un = u + kStage - 1;
+      if (un < T && pw) stage(un, ncol + (kStage - 1) * dt);
+      cp_async_commit();
+      cp_async_wait<kStage - 1>();
+    }
+    const bool first = (u + 1 == T);
+    float dl_keep = 0.f;
+    const unsigned wbar = bar0 + ((u & 1) << 3);                   // barrier of the buffer that receives this step's partials
+    if (tid0 == 0 && !first) mbar_arm_(wbar, NO * 4);
+    if (pw) {
+      if (u > 0) mbar_wait_(bar0 + (((u - 1) & 1) << 3), ((unsigned)(u - 1) >> 1) & 1u);   // partials of step u-1 are complete
+      const unsigned sa = st_addr0 + (u & (kStage - 1)) * STG;
+      const ulonglong2 gq = lds_v2u64(sa);
+      const ulonglong2 cq = lds_v2u64(sa + 16);
+      float gi, gf, go, ci, c, cprev, dhu, unused;
+      unpack2(gq.x, gi, gf); unpack2(gq.y, go, ci);
+      unpack2(cq.x, c, cprev); unpack2(cq.y, dhu, unused);
+      if (first) cprev = 0.f;
+      float dhrec = 0.f;
+#pragma unroll
+      for (int cc = 0; cc < CS; cc++) dhrec += lds_f32(pread + cc * (UC * 4));   // partials from every CTA, fixed order
+      const float dh = dhu + dhrec;
+      const float th = fmaf(2.f, rcp_approx(1.0f + ex2_approx(-2.f * kLog2e * c)), -1.f);
+      const float dc = fmaf(1.f - th * th, go * dh, dcc);
+      dcc = first ? 0.f : dc * gf;
+      const float y0 = p_lo ? gf : gi, y1 = p_lo ? ci : go;
+      const float y = p_hi ? y1 : y0;
+      const float B0 = p_lo ? cprev : ci, B1 = p_lo ? gi : dh;
+      const float Bv = p_hi ? B1 : B0;
+      const float Av = (pg == 2) ? th : dc;
+      const float fp = (1.f - y) * ((pg == 3) ? (1.f + y) : y);
+      const float dl = fp * (Av * Bv);
+      sts_f32(wr_addr, dl);
+      dl_keep = dl;
+    }
+    __syncthreads();
+    u64 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+    float dtail = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      const ulonglong2 d2 = lds_v2u64(rd_addr + 16 * i);
+      if (i < 6) {
+        ffma2(acc0, w[0][2 * i], d2.x); ffma2(acc1, w[1][2 * i], d2.x);
+        ffma2(acc2, w[2][2 * i], d2.x); ffma2(acc3, w[3][2 * i], d2.x);
+        ffma2(acc0, w[0][2 * i + 1], d2.y); ffma2(acc1, w[1][2 * i + 1], d2.y);
+        ffma2(acc2, w[2][2 * i + 1], d2.y); ffma2(acc3, w[3][2 * i + 1], d2.y);
+      } else {
+        float dummy; unpack2(d2.x, dtail, dummy);
+      }
+    }
+    float l0, l1;
+    unpack2(acc0, l0, l1); const float p0 = fmaf(wt[0], dtail, l0 + l1);
+    unpack2(acc1, l0, l1); const float p1 = fmaf(wt[1], dtail, l0 + l1);
+    unpack2(acc2, l0, l1); const float p2 = fmaf(wt[2], dtail, l0 + l1);
+    unpack2(acc3, l0, l1); const float p3 = fmaf(wt[3], dtail, l0 + l1);
+    const float part = group_reduce4<RB>(p0, p1, p2, p3, hi, lo);
+    if (!first && send && tid0 < Cfg::THREADS) st_async_f32(pdst, wbar, dst_rank, part);   // my rows' share of dh_prev[kout]
+    if (pw) DGb[ncol * ROWS + 4 * punit + pg] = dl_keep;
+    ncol += dt;
+    rd_addr += dtog; wr_addr += dtog; dtog = -dtog;
+    pread = psrc + ((ptog > 0) ? 0u : PBUF);                                    // the buffer that was just filled
+    pdst += ptog; ptog = -ptog;
+  }
+  cluster_sync_();        // nobody leaves while a peer might still be using the cluster's shared memory windows
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward, exchange through mbarriers: every CTA owns one mbarrier per h buffer.  At step s a CTA arms the barrier of the
+// buffer that will receive h_s (one arrival + NO*4 expected bytes); the lanes that used to store h remotely now issue
+// st.async, which delivers the value AND completes 4 bytes on the destination's barrier; step s+1 starts with a wait on
+// the local barrier.  No cluster-wide rendezvous and no release fence in the loop: a CTA only waits for the data it
+// reads.  Double buffering is safe by data flow (a CTA sends h_s only after it has received all of h_{s-1}, i.e. after
+// every peer finished reading the buffer that h_s overwrites).
+template <int NO>
+__global__ void __launch_bounds__(ClCfg<NO>::TPAD, 1) lstm_fwd_cluster3(Lines ln, LstmFwdArgs a) {
+  typedef ClCfg<NO> Cfg;
+  constexpr int SL = Cfg::SL, NPF = Cfg::NPF, SSTR = Cfg::SSTR, LU = Cfg::LU, CS = Cfg::CS, UC = Cfg::UC, LB = Cfg::LB;
+  constexpr int ROWS = 4 * NO, TPAD = Cfg::TPAD;
+  __shared__ __align__(16) float h_s[2][LU * SSTR];
+  __shared__ float xp_s[kStage][TPAD];
+  __shared__ __align__(8) unsigned long long hbar[2];
+  const int tid0 = threadIdx.x;
+  const unsigned crank = cluster_rank_();
+  const int b = ln.order[blockIdx.x / CS], d = a.d0 + blockIdx.y;
+  const int T = ln.T[b], off = ln.off[b];
+  const int tid = (tid0 < Cfg::THREADS) ? tid0 : Cfg::THREADS - LU + (tid0 % LU);
+  const int ul = tid / LU, lg = tid % LU;
+  const int unit = (int)crank * UC + ul;
+  const bool hi = (lg >> (LB - 1)) & 1, lo = (lg >> (LB - 2)) & 1;
+  const int q = 2 * (int)hi + (int)lo;
+  const bool lead = (lg & ((1 << (LB - 2)) - 1)) == 0;
+  const int row = 4 * unit + q;
+  const float* __restrict__ XPb = d ? a.XP[1] : a.XP[0];
+  float* __restrict__ Gb = d ? a.G[1] : a.G[0];
+  float* __restrict__ Cb = d ? a.C[1] : a.C[0];
+  float* __restrict__ Hpb = d ? a.Hprev[1] : a.Hprev[0];
+  float* __restrict__ Hb = a.H + a.hoff[d];
+
+  u64 w[4][NPF];
+  float wt[4];
+  {
+    const float* Rd = d ? a.R[1] : a.R[0];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const float* Rr = Rd + (size_t)(4 * unit + g) * NO + lg * SL;
+#pragma unroll
+      for (int p = 0; p < NPF; p++) w[g][p] = pack2(Rr[2 * p], Rr[2 * p + 1]);
+      wt[g] = Rr[SL - 1];
+    }
+  }
+  for (int k = tid0; k < 2 * LU * SSTR; k += blockDim.x) (&h_s[0][0])[k] = 0.f;
+  const unsigned bar0 = (unsigned)__cvta_generic_to_shared(&hbar[0]);
+  if (tid0 == 0) {
+    mbar_init_(bar0, 1);
+    mbar_init_(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  const unsigned hs_base = (unsigned)__cvta_generic_to_shared(&h_s[0][0]);
+  constexpr unsigned BUFB = LU * SSTR * 4;
+  unsigned rd_addr = hs_base + lg * (SSTR * 4);
+  unsigned wr_addr = hs_base + BUFB + ((unit / SL) * SSTR + (unit % SL)) * 4;
+  const unsigned xs_addr = (unsigned)__cvta_generic_to_shared(&xp_s[0][tid0]);
+  const int dt = d ? -1 : 1;
+  unsigned ncol = off + (d ? T - 1 : 0);
+  float* __restrict__ obase = (q == 0) ? Hb : (q == 1) ? Cb : Hpb;
+  const unsigned ostride = (q == 0) ? (unsigned)a.hstride : NO;
+#pragma unroll
+  for (int u = 0; u < kStage - 1; u++) {
+    if (u < T) cp_async4(xs_addr + u * (TPAD * 4), XPb + (size_t)(ncol + u * dt) * ROWS + row);
+    cp_async_commit();
+  }
+  cluster_sync_();        // buffers zeroed and barriers initialised in every CTA before the first remote store
+
+  float c = 0.f, hprev = 0.f;
+  const float sc = (q == 3) ? -2.f * kLog2e : -kLog2e;
+  int tog = (int)BUFB;
+  for (int s = 0; s < T; s++) {
+    {
+      const int sn = s + kStage - 1;
+      if (sn < T) cp_async4(xs_addr + (sn & (kStage - 1)) * (TPAD * 4), XPb + (size_t)(ncol + (kStage - 1) * dt) * ROWS + row);
+      cp_async_commit();
+      cp_async_wait<kStage - 1>();
+    }
+    const unsigned wbar = bar0 + (((s + 1) & 1) << 3);             // barrier of the buffer that receives h_s
+    if (tid0 == 0 && s + 1 < T) mbar_arm_(wbar, NO * 4);
+    if (s > 0) mbar_wait_(bar0 + ((s & 1) << 3), ((unsigned)(s - 1) >> 1) & 1u);   // h_{s-1} complete in this CTA
+    u64 acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;
+    float htail = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+      const ulonglong2 h2 = lds_v2u64(rd_addr + 16 * i);
+      if (i < 6) {
+        ffma2(acc0, w[0][2 * i], h2.x); ffma2(acc1, w[1][2 * i], h2.x);
+        ffma2(acc2, w[2][2 * i], h2.x); ffma2(acc3, w[3][2 * i], h2.x);
+        ffma2(acc0, w[0][2 * i + 1], h2.y); ffma2(acc1, w[1][2 * i + 1], h2.y);
+        ffma2(acc2, w[2][2 * i + 1], h2.y); ffma2(acc3, w[3][2 * i + 1], h2.y);
+      } else {
+        float dummy; unpack2(h2.x, htail, dummy);
+      }
+    }
+    const float xp = lds_f32(xs_addr + (s & (kStage - 1)) * (TPAD * 4));
+    float l0, l1;
+    unpack2(acc0, l0, l1); const float p0 = fmaf(wt[0], htail, l0 + l1);
+    unpack2(acc1, l0, l1); const float p1 = fmaf(wt[1], htail, l0 + l1);
+    unpack2(acc2, l0, l1); const float p2 = fmaf(wt[2], htail, l0 + l1);
+    unpack2(acc3, l0, l1); const float p3 = fmaf(wt[3], htail, l0 + l1);
+    const float pre = group_reduce4<LB>(p0, p1, p2, p3, hi, lo) + xp;
+    const float sg = rcp_approx(1.0f + ex2_approx(sc * pre));
+    const float act = (q == 3) ? fmaf(2.f, sg, -1.f) : sg;
+    const float gi = __shfl_sync(0xffffffffu, act, 0 << (LB - 2), LU);
+    const float gf = __shfl_sync(0xffffffffu, act, 1 << (LB - 2), LU);
+    const float go = __shfl_sync(0xffffffffu, act, 2 << (LB - 2), LU);
+    const float ci = __shfl_sync(0xffffffffu, act, 3 << (LB - 2), LU);
+    c = fmaf(gf, c, ci * gi);
+    const float th = fmaf(2.f, rcp_approx(1.0f + ex2_approx(-2.f * kLog2e * c)), -1.f);
+    const float hh = th * go;
+    if (s + 1 < T && lg < CS && tid0 < Cfg::THREADS) st_async_f32(wr_addr, wbar, (unsigned)lg, hh);
+    if (lead) Gb[ncol * ROWS + row] = act;
+    if (lead && q < 3) obase[(size_t)ncol * ostride + unit] = (q == 1) ? c : (q == 2) ? hprev : hh;
+    hprev = hh;
+    ncol += dt;
+    rd_addr += tog; wr_addr -= tog; tog = -tog;
+  }
+  cluster_sync_();        // nobody leaves while a peer might still be using the cluster's shared memory windows
 }
 
 // =====================================================================================================================
@@ -692,17 +1001,19 @@ template <int NO> constexpr size_t bwd_cluster_smem() {
   return (size_t)(2 * (4 * Cfg::UC / Cfg::SL) * Cfg::SSTR + 2 * Cfg::CS * Cfg::UC + kStage * Cfg::TPAD * 8) * sizeof(float);
 }
 
-// -1: pair two lines per cluster when there are more (line, direction) chains than clusters can be resident (throughput
-// regime); 0 / 1: never / always (CLSTM_B200_CLUSTER_PAIR, for A/B runs and the parity tests)
-int g_pair_mode = -1;
+// 1: two lines per cluster with the cluster-barrier exchange (lstm_*_cluster2); default 0 (CLSTM_B200_CLUSTER_PAIR, kept for
+// A/B runs and the parity tests -- the mbarrier kernels are faster)
+int g_pair_mode = 0;
+int g_fwd_mbar = 1;      // exchange through mbarrier + st.async (lstm_*_cluster3); 0: cluster barrier (CLSTM_B200_CLUSTER_MBAR)
 
 template <int NO>
 cudaError_t launch_cluster(bool fwd, cudaStream_t st, const Lines& ln, const void* args) {
   typedef ClCfg<NO> Cfg;
   cudaLaunchConfig_t cfg{};
   const int ndir = fwd ? static_cast<const LstmFwdArgs*>(args)->ndir : static_cast<const LstmBwdArgs*>(args)->ndir;
-  // measured (B200): 16-CTA clusters gain 11-14% per pass from pairing (cfg4: 216 -> 190 ms/step), 4-CTA clusters break even
-  const bool pair = g_pair_mode == 1 || (g_pair_mode < 0 && Cfg::CS == 16 && ln.B * ndir > 2 * (148 / Cfg::CS));
+  // measured (B200, ms per pass fwd / bwd): cfg3 (4-CTA clusters) barrier 9.5 / 9.9, mbarrier 7.0 / 9.5;
+  // cfg4 (16-CTA clusters) barrier 99.6 / 100.8, paired barrier 88.8 / 85.7, mbarrier 68.2 / 87.2 => mbarrier kernels by default
+  const bool pair = g_pair_mode == 1;
   cfg.gridDim = dim3((pair ? (ln.B + 1) / 2 : ln.B) * Cfg::CS, ndir, 1);
   cfg.blockDim = dim3(Cfg::TPAD, 1, 1);
   cfg.dynamicSmemBytes = fwd ? 0 : (pair ? bwd_cluster2_smem<NO>() : bwd_cluster_smem<NO>());
@@ -714,6 +1025,10 @@ cudaError_t launch_cluster(bool fwd, cudaStream_t st, const Lines& ln, const voi
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (!pair && g_fwd_mbar) {
+    if (fwd) return cudaLaunchKernelEx(&cfg, lstm_fwd_cluster3<NO>, ln, *static_cast<const LstmFwdArgs*>(args));
+    return cudaLaunchKernelEx(&cfg, lstm_bwd_cluster3<NO>, ln, *static_cast<const LstmBwdArgs*>(args));
+  }
   if (pair) {
     if (fwd) return cudaLaunchKernelEx(&cfg, lstm_fwd_cluster2<NO>, ln, *static_cast<const LstmFwdArgs*>(args));
     return cudaLaunchKernelEx(&cfg, lstm_bwd_cluster2<NO>, ln, *static_cast<const LstmBwdArgs*>(args));
@@ -729,10 +1044,14 @@ cudaError_t configure_one() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(lstm_bwd_cluster2<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_cluster2_smem<NO>());
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(lstm_bwd_cluster3<NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_cluster_smem<NO>());
+  if (e != cudaSuccess) return e;
   if (ClCfg<NO>::CS > 8) {
     e = cudaFuncSetAttribute(lstm_fwd_cluster<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_cluster<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_cluster2<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_fwd_cluster3<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_cluster3<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_bwd_cluster2<NO>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   }
   return e;
@@ -743,8 +1062,9 @@ cudaError_t configure_one() {
 bool lstm_cluster_supported(int no) { return no == 200 || no == 400; }
 
 int lstm_cluster_configure() {
-  if (const char* m = getenv("CLSTM_B200_CLUSTER_PAIR")) g_pair_mode = (m[0] == '0') ? 0 : (m[0] == '1' ? 1 : -1);
-  else g_pair_mode = -1;
+  if (const char* m = getenv("CLSTM_B200_CLUSTER_PAIR")) g_pair_mode = (m[0] == '1') ? 1 : 0;
+  else g_pair_mode = 0;
+  if (const char* m = getenv("CLSTM_B200_CLUSTER_MBAR")) g_fwd_mbar = (m[0] != '0');
   cudaError_t e = configure_one<200>();
   if (e == cudaSuccess) e = configure_one<400>();
   return (int)e;
