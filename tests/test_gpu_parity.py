@@ -273,3 +273,40 @@ def test_cluster_exchange_variants_parity(ffi, oracle, monkeypatch, nh, B, T, mo
         assert np.abs(onet.backward(pp) - dd).max() < 2e-4 * max(1.0, np.abs(dd).max())
     od = onet.get_derivs()
     assert np.abs(od - gd).max() < 3e-4 * max(1.0, np.abs(od).max())
+
+
+def test_ctc_limits_max_states_and_classes(ffi, oracle):
+    # the device aligner's documented limits: 511 labels (S = 1023 lattice states, 32 per lane) and 512 classes;
+    # alignment indices stay bit-exact there, one label more is refused (it must not silently truncate)
+    ni, nh, nc = 16, 16, 512
+    rng = np.random.default_rng(12)
+    T = np.array([1100, 40], np.int32)
+    x = rng.uniform(0, 1, (int(T.sum()), ni)).astype(np.float32)
+    L = np.array([511, 0], np.int32)                                # second line: empty transcript (blank only)
+    labels = rng.integers(1, nc, int(L.sum())).astype(np.int32)
+    onet, gnet = make_pair(ffi, oracle, ni, nh, nc, "init")
+    out = gnet.forward(x, T)
+    aligned = gnet.ctc_align(labels, L)
+    amax = gnet.argmax(1)
+    for xx, oo, aa, ll, am in zip(split(x, T), split(out, T), split(aligned, T), split(labels, L), split(amax, T)):
+        assert np.abs(onet.forward(xx) - oo).max() < TOL
+        o_al = oracle.ctc_align_labels(oo, ll)
+        assert np.abs(o_al - aa).max() < 5e-4                        # lattice values reach ~ -6.2*T here (see long-line test)
+        assert np.array_equal(oracle.argmax_rows(o_al), am)
+    assert np.array_equal(amax[T[0]:], np.zeros(T[1], np.int32))     # empty transcript aligns to blank everywhere
+    with pytest.raises(ffi.Error, match="too long"):
+        gnet.ctc_align(rng.integers(1, nc, 512).astype(np.int32), [512, 0])
+    with pytest.raises(ffi.Error, match="not supported"):
+        ffi.Net(ni, nh, 513)
+
+
+def test_single_column_single_line(ffi, oracle):
+    # B = 1, T = 1: every kernel's degenerate case (no recurrence step, lattice of one row)
+    ni, nh, nc = 48, 100, 11
+    onet, gnet = make_pair(ffi, oracle, ni, nh, nc, "trained")
+    x = np.random.default_rng(2).uniform(0, 1, (1, ni)).astype(np.float32)
+    dec, out, al = gnet.train_step(x, [1], np.array([3], np.int32), [1], 1e-3, 0.9, want_out=True, want_aligned=True)
+    o_out, o_al = onet.fwdbwd(x, np.array([3], np.int32))
+    onet.sgd_update(1e-3, 0.9)
+    assert np.abs(o_out - out).max() < TOL and np.abs(o_al - al).max() < TOL
+    assert np.abs(onet.get_params() - gnet.get_params()).max() < TOL
