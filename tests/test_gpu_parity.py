@@ -248,15 +248,17 @@ def test_input_pipeline_matches_sequential_steps(ffi):
         pipe.step_prefetched(1e-3, 0.9)
 
 
-@pytest.mark.parametrize("mode", ["pair", "barrier"])
+@pytest.mark.parametrize("mode", ["pair", "pair-barrier", "barrier"])
 @pytest.mark.parametrize("nh,B,T", [(200, 5, (1, 70)), (400, 3, (20, 45)), (200, 2, (33, 33))])
 def test_cluster_exchange_variants_parity(ffi, oracle, monkeypatch, nh, B, T, mode):
-    # the default cluster kernels exchange through mbarrier + st.async (covered by CASES above); the two cluster-barrier
-    # variants (one line per cluster / two lines software pipelined) stay selectable for A/B runs and stay tested:
-    # odd line counts and very different lengths inside a pair included
-    if mode == "pair":
+    # the cluster kernels exchange through mbarrier + st.async, one line per cluster by default (covered by CASES above) or
+    # two lines software pipelined ("pair"); the cluster-barrier variants of both stay selectable for A/B runs and stay
+    # tested: odd line counts and very different lengths inside a pair included
+    if mode.startswith("pair"):
         monkeypatch.setenv("CLSTM_B200_CLUSTER_PAIR", "1")
     else:
+        monkeypatch.setenv("CLSTM_B200_CLUSTER_PAIR", "0")
+    if mode.endswith("barrier"):
         monkeypatch.setenv("CLSTM_B200_CLUSTER_MBAR", "0")
     ni, nc = 48, 83
     x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=77)
