@@ -154,6 +154,25 @@ def normalizer_leg(net, a):
     res = {"kind": "center", "lines": B, "raw_shape": [h, w], "normalized_columns": int(T.sum()),
            "ms_per_batch_host_to_resident": dt * 1e3, "device_ms_per_batch": dev_ms,
            "value": B * w * h / dt, "unit": "raw px/s", "launches_per_batch": stats.get("normalize", (0.0, 0))[1] / reps}
+    # training straight from raw lines through the two-deep input pipeline: normalisation of batch i+1 runs on the copy
+    # stream underneath step i (clstm_b200_prefetch_raw_batch / step_prefetched / fetch_decoded)
+    rng = np.random.default_rng(5)
+    L = [20] * B
+    labels = rng.integers(1, a.nclasses, 20 * B).astype(np.int32)
+    mpl = int(T.max()) // 2 + 1
+    net.prefetch_raw_batch(imgs, labels, L)
+
+    def raw_step():
+        net.step_prefetched(LR, MOM, CLIP)
+        net.prefetch_raw_batch(imgs, labels, L)
+        net.fetch_decoded(mpl)
+    for _ in range(3):
+        raw_step()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        raw_step()
+    res["train_from_raw_ms_per_step"] = (time.perf_counter() - t0) / 10 * 1e3
+    res["train_from_raw_note"] = "wall clock per step incl. H2D of the raw pixels, device normalisation of the next batch, the training step on %d normalised columns and the D2H of its result" % int(T.sum())
     if not a.no_cpu_baseline:
         from oracle import binding as ob
         t0 = time.perf_counter()

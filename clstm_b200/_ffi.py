@@ -63,6 +63,7 @@ EXPORTS = {
     "clstm_b200_fetch_decoded": (C.c_int, [C.c_void_p, C.c_int, i32p, i32p, i32p, C.c_int]),
     "clstm_b200_synchronize": (C.c_int, [C.c_void_p]),
     "clstm_b200_prefetch_batch": (C.c_int, [C.c_void_p, f32p, i32p, C.c_int, i32p, i32p]),
+    "clstm_b200_prefetch_raw_batch": (C.c_int, [C.c_void_p, f32p, i32p, i32p, C.c_int, C.c_int, f32p, i32p, i32p, i32p]),
     "clstm_b200_step_prefetched": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float]),
     "clstm_b200_normalize_batch": (C.c_int, [C.c_void_p, f32p, i32p, i32p, C.c_int, C.c_int, f32p, i32p, i32p, i32p]),
     "clstm_b200_normalizer_state": (C.c_int, [C.c_void_p, f32p, f32p]),
@@ -314,6 +315,23 @@ class Net:
         self._prefetch_keep = (xa, Ta, la, La)
         self._prefetch_geom = (int(Ta.sum()), Ta.size)
         _chk(lib().clstm_b200_prefetch_batch(self.h, xp, Tp, Ta.size, lp, Lp))
+
+    def prefetch_raw_batch(self, images, labels, L, kind="center", params=None):
+        """normalise the next batch of raw line images on the copy stream while the current step runs"""
+        W = np.array([im.shape[1] for im in images], np.int32)
+        H = np.array([im.shape[0] for im in images], np.int32)
+        raw = np.concatenate([np.ascontiguousarray(im, np.float32).ravel() for im in images])
+        ra, rp = _f32(raw)
+        T = np.zeros(len(images), np.int32)
+        pp = None
+        if params is not None:
+            pa, pp = _f32(params)
+        la, lp = _i32(labels)
+        La, Lp = _i32(L)
+        _chk(lib().clstm_b200_prefetch_raw_batch(self.h, rp, W.ctypes.data_as(i32p), H.ctypes.data_as(i32p), len(images),
+                                                 self.KINDS[kind], pp, lp, Lp, T.ctypes.data_as(i32p)))
+        self._prefetch_geom = (int(T.sum()), T.size)
+        return T
 
     def step_prefetched(self, lr, momentum, clip=100.0):
         _chk(lib().clstm_b200_step_prefetched(self.h, lr, momentum, clip))

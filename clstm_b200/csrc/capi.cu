@@ -214,11 +214,12 @@ struct Scope {  // brackets one phase with events when profiling is on
   clstm_b200_net* n;
   int ph;
   cudaEvent_t a = nullptr, b = nullptr;
-  Scope(clstm_b200_net* net, int phase) : n(net), ph(phase) {
+  cudaStream_t cs;
+  Scope(clstm_b200_net* net, int phase, cudaStream_t stream = nullptr) : n(net), ph(phase), cs(stream ? stream : net->st) {
     if (!n->prof) return;
     a = get();
     b = get();
-    cudaEventRecord(a, n->st);
+    cudaEventRecord(a, cs);
   }
   cudaEvent_t get() {
     cudaEvent_t e;
@@ -229,7 +230,7 @@ struct Scope {  // brackets one phase with events when profiling is on
   void launches(int k) { n->ph_launch[ph] += k; }
   ~Scope() {
     if (!n->prof) return;
-    cudaEventRecord(b, n->st);
+    cudaEventRecord(b, cs);
     n->recs.push_back({ph, a, b});
   }
 };
@@ -521,6 +522,7 @@ void host_gauss_mask(float sigma, std::vector<float>& mask, int& range) {
 int ensure_norm(clstm_b200_net* n, size_t pix, size_t cols, int B, size_t nmask) {
   if (pix > n->n_capPix || cols > n->n_capCols || B > n->n_capB || nmask > n->n_capMask) {
     CU(cudaStreamSynchronize(n->st));
+    CU(cudaStreamSynchronize(n->stc));
     dev_free(n->n_raw); dev_free(n->n_tmp); dev_free(n->n_smooth); dev_free(n->n_a); dev_free(n->n_center);
     dev_free(n->n_r); dev_free(n->n_scale); dev_free(n->n_masks); dev_free(n->n_ym); dev_free(n->n_yd); dev_free(n->n_meta);
     n->n_capPix = std::max(pix + pix / 8 + 1024, n->n_capPix);
@@ -1074,8 +1076,10 @@ int clstm_b200_forward(clstm_b200_net* n, const float* x, const int* T, int B, f
   return 0;
 }
 
-int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W, const int* H, int B, int kind,
-                               const float* params, const int* labels, const int* L, int* T_out) {
+// measure + normalize B raw lines into the CURRENT input set on stream `cs` (the step stream, or the copy stream when
+// called for the spare set by the input pipeline)
+static int normalize_into(clstm_b200_net* n, const float* raw, const int* W, const int* H, int B, int kind,
+                          const float* params, const int* labels, const int* L, int* T_out, cudaStream_t cs) {
   if (!n || !raw || !W || !H) return fail("null argument");
   if (B <= 0) return fail("batch must contain at least one line");
   if (kind < 0 || kind > 2) return fail("unknown normalizer name");      // extras.cc:299
@@ -1126,21 +1130,21 @@ int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W
   std::vector<float> scale(B, 0.f);
   std::vector<double> ym(B, 0.0), yd(B, 0.0);
   {
-    Scope s(n, PH_H2D);
-    CU(cudaMemcpyAsync(n->n_raw, raw, pix * sizeof(float), cudaMemcpyHostToDevice, n->st));
-    CU(cudaMemcpyAsync(n->n_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, n->st));
-    if (!masks.empty()) CU(cudaMemcpyAsync(n->n_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice, n->st));
+    Scope s(n, PH_H2D, cs);
+    CU(cudaMemcpyAsync(n->n_raw, raw, pix * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CU(cudaMemcpyAsync(n->n_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice, cs));
+    if (!masks.empty()) CU(cudaMemcpyAsync(n->n_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice, cs));
   }
   n->n_hr.assign(B, 0.f);
   if (kind == 2) {
     {
-      Scope s(n, PH_NORMALIZE);
+      Scope s(n, PH_NORMALIZE, cs);
       if (maxrange > kNormMaxRange) return fail("normalizer smoothing width %d exceeds the supported %d", maxrange, kNormMaxRange);
-      s.launches(norm_center_measure(n->st, nl, B, maxw, maxh, maxrange, n->n_raw, n->n_tmp, n->n_smooth, n->n_a, n->n_center, n->n_r));
+      s.launches(norm_center_measure(cs, nl, B, maxw, maxh, maxrange, n->n_raw, n->n_tmp, n->n_smooth, n->n_a, n->n_center, n->n_r));
       TRY(check_launch("normalizer measure"));
     }
-    CU(cudaMemcpyAsync(n->n_hr.data(), n->n_r, B * sizeof(float), cudaMemcpyDeviceToHost, n->st));
-    CU(cudaStreamSynchronize(n->st));
+    CU(cudaMemcpyAsync(n->n_hr.data(), n->n_r, B * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
     for (int b = 0; b < B; b++) {                         // CenterNormalizer::normalize, extras.cc:275-276
       const float r = n->n_hr[b];
       scale[b] = (2.0 * r) / th;
@@ -1148,13 +1152,13 @@ int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W
     }
   } else if (kind == 1) {
     {
-      Scope s(n, PH_NORMALIZE);
-      s.launches(norm_mean_measure(n->st, nl, B, maxh, n->n_raw, n->n_ym, n->n_yd));
+      Scope s(n, PH_NORMALIZE, cs);
+      s.launches(norm_mean_measure(cs, nl, B, maxh, n->n_raw, n->n_ym, n->n_yd));
       TRY(check_launch("normalizer measure"));
     }
-    CU(cudaMemcpyAsync(ym.data(), n->n_ym, B * sizeof(double), cudaMemcpyDeviceToHost, n->st));
-    CU(cudaMemcpyAsync(yd.data(), n->n_yd, B * sizeof(double), cudaMemcpyDeviceToHost, n->st));
-    CU(cudaStreamSynchronize(n->st));
+    CU(cudaMemcpyAsync(ym.data(), n->n_ym, B * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(yd.data(), n->n_yd, B * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
     for (int b = 0; b < B; b++) {                         // MeanNormalizer::normalize, extras.cc:185-188
       float actual = vscale * 2 * range * yd[b];
       scale[b] = actual / th;
@@ -1166,17 +1170,44 @@ int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W
   }
   for (int b = 0; b < B; b++)
     if ((long long)tw[b] > 64LL * 1024 * 1024) return fail("line %d: normalised width %d is not plausible", b, tw[b]);
-  TRY(stage_lines(n, tw.data(), B, labels, L));
+  TRY(stage_lines(n, tw.data(), B, labels, L, false, cs));
   {
-    Scope s(n, PH_NORMALIZE);
-    CU(cudaMemcpyAsync(n->n_scale, scale.data(), B * sizeof(float), cudaMemcpyHostToDevice, n->st));
-    s.launches(norm_resample(n->st, nl, B, n->ln.Tmax, n->n_raw, n->n_center, n->n_scale, n->n_ym, n->ln.T, n->ln.off, n->x, th, kind));
+    Scope s(n, PH_NORMALIZE, cs);
+    CU(cudaMemcpyAsync(n->n_scale, scale.data(), B * sizeof(float), cudaMemcpyHostToDevice, cs));
+    s.launches(norm_resample(cs, nl, B, n->ln.Tmax, n->n_raw, n->n_center, n->n_scale, n->n_ym, n->ln.T, n->ln.off, n->x, th, kind));
     TRY(check_launch("normalizer resample"));
   }
   n->n_B = B; n->n_cols = (int)cols;
   if (T_out) memcpy(T_out, tw.data(), B * sizeof(int));
-  CU(cudaStreamSynchronize(n->st));     // `scale` and `meta` are stack/heap temporaries of this call
+  CU(cudaStreamSynchronize(cs));     // `scale` and `meta` are stack/heap temporaries of this call
   return 0;
+}
+
+
+int clstm_b200_normalize_batch(clstm_b200_net* n, const float* raw, const int* W, const int* H, int B, int kind,
+                               const float* params, const int* labels, const int* L, int* T_out) {
+  if (!n) return fail("null argument");
+  return normalize_into(n, raw, W, H, B, kind, params, labels, L, T_out, n->st);
+}
+
+// input pipeline for RAW lines: normalise batch i+1 into the spare input set on the copy stream while step i runs (the
+// recurrent kernels leave more than half of the SMs idle at 32 lines per GPU, so the normaliser is hidden behind them)
+int clstm_b200_prefetch_raw_batch(clstm_b200_net* n, const float* raw, const int* W, const int* H, int B, int kind,
+                                  const float* params, const int* labels, const int* L, int* T_out) {
+  if (!n || !labels || !L) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  const bool keep_fwd = n->have_forward, keep_ctc = n->have_ctc;
+  swap_sets(n);
+  int rc = 0;
+  do {
+    if (n->consumed_recorded && cudaStreamWaitEvent(n->stc, n->ev_consumed, 0) != cudaSuccess) { rc = fail("cudaStreamWaitEvent failed"); break; }
+    if ((rc = normalize_into(n, raw, W, H, B, kind, params, labels, L, T_out, n->stc)) != 0) break;
+    if (cudaEventRecord(n->ev_ready, n->stc) != cudaSuccess) { rc = fail("cudaEventRecord failed"); break; }
+  } while (0);
+  swap_sets(n);
+  n->have_forward = keep_fwd; n->have_ctc = keep_ctc;
+  n->prefetched = (rc == 0);
+  return rc;
 }
 
 int clstm_b200_normalizer_state(clstm_b200_net* n, float* center, float* r) {

@@ -882,47 +882,90 @@ void CLSTMOCR::get_outputs(Tensor2& outputs) {  // clstmhl.h:265-271
   for (int t = 0; t < outputs.dimension(0); t++)
     for (int c = 0; c < outputs.dimension(1); c++) outputs(t, c) = o[t].v(c, 0);
 }
-std::vector<std::wstring> CLSTMOCR::train_batch(std::vector<Tensor2>& images, const std::vector<std::wstring>& tg) {
-  if (images.size() != tg.size() || images.empty()) THROW("train_batch: need one transcript per image");
-  if (!normalizer) THROW("CLSTMOCR: no normalizer (createBidi or load first)");
-  Stacked* s = as_device_root(net.get());
-  if (!s) THROW("CLSTMOCR: the network root is not a device network");
-  s->upload();
-  clstm_b200_net* h = s->h;
-  const int B = (int)images.size();
-  vector<int> W(B), H(B), T(B), L(B), labels;
-  size_t npix = 0;
-  for (int b = 0; b < B; b++) {
-    W[b] = images[b].dimension(0); H[b] = images[b].dimension(1);
-    npix += (size_t)W[b] * H[b];
-    Classes cs;
-    net->codec.encode(cs, tg[b]);
-    L[b] = (int)cs.size();
-    labels.insert(labels.end(), cs.begin(), cs.end());
-  }
+namespace {
+struct RawBatch {   // B raw lines + transcripts marshalled for clstm_b200_normalize_batch / prefetch_raw_batch
+  vector<int> W, H, T, L, labels;
   vector<float> raw;
-  raw.reserve(npix);
-  for (int b = 0; b < B; b++) raw.insert(raw.end(), images[b].data.begin(), images[b].data.end());
-  normalizer->target_height = target_height;
   float p[4];
-  normalizer->abi_params(p);
-  check(clstm_b200_normalize_batch(h, raw.data(), W.data(), H.data(), B, normalizer->kind(), p,
-                                   labels.empty() ? L.data() : labels.data(), L.data(), T.data()));
-  const Float lr = net->effective_lr();
-  const Float momentum = (double)net->attr.get("momentum", 0.9), gc = (double)net->attr.get("gradient_clip", 100.0);
-  check(clstm_b200_step_resident(h, lr, momentum, gc));
-  int tmax = 0;
-  for (int b = 0; b < B; b++) tmax = std::max(tmax, T[b]);
-  const int cap = tmax / 2 + 1;
+  int kind;
+};
+void marshal(CLSTMOCR& ocr, std::vector<Tensor2>& images, const std::vector<std::wstring>& tg, RawBatch& rb) {
+  if (images.size() != tg.size() || images.empty()) THROW("train_batch: need one transcript per image");
+  if (!ocr.normalizer) THROW("CLSTMOCR: no normalizer (createBidi or load first)");
+  const int B = (int)images.size();
+  rb.W.resize(B); rb.H.resize(B); rb.T.assign(B, 0); rb.L.resize(B); rb.labels.clear(); rb.raw.clear();
+  for (int b = 0; b < B; b++) {
+    rb.W[b] = images[b].dimension(0); rb.H[b] = images[b].dimension(1);
+    Classes cs;
+    ocr.net->codec.encode(cs, tg[b]);
+    rb.L[b] = (int)cs.size();
+    rb.labels.insert(rb.labels.end(), cs.begin(), cs.end());
+    rb.raw.insert(rb.raw.end(), images[b].data.begin(), images[b].data.end());
+  }
+  if (rb.labels.empty()) rb.labels.push_back(0);   // never dereferenced with all-empty transcripts, but must not be null
+  ocr.normalizer->target_height = ocr.target_height;
+  ocr.normalizer->abi_params(rb.p);
+  rb.kind = ocr.normalizer->kind();
+}
+std::vector<std::wstring> decoded(CLSTMOCR& ocr, clstm_b200_net* h, int B, int cap) {
   vector<int> cls((size_t)B * cap), locs((size_t)B * cap), cnt(B);
   check(clstm_b200_fetch_decoded(h, 0, cls.data(), locs.data(), cnt.data(), cap));
-  s->host_stale = true;
   std::vector<std::wstring> out(B);
   for (int b = 0; b < B; b++) {
     Classes cs(cls.begin() + (size_t)b * cap, cls.begin() + (size_t)b * cap + cnt[b]);
-    out[b] = net->codec.decode(cs);
+    out[b] = ocr.net->codec.decode(cs);
   }
   return out;
+}
+Stacked* device_root_of(CLSTMOCR& ocr) {
+  Stacked* s = as_device_root(ocr.net.get());
+  if (!s) THROW("CLSTMOCR: the network root is not a device network");
+  s->upload();
+  return s;
+}
+}  // namespace
+
+std::vector<std::wstring> CLSTMOCR::train_batch(std::vector<Tensor2>& images, const std::vector<std::wstring>& tg) {
+  RawBatch rb;
+  marshal(*this, images, tg, rb);
+  Stacked* s = device_root_of(*this);
+  const int B = (int)images.size();
+  check(clstm_b200_normalize_batch(s->h, rb.raw.data(), rb.W.data(), rb.H.data(), B, rb.kind, rb.p, rb.labels.data(),
+                                   rb.L.data(), rb.T.data()));
+  const Float lr = net->effective_lr();
+  const Float momentum = (double)net->attr.get("momentum", 0.9), gc = (double)net->attr.get("gradient_clip", 100.0);
+  check(clstm_b200_step_resident(s->h, lr, momentum, gc));
+  s->host_stale = true;
+  int tmax = 0;
+  for (int b = 0; b < B; b++) tmax = std::max(tmax, rb.T[b]);
+  return decoded(*this, s->h, B, tmax / 2 + 1);
+}
+void CLSTMOCR::prefetch_batch(std::vector<Tensor2>& images, const std::vector<std::wstring>& tg) {
+  RawBatch rb;
+  marshal(*this, images, tg, rb);
+  Stacked* s = device_root_of(*this);
+  const int B = (int)images.size();
+  // returns after the normaliser's round trip on the copy stream; the raw pixels have been consumed by then
+  check(clstm_b200_prefetch_raw_batch(s->h, rb.raw.data(), rb.W.data(), rb.H.data(), B, rb.kind, rb.p, rb.labels.data(),
+                                      rb.L.data(), rb.T.data()));
+  int tmax = 0;
+  for (int b = 0; b < B; b++) tmax = std::max(tmax, rb.T[b]);
+  next_B = B; next_cap = tmax / 2 + 1;
+}
+void CLSTMOCR::train_prefetched() {
+  Stacked* s = device_root_of(*this);
+  if (next_B <= 0) THROW("train_prefetched: no prefetched batch");
+  const Float lr = net->effective_lr();
+  const Float momentum = (double)net->attr.get("momentum", 0.9), gc = (double)net->attr.get("gradient_clip", 100.0);
+  check(clstm_b200_step_prefetched(s->h, lr, momentum, gc));
+  s->host_stale = true;
+  pipe_B = next_B; pipe_cap = next_cap;
+  next_B = 0;
+}
+std::vector<std::wstring> CLSTMOCR::fetch_results() {
+  Stacked* s = device_root_of(*this);
+  if (pipe_B <= 0) THROW("fetch_results: no step in flight");
+  return decoded(*this, s->h, pipe_B, pipe_cap);
 }
 
 }  // namespace ocropus

@@ -209,6 +209,14 @@ struct CLSTMOCR {
   // minibatch extension: B raw lines -> normalise + forward + CTC + backward + update in one device step
   // (clstm_b200_normalize_batch + clstm_b200_step_resident); returns the decoded strings
   std::vector<std::wstring> train_batch(std::vector<Tensor2>& images, const std::vector<std::wstring>& targets);
+  // the same as a two-deep input pipeline: prefetch_batch(i+1) normalises the next batch on the copy stream while the
+  // step on batch i is still running; train_prefetched() launches the step on the prefetched batch and returns at once;
+  // fetch_results() waits for it and returns its decoded strings.  Loop:  prefetch(0); { train_prefetched();
+  // prefetch(next); fetch_results(); } ...
+  void prefetch_batch(std::vector<Tensor2>& images, const std::vector<std::wstring>& targets);
+  void train_prefetched();
+  std::vector<std::wstring> fetch_results();
+  int pipe_B = 0, pipe_cap = 0, next_B = 0, next_cap = 0;
 };
 
 }  // namespace ocropus

@@ -124,6 +124,15 @@ static int main1(int argc, char** argv) {
   save_trigger.enable(save_name != "").skip0();
   Trigger report_trigger(getienv("report_every", 100), ntrain, start);
 
+  // batch > 1: two-deep input pipeline -- while the device runs step `trial`, the host reads and the copy stream
+  // normalises the lines of step `trial + 1`
+  vector<Tensor2> raws(batch);
+  vector<wstring> gts(batch), next_gts(batch);
+  auto draw = [&](vector<wstring>& into) {
+    for (int k = 0; k < batch; k++) trainingset.readSample(raws[k], into[k], lrand48() % trainingset.size());
+    clstm.prefetch_batch(raws, into);
+  };
+  if (batch > 1 && start < ntrain) draw(next_gts);
   for (int trial = start; trial < ntrain; trial++) {
     wstring gt, pred;
     if (batch == 1) {
@@ -132,10 +141,10 @@ static int main1(int argc, char** argv) {
       trainingset.readSample(raw, gt, sample);
       pred = clstm.train(raw, gt);
     } else {
-      vector<Tensor2> raws(batch);
-      vector<wstring> gts(batch);
-      for (int k = 0; k < batch; k++) trainingset.readSample(raws[k], gts[k], lrand48() % trainingset.size());
-      vector<wstring> preds = clstm.train_batch(raws, gts);
+      gts.swap(next_gts);
+      clstm.train_prefetched();                       // launches the step on the prefetched batch and returns
+      if (trial + 1 < ntrain) draw(next_gts);         // host PNG decoding + device normalisation overlap the step
+      vector<wstring> preds = clstm.fetch_results();
       gt = gts[0];
       pred = preds[0];
     }

@@ -267,6 +267,22 @@ static int run_gpu() {
     for (int k = 0; k < 200; k++) o3.train_batch(raws, tgs);
     auto r3 = o3.train_batch(raws, tgs);
     CHECK(r3[0] == tgs[0] && r3[1] == tgs[1] && r3[2] == tgs[2]);
+    // two-deep input pipeline (what clstmocrtrain batch=N runs): prefetch the next batch while the step is in flight
+    o3.prefetch_batch(raws, tgs);
+    std::vector<std::wstring> rp;
+    for (int k = 0; k < 30; k++) {
+      o3.train_prefetched();
+      o3.prefetch_batch(raws, tgs);
+      rp = o3.fetch_results();
+    }
+    CHECK(rp.size() == 3 && rp[0] == tgs[0] && rp[1] == tgs[1] && rp[2] == tgs[2]);
+    CHECK(o3.predict(raw) == text);                 // a synchronous call between pipeline steps leaves the prefetched batch intact
+    o3.train_prefetched();
+    rp = o3.fetch_results();
+    CHECK(rp[2] == tgs[2]);
+    bool threw2 = false;
+    try { o3.train_prefetched(); } catch (const char*) { threw2 = true; }
+    CHECK(threw2);
   }
   // ---- rank 4: a two-block net (bidi2) learns the same line; a sigmoid-output lstm1 runs forward/backward/update
   {

@@ -150,6 +150,11 @@ int clstm_b200_synchronize(clstm_b200_net* net);
  * If the prefetched batch needs larger device buffers than any batch before, the call waits for the running step and
  * re-allocates (device-resident activations of the current batch are lost; decoded results are kept). */
 int clstm_b200_prefetch_batch(clstm_b200_net* net, const float* x, const int* T, int B, const int* labels, const int* L);
+/* the same for RAW line images: clstm_b200_normalize_batch of batch i+1 on the copy stream into the spare input set
+ * (its kernels run on the SMs the recurrent kernels of step i leave idle); blocks the calling thread only for the
+ * normaliser's own round trip (the line widths), never for the running step.  Follow with step_prefetched. */
+int clstm_b200_prefetch_raw_batch(clstm_b200_net* net, const float* raw, const int* W, const int* H, int B, int kind,
+                                  const float* params, const int* labels, const int* L, int* T_out);
 int clstm_b200_step_prefetched(clstm_b200_net* net, float lr, float momentum, float clip);
 
 /* Text-line normalizers on the device (extras.h:31-47, extras.cc:146-301): measure() + normalize() of B raw line

@@ -97,3 +97,33 @@ def test_normalizer_errors(ffi):
         net.normalize_batch([np.ones((2000, 3), np.float32)], "center")
     with pytest.raises(KeyError):
         net.normalize_batch([np.ones((48, 3), np.float32)], "fancy")
+
+
+def test_raw_input_pipeline_matches_sequential(ffi):
+    # prefetch_raw_batch normalises batch i+1 on the copy stream while step i runs; results must be bit-identical to
+    # normalize_batch + step_resident per batch (batches of different geometry)
+    ni, nh, nc = 48, 100, 12
+    batches = []
+    for k, shapes in enumerate([[(200, 60), (120, 44)], [(90, 52), (300, 66), (40, 30)], [(150, 48)]]):
+        imgs = lines(shapes, seed=100 + 10 * k)
+        L = [2] * len(imgs)
+        labels = np.arange(1, 2 * len(imgs) + 1, dtype=np.int32) % (nc - 1) + 1
+        batches.append((imgs, labels, L))
+    p0 = synth.reference_init(ni, nh, nc, seed=0.3)
+    seq = ffi.Net(ni, nh, nc); seq.set_params(p0)
+    ref = []
+    for imgs, labels, L in batches:
+        T = seq.normalize_batch(imgs, "center", labels=labels, L=L)
+        seq.step_resident(1e-3, 0.9)
+        ref.append((T, seq.fetch_decoded(int(T.max()) // 2 + 1)))
+    pipe = ffi.Net(ni, nh, nc); pipe.set_params(p0)
+    Ts = [pipe.prefetch_raw_batch(batches[0][0], batches[0][1], batches[0][2])]
+    for k in range(len(batches)):
+        pipe.step_prefetched(1e-3, 0.9)
+        if k + 1 < len(batches):
+            Ts.append(pipe.prefetch_raw_batch(*batches[k + 1]))
+        dec = pipe.fetch_decoded(int(Ts[k].max()) // 2 + 1)
+        assert np.array_equal(Ts[k], ref[k][0])
+        for (c0, l0), (c1, l1) in zip(ref[k][1], dec):
+            assert np.array_equal(c0, c1) and np.array_equal(l0, l1)
+    assert np.array_equal(seq.get_params(), pipe.get_params())
