@@ -1,0 +1,51 @@
+"""Mechanical evidence that the kernels are what DESIGN.md says they are: the mnemonics that only sm_100a tensor-core /
+cluster / async-copy code produces must be present in the compiled objects (no GPU needed: cuobjdump on the in-tree
+build products, see /opt/skills/guides/B200_PROFILING.md for the mnemonic list)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "clstm_b200", "build")
+
+
+def sass(obj):
+    path = os.path.join(BUILD, obj)
+    if not os.path.exists(path):
+        import clstm_b200
+        clstm_b200.build()
+    return subprocess.check_output(["cuobjdump", "-sass", path], text=True)
+
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
+
+
+def test_dense_products_use_tcgen05_with_tmem():
+    s = sass("gemm_tc.o")
+    assert "sm_100a" in s
+    assert s.count("UTCHMMA") >= 24          # tcgen05.mma kind::tf32: 3 MMAs (3xTF32) x 4 K-slices per k-block, 2+ kernels
+    assert "LDTM" in s                        # tcgen05.ld: accumulators come back from tensor memory
+    assert "UTCBAR" in s                      # tcgen05.commit -> mbarrier
+    assert "HMMA" not in s.replace("UTCHMMA", "")   # no legacy mma.sync path
+
+
+def test_recurrent_kernels_use_packed_fp32_and_async_staging():
+    s = sass("lstm.o")
+    assert s.count("FFMA2") >= 200            # fma.rn.f32x2 chains of the register-resident kernels
+    assert "LDGSTS" in s                      # cp.async staging of the streamed operands
+    assert "MUFU.EX2" in s and "MUFU.RCP" in s
+
+
+def test_cluster_kernels_use_dsmem_async_stores_and_mbarriers():
+    s = sass("lstm_cluster.o")
+    assert "STAS" in s                        # st.async into a peer CTA's shared memory
+    assert "SYNCS.ARRIVE.TRANS64" in s and "TRYWAIT" in s     # mbarrier expect-tx / try_wait
+    assert "UCGABAR_ARV" in s                 # barrier.cluster (prologue / epilogue, A/B variants)
+    assert s.count("FFMA2") >= 400
+
+
+def test_fused_peer_update_uses_system_scope_flags():
+    s = sass("misc.o")
+    assert ".SYS" in s                        # st.release.sys / ld.acquire.sys on the NVLink peer flags
