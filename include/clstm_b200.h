@@ -150,7 +150,8 @@ int clstm_b200_synchronize(clstm_b200_net* net);
  * If the prefetched batch needs larger device buffers than any batch before, the call waits for the running step and
  * re-allocates (device-resident activations of the current batch are lost; decoded results are kept). */
 int clstm_b200_prefetch_batch(clstm_b200_net* net, const float* x, const int* T, int B, const int* labels, const int* L);
-/* the same for RAW line images: clstm_b200_normalize_batch of batch i+1 on the copy stream into the spare input set
+/* the same for RAW line images (the readSample -> normalizer->measure/normalize -> set_inputs prefix of
+ * clstmocrtrain.cc:173-176 / clstmhl.h:202-205): clstm_b200_normalize_batch of batch i+1 on the copy stream into the spare input set
  * (its kernels run on the SMs the recurrent kernels of step i leave idle); blocks the calling thread only for the
  * normaliser's own round trip (the line widths), never for the running step.  Follow with step_prefetched. */
 int clstm_b200_prefetch_raw_batch(clstm_b200_net* net, const float* raw, const int* W, const int* H, int B, int kind,
