@@ -158,3 +158,41 @@ def test_prefab_variants_gradcheck(oracle, prefab, cell, output):
         xx[t, i] -= 2 * eps; lm = float((net.forward(xx) * probe).sum())
         num = (lp - lm) / (2 * eps)
         assert abs(num - din[t, i]) < 3e-2 * max(1.0, abs(num)), (prefab, t, i, num, din[t, i])
+
+
+def test_bidi_forward_matches_independent_numpy_restatement(oracle):
+    # SURVEY Appendix A.1/A.3 written out in numpy float64, straight from the prose (not from the oracle's loops):
+    # per direction  src=[x_t; h_{t-1}], gi/gf/go = sigmoid, ci = tanh, c = ci*gi + gf*c_prev, h = tanh(c)*go,
+    # second LSTM on the time-reversed input, outputs concatenated, softmax = limexp(W [1; h]) normalised.
+    ni, nh, nc, T = 6, 5, 4, 9
+    rng = np.random.default_rng(3)
+    net = oracle.BidiOracle(ni, nh, nc, seed=0.2)
+    p = rng.normal(0, 0.5, net.nparams)
+    net.set_params(p.astype(np.float32))
+    p = net.get_params().astype(np.float64)            # exactly the float32 values the oracle holds
+    x = rng.uniform(-1, 1, (T, ni)).astype(np.float32)
+    nf = ni + nh
+    msz = nh * (1 + nf)
+
+    def mats(block):                                   # walk_params order inside one LSTM: WCI, WGF, WGI, WGO (col-major)
+        W = [block[k * msz:(k + 1) * msz].reshape(1 + nf, nh).T for k in range(4)]
+        return {"ci": W[0], "gf": W[1], "gi": W[2], "go": W[3]}
+    sig = lambda z: 1.0 / (1.0 + np.exp(-z))
+
+    def lstm(W, xs):
+        h = np.zeros(nh); c = np.zeros(nh); out = []
+        for t in range(len(xs)):
+            src = np.concatenate([[1.0], xs[t], h])
+            gi, gf, go = sig(W["gi"] @ src), sig(W["gf"] @ src), sig(W["go"] @ src)
+            ci = np.tanh(W["ci"] @ src)
+            c = ci * gi + (gf * c if t > 0 else 0.0)
+            h = np.tanh(c) * go
+            out.append(h)
+        return np.array(out)
+    xs = x.astype(np.float64)
+    hf = lstm(mats(p[0:4 * msz]), xs)
+    hb = lstm(mats(p[4 * msz:8 * msz]), xs[::-1])[::-1]
+    W1 = p[8 * msz:].reshape(1 + 2 * nh, nc).T
+    z = np.exp(np.clip(np.concatenate([np.ones((T, 1)), hf, hb], 1) @ W1.T, -30, 30))
+    ref = z / z.sum(1, keepdims=True)
+    assert np.abs(net.forward(x) - ref).max() < 2e-6    # float32 oracle vs float64 restatement
