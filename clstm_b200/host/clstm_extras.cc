@@ -164,6 +164,7 @@ void decode_png(PngImage& img, const vector<u8>& file) {
     pos += 12 + (size_t)len;
   }
   if (!have_hdr || img.w <= 0 || img.h <= 0) THROW("internal png error");
+  if (img.w > (1 << 20) || img.h > (1 << 20) || (long long)img.w * img.h > (1LL << 28)) THROW("internal png error");   // absurd header
   int channels;
   switch (ctype) {
     case 0: channels = 1; break;

@@ -726,6 +726,7 @@ Network decode_net(Reader r) {  // net_of_proto clstm_proto.cc:100-137
     auto it = net->parameters.find(a.name);
     if (it == net->parameters.end()) throwf("unknown parameter in file: %s", a.name.c_str());
     if (a.dim.size() != 2) throwf("bad format (Mat, %s, %d)", a.name.c_str(), (int)a.dim.size());
+    if (a.dim[0] < 0 || a.dim[1] < 0 || (long long)a.dim[0] * a.dim[1] > (1LL << 30)) THROW("bad size (Mat)");
     Params* p = it->second;
     p->resize(a.dim[0], a.dim[1]);
     if (!a.val.empty()) {
