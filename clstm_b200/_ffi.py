@@ -76,6 +76,7 @@ EXPORTS = {
     "clstm_b200_stream": (C.c_void_p, [C.c_void_p]),
     "clstm_b200_lstm_variant": (C.c_char_p, [C.c_void_p]),
     "clstm_b200_selftest_gemm": (C.c_int, [C.c_void_p, f32p, C.c_int]),
+    "clstm_b200_selftest_lstm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_float, f32p]),
     "clstm_b200_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "clstm_b200_free_pinned": (None, [C.c_void_p]),
     "clstm_b200_last_error": (C.c_char_p, []),
@@ -116,6 +117,17 @@ def _f32(a):
 def _i32(a):
     a = np.ascontiguousarray(a, dtype=np.int32)
     return a, a.ctypes.data_as(i32p)
+
+
+def selftest_lstm(nhidden, nlines, tmin, tmax, seed=1, wscale=None, device=0):
+    """Device A/B of the batched tensor-core recurrence against the fp32 SIMT kernels (clstm_b200_selftest_lstm).
+    Returns dict(d_gates, d_cell, d_h, d_hprev, d_delta_rel, ms_tc_fwd, ms_tc_bwd, ms_simt_fwd, ms_simt_bwd)."""
+    out = np.zeros(9, np.float32)
+    if wscale is None:
+        wscale = 0.5 / np.sqrt(nhidden)
+    _chk(lib().clstm_b200_selftest_lstm(device, nhidden, nlines, tmin, tmax, seed, float(wscale), out.ctypes.data_as(f32p)))
+    keys = ["d_gates", "d_cell", "d_h", "d_hprev", "d_delta_rel", "ms_tc_fwd", "ms_tc_bwd", "ms_simt_fwd", "ms_simt_bwd"]
+    return dict(zip(keys, (float(v) for v in out)))
 
 
 def pinned_array(shape, dtype):

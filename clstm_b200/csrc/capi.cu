@@ -115,6 +115,8 @@ struct clstm_b200_net {
     float *Rt[2] = {}, *WxT[2] = {};       // derived layouts, refreshed by prepare_weights(): R^T, Wx^T [ni][4no]
     float *XP[2] = {}, *G[2] = {}, *C[2] = {}, *Hprev[2] = {}, *DG[2] = {};
     float *H = nullptr, *dH = nullptr;     // [N][ndir*no]
+    LstmTcPlan* tc = nullptr;              // batched tensor-core recurrence (lstm_tc.cu), nullptr if the size is not covered
+    bool tc_used = false;                  // the forward pass of the current batch ran on it (backward follows suit)
     int nout() const { return ndir * no; }
   } blk[2];
   int nblk = 1;
@@ -129,6 +131,7 @@ struct clstm_b200_net {
   float* W1T = nullptr;                    // W1^T [nfeat][nc]
   bool g_pending = false;
   bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
+  int lstm_mode = 0;            // recurrence: 0 auto (by size and batch), 1 always the tensor-core kernels, 2 never
 
   // ---- batch capacity and buffers.  The INPUT SET (x, metadata, tiles, their pinned staging, host geometry, Lines view)
   // exists twice: the members below are the current set, `spare` holds the other one, swap_sets() exchanges them.
@@ -549,6 +552,7 @@ void prepare_weights(clstm_b200_net* n) {   // after every change of v
   TransposeJobs j{};
   for (int k = 0; k < n->nblk; k++) {
     auto& bk = n->blk[k];
+    lstm_tc_mark_stale(bk.tc);
     for (int d = bk.d0; d < bk.d0 + bk.ndir; d++) {
       j.job[j.n++] = {n->v + bk.oR[d], bk.Rt[d], 4 * bk.no, bk.no};
       j.job[j.n++] = {n->v + bk.oWx[d], bk.WxT[d], 4 * bk.no, bk.ni};
@@ -607,6 +611,20 @@ int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, con
 }
 
 // ------------------------------------------------------------------------------------------------ device passes
+// The batched tensor-core recurrence advances all lines of a 128-slot tile in lock step: its time per pass is
+// (longest line) x (step latency, ~2-4 us), independent of the number of lines, while the register / cluster kernels run
+// one chain per (line, direction) at ~0.3-1 us per step but only as many chains at a time as fit the SMs.
+bool want_lstm_tc(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int B) {
+  if (!bk.tc || n->cell != 0 || n->lstm_mode == 2) return false;
+  if (n->lstm_mode == 1) return true;
+  const int no = bk.no;
+  if (no >= 400) return B >= 12 || no > 400;      // 16-CTA clusters: <= 9 chains at a time; beyond 400 only the generic kernels remain
+  if (no > 200) return B >= 24;
+  if (no == 200) return B >= 48;                  // 4-CTA clusters: 37 chains at a time
+  if (no > 100) return B >= 48;                   // generic kernels otherwise
+  return false;                                   // register-resident kernels: one SM per chain, up to 148 chains
+}
+
 const float* block_input(const clstm_b200_net* n, int k) { return k == 0 ? n->x : n->blk[k - 1].H; }
 int run_forward(clstm_b200_net* n) {
   const Lines& ln = n->ln;
@@ -629,7 +647,14 @@ int run_forward(clstm_b200_net* n) {
         a.G[d] = bk.G[d]; a.C[d] = bk.C[d]; a.Hprev[d] = bk.Hprev[d];
       }
       a.H = bk.H;
-      const char* var = lstm_forward(n->st, ln, a);
+      const char* var = nullptr;
+      bk.tc_used = false;
+      if (want_lstm_tc(n, bk, ln.B)) {
+        const int r = lstm_tc_forward(bk.tc, n->st, ln, a);
+        if (r > 0) return fail("%s", lstm_tc_error(bk.tc));
+        if (r == 0) { var = "tc"; bk.tc_used = true; s.launches(1); }
+      }
+      if (!var) var = lstm_forward(n->st, ln, a);
       if (k == 0) n->variant = var;
       s.launches(1);
     }
@@ -704,7 +729,14 @@ int run_backward(clstm_b200_net* n, bool defer_dx = false) {
         a.hoff[d] = bk.hoff[d];
         a.R[d] = n->v + bk.oR[d]; a.G[d] = bk.G[d]; a.C[d] = bk.C[d]; a.DG[d] = bk.DG[d];
       }
-      lstm_backward(n->st, ln, a);
+      bool done = false;
+      if (bk.tc_used) {
+        const int r = lstm_tc_backward(bk.tc, n->st, ln, a);
+        if (r > 0) return fail("%s", lstm_tc_error(bk.tc));
+        done = (r == 0);
+        if (done) s.launches(1);
+      }
+      if (!done) lstm_backward(n->st, ln, a);
       s.launches(1);
     }
     cudaStream_t dxs = n->st;
@@ -950,6 +982,14 @@ int clstm_b200_create_ex(const clstm_b200_cfg_ex* cfg, clstm_b200_net** out) {
     const char* e = getenv("CLSTM_B200_GEMM");   // "simt" selects the fp32 SIMT tiles (A/B testing against tcgen05)
     n->use_tc = !(e && strcmp(e, "simt") == 0);
   }
+  {
+    const char* e = getenv("CLSTM_B200_LSTM");   // "tc": always the batched tensor-core recurrence; "simt": never
+    n->lstm_mode = (e && strcmp(e, "tc") == 0) ? 1 : ((e && strcmp(e, "simt") == 0) ? 2 : 0);
+  }
+  if (lstm_tc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
+  if (n->cell == 0 && n->lstm_mode != 2)
+    for (int k = 0; k < n->nblk; k++)
+      if (lstm_tc_supported(n->blk[k].no)) n->blk[k].tc = lstm_tc_create(n->blk[k].no, n->num_sms);
   if (lstm_configure() != 0 || ctc_configure() != 0 || gemm_tc_configure() != 0 || norm_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   n->variant = n->cell == 0 ? lstm_variant_for(n->no) : "generic";
   if (cudaStreamSynchronize(n->st) != cudaSuccess) { clstm_b200_destroy(n); return fail("device initialisation failed"); }
@@ -981,8 +1021,11 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   for (int r = 0; r < kMaxPeers; r++)
     if (n->peer_buf[r] && r != n->rank) cudaIpcCloseMemHandle(n->peer_buf[r]);
   dev_free(n->v); dev_free(n->d); dev_free(n->comm_buf); n->g = nullptr; dev_free(n->W1T);
-  for (int k = 0; k < 2; k++)
+  for (int k = 0; k < 2; k++) {
+    lstm_tc_destroy(n->blk[k].tc);
+    n->blk[k].tc = nullptr;
     for (int d = 0; d < 2; d++) { dev_free(n->blk[k].Rt[d]); dev_free(n->blk[k].WxT[d]); }
+  }
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->status);
   dev_free(n->ws); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
   dev_free(n->n_raw); dev_free(n->n_tmp); dev_free(n->n_smooth); dev_free(n->n_a); dev_free(n->n_center);
@@ -1502,6 +1545,19 @@ const char* clstm_b200_lstm_variant(const clstm_b200_net* n) { return n ? n->var
 
 // Self-test of the tcgen05 (3xTF32) dense products against the fp32 SIMT tiles on random data, same shapes/strides
 // as the products of the path.  err[i] = max |tc - simt| / max|simt| for case i.  Returns the number of cases.
+int clstm_b200_selftest_lstm(int device, int nhidden, int nlines, int tmin, int tmax, unsigned seed, float wscale, float* out9) {
+  if (!out9) return fail("null argument");
+  if (nhidden <= 0 || nlines <= 0 || tmin <= 0 || tmax < tmin) return fail("bad self-test geometry");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail("no CUDA device %d; clstm_b200 has no CPU fallback", device);
+  CU(cudaSetDevice(device));
+  char msg[256];
+  const int rc = lstm_tc_selftest(nhidden, nlines, tmin, tmax, seed, wscale, out9, msg, (int)sizeof msg);
+  if (rc != 0) return fail("selftest_lstm (nhidden %d, %d lines): %s", nhidden, nlines, msg);
+  return 0;
+}
+
 int clstm_b200_selftest_gemm(clstm_b200_net* n, float* err, int max_cases) {
   if (!n || !err) return -1;
   if (cudaSetDevice(n->cfg.device) != cudaSuccess) return -1;

@@ -92,6 +92,25 @@ const char* lstm_backward(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a
 const char* lstm_variant_for(int no);
 int lstm_configure();   // opt in to large dynamic smem etc.; returns cudaError_t as int
 
+// the L2-streaming kernels for any size / cell variant (also the comparison baseline of the recurrent self-test)
+void lstm_forward_generic(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a);
+void lstm_backward_generic(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
+
+// ---------------------------------------------------------------- lstm_tc.cu (batched recurrence on tcgen05 + TMEM + TMA)
+struct LstmTcPlan;                                   // split weight copies, exchange buffers, tensor maps of one block
+bool lstm_tc_supported(int no);
+int lstm_tc_configure();
+LstmTcPlan* lstm_tc_create(int no, int num_sms);     // nullptr: size not supported / driver entry point missing
+void lstm_tc_destroy(LstmTcPlan* p);
+void lstm_tc_mark_stale(LstmTcPlan* p);              // the weights changed: the fp16 hi/lo copies are rebuilt on next use
+const char* lstm_tc_error(const LstmTcPlan* p);
+// 0: launched, -1: not applicable to this batch (use another variant), > 0: CUDA error (see lstm_tc_error)
+int lstm_tc_forward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmFwdArgs& a);
+int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
+// device-side A/B of the tensor-core recurrence against the generic kernels on random data; out[0..4] = max abs
+// difference of gates, cell, h, h_prev and (relative) deltas, out[5..8] = ms of tc fwd, tc bwd, generic fwd, generic bwd
+int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wscale, float* out, char* msg, int msglen);
+
 // ---------------------------------------------------------------- lstm_cluster.cu (thread-block clusters + DSMEM)
 bool lstm_cluster_supported(int no);
 int lstm_cluster_configure();

@@ -539,6 +539,13 @@ int lstm_configure() {
   return lstm_cluster_configure();
 }
 
+void lstm_forward_generic(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
+  lstm_fwd_generic<<<dim3(ln.B, a.ndir), generic_threads(a.no), (size_t)6 * a.no * sizeof(float), st>>>(ln, a);
+}
+void lstm_backward_generic(cudaStream_t st, const Lines& ln, const LstmBwdArgs& a) {
+  lstm_bwd_generic<<<dim3(ln.B, a.ndir), generic_threads(a.no), (size_t)9 * a.no * sizeof(float), st>>>(ln, a);
+}
+
 const char* lstm_forward(cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
   switch (a.cell == 0 ? a.no : -1) {        // the register / cluster kernels hard-wire the NPLSTM nonlinearities
     case 16: launch_fwd_regs<16>(st, ln, a); return "regs";

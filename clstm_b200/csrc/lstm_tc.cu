@@ -1,0 +1,997 @@
+// lstm_tc.cu -- the recurrence of the NPLSTM as a BATCHED tensor-core problem (tcgen05 + TMEM + TMA), for batches with
+// many lines per GPU and for hidden sizes whose recurrent matrix no longer fits one SM's registers.
+//
+// Reference semantics (paths relative to /root/reference), identical to lstm.cu:
+//   GenericNPLSTM<SIG,TANH,TANH>::forward   clstm.cc:600-621   loop body  :612-620
+//   GenericNPLSTM::backward                 clstm.cc:622-653   loop body  :629-650
+//   the two contractions that stay inside the time loop: forward_lin1 (clstm_compute.cc:286, the R h_{t-1} half) and
+//   backward_lin1 (clstm_compute.cc:296, the R^T delta half); Reversed / Parallel wiring clstm.cc:458-479, 506-544.
+//
+// Formulation.  Lines are sorted by decreasing length (Lines::order) and cut into TILES of 128 line slots; all lines of a
+// tile advance in lock step, so one step of one direction is a real GEMM
+//        pre[128 lines x 4no gate rows] = h_{s-1}[128 x no] * R^T[no x 4no]            (UMMA M = 128 lines)
+// The 4no gate rows (gate-interleaved: row 4j+g) are cut into NT slices of NR rows; CTA (slice m, tile, direction) keeps
+// its slice of R resident in shared memory for the whole sequence, as fp16 hi/lo parts (tc_common.cuh::split_f16):
+// three kind::f16 MMAs (lo*hi, hi*lo, hi*hi) per K = 16 give fp32-grade products at half the bytes of 3xTF32.
+// Accumulators live in TMEM, lane = line, column = gate row, so the four gates of a hidden unit arrive in four adjacent
+// registers of ONE thread and the cell update needs no shuffles; the cell state stays in registers across the sequence.
+//
+// Forward step s of a (tile, direction), per CTA (warp-specialised):
+//   producer warp : waits until every slice has published h_{s-1} (global step counter), then streams the h tile
+//                   [active lines x no] (fp16 hi/lo, K-major) from L2 into a shared-memory ring with TMA (SWIZZLE_128B)
+//   MMA warp      : one thread issues the 3 x ceil(no/16) tcgen05.mma of the step; tcgen05.commit frees ring stages
+//                   and signals the accumulator
+//   8 epilogue warps (thread = line, two warps per TMEM lane quadrant split the columns): tcgen05.ld, + input
+//                   projection, sigma / tanh, cell update, publish h_s as fp16 hi/lo (the next step's TMA source),
+//                   bump the step counter, then write the stash (gates, cell, h, h_prev) for the backward pass.
+// Backward step: each CTA owns the same NR = 64 gate rows (16 units).  It sums the partial products that every slice
+// wrote for ITS units in the previous step (fixed order => deterministic), does the pointwise delta math, stores the
+// deltas (DG) and puts them -- fp16 hi/lo -- into shared memory as the A operand [128 lines x 64]; the MMA warp multiplies
+// with the resident (or TMA-streamed) R slice [no x 64] in chunks of 256 outputs, double buffered in TMEM, and the
+// epilogue warps drain the chunks into the partial-sum exchange buffer (L2).
+// The recurrence never leaves the GPU; the per-step exchange between the CTAs of a (tile, direction) goes through L2 and
+// one release/acquire counter.  All CTAs of a launch must be co-resident: the launch is cooperative.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace cb200 {
+namespace {
+using namespace tc;
+
+constexpr int kTcLines = 128;          // line slots per tile = UMMA M = TMEM lanes
+constexpr int kTcThreads = 320;        // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kEpiThreads = 256;
+constexpr int kMaxStages = 6;
+constexpr float kScaleH = 16.f;        // h in (-1,1)  -> fp16 hi/lo of 16 h
+constexpr float kScaleR = 16.f;        // weights      -> fp16 hi/lo of 16 R   (|R| < 4096)
+constexpr float kScaleD = 256.f;       // deltas       -> fp16 hi/lo of 256 d  (|d| < 256)
+constexpr unsigned kStageBytes = 2 * kTcLines * 128;   // one ring stage: hi tile + lo tile of [128 lines x 64 k] fp16
+constexpr int kBwdNR = 64;             // gate rows per CTA in the backward kernel (one 128-byte swizzle row of K)
+constexpr int kBwdChunk = 256;         // outputs per MMA chunk in the backward kernel (UMMA N)
+constexpr unsigned kBwdStageBytes = 2 * kBwdChunk * 128;
+
+struct TcFwd {
+  int no, no4;            // hidden units, gate rows
+  int KC, nks;            // 64-wide k chunks / 16-wide k slices of h
+  int NT, ntiles, nst;    // row slices per direction, line tiles in the batch, ring stages
+  int d0, hstride, hoff[2];
+  int rows_pad;           // rows per direction of the split weight copy (NT * NR)
+  int KP;                 // row pitch (halves) of the h exchange buffer
+  const float* XP[2];
+  float* G[2];
+  float* C[2];
+  float* Hprev[2];
+  float* H;
+  __half* hx_hi;          // [direction slot][parity][tile][128][KP]
+  __half* hx_lo;
+  unsigned* flags;        // [direction slot][tile] steps published
+};
+
+struct TcBwd {
+  int no, no4;
+  int NT, ntiles, nst, resident;   // resident: every B chunk has its own stage and is loaded once
+  int nchunk, nop16;      // output chunks of 256, outputs padded to 16
+  int d0, hstride, hoff[2];
+  int kp_rows;            // rows per direction of the transposed split copy
+  const float* G[2];
+  const float* C[2];
+  const float* dH;
+  float* DG[2];
+  float* part;            // [direction slot][tile][parity][dest slice][src slice][128][16]
+  unsigned* flags;
+};
+
+// vectorised per-thread stores of N consecutive floats (N % VW == 0, address VW-float aligned)
+template <int N, int VW>
+__device__ __forceinline__ void store_run(float* dst, const float* v) {
+#pragma unroll
+  for (int i = 0; i < N; i += VW) {
+    if (VW == 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    else if (VW == 2) *reinterpret_cast<float2*>(dst + i) = make_float2(v[i], v[i + 1]);
+    else dst[i] = v[i];
+  }
+}
+template <int N, int VW>
+__device__ __forceinline__ void load_run(float* v, const float* src) {
+#pragma unroll
+  for (int i = 0; i < N; i += VW) {
+    if (VW == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(src + i);
+      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    } else if (VW == 2) {
+      const float2 t = *reinterpret_cast<const float2*>(src + i);
+      v[i] = t.x; v[i + 1] = t.y;
+    } else v[i] = src[i];
+  }
+}
+
+// ================================================================================================ forward
+template <int NR>
+__global__ void __launch_bounds__(kTcThreads, 1)
+lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
+            const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo, Lines ln, TcFwd p) {
+  constexpr int NC = NR / 2;                      // accumulator columns (gate rows) per epilogue thread
+  constexpr int NU = NR / 8;                      // hidden units per epilogue thread
+  constexpr int VW = (NU % 4 == 0) ? 4 : 2;       // vector width of the per-unit runs
+  constexpr unsigned r_bytes = NR * 128;          // hi (or lo) part of one k chunk of the weight slice
+  constexpr int TMEM_COLS = 64;
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxStages + 2];
+  __shared__ unsigned tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = blockIdx.x, q = blockIdx.z, d = p.d0 + q;
+  const unsigned smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const unsigned rs0 = smem0;                                   // weight slice: chunk kc at rs0 + kc*2*r_bytes (hi | lo)
+  const unsigned ring0 = rs0 + (unsigned)p.KC * 2 * r_bytes;    // stage st at ring0 + st*kStageBytes (hi | lo)
+  const unsigned bar0 = smem_u32(&bars[0]);
+  auto full = [&](unsigned st) { return bar0 + 8 * st; };
+  auto empty = [&](unsigned st) { return bar0 + 8 * (kMaxStages + st); };
+  const unsigned rfull = bar0 + 8 * (2 * kMaxStages), accfull = rfull + 8;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kMaxStages + 2; i++) mbar_init(bar0 + 8 * i, 1);
+    mbar_init_fence();
+    tma_prefetch_desc(&tmR_hi); tma_prefetch_desc(&tmR_lo); tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_d = tmem_base_s;
+  unsigned* const flag_q = p.flags + (size_t)q * p.ntiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(rfull, (unsigned)p.KC * 2 * r_bytes);
+      for (int kc = 0; kc < p.KC; kc++) {
+        tma_load_2d(rs0 + kc * 2 * r_bytes, &tmR_hi, kc * 64, d * p.rows_pad + m * NR, rfull);
+        tma_load_2d(rs0 + kc * 2 * r_bytes + r_bytes, &tmR_lo, kc * 64, d * p.rows_pad + m * NR, rfull);
+      }
+      unsigned it = 0;
+      for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+        const int l0 = tile * kTcLines;
+        const int nl = min(kTcLines, ln.B - l0);
+        const int Tt = ln.T[ln.order[l0]];
+        int act = nl;
+        for (int s = 1; s < Tt; s++) {
+          while (act > 0 && ln.T[ln.order[l0 + act - 1]] <= s) act--;      // lines still running at step s: a prefix
+          const int nb = (act + 31) >> 5;                                   // 32-row TMA boxes that hold them
+          wait_counter(flag_q + tile, (unsigned)p.NT * (unsigned)s);        // h_{s-1} of every row slice is in L2
+          fence_proxy_async();                                              // generic-proxy writes -> async-proxy reads
+          const int row0 = ((q * 2 + ((s - 1) & 1)) * p.ntiles + tile) * kTcLines;
+          for (int kc = 0; kc < p.KC; kc++, it++) {
+            const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
+            if (use > 0) mbar_wait(empty(st), (use - 1) & 1);
+            mbar_expect_tx(full(st), (unsigned)nb * 2 * 4096);
+            const unsigned dst = ring0 + st * kStageBytes;
+            for (int j = 0; j < nb; j++) {
+              tma_load_2d(dst + j * 4096, &tmH_hi, kc * 64, row0 + 32 * j, full(st));
+              tma_load_2d(dst + kTcLines * 128 + j * 4096, &tmH_lo, kc * 64, row0 + 32 * j, full(st));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const unsigned idesc = make_idesc_f16(kTcLines, NR);
+      mbar_wait(rfull, 0);
+      unsigned it = 0;
+      for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+        const int Tt = ln.T[ln.order[tile * kTcLines]];
+        for (int s = 1; s < Tt; s++) {
+          for (int kc = 0; kc < p.KC; kc++, it++) {
+            const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
+            mbar_wait(full(st), use & 1);
+            tc_fence_after();
+            const unsigned a_hi = ring0 + st * kStageBytes, a_lo = a_hi + kTcLines * 128;
+            const unsigned b_hi = rs0 + kc * 2 * r_bytes, b_lo = b_hi + r_bytes;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              if (kc * 4 + ks < p.nks) {
+                const unsigned long long ah = make_desc(a_hi + ks * 32), al = make_desc(a_lo + ks * 32);
+                const unsigned long long bh = make_desc(b_hi + ks * 32), bl = make_desc(b_lo + ks * 32);
+                mma_f16(tmem_d, al, bh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);   // small terms first
+                mma_f16(tmem_d, ah, bl, idesc, 1u);
+                mma_f16(tmem_d, ah, bh, idesc, 1u);
+              }
+            }
+            mma_commit(empty(st));
+          }
+          mma_commit(accfull);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int lq = warp & 3, ch = ew >> 2;                 // TMEM lane quadrant (fixed by the warp id), column half
+    const int pl = 32 * lq + lane;                         // line slot of this thread
+    const unsigned taddr = tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * NC);
+    const int ub = m * (NR / 4) + ch * NU;                 // first hidden unit of this thread
+    const int no = p.no, no4 = p.no4;
+    const float* __restrict__ XPd = p.XP[d];
+    float* __restrict__ Gd = p.G[d];
+    float* __restrict__ Cd = p.C[d];
+    float* __restrict__ Hpd = p.Hprev[d];
+    float* __restrict__ Hd = p.H + p.hoff[d];
+    constexpr float inv_scale = 1.0f / (kScaleH * kScaleR);
+    unsigned accph = 0;
+    for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+      const int l0 = tile * kTcLines;
+      const int nl = min(kTcLines, ln.B - l0);
+      const int Tt = ln.T[ln.order[l0]];
+      const int li = (pl < nl) ? ln.order[l0 + pl] : -1;
+      const int Tp = (li >= 0) ? ln.T[li] : 0;
+      const int off = (li >= 0) ? ln.off[li] : 0;
+      float c[NU];
+#pragma unroll
+      for (int u = 0; u < NU; u++) c[u] = 0.f;
+      for (int s = 0; s < Tt; s++) {
+        const bool active = s < Tp;
+        const int t = d ? Tp - 1 - s : s;
+        const size_t col = (size_t)off + t;
+        float xp[NC];
+        if (active) {
+#pragma unroll
+          for (int u = 0; u < NU; u++) {
+            if (ub + u < no) load_run<4, 4>(xp + 4 * u, XPd + col * no4 + 4 * (ub + u));
+            else { xp[4 * u] = xp[4 * u + 1] = xp[4 * u + 2] = xp[4 * u + 3] = 0.f; }
+          }
+        }
+        float acc[NC];
+        if (s > 0) {
+          mbar_wait(accfull, accph);
+          accph ^= 1;
+          tc_fence_after();
+          tmem_ld<NC>(taddr, acc);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NC; i++) acc[i] = 0.f;
+        }
+        float gv[NC], hh[NU];
+        if (active) {
+#pragma unroll
+          for (int u = 0; u < NU; u++) {
+            const float gi = sigmoid_fast(fmaf(acc[4 * u + 0], inv_scale, xp[4 * u + 0]));   // forward_full1 clstm.cc:614-617
+            const float gf = sigmoid_fast(fmaf(acc[4 * u + 1], inv_scale, xp[4 * u + 1]));
+            const float go = sigmoid_fast(fmaf(acc[4 * u + 2], inv_scale, xp[4 * u + 2]));
+            const float ci = tanh_fast(fmaf(acc[4 * u + 3], inv_scale, xp[4 * u + 3]));
+            c[u] = fmaf(gf, c[u], ci * gi);                // forward_statemem clstm_compute.cc:504-508 (c = 0 before step 0)
+            hh[u] = tanh_fast(c[u]) * go;                  // forward_nonlingate :530-537
+            gv[4 * u + 0] = gi; gv[4 * u + 1] = gf; gv[4 * u + 2] = go; gv[4 * u + 3] = ci;
+          }
+          // publish h_s for the next step's TMA loads: fp16 hi/lo of 16 h, row = line slot, K-major
+          const size_t hrow = ((size_t)((q * 2 + (s & 1)) * p.ntiles + tile) * kTcLines + pl) * p.KP + ub;
+          unsigned short hi[NU], lo[NU];
+#pragma unroll
+          for (int u = 0; u < NU; u++) split_f16((ub + u < no) ? hh[u] * kScaleH : 0.f, hi[u], lo[u]);
+          if (NU % 8 == 0) {
+#pragma unroll
+            for (int u = 0; u < NU; u += 8) {
+              *reinterpret_cast<uint4*>(p.hx_hi + hrow + u) = make_uint4(pack_h2(hi[u], hi[u + 1]), pack_h2(hi[u + 2], hi[u + 3]),
+                                                                         pack_h2(hi[u + 4], hi[u + 5]), pack_h2(hi[u + 6], hi[u + 7]));
+              *reinterpret_cast<uint4*>(p.hx_lo + hrow + u) = make_uint4(pack_h2(lo[u], lo[u + 1]), pack_h2(lo[u + 2], lo[u + 3]),
+                                                                         pack_h2(lo[u + 4], lo[u + 5]), pack_h2(lo[u + 6], lo[u + 7]));
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < NU; u += 2) {
+              *reinterpret_cast<unsigned*>(p.hx_hi + hrow + u) = pack_h2(hi[u], hi[u + 1]);
+              *reinterpret_cast<unsigned*>(p.hx_lo + hrow + u) = pack_h2(lo[u], lo[u + 1]);
+            }
+          }
+        }
+        // every epilogue thread has read its accumulators and written its h: publish the step
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar_sync(1, kEpiThreads);
+        if (ew == 0 && lane == 0) {
+          __threadfence();
+          atomicAdd(flag_q + tile, 1u);
+        }
+        if (active) {   // stash for the backward pass and the dense products, off the critical path
+#pragma unroll
+          for (int u = 0; u < NU; u++)
+            if (ub + u < no) store_run<4, 4>(Gd + col * no4 + 4 * (ub + u), gv + 4 * u);
+          if (ub + NU <= no) {
+            store_run<NU, VW>(Cd + col * no + ub, c);
+            store_run<NU, VW>(Hd + col * p.hstride + ub, hh);
+            if (s + 1 < Tp) store_run<NU, VW>(Hpd + (col + (d ? -1 : 1)) * (size_t)no + ub, hh);
+            if (s == 0) {
+              float z[NU];
+#pragma unroll
+              for (int u = 0; u < NU; u++) z[u] = 0.f;
+              store_run<NU, VW>(Hpd + col * no + ub, z);
+            }
+          } else {
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+              if (ub + u < no) {
+                Cd[col * no + ub + u] = c[u];
+                Hd[col * p.hstride + ub + u] = hh[u];
+                if (s + 1 < Tp) Hpd[(col + (d ? -1 : 1)) * (size_t)no + ub + u] = hh[u];
+                if (s == 0) Hpd[col * no + ub + u] = 0.f;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ================================================================================================ backward
+__global__ void __launch_bounds__(kTcThreads, 1)
+lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ CUtensorMap tmT_lo, Lines ln, TcBwd p) {
+  constexpr int NU = 8;                    // hidden units per epilogue thread (two warps share the CTA's 16 units)
+  constexpr int TMEM_COLS = 512;           // two accumulator buffers of 256 columns
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxStages + 5];
+  __shared__ unsigned tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = blockIdx.x, q = blockIdx.z, d = p.d0 + q;
+  const unsigned smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const unsigned a_hi = smem0, a_lo = smem0 + kTcLines * 128;          // A operand: deltas of this CTA's 64 gate rows
+  const unsigned ring0 = smem0 + 2 * kTcLines * 128;                   // B stages (hi | lo), kBwdStageBytes each
+  const unsigned bar0 = smem_u32(&bars[0]);
+  auto bfull = [&](unsigned st) { return bar0 + 8 * st; };
+  auto bempty = [&](unsigned st) { return bar0 + 8 * (kMaxStages + st); };
+  const unsigned afull = bar0 + 8 * (2 * kMaxStages);
+  auto accfull = [&](unsigned b) { return afull + 8 + 8 * b; };
+  auto accempty = [&](unsigned b) { return afull + 24 + 8 * b; };
+
+  if (tid == 0) {
+    for (int i = 0; i < 2 * kMaxStages; i++) mbar_init(bar0 + 8 * i, 1);
+    mbar_init(afull, kEpiThreads);
+    mbar_init(accfull(0), 1); mbar_init(accfull(1), 1);
+    mbar_init(accempty(0), kEpiThreads); mbar_init(accempty(1), kEpiThreads);
+    mbar_init_fence();
+    tma_prefetch_desc(&tmT_hi); tma_prefetch_desc(&tmT_lo);
+  }
+  // the A tile must never hold NaN patterns (rows of line slots that are not running are written as zeros below, but only
+  // from the first step on; the MMA of a step multiplies whatever the tile holds)
+  for (unsigned i = tid; i < 2 * kTcLines * 128 / 16; i += blockDim.x)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(smem0 + 16 * i), "r"(0u) : "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_d = tmem_base_s;
+  unsigned* const flag_q = p.flags + (size_t)q * p.ntiles;
+  const int row_t = d * p.kp_rows;                     // first row of this direction in the transposed split copy
+
+  auto load_chunk = [&](unsigned st, int chunk) {      // B chunk: outputs [256*chunk, +256) x this CTA's 64 gate rows
+    mbar_expect_tx(bfull(st), kBwdStageBytes);
+    const unsigned dst = ring0 + st * kBwdStageBytes;
+    for (int j = 0; j < kBwdChunk / 64; j++) {
+      tma_load_2d(dst + j * 8192, &tmT_hi, m * kBwdNR, row_t + chunk * kBwdChunk + 64 * j, bfull(st));
+      tma_load_2d(dst + kBwdChunk * 128 + j * 8192, &tmT_lo, m * kBwdNR, row_t + chunk * kBwdChunk + 64 * j, bfull(st));
+    }
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer (weights)
+    if (lane == 0) {
+      if (p.resident) {
+        for (int i = 0; i < p.nchunk; i++) load_chunk(i, i);
+      } else {
+        unsigned it = 0;
+        for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+          const int Tt = ln.T[ln.order[tile * kTcLines]];
+          for (int fs = Tt - 1; fs >= 1; fs--)
+            for (int i = 0; i < p.nchunk; i++, it++) {
+              const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
+              if (use > 0) mbar_wait(bempty(st), (use - 1) & 1);
+              load_chunk(st, i);
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      unsigned it = 0, cnt = 0, aph = 0;
+      for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+        const int Tt = ln.T[ln.order[tile * kTcLines]];
+        for (int fs = Tt - 1; fs >= 1; fs--) {
+          mbar_wait(afull, aph);                      // the deltas of this step are in shared memory
+          aph ^= 1;
+          tc_fence_after();
+          for (int i = 0; i < p.nchunk; i++, it++, cnt++) {
+            const unsigned buf = cnt & 1;
+            if (cnt >= 2) mbar_wait(accempty(buf), ((cnt >> 1) - 1) & 1);   // the chunk that used this buffer is drained
+            unsigned st;
+            if (p.resident) { st = i; if (it < (unsigned)p.nchunk) mbar_wait(bfull(st), 0); }
+            else { st = it % (unsigned)p.nst; mbar_wait(bfull(st), (it / (unsigned)p.nst) & 1); }
+            tc_fence_after();
+            const int nw = min(kBwdChunk, p.nop16 - i * kBwdChunk);
+            const unsigned idesc = make_idesc_f16(kTcLines, nw);
+            const unsigned b_hi = ring0 + st * kBwdStageBytes, b_lo = b_hi + kBwdChunk * 128;
+            const unsigned dcol = tmem_d + buf * kBwdChunk;
+#pragma unroll
+            for (int ks = 0; ks < kBwdNR / 16; ks++) {
+              const unsigned long long ah = make_desc(a_hi + ks * 32), al = make_desc(a_lo + ks * 32);
+              const unsigned long long bh = make_desc(b_hi + ks * 32), bl = make_desc(b_lo + ks * 32);
+              mma_f16(dcol, al, bh, idesc, ks > 0 ? 1u : 0u);
+              mma_f16(dcol, ah, bl, idesc, 1u);
+              mma_f16(dcol, ah, bh, idesc, 1u);
+            }
+            if (!p.resident) mma_commit(bempty(st));
+            mma_commit(accfull(buf));
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int lq = warp & 3, ch = ew >> 2;
+    const int pl = 32 * lq + lane;
+    const int ub = m * (kBwdNR / 4) + ch * NU;             // first hidden unit of this thread
+    const int no = p.no, no4 = p.no4, NT = p.NT;
+    const float* __restrict__ Gd = p.G[d];
+    const float* __restrict__ Cd = p.C[d];
+    const float* __restrict__ dHd = p.dH + p.hoff[d];
+    float* __restrict__ DGd = p.DG[d];
+    const bool mine = ub + NU <= no;                       // no % 8 == 0: a thread's units are all real or all padding
+    constexpr float inv_scale = 1.0f / (kScaleD * kScaleR);
+    const size_t slab = (size_t)NT * NT * (kTcLines * 16);     // floats of one [dest][src][128][16] exchange buffer
+    unsigned cnt = 0;
+    for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+      const int l0 = tile * kTcLines;
+      const int nl = min(kTcLines, ln.B - l0);
+      const int Tt = ln.T[ln.order[l0]];
+      const int li = (pl < nl) ? ln.order[l0 + pl] : -1;
+      const int Tp = (li >= 0) ? ln.T[li] : 0;
+      const int off = (li >= 0) ? ln.off[li] : 0;
+      float* const part_t = p.part + (size_t)(q * p.ntiles + tile) * 2 * slab;
+      float dcc[NU];
+#pragma unroll
+      for (int u = 0; u < NU; u++) dcc[u] = 0.f;
+      for (int it = 0; it < Tt; it++) {
+        const int fs = Tt - 1 - it;                        // forward step index handled now
+        const bool active = mine && fs < Tp;
+        const int t = d ? Tp - 1 - fs : fs;
+        const size_t col = (size_t)off + t;
+        float g[4 * NU], cc[NU], cp[NU], dh[NU];
+        if (active) {                                      // operands that do not depend on the exchange: issue first
+          load_run<4 * NU, 4>(g, Gd + col * no4 + 4 * ub);
+          load_run<NU, 4>(cc, Cd + col * no + ub);
+          if (fs > 0) load_run<NU, 4>(cp, Cd + (col + (d ? 1 : -1)) * (size_t)no + ub);
+          load_run<NU, 4>(dh, dHd + col * p.hstride + ub);
+        }
+        if (it > 0) {                                      // partial products of the previous step, all slices
+          if (lane == 0) wait_counter(flag_q + tile, (unsigned)NT * (unsigned)it);
+          __syncwarp();
+          if (active && fs < Tp - 1) {
+            const float* src = part_t + (size_t)((it - 1) & 1) * slab + (size_t)m * NT * (kTcLines * 16) + pl * 16 + ch * NU;
+            float r[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) r[u] = 0.f;
+#pragma unroll 4
+            for (int sm = 0; sm < NT; sm++) {             // fixed order => deterministic
+              const float4 x0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sm * (kTcLines * 16)));
+              const float4 x1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sm * (kTcLines * 16) + 4));
+              r[0] += x0.x; r[1] += x0.y; r[2] += x0.z; r[3] += x0.w;
+              r[4] += x1.x; r[5] += x1.y; r[6] += x1.z; r[7] += x1.w;
+            }
+#pragma unroll
+            for (int u = 0; u < NU; u++) dh[u] += r[u];
+          }
+        }
+        unsigned hi[2 * NU], lo[2 * NU];                    // packed half2: 4 gate rows of a unit = 2 words
+        if (active) {
+          float dl[4 * NU];
+#pragma unroll
+          for (int u = 0; u < NU; u++) {
+            const float gi = g[4 * u], gf = g[4 * u + 1], go = g[4 * u + 2], ci = g[4 * u + 3];
+            const float th = tanh_fast(cc[u]);                            // backward_nonlingate clstm_compute.cc:539-547
+            const float dgo = th * dh[u];
+            const float dc = fmaf(1.f - th * th, go * dh[u], dcc[u]);
+            float dgf = 0.f, carry = 0.f;
+            if (fs > 0) { dgf = dc * cp[u]; carry = dc * gf; }            // backward_statemem :509-515
+            dcc[u] = carry;
+            const float dgi = dc * ci, dci = dc * gi;
+            dl[4 * u + 0] = gi * (1.f - gi) * dgi;                        // backward_nonlin0 :231-267
+            dl[4 * u + 1] = gf * (1.f - gf) * dgf;
+            dl[4 * u + 2] = go * (1.f - go) * dgo;
+            dl[4 * u + 3] = (1.f - ci * ci) * dci;
+          }
+          store_run<4 * NU, 4>(DGd + col * no4 + 4 * ub, dl);
+#pragma unroll
+          for (int i = 0; i < 2 * NU; i++) {
+            unsigned short h0, l0_, h1, l1_;
+            split_f16(dl[2 * i] * kScaleD, h0, l0_);
+            split_f16(dl[2 * i + 1] * kScaleD, h1, l1_);
+            hi[i] = pack_h2(h0, h1);
+            lo[i] = pack_h2(l0_, l1_);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2 * NU; i++) { hi[i] = 0u; lo[i] = 0u; }
+        }
+        if (fs == 0) break;                                // the first forward step has no predecessor: nothing to propagate
+        // A operand row `pl`, k = 32*ch .. 32*ch+31: four 16-byte chunks of the 128-byte swizzled row
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const unsigned chunk = (unsigned)(ch * 4 + i) ^ (unsigned)(pl & 7);
+          const unsigned o = (unsigned)pl * 128 + (chunk << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + o), "r"(hi[4 * i]), "r"(hi[4 * i + 1]),
+                       "r"(hi[4 * i + 2]), "r"(hi[4 * i + 3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + o), "r"(lo[4 * i]), "r"(lo[4 * i + 1]),
+                       "r"(lo[4 * i + 2]), "r"(lo[4 * i + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(afull);
+        // drain the output chunks into the exchange buffer: group gq of 16 outputs belongs to slice (16 chunk + gq)
+        float* const dst_par = part_t + (size_t)(it & 1) * slab + (size_t)m * (kTcLines * 16) + pl * 16;
+        const bool wr = (li >= 0) && fs < Tp;              // rows of lines that are not running are never read
+        for (int i = 0; i < p.nchunk; i++, cnt++) {
+          const unsigned buf = cnt & 1;
+          mbar_wait(accfull(buf), (cnt >> 1) & 1);
+          tc_fence_after();
+          const int nw = min(kBwdChunk, p.nop16 - i * kBwdChunk);
+          const unsigned tbase = tmem_d + ((unsigned)(32 * lq) << 16) + buf * kBwdChunk;
+          for (int gq = ch; gq < nw / 16; gq += 2) {
+            float v[16];
+            tmem_ld<16>(tbase + 16 * gq, v);
+            if (wr) {
+              float* o = dst_par + (size_t)(i * 16 + gq) * NT * (kTcLines * 16);
+#pragma unroll
+              for (int e = 0; e < 16; e += 4)
+                __stcg(reinterpret_cast<float4*>(o + e),
+                       make_float4(v[e] * inv_scale, v[e + 1] * inv_scale, v[e + 2] * inv_scale, v[e + 3] * inv_scale));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(accempty(buf));
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (ew == 0 && lane == 0) {
+          __threadfence();
+          atomicAdd(flag_q + tile, 1u);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ================================================================================================ weight split
+// R [4no x no] fp32 (row-major, gate-interleaved rows) -> fp16 hi/lo of 16 R, once per update:
+//   Rs [rows_pad x KP]     rows = gate rows, K = k   : B operand of the forward kernel (box NR x 64)
+//   Rt [kp_rows x RP]      rows = k, K = gate rows   : B operand of the backward kernel (box 64 x 64)
+// Padding (rows / columns beyond the matrix) stays zero from the allocation.
+__global__ void lstm_tc_split_kernel(const float* __restrict__ R, int no, __half* __restrict__ rs_hi, __half* __restrict__ rs_lo,
+                                     int KP, __half* __restrict__ rt_hi, __half* __restrict__ rt_lo, int RP) {
+  const size_t total = (size_t)4 * no * no;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / no), k = (int)(i % no);
+    unsigned short hi, lo;
+    split_f16(R[i] * kScaleR, hi, lo);
+    reinterpret_cast<unsigned short*>(rs_hi)[(size_t)r * KP + k] = hi;
+    reinterpret_cast<unsigned short*>(rs_lo)[(size_t)r * KP + k] = lo;
+    reinterpret_cast<unsigned short*>(rt_hi)[(size_t)k * RP + r] = hi;
+    reinterpret_cast<unsigned short*>(rt_lo)[(size_t)k * RP + r] = lo;
+  }
+}
+
+// ================================================================================================ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int load_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return 1;
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+// 2-D fp16 tensor [rows][cols] (cols contiguous), box [box_rows][64 halves = 128 bytes], SWIZZLE_128B
+int make_map(CUtensorMap* m, void* base, size_t rows, size_t cols, int box_rows) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0 : 1;
+}
+constexpr size_t kSmemLimit = 232448;     // 227 KB per CTA on sm_100
+constexpr size_t kSmemSlack = 1024 + 256; // alignment of the dynamic part + static barriers
+
+template <int NR> size_t fwd_smem(int KC, int nst) { return (size_t)KC * 2 * NR * 128 + (size_t)nst * kStageBytes + 1024; }
+
+}  // namespace
+
+struct LstmTcPlan {
+  int no = 0, num_sms = 148;
+  int KC = 0, KP = 0, nks = 0;
+  int nr_max_rows = 0;            // rows per direction of the forward split copy (4no padded to a multiple of 192)
+  int kp_rows = 0, RP = 0;        // backward split copy: rows per direction (outputs padded to 256), row pitch (gate rows padded to 64)
+  __half *rs_hi = nullptr, *rs_lo = nullptr, *rt_hi = nullptr, *rt_lo = nullptr;
+  bool stale[2] = {true, true};
+  // exchange buffers, sized for cap_tiles line tiles
+  int cap_tiles = 0, cap_nt_b = 0;
+  __half *hx_hi = nullptr, *hx_lo = nullptr;
+  float* part = nullptr;
+  unsigned* flags = nullptr;
+  CUtensorMap tmR_hi[3], tmR_lo[3];   // box rows 32 / 48 / 64
+  CUtensorMap tmT_hi, tmT_lo, tmH_hi, tmH_lo;
+  bool coop = true;
+  char err[256] = {0};
+};
+
+namespace {
+int fwd_nr_options[3] = {32, 48, 64};
+
+// choose the forward row-slice width: the smallest NR that lets every tile run concurrently and fits shared memory; if no
+// width does, the smallest that fits at all (tiles then run in groups)
+bool pick_fwd(const LstmTcPlan* pl, int ndir, int ntiles, int* NR, int* NT, int* tg, int* nst) {
+  for (int pass = 0; pass < 2; pass++) {
+    for (int o = 0; o < 3; o++) {
+      const int nr = fwd_nr_options[o];
+      const int nt = (4 * pl->no + nr - 1) / nr;
+      if (nt * ndir > pl->num_sms) continue;
+      const size_t base = (size_t)pl->KC * 2 * nr * 128 + kSmemSlack;
+      if (base + 2 * kStageBytes > kSmemLimit) continue;
+      int st = (int)((kSmemLimit - base) / kStageBytes);
+      st = std::min(st, std::min(kMaxStages, std::max(2, pl->KC)));
+      const int groups = std::min(ntiles, pl->num_sms / (nt * ndir));
+      if (pass == 0 && groups < ntiles) continue;
+      *NR = nr; *NT = nt; *tg = groups; *nst = st;
+      return true;
+    }
+  }
+  return false;
+}
+}  // namespace
+
+bool lstm_tc_supported(int no) {
+  if (no < 32 || no % 8 != 0 || no > 1024) return false;
+  return true;
+}
+
+void lstm_tc_destroy(LstmTcPlan* p) {
+  if (!p) return;
+  cudaFree(p->rs_hi); cudaFree(p->rs_lo); cudaFree(p->rt_hi); cudaFree(p->rt_lo);
+  cudaFree(p->hx_hi); cudaFree(p->hx_lo); cudaFree(p->part); cudaFree(p->flags);
+  delete p;
+}
+
+const char* lstm_tc_error(const LstmTcPlan* p) { return p ? p->err : "no plan"; }
+
+LstmTcPlan* lstm_tc_create(int no, int num_sms) {
+  if (!lstm_tc_supported(no) || load_encode() != 0) return nullptr;
+  auto* p = new LstmTcPlan;
+  p->no = no; p->num_sms = num_sms;
+  p->KC = (no + 63) / 64; p->KP = p->KC * 64; p->nks = (no + 15) / 16;
+  p->nr_max_rows = ((4 * no + 191) / 192) * 192;                 // multiple of 32, 48 and 64
+  p->kp_rows = ((no + kBwdChunk - 1) / kBwdChunk) * kBwdChunk;
+  p->RP = ((4 * no + 63) / 64) * 64;
+  const size_t rs = (size_t)2 * p->nr_max_rows * p->KP, rt = (size_t)2 * p->kp_rows * p->RP;
+  bool ok = cudaMalloc((void**)&p->rs_hi, rs * 2) == cudaSuccess && cudaMalloc((void**)&p->rs_lo, rs * 2) == cudaSuccess &&
+            cudaMalloc((void**)&p->rt_hi, rt * 2) == cudaSuccess && cudaMalloc((void**)&p->rt_lo, rt * 2) == cudaSuccess;
+  if (ok) {
+    cudaMemset(p->rs_hi, 0, rs * 2); cudaMemset(p->rs_lo, 0, rs * 2);
+    cudaMemset(p->rt_hi, 0, rt * 2); cudaMemset(p->rt_lo, 0, rt * 2);
+    for (int o = 0; o < 3 && ok; o++)
+      ok = make_map(&p->tmR_hi[o], p->rs_hi, (size_t)2 * p->nr_max_rows, p->KP, fwd_nr_options[o]) == 0 &&
+           make_map(&p->tmR_lo[o], p->rs_lo, (size_t)2 * p->nr_max_rows, p->KP, fwd_nr_options[o]) == 0;
+    ok = ok && make_map(&p->tmT_hi, p->rt_hi, (size_t)2 * p->kp_rows, p->RP, 64) == 0 &&
+         make_map(&p->tmT_lo, p->rt_lo, (size_t)2 * p->kp_rows, p->RP, 64) == 0;
+  }
+  if (const char* e = getenv("CLSTM_B200_TC_COOP")) p->coop = atoi(e) != 0;
+  if (!ok) { lstm_tc_destroy(p); return nullptr; }
+  return p;
+}
+
+void lstm_tc_mark_stale(LstmTcPlan* p) { if (p) p->stale[0] = p->stale[1] = true; }
+
+namespace {
+int ensure_split(LstmTcPlan* p, cudaStream_t st, const float* const R[2], int d0, int ndir) {
+  for (int d = d0; d < d0 + ndir; d++) {
+    if (!p->stale[d]) continue;
+    const size_t so = (size_t)d * p->nr_max_rows * p->KP, to = (size_t)d * p->kp_rows * p->RP;
+    const size_t total = (size_t)4 * p->no * p->no;
+    const int nb = (int)std::min<size_t>((total + 255) / 256, (size_t)p->num_sms * 8);
+    lstm_tc_split_kernel<<<nb, 256, 0, st>>>(R[d], p->no, p->rs_hi + so, p->rs_lo + so, p->KP, p->rt_hi + to, p->rt_lo + to, p->RP);
+    p->stale[d] = false;
+  }
+  return (int)cudaGetLastError();
+}
+int ensure_exchange(LstmTcPlan* p, cudaStream_t st, int ntiles, int nt_b) {
+  if (ntiles <= p->cap_tiles && nt_b <= p->cap_nt_b) return 0;
+  cudaStreamSynchronize(st);
+  cudaFree(p->hx_hi); cudaFree(p->hx_lo); cudaFree(p->part); cudaFree(p->flags);
+  p->hx_hi = p->hx_lo = nullptr; p->part = nullptr; p->flags = nullptr;
+  const int ct = std::max(ntiles, p->cap_tiles), cn = std::max(nt_b, p->cap_nt_b);
+  const size_t hrows = (size_t)2 * 2 * ct * kTcLines;
+  const size_t pf = (size_t)2 * ct * 2 * cn * cn * (kTcLines * 16);
+  if (cudaMalloc((void**)&p->hx_hi, hrows * p->KP * 2) != cudaSuccess || cudaMalloc((void**)&p->hx_lo, hrows * p->KP * 2) != cudaSuccess ||
+      cudaMalloc((void**)&p->part, pf * sizeof(float)) != cudaSuccess || cudaMalloc((void**)&p->flags, (size_t)2 * ct * sizeof(unsigned)) != cudaSuccess) {
+    snprintf(p->err, sizeof p->err, "out of memory for the exchange buffers (%d tiles)", ct);
+    p->cap_tiles = 0; p->cap_nt_b = 0;
+    return 1;
+  }
+  cudaMemsetAsync(p->hx_hi, 0, hrows * p->KP * 2, st);
+  cudaMemsetAsync(p->hx_lo, 0, hrows * p->KP * 2, st);
+  if (make_map(&p->tmH_hi, p->hx_hi, hrows, p->KP, 32) != 0 || make_map(&p->tmH_lo, p->hx_lo, hrows, p->KP, 32) != 0) {
+    snprintf(p->err, sizeof p->err, "cuTensorMapEncodeTiled failed for the h exchange buffer");
+    return 1;
+  }
+  p->cap_tiles = ct; p->cap_nt_b = cn;
+  return 0;
+}
+
+template <class K, class... Args>
+cudaError_t launch_coop(K kernel, dim3 grid, size_t smem, cudaStream_t st, bool coop, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+}  // namespace
+
+int lstm_tc_configure() {
+  cudaError_t e = cudaFuncSetAttribute(lstm_tc_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - 1024));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_fwd<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - 1024));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - 1024));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lstm_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - 1024));
+  return (int)e;
+}
+
+// 0: launched; -1: this batch / size is not handled by the tensor-core recurrence (caller uses another variant);
+// > 0: CUDA error (message in lstm_tc_error)
+int lstm_tc_forward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
+  if (!p || a.cell != 0 || a.no != p->no) return -1;
+  const int ntiles = (ln.B + kTcLines - 1) / kTcLines;
+  int NR, NT, tg, nst;
+  if (!pick_fwd(p, a.ndir, ntiles, &NR, &NT, &tg, &nst)) return -1;
+  const int nt_b = (4 * p->no + kBwdNR - 1) / kBwdNR;
+  if (ensure_exchange(p, st, ntiles, nt_b) != 0) return 1;
+  if (ensure_split(p, st, a.R, a.d0, a.ndir) != 0) { snprintf(p->err, sizeof p->err, "weight split launch failed"); return 1; }
+  cudaMemsetAsync(p->flags, 0, (size_t)2 * p->cap_tiles * sizeof(unsigned), st);
+  TcFwd f{};
+  f.no = p->no; f.no4 = 4 * p->no; f.KC = p->KC; f.nks = p->nks; f.NT = NT; f.ntiles = ntiles; f.nst = nst;
+  f.d0 = a.d0; f.hstride = a.hstride; f.hoff[0] = a.hoff[0]; f.hoff[1] = a.hoff[1];
+  f.rows_pad = p->nr_max_rows; f.KP = p->KP;
+  for (int d = 0; d < 2; d++) { f.XP[d] = a.XP[d]; f.G[d] = a.G[d]; f.C[d] = a.C[d]; f.Hprev[d] = a.Hprev[d]; }
+  f.H = a.H; f.hx_hi = p->hx_hi; f.hx_lo = p->hx_lo; f.flags = p->flags;
+  const dim3 grid(NT, tg, a.ndir);
+  cudaError_t e;
+  const int o = NR == 32 ? 0 : (NR == 48 ? 1 : 2);
+  if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi, p->tmH_lo, ln, f);
+  else if (NR == 48) e = launch_coop(lstm_tc_fwd<48>, grid, fwd_smem<48>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi, p->tmH_lo, ln, f);
+  else e = launch_coop(lstm_tc_fwd<64>, grid, fwd_smem<64>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi, p->tmH_lo, ln, f);
+  if (e != cudaSuccess) {
+    snprintf(p->err, sizeof p->err, "lstm_tc_fwd<%d> launch (grid %d x %d x %d, %d stages): %s", NR, NT, tg, a.ndir, nst, cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  return 0;
+}
+
+int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmBwdArgs& a) {
+  if (!p || a.cell != 0 || a.no != p->no) return -1;
+  const int ntiles = (ln.B + kTcLines - 1) / kTcLines;
+  const int NT = (4 * p->no + kBwdNR - 1) / kBwdNR;
+  if (NT * a.ndir > p->num_sms) return -1;
+  const int tg = std::min(ntiles, p->num_sms / (NT * a.ndir));
+  const int nop16 = ((p->no + 15) / 16) * 16;
+  const int nchunk = (nop16 + kBwdChunk - 1) / kBwdChunk;
+  const size_t a_bytes = 2 * kTcLines * 128;
+  const int max_st = (int)((kSmemLimit - kSmemSlack - a_bytes) / kBwdStageBytes);   // 3
+  const bool resident = nchunk <= std::min(max_st, kMaxStages);
+  const int nst = resident ? nchunk : std::min(max_st, kMaxStages);
+  if (nst < 2 && !resident) return -1;
+  if (ensure_exchange(p, st, ntiles, NT) != 0) return 1;
+  if (ensure_split(p, st, a.R, a.d0, a.ndir) != 0) { snprintf(p->err, sizeof p->err, "weight split launch failed"); return 1; }
+  cudaMemsetAsync(p->flags, 0, (size_t)2 * p->cap_tiles * sizeof(unsigned), st);
+  TcBwd b{};
+  b.no = p->no; b.no4 = 4 * p->no; b.NT = NT; b.ntiles = ntiles; b.nst = nst; b.resident = resident ? 1 : 0;
+  b.nchunk = nchunk; b.nop16 = nop16;
+  b.d0 = a.d0; b.hstride = a.hstride; b.hoff[0] = a.hoff[0]; b.hoff[1] = a.hoff[1];
+  b.kp_rows = p->kp_rows;
+  for (int d = 0; d < 2; d++) { b.G[d] = a.G[d]; b.C[d] = a.C[d]; b.DG[d] = a.DG[d]; }
+  b.dH = a.dH; b.part = p->part; b.flags = p->flags;
+  const size_t smem = a_bytes + (size_t)nst * kBwdStageBytes + 1024;
+  const dim3 grid(NT, tg, a.ndir);
+  cudaError_t e = launch_coop(lstm_tc_bwd, grid, smem, st, p->coop, p->tmT_hi, p->tmT_lo, ln, b);
+  if (e != cudaSuccess) {
+    snprintf(p->err, sizeof p->err, "lstm_tc_bwd launch (grid %d x %d x %d, %d stages%s): %s", NT, tg, a.ndir, nst,
+             resident ? ", resident" : "", cudaGetErrorString(e));
+    cudaGetLastError();
+    return (int)e;
+  }
+  return 0;
+}
+
+
+// ================================================================================================ self-test (device A/B)
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  template <class T> T* as() { return reinterpret_cast<T*>(p); }
+  bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
+};
+float max_abs_diff(const std::vector<float>& a, const std::vector<float>& b, float* maxref = nullptr) {
+  float m = 0.f, r = 0.f;
+  for (size_t i = 0; i < a.size(); i++) {
+    const float d = std::fabs(a[i] - b[i]);
+    if (!(d <= m)) m = d;                 // NaN propagates into the result
+    r = std::max(r, std::fabs(a[i]));
+  }
+  if (maxref) *maxref = r;
+  return m;
+}
+}  // namespace
+
+int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wscale, float* out, char* msg, int msglen) {
+  auto say = [&](const char* m) { if (msg && msglen > 0) snprintf(msg, msglen, "%s", m); };
+  say("");
+  for (int i = 0; i < 9; i++) out[i] = -1.f;
+  if (!lstm_tc_supported(no)) { say("size not supported"); return 1; }
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  if (lstm_configure() != 0 || lstm_tc_configure() != 0) { say("configure failed"); return 1; }
+  LstmTcPlan* plan = lstm_tc_create(no, prop.multiProcessorCount);
+  if (!plan) { say("lstm_tc_create failed"); return 1; }
+  unsigned long long rng = 0x9E3779B97F4A7C15ull ^ seed;
+  auto uni = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (float)((rng >> 40) & 0xFFFFFF) / 16777216.f; };
+  auto nrm = [&]() { float s = 0.f; for (int i = 0; i < 4; i++) s += uni(); return (s - 2.f) * 1.7320508f; };
+  std::vector<int> T(B), off(B), order(B), zero(B, 0);
+  int N = 0, tmax = 0;
+  for (int b = 0; b < B; b++) { T[b] = Tmin + (int)(uni() * (Tmax - Tmin + 1)); if (T[b] > Tmax) T[b] = Tmax; off[b] = N; N += T[b]; tmax = std::max(tmax, T[b]); }
+  for (int b = 0; b < B; b++) order[b] = b;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return T[a] > T[c]; });
+  const size_t n4 = (size_t)N * 4 * no, n1 = (size_t)N * no, n2 = (size_t)N * 2 * no, nr = (size_t)4 * no * no;
+  std::vector<float> hR(2 * nr), hXP(2 * n4), hdH(n2);
+  for (auto& v : hR) v = nrm() * wscale;
+  for (auto& v : hXP) v = nrm();
+  for (auto& v : hdH) v = nrm() * 0.01f;
+  DevBuf dT, dOff, dOrd, dR, dRt, dXP, dG[2], dC[2], dH[2], dHp[2], ddH, dDG[2];
+  bool ok = dT.alloc(B * 4) && dOff.alloc(B * 4) && dOrd.alloc(B * 4) && dR.alloc(2 * nr * 4) && dRt.alloc(2 * nr * 4) &&
+            dXP.alloc(2 * n4 * 4) && ddH.alloc(n2 * 4);
+  for (int v = 0; v < 2; v++)
+    ok = ok && dG[v].alloc(2 * n4 * 4) && dC[v].alloc(2 * n1 * 4) && dH[v].alloc(n2 * 4) && dHp[v].alloc(2 * n1 * 4) && dDG[v].alloc(2 * n4 * 4);
+  if (!ok) { say("out of memory"); lstm_tc_destroy(plan); return 1; }
+  cudaMemcpy(dT.p, T.data(), B * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dOff.p, off.data(), B * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dOrd.p, order.data(), B * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dR.p, hR.data(), 2 * nr * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dXP.p, hXP.data(), 2 * n4 * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(ddH.p, hdH.data(), n2 * 4, cudaMemcpyHostToDevice);
+  {  // transposed copy for the generic forward kernel
+    std::vector<float> hRt(2 * nr);
+    for (int d = 0; d < 2; d++)
+      for (int r = 0; r < 4 * no; r++)
+        for (int k = 0; k < no; k++) hRt[d * nr + (size_t)k * 4 * no + r] = hR[d * nr + (size_t)r * no + k];
+    cudaMemcpy(dRt.p, hRt.data(), 2 * nr * 4, cudaMemcpyHostToDevice);
+  }
+  for (int v = 0; v < 2; v++) {
+    cudaMemset(dG[v].p, 0xff, 2 * n4 * 4); cudaMemset(dC[v].p, 0xff, 2 * n1 * 4); cudaMemset(dH[v].p, 0xff, n2 * 4);
+    cudaMemset(dHp[v].p, 0xff, 2 * n1 * 4); cudaMemset(dDG[v].p, 0xff, 2 * n4 * 4);
+  }
+  Lines ln{};
+  ln.B = B; ln.N = N; ln.Tmax = tmax; ln.T = dT.as<int>(); ln.off = dOff.as<int>(); ln.order = dOrd.as<int>();
+  cudaStream_t st;
+  cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaEvent_t ev[5];
+  for (auto& e : ev) cudaEventCreate(&e);
+  auto fargs = [&](int v) {
+    LstmFwdArgs a;
+    a.no = no; a.d0 = 0; a.ndir = 2; a.hstride = 2 * no; a.hoff[0] = 0; a.hoff[1] = no; a.cell = 0;
+    for (int d = 0; d < 2; d++) {
+      a.XP[d] = dXP.as<float>() + d * n4; a.R[d] = dR.as<float>() + d * nr; a.Rt[d] = dRt.as<float>() + d * nr;
+      a.G[d] = dG[v].as<float>() + d * n4; a.C[d] = dC[v].as<float>() + d * n1; a.Hprev[d] = dHp[v].as<float>() + d * n1;
+    }
+    a.H = dH[v].as<float>();
+    return a;
+  };
+  auto bargs = [&](int v) {   // both variants differentiate the SAME stash (the generic forward's)
+    LstmBwdArgs a;
+    a.no = no; a.d0 = 0; a.ndir = 2; a.hstride = 2 * no; a.hoff[0] = 0; a.hoff[1] = no; a.cell = 0; a.dH = ddH.as<float>();
+    for (int d = 0; d < 2; d++) {
+      a.R[d] = dR.as<float>() + d * nr; a.G[d] = dG[0].as<float>() + d * n4; a.C[d] = dC[0].as<float>() + d * n1;
+      a.DG[d] = dDG[v].as<float>() + d * n4;
+    }
+    return a;
+  };
+  int rc = 0;
+  float ms[4] = {-1.f, -1.f, -1.f, -1.f};
+  cudaEventRecord(ev[0], st);
+  lstm_forward_generic(st, ln, fargs(0));
+  cudaEventRecord(ev[1], st);
+  lstm_backward_generic(st, ln, bargs(0));
+  cudaEventRecord(ev[2], st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { say("generic kernels failed"); rc = 2; }
+  if (!rc) { cudaEventElapsedTime(&ms[2], ev[0], ev[1]); cudaEventElapsedTime(&ms[3], ev[1], ev[2]); }
+  if (!rc) {
+    for (int rep = 0; rep < 2 && !rc; rep++) {    // second repetition = warm timing
+      cudaEventRecord(ev[0], st);
+      int r = lstm_tc_forward(plan, st, ln, fargs(1));
+      cudaEventRecord(ev[1], st);
+      if (r != 0) { say(r < 0 ? "lstm_tc_forward: not applicable" : lstm_tc_error(plan)); rc = 3; break; }
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { char b2[200]; snprintf(b2, sizeof b2, "lstm_tc_fwd failed: %s", cudaGetErrorString(e)); say(b2); rc = 4; break; }
+      cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+    }
+  }
+  if (!rc) {
+    for (int rep = 0; rep < 2 && !rc; rep++) {
+      cudaEventRecord(ev[0], st);
+      int r = lstm_tc_backward(plan, st, ln, bargs(1));
+      cudaEventRecord(ev[1], st);
+      if (r != 0) { say(r < 0 ? "lstm_tc_backward: not applicable" : lstm_tc_error(plan)); rc = 5; break; }
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { char b2[200]; snprintf(b2, sizeof b2, "lstm_tc_bwd failed: %s", cudaGetErrorString(e)); say(b2); rc = 6; break; }
+      cudaEventElapsedTime(&ms[1], ev[0], ev[1]);
+    }
+  }
+  if (rc == 0 || rc >= 5) {
+    auto fetch = [&](DevBuf& b, size_t n) { std::vector<float> h(n); cudaMemcpy(h.data(), b.p, n * 4, cudaMemcpyDeviceToHost); return h; };
+    out[0] = max_abs_diff(fetch(dG[0], 2 * n4), fetch(dG[1], 2 * n4));
+    out[1] = max_abs_diff(fetch(dC[0], 2 * n1), fetch(dC[1], 2 * n1));
+    out[2] = max_abs_diff(fetch(dH[0], n2), fetch(dH[1], n2));
+    out[3] = max_abs_diff(fetch(dHp[0], 2 * n1), fetch(dHp[1], 2 * n1));
+    if (rc == 0) {
+      float ref = 0.f;
+      const float dd = max_abs_diff(fetch(dDG[0], 2 * n4), fetch(dDG[1], 2 * n4), &ref);
+      out[4] = dd / std::max(ref, 1e-30f);
+    }
+  }
+  out[5] = ms[0]; out[6] = ms[1]; out[7] = ms[2]; out[8] = ms[3];
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaStreamDestroy(st);
+  lstm_tc_destroy(plan);
+  return rc;
+}
+
+}  // namespace cb200

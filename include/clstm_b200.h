@@ -186,12 +186,22 @@ const char* clstm_b200_phase_name(int i);
 int clstm_b200_phase_stats(clstm_b200_net* net, float* ms, long long* launches, int n);
 /* cudaStream_t of the handle (for external event timing) */
 void* clstm_b200_stream(clstm_b200_net* net);
-/* which LSTM kernel variant the handle selected: "regs" (weights register-resident) or "generic" */
+/* which recurrent kernel variant the last forward pass used: "regs" (weights register-resident, one CTA per line and
+ * direction), "cluster" (thread-block cluster per line and direction), "tc" (batched tcgen05 recurrence: all lines of a
+ * 128-slot tile in lock step, clstm.cc:612-620 / 629-650 as one GEMM per step) or "generic".
+ * Environment: CLSTM_B200_LSTM=tc|simt forces / forbids the tensor-core recurrence (default: by size and batch). */
 const char* clstm_b200_lstm_variant(const clstm_b200_net* net);
 
 /* device self-test: tcgen05 (3xTF32) dense products vs the fp32 SIMT tiles on random data with the shapes of
  * this net; err[i] = max|difference| / max|reference| per case; returns the number of cases (<0 on error). */
 int clstm_b200_selftest_gemm(clstm_b200_net* net, float* err, int max_cases);
+
+/* device self-test of the batched tensor-core recurrence (no net needed): random bidirectional problem with `nlines`
+ * lines of tmin..tmax columns; out9[0..3] = max |difference| of gates, cell states, outputs and previous outputs against
+ * the fp32 SIMT kernels, out9[4] = max |difference| of the backward deltas relative to their maximum,
+ * out9[5..8] = milliseconds of tensor-core forward / backward and SIMT forward / backward.
+ * Replaces nothing in the reference; it checks GenericNPLSTM::forward/backward (clstm.cc:600-653) computed two ways. */
+int clstm_b200_selftest_lstm(int device, int nhidden, int nlines, int tmin, int tmax, unsigned seed, float wscale, float* out9);
 
 /* page-locked host memory for batches that are copied every step (cudaHostAlloc) */
 void* clstm_b200_alloc_pinned(size_t bytes);

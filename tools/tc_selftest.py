@@ -1,0 +1,25 @@
+"""A/B of the batched tensor-core recurrence (lstm_tc.cu) against the fp32 SIMT kernels on the device, for a list of
+(nhidden, lines, tmin, tmax) cases.  usage: python tools/tc_selftest.py [small|sizes|timing ...] ; one JSON line per case."""
+import json
+import sys
+import clstm_b200
+
+CASES = {
+    "small": [(64, 8, 5, 12), (64, 130, 3, 9), (200, 16, 10, 30), (104, 40, 1, 20)],
+    "sizes": [(200, 128, 20, 60), (400, 256, 20, 50), (800, 128, 10, 30), (400, 32, 30, 40), (256, 100, 17, 33)],
+    "timing": [(200, 128, 200, 2000), (400, 256, 200, 2000), (400, 32, 200, 2000)],
+    "timing800": [(800, 128, 512, 512)],
+}
+
+if __name__ == "__main__":
+    groups = sys.argv[1:] or ["small"]
+    for g in groups:
+        for (no, B, t0, t1) in CASES[g]:
+            try:
+                r = clstm_b200.selftest_lstm(no, B, t0, t1, seed=7)
+                r.update(case=[no, B, t0, t1], ok=bool(max(r["d_gates"], r["d_cell"], r["d_h"], r["d_hprev"]) < 2e-5 and r["d_delta_rel"] < 1e-4))
+            except Exception as e:  # noqa: BLE001
+                r = dict(case=[no, B, t0, t1], ok=False, error=str(e))
+            print(json.dumps(r), flush=True)
+            if "error" in r:
+                sys.exit(1)   # a trapped kernel poisons the context: stop here
