@@ -2,22 +2,30 @@
 """bench.py -- text-line-pixels/sec of one full training step of clstm's hot path on B200.
 
 A "step" = one pass of the hot path over one minibatch of synthetic text lines:
-    forward (bidi NPLSTM + Softmax) -> CTC alignment -> backward -> [grad all-reduce] -> clip+SGD update -> decode
-Workload (BASELINE.json configs[1], "cfg2"): nhidden=100, H=48, T=500, 32 lines per GPU, 83 classes, fp32.
-Multi-GPU: one process per GPU (torchrun), lines sharded 32 per rank (weak scaling), one NCCL all-reduce of the
-flat fp32 derivative buffer per step issued from inside libclstm_b200.so.
+    forward (bidi NPLSTM + Softmax) -> CTC alignment -> backward -> [derivative exchange] -> clip+SGD update -> decode
+Default workload (BASELINE.json configs[1], "cfg2"): nhidden=100, H=48, T=500, 32 lines per GPU, 83 classes, fp32.
+`--config cfg3|cfg4` select BASELINE configs[2] / [3]:
+    cfg3: nhidden=200, 128 ragged lines (T = 200..2000) per GPU
+    cfg4: nhidden=400, 256 ragged lines in the GLOBAL minibatch, split 256/N per GPU (strong scaling), derivative sum over
+          NVLink (share_deltas, /root/reference/clstm.cc:731-744)
+(configs[4], the nhidden x T sweep, is tools/sweep_cfg5.py, which calls this file once per cell.)
+Multi-GPU: one process per GPU (torchrun), lines sharded per rank, ONE fused all-reduce + clip + update kernel over NVLink
+peer memory per step (CLSTM_B200_DP=nccl selects ncclAllReduce + update instead).
 
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference --gpus 1 --steps 3 --warmup 1     # the reference's CPU path (oracle port)
 
-Prints ONE JSON line (rank 0).  `value` = whole-job px/s with the batch resident in HBM; `e2e` = the same through
-clstm_b200_train_step with pinned host buffers (H2D of the lines, D2H of the decoded result inside the timed
-region); `roofline` for the dominant kernel from live CUDA-event phase timings; `cpu_baseline` = the CPU oracle
-port timed on this box's host cores on a bounded sample.
+Prints ONE JSON line (rank 0).  Timing: every iteration is bracketed by CUDA events on the handle's stream, L2 is flushed
+in between; a reported step is the MEDIAN over steps x inner iterations of the per-iteration maximum over ranks (the mean
+and the full list are in the line as well).  `value` = whole-job px/s with the batch resident in HBM; `e2e` = the same
+through the input pipeline with pinned host buffers (H2D of the lines, D2H of the decoded result inside the timed region);
+`roofline` for the dominant kernel from live CUDA-event phase timings; `cpu_baseline` = the CPU oracle port timed on this
+box's host cores on a bounded sample.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -34,6 +42,12 @@ from clstm_b200 import synth  # noqa: E402
 
 LR, MOM, CLIP = 1e-4, 0.9, 100.0   # clstmocrtrain defaults (clstmocrtrain.cc:99-115), gradient_clip clstm.cc:204
 
+CONFIGS = {   # BASELINE.json configs[1..3]
+    "cfg2": dict(nhidden=100, batch=32, T=500, Tmax=0, split=False),
+    "cfg3": dict(nhidden=200, batch=128, T=200, Tmax=2000, split=False),
+    "cfg4": dict(nhidden=400, batch=256, T=200, Tmax=2000, split=True),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -41,33 +55,46 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nhidden", type=int, default=100)
-    ap.add_argument("--batch", type=int, default=32, help="lines per GPU")
-    ap.add_argument("--T", type=int, default=500)
-    ap.add_argument("--Tmax", type=int, default=0, help="if > T: variable lengths uniform in [T, Tmax]")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="BASELINE.json config preset")
+    ap.add_argument("--nhidden", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="lines per GPU (global lines with --split)")
+    ap.add_argument("--T", type=int, default=None)
+    ap.add_argument("--Tmax", type=int, default=None, help="if > T: variable lengths uniform in [T, Tmax]")
+    ap.add_argument("--split", action="store_true", default=None,
+                    help="--batch is the GLOBAL minibatch, split over the ranks (strong scaling)")
     ap.add_argument("--nclasses", type=int, default=83)
+    ap.add_argument("--inner", type=int, default=0, help="timed iterations per reported step (0: auto, ~20 ms per step)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the normalizer leg and the synchronous e2e form")
+    a = ap.parse_args()
+    preset = CONFIGS[a.config or "cfg2"]
+    for k, v in preset.items():
+        if getattr(a, k) is None:
+            setattr(a, k, v)
+    a.config = a.config or ("cfg2" if all(getattr(a, k) == v for k, v in CONFIGS["cfg2"].items()) else "custom")
+    return a
 
 
-def workload_name(a):
+def workload_name(a, world=1):
     t = "T=%d" % a.T if a.Tmax <= a.T else "T=%d..%d" % (a.T, a.Tmax)
-    tag = "cfg2 " if (a.nhidden, a.batch, a.T, a.Tmax <= a.T) == (100, 32, 500, True) else ""
-    return "%sbidi-LSTM nhidden=%d H=48 %s batch=%d/GPU nclasses=%d fwd+CTC+bwd+update" % (
-        tag, a.nhidden, t, a.batch, a.nclasses)
+    b = ("batch=%d global (%d/GPU)" % (a.batch, a.batch // world)) if a.split else "batch=%d/GPU" % a.batch
+    tag = (a.config + " ") if a.config != "custom" else ""
+    return "%sbidi-LSTM nhidden=%d H=48 %s %s nclasses=%d fwd+CTC+bwd+update" % (tag, a.nhidden, t, b, a.nclasses)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "src": "measured (MEASURED_PEAKS.json)"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """nvidia-smi clock / throttle-reason samples; started well before the timed region (the process spawn must not sit
+    between the barrier and the first timed step), filtered to the timed window afterwards."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -107,19 +134,43 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def make_batch(a, rank):
-    T = (a.T, a.Tmax) if a.Tmax > a.T else a.T
-    return synth.make_lines(a.batch, T, 48, a.nclasses, seed=1000 + rank)
+def lines_T(a):
+    return (a.T, a.Tmax) if a.Tmax > a.T else a.T
+
+
+def make_batch(a, rank, world=1):
+    """The lines of `rank`.  Weak scaling: every rank draws its own a.batch lines.  --split: the global minibatch of
+    a.batch lines (seed 1000) is sorted by length and dealt round-robin to the ranks."""
+    if not a.split:
+        return synth.make_lines(a.batch, lines_T(a), 48, a.nclasses, seed=1000 + rank)
+    x, T, labels, L = synth.make_lines(a.batch, lines_T(a), 48, a.nclasses, seed=1000)
+    if world == 1:
+        return x, T, labels, L
+    offs = np.concatenate([[0], np.cumsum(T)])
+    loffs = np.concatenate([[0], np.cumsum(L)])
+    order = np.argsort(-T, kind="stable")
+    mine = order[rank::world]
+    xs = np.concatenate([x[offs[b]:offs[b + 1]] for b in mine], 0)
+    labs = np.concatenate([labels[loffs[b]:loffs[b + 1]] for b in mine])
+    return np.ascontiguousarray(xs), T[mine].copy(), labs.astype(np.int32), L[mine].copy()
 
 
 # ------------------------------------------------------------------------------------------ reference arm (CPU)
 def cpu_reference(a, budget_s, threads):
-    """Times the CPU oracle port (reference algorithm, oracle/clstm_oracle.cc) on a bounded sample of the
-    workload: `threads` host threads, one line each per repetition."""
+    """Times the CPU oracle port (reference algorithm, oracle/clstm_oracle.cc) on a bounded sample of the workload:
+    `threads` host threads each run whole lines (fwdbwd per line, one sgd_update per repetition).  The sample holds at
+    least as many lines as threads (several minibatches' worth if the workload's batch is smaller), so every thread has
+    work."""
     from oracle import binding as ob
     net = ob.BidiOracle(48, a.nhidden, a.nclasses, seed=0.222)
-    x, T, labels, L = make_batch(a, 0)
-    nl = max(1, min(a.batch, threads))
+    nl = max(1, threads)
+    parts = []
+    k = 0
+    while sum(len(p[1]) for p in parts) < nl:
+        parts.append(synth.make_lines(a.batch, lines_T(a), 48, a.nclasses, seed=1000 + k))
+        k += 1
+    x = np.concatenate([p[0] for p in parts], 0); T = np.concatenate([p[1] for p in parts])
+    labels = np.concatenate([p[2] for p in parts]); L = np.concatenate([p[3] for p in parts])
     n_cols = int(T[:nl].sum())
     xs, Ts, Ls = x[: n_cols], T[:nl], L[:nl]
     labs = labels[: int(L[:nl].sum())]
@@ -128,8 +179,9 @@ def cpu_reference(a, budget_s, threads):
     t = net.train_lines(xs, Ts, labs, Ls, LR, MOM, threads=threads, reps=reps)
     px = reps * n_cols * 48
     return {"value": px / t, "unit": "px/s", "cores": threads, "kind": "port",
-            "sample": "%d line(s) x %d rep(s) of the workload (T=%s), %d host thread(s), fwdbwd per line + one "
-                      "sgd_update per rep; reference's O(T^2) anynan asserts excluded" % (nl, reps, a.T, threads),
+            "sample": "%d line(s) x %d rep(s) of the workload (%s), %d host thread(s), fwdbwd per line + one "
+                      "sgd_update per rep; reference's O(T^2) anynan asserts excluded" % (
+                          nl, reps, ("T=%d" % a.T) if a.Tmax <= a.T else "T=%d..%d" % (a.T, a.Tmax), threads),
             "seconds": t}
 
 
@@ -137,9 +189,7 @@ def normalizer_leg(net, a):
     """Side measurement (not part of `value`): the step in front of the path, CenterNormalizer measure + normalize of
     one batch of raw 60-row line images from host memory into the resident input batch (clstm_b200_normalize_batch),
     next to the CPU restatement of extras.cc on one line."""
-    import time
-    from clstm_b200 import synth
-    B, h, w = a.batch, 60, 640
+    B, h, w = min(a.batch, 32), 60, 640
     imgs = [synth.make_raw_line(w, h, seed=900 + b) for b in range(B)]
     net.normalize_batch(imgs, "center")
     net.profile(True)
@@ -187,19 +237,22 @@ def run_reference(a):
         return
     cores = os.cpu_count() or 1
     vals = []
-    for _ in range(max(0, a.warmup)):
+    # a sample of the big configs is long: bound every repetition
+    per_step = 2.0 if a.nhidden <= 100 else 6.0
+    for _ in range(max(0, min(a.warmup, 1))):
         cpu_reference(a, 0.5, cores)
-    t0 = time.time()
-    for _ in range(max(1, a.steps)):
-        vals.append(cpu_reference(a, 2.0, cores))
+    for _ in range(max(1, min(a.steps, 5))):
+        vals.append(cpu_reference(a, per_step, cores))
     px = sum(v["value"] * v["seconds"] for v in vals)
     sec = sum(v["seconds"] for v in vals)
     val = px / sec
     out = {"impl": "reference", "metric": "text-line-pixels/sec (fwd+bwd+CTC+update)", "value": val, "unit": "px/s",
-           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * sec / max(1, a.steps),
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(a), "note": "reference CPU path = oracle port (Eigen absent, "
-                      "reference not buildable); each step = bounded sample, all host threads"},
+           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * sec / max(1, len(vals)),
+           "higher_is_better": True, "scaling": "strong" if a.split else "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": workload_name(a, max(1, a.gpus)), "note": "reference CPU path = oracle port (Eigen absent, "
+                      "reference not buildable); each step = bounded sample (>= one line per host thread), all host threads",
+                      "samples_timed": len(vals)},
            "cpu_baseline": {"value": val, "unit": "px/s", "cores": cores, "kind": "port", "sample": vals[-1]["sample"]},
            "e2e": {"value": val, "unit": "px/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -219,7 +272,10 @@ def run_b200(a):
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (a.gpus, world))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    if a.split and a.batch % world:
+        raise SystemExit("--split: global batch %d not divisible by %d ranks" % (a.batch, world))
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local)                       # every rank, long before the timed region
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -229,8 +285,9 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     dp_mode = "none"
+    init = synth.reference_init(48, a.nhidden, a.nclasses, seed=0.222)
     net = clstm_b200.Net(48, a.nhidden, a.nclasses, device=local)
-    net.set_params(synth.reference_init(48, a.nhidden, a.nclasses, seed=0.222))
+    net.set_params(init)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -247,11 +304,13 @@ def run_b200(a):
         else:
             dp_mode = "nccl"
 
-    x, T, labels, L = make_batch(a, rank)
+    x, T, labels, L = make_batch(a, rank, world)
     N = int(T.sum())
-    px_per_step_rank = N * 48
-    # pinned host copies for the end-to-end path
-    hx = clstm_b200.pinned_array(x.shape, np.float32); hx[...] = x
+    cols = torch.tensor([N], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cols)
+    px_per_step = float(cols.item()) * 48                 # whole job, all ranks
+    hx = clstm_b200.pinned_array(x.shape, np.float32); hx[...] = x   # pinned host copy for the end-to-end path
     stream = torch.cuda.ExternalStream(net.stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -259,9 +318,10 @@ def run_b200(a):
         with torch.cuda.stream(stream):
             flush.zero_()
 
-    def timed(fn, steps):
+    def timed(fn, iters):
+        """per-iteration device time (ms) of `iters` calls, each after an L2 flush; elementwise max over ranks"""
         evs = []
-        for _ in range(steps):
+        for _ in range(iters):
             l2_flush()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -269,48 +329,40 @@ def run_b200(a):
             e1.record(stream)
             evs.append((e0, e1))
         torch.cuda.synchronize()
-        return sum(e0.elapsed_time(e1) for e0, e1 in evs)   # ms
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        ms = torch.tensor([e0.elapsed_time(e1) for e0, e1 in evs], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.cpu().numpy()
 
     # ---- resident-batch measurement (value)
     net.upload_batch(hx, T, labels, L)
     step_res = lambda: net.step_resident(LR, MOM, CLIP)  # noqa: E731
-    for _ in range(max(3, a.warmup)):
-        l2_flush(); step_res()
+    warm = max(3, a.warmup)
+    est = float(np.median(timed(step_res, warm)))         # warm-up, also calibrates the inner iteration count
+    inner = a.inner if a.inner > 0 else int(min(10, max(1, round(20.0 / max(est, 1e-3)))))
+    iters = a.steps * inner
     net.synchronize()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     t0 = time.time()
-    ms_total = timed(step_res, a.steps)          # the timed region of `value`: no phase events, nothing but the step
+    ms_it = timed(step_res, iters)                # the timed region of `value`: no phase events, nothing but the step
     barrier()
     t1 = time.time()
-    clocks = sampler.stop(t0, t1) if sampler else None
+    clocks = sampler.stop(t0, t1)
+    ms_step = float(np.median(ms_it))
+    value = px_per_step / (ms_step / 1000.0)
     # second pass with per-phase CUDA events for the kernel table / roofline (everything on one stream)
     net.profile(True)
-    timed(step_res, a.steps)
+    prof_iters = min(iters, max(3, a.steps))
+    timed(step_res, prof_iters)
     stats = net.phase_stats()
     net.profile(False)
-    ms_total = max_over_ranks(ms_total)
-    value = world * px_per_step_rank * a.steps / (ms_total / 1000.0)
 
     # ---- end to end through the public C ABI with host buffers.  Two ways a caller can drive it:
-    #  sync     : clstm_b200_train_step per batch (upload, step, fetch; nothing overlaps)
     #  pipeline : the training-loop form -- while step i runs, batch i+1 is staged from pinned host memory on the copy
     #             stream (clstm_b200_prefetch_batch), then clstm_b200_fetch_decoded(i) reads the result back.
+    #  sync     : clstm_b200_train_step per batch (upload, step, fetch; nothing overlaps)
     # Every timed iteration contains one full H2D of a batch and one D2H of a step's decoded result.
     mpl = int(T.max()) // 2 + 1
-    sync_fn = lambda: net.train_step(hx, T, labels, L, LR, MOM, CLIP, max_per_line=mpl)  # noqa: E731
-    for _ in range(3):
-        sync_fn()
-    barrier()
-    ms_sync = max_over_ranks(timed(sync_fn, a.steps))
-    barrier()
 
     def pipe_fn():
         net.step_prefetched(LR, MOM, CLIP)          # batch i (staged during step i-1)
@@ -320,12 +372,53 @@ def run_b200(a):
     for _ in range(3):
         pipe_fn()
     barrier()
-    ms_e2e = max_over_ranks(timed(pipe_fn, a.steps))
+    ms_e2e_it = timed(pipe_fn, iters)
     barrier()
-    e2e = world * px_per_step_rank * a.steps / (ms_e2e / 1000.0)
-    e2e_sync = world * px_per_step_rank * a.steps / (ms_sync / 1000.0)
-    h2d = int(x.nbytes + T.nbytes * 5 + labels.nbytes + 8 * len(T))
-    d2h = int(len(T) * 4 + 2 * len(T) * mpl * 4 + 4)
+    ms_e2e = float(np.median(ms_e2e_it))
+    e2e = px_per_step / (ms_e2e / 1000.0)
+    e2e_obj = {"value": e2e, "unit": "px/s", "ms_per_step": ms_e2e, "ms_per_step_mean": float(ms_e2e_it.mean()),
+               "h2d_bytes_per_step": int(x.nbytes + T.nbytes * 5 + labels.nbytes + 8 * len(T)),
+               "d2h_bytes_per_step": int(len(T) * 4 + 2 * len(T) * mpl * 4 + 4),
+               "bytes_note": "per rank", "mode": "input pipeline: prefetch_batch(i+1) on the copy stream during step i, fetch_decoded(i)"}
+    if not a.no_extras:
+        sync_fn = lambda: net.train_step(hx, T, labels, L, LR, MOM, CLIP, max_per_line=mpl)  # noqa: E731
+        for _ in range(3):
+            sync_fn()
+        barrier()
+        ms_sync = float(np.median(timed(sync_fn, iters)))
+        barrier()
+        e2e_obj.update(sync_value=px_per_step / (ms_sync / 1000.0), sync_ms_per_step=ms_sync,
+                       sync_mode="clstm_b200_train_step per batch, nothing overlapped")
+
+    # ---- data-parallel check (N > 1): one update from the same start on (a) the N ranks, each on its shard, and (b) one
+    # GPU on the whole minibatch must give the same weights (share_deltas semantics, clstm.cc:731-744)
+    dp_check = None
+    if world > 1:
+        net.set_params(init)
+        net.clear_derivs()
+        net.upload_batch(hx, T, labels, L)
+        net.step_resident(LR, MOM, CLIP)
+        p_dp = net.get_params()
+        dig = np.frombuffer(hashlib.sha256(p_dp.tobytes()).digest()[:8], dtype=np.int64).copy()
+        digs = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(digs, torch.from_numpy(dig).cuda())
+        same = all(int(d.item()) == int(digs[0].item()) for d in digs)
+        dp_check = {"ranks_bit_identical": bool(same)}
+        if rank == 0:
+            shards = [make_batch(a, r, world) for r in range(world)]
+            gx = np.concatenate([s[0] for s in shards], 0); gT = np.concatenate([s[1] for s in shards])
+            gl = np.concatenate([s[2] for s in shards]); gL = np.concatenate([s[3] for s in shards])
+            single = clstm_b200.Net(48, a.nhidden, a.nclasses, device=local)
+            single.set_params(init)
+            single.upload_batch(gx, gT, gl, gL)
+            single.step_resident(LR, MOM, CLIP)
+            p1 = single.get_params()
+            single.close()
+            dp_check["max_rel_err_vs_1gpu"] = float(np.abs(p_dp - p1).max() / max(np.abs(p1).max(), 1e-30))
+            dp_check["max_rel_update_err_vs_1gpu"] = float(np.abs((p_dp - init) - (p1 - init)).max() / max(np.abs(p1 - init).max(), 1e-30))
+            dp_check["note"] = ("one update from the reference init: N ranks on their shards (fused NVLink all-reduce + update) "
+                                "vs one GPU on the concatenated minibatch; bar 1e-5 relative (SURVEY 8(d))")
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -336,7 +429,6 @@ def run_b200(a):
     pk = peaks()
     no, ni, nc = a.nhidden, 48, a.nclasses
     P = synth.nparams(ni, no, nc)
-    S_lat = float(np.sum(T.astype(np.int64) * (2 * L + 1)))
     alg = {   # per launch of the phase (one step, this rank): (flops, bytes, bound)
         "xproj_gemm": (2.0 * 2 * N * 4 * no * ni, None, "tensor"),
         "lstm_fwd": (2.0 * 2 * N * 4 * no * no, None, "tensor"),
@@ -347,54 +439,56 @@ def run_b200(a):
         "wgrad_gemm": (2.0 * 2 * N * 4 * no * (ni + no), None, "tensor"),
         "dx_gemm": (2.0 * 2 * N * 4 * no * ni, None, "tensor"),
         "sgd_update": (None, 16.0 * P, "hbm"),
-        "decode": (None, 4.0 * N * nc, "hbm"),
+        "decode": (None, 8.0 * N, "hbm"),          # per-column argmax index + value
     }
     kernels = {}
     for name, (ms, launches) in stats.items():
         if name in alg and ms > 0:
             fl, by, bound = alg[name]
-            per = ms / a.steps / 1000.0
+            per = ms / prof_iters / 1000.0
             if bound == "tensor":
                 ach = fl / per / 1e12; peak = pk["bf16_tflops"]; unit = "TFLOP/s"
             else:
                 ach = by / per / 1e9; peak = pk["hbm_gbs"]; unit = "GB/s"
-            kernels[name] = {"ms_per_step": ms / a.steps, "launches_per_step": launches / a.steps, "bound": bound,
+            kernels[name] = {"ms_per_step": ms / prof_iters, "launches_per_step": launches / prof_iters, "bound": bound,
                              "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     roof = dict(kernels[dom]); roof["kernel"] = dom; roof["traffic"] = None
-    try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r1_summary.json)
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json")))
-        if (a.nhidden, a.batch, a.T) == (100, 32, 500):
-            for cap in summ.get("full_capture", []):
-                if cap["Kernel Name"].startswith(dom):
-                    def mb(x):
-                        v, u = x.split()[:2]
-                        return float(v) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}[u]
-                    roof["traffic"] = mb(cap["dram__bytes_read.sum"]) + mb(cap["dram__bytes_write.sum"])
-                    roof["traffic_unit"] = "bytes per launch (ncu --set full, profiles/r1_summary.json)"
+    try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of the same configuration
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r2_summary.json")))
+        for cap in summ.get("full_capture", []):
+            if cap.get("config") == a.config and cap.get("phase") == dom:
+                roof["traffic"] = cap["dram_bytes_per_launch"]
+                roof["traffic_unit"] = "bytes per launch (ncu --set full, profiles/r2_summary.json)"
     except Exception:
         pass
     roof["peak_source"] = pk["src"]
     roof.pop("ms_per_step"); roof.pop("launches_per_step")
     roof["kernel_ms"] = kernels[dom]["ms_per_step"]
-    launches = int(sum(c for (_, c) in stats.values()))
+    roof["lstm_kernel"] = net.lstm_variant
+    launches = int(round(sum(c for (_, c) in stats.values()) / prof_iters))
 
     out = {"metric": "text-line-pixels/sec (fwd+bwd+CTC+update)", "value": value, "unit": "px/s", "n_gpus": world,
-           "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(a), "lines_per_gpu": a.batch, "global_lines": a.batch * world,
-                      "columns_per_gpu": N, "l2": "flushed between timed steps (256 MiB memset)",
+           "steps": a.steps, "warmup": warm, "ms_per_step": ms_step, "ms_per_step_mean": float(ms_it.mean()),
+           "ms_per_step_min": float(ms_it.min()), "ms_per_step_max": float(ms_it.max()),
+           "step_ms": [round(float(v), 4) for v in ms_it[:400]],
+           "higher_is_better": True, "scaling": "strong" if a.split else "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": workload_name(a, world), "config": a.config,
+                      "lines_per_gpu": len(T), "global_lines": a.batch if a.split else a.batch * world,
+                      "columns_per_gpu": N, "global_columns": int(px_per_step // 48),
+                      "l2": "flushed between timed iterations (256 MiB memset)",
+                      "timing": "median over steps x inner = %d x %d iterations, each its own CUDA-event pair, per-iteration max over ranks" % (a.steps, inner),
+                      "inner": inner,
                       "weights": "reference LCG init (negbiased, 0.01), seed 0.222", "lr": LR, "momentum": MOM,
                       "lstm_kernel": net.lstm_variant, "parallelism": "dp%d" % world,
                       "grad_exchange": dp_mode},
-           "e2e": {"value": e2e, "unit": "px/s", "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": d2h,
-                   "mode": "input pipeline: prefetch_batch(i+1) on the copy stream during step i, fetch_decoded(i)",
-                   "sync_value": e2e_sync, "sync_ms_per_step": ms_sync / a.steps,
-                   "sync_mode": "clstm_b200_train_step per batch, nothing overlapped"},
+           "e2e": e2e_obj,
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
-           "allreduce_ms_per_step": (stats.get("allreduce", (0.0, 0))[0] / a.steps) if world > 1 else 0.0}
-    if world == 1:
+           "allreduce_ms_per_step": (stats.get("allreduce", (0.0, 0))[0] / prof_iters) if world > 1 else 0.0}
+    if dp_check is not None:
+        out["dp_check"] = dp_check
+    if world == 1 and not a.no_extras:
         out["normalizer"] = normalizer_leg(net, a)
     if world == 1 and not a.no_cpu_baseline:
         cb = cpu_reference(a, a.cpu_seconds, 1)

@@ -160,6 +160,7 @@ struct clstm_b200_net {
   float* amaxv[2] = {};
   int *dcls[2] = {}, *dlocs[2] = {}, *dcnt[2] = {};
   int capDec = 0;               // max_per_line capacity of the decode buffers
+  int decB = 0;                 // lines the decode buffers were sized for (they outlive a regrow of the per-line scratch)
   float* ws = nullptr;
   size_t ws_floats = 0;
   // pinned host staging for metadata and small results
@@ -384,10 +385,10 @@ int ensure_lines(clstm_b200_net* n, int B, int nlab) {
     dev_free(n->mx_part);
     TRY(dev_alloc(&n->mx_part, (size_t)cb * 8));
     CU(cudaHostAlloc((void**)&n->h_small, ((size_t)2 * cb + 8) * sizeof(int), cudaHostAllocDefault));
-    for (int w = 0; w < 2; w++) { dev_free(n->dcnt[w]); TRY(dev_alloc(&n->dcnt[w], (size_t)cb)); }
+    // the decode buffers (dcnt / dcls / dlocs) are NOT touched here: in the pipelined order step(i), prefetch(i+1),
+    // fetch_decoded(i) they still hold step i's result; ensure_decode() regrows them when the next decode needs more lines
     n->capB2 = cb;
     n->capLab2 = cl;
-    n->capDec = 0;  // decode buffers depend on capB2
   }
   return 0;
 }
@@ -404,14 +405,17 @@ int ensure_tiles(clstm_b200_net* n, int ntiles) {
   return 0;
 }
 int ensure_decode(clstm_b200_net* n, int max_per_line) {
-  if (max_per_line <= n->capDec) return 0;
+  if (max_per_line <= n->capDec && n->capB2 <= n->decB) return 0;
   CU(cudaStreamSynchronize(n->st));
+  max_per_line = std::max(max_per_line, n->capDec);
   for (int w = 0; w < 2; w++) {
-    dev_free(n->dcls[w]); dev_free(n->dlocs[w]);
+    dev_free(n->dcls[w]); dev_free(n->dlocs[w]); dev_free(n->dcnt[w]);
     TRY(dev_alloc(&n->dcls[w], (size_t)n->capB2 * max_per_line));
     TRY(dev_alloc(&n->dlocs[w], (size_t)n->capB2 * max_per_line));
+    TRY(dev_alloc(&n->dcnt[w], (size_t)n->capB2));
   }
   n->capDec = max_per_line;
+  n->decB = n->capB2;
   return 0;
 }
 int ensure_lattice(clstm_b200_net* n, long long elems) {
@@ -1191,6 +1195,9 @@ static int normalize_into(clstm_b200_net* n, const float* raw, const int* W, con
     for (int b = 0; b < B; b++) {                         // CenterNormalizer::normalize, extras.cc:275-276
       const float r = n->n_hr[b];
       scale[b] = (2.0 * r) / th;
+      // a blank (all-zero) line makes r NaN in the reference and int(W / NaN) is undefined behaviour there; fail loudly
+      if (!(scale[b] > 0.f) || !std::isfinite(scale[b]))
+        return fail("line %d: the centre normalizer measured no ink (r = %g); blank line images cannot be normalised", b, (double)r);
       tw[b] = std::max(int(W[b] / scale[b]), 1);
     }
   } else if (kind == 1) {
@@ -1205,6 +1212,8 @@ static int normalize_into(clstm_b200_net* n, const float* raw, const int* W, con
     for (int b = 0; b < B; b++) {                         // MeanNormalizer::normalize, extras.cc:185-188
       float actual = vscale * 2 * range * yd[b];
       scale[b] = actual / th;
+      if (!(scale[b] > 0.f) || !std::isfinite(scale[b]))
+        return fail("line %d: the mean normalizer measured no ink (y_mad = %g); blank line images cannot be normalised", b, yd[b]);
       tw[b] = int(W[b] / scale[b]);
       if (tw[b] <= 0) return fail("line %d: normalised width %d", b, tw[b]);
     }

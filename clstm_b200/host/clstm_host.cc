@@ -141,6 +141,12 @@ inline double randu() {  // batches.cc:13-17
   return st;
 }
 }  // namespace
+inline double randn_() {  // batches.cc:19-27: two LCG draws; the reference multiplies by r = -2 log(u1) itself (no square root)
+  const double u1 = randu();
+  const double u2 = randu();
+  const double rr = -2 * std::log(u1);
+  return rr * std::cos(2 * M_PI * u2);
+}
 void rinit(Params& m, int r, int c, Float s, const char* mode_, Float offset) {  // batches.cc:31-52 (draws: i outer, j inner)
   m.resize(r, c);
   const string mode(mode_);
@@ -150,6 +156,7 @@ void rinit(Params& m, int r, int c, Float s, const char* mode_, Float offset) { 
       else if (mode == "negbiased") m.v(i, j) = 3 * s * randu() - 2 * s + offset;
       else if (mode == "pos") m.v(i, j) = s * randu() + offset;
       else if (mode == "neg") m.v(i, j) = -s * randu() + offset;
+      else if (mode == "normal") m.v(i, j) = s * randn_() + offset;
       else throwf("unsupported init_mode: %s", mode_);
     }
 }
@@ -654,11 +661,10 @@ struct Reader {
   }
   void skip(int wire) {
     if (wire == 0) varint();
-    else if (wire == 1) p += 8;
+    else if (wire == 1) { if (e - p < 8) ok = false; else p += 8; }
     else if (wire == 2) sub();
-    else if (wire == 5) p += 4;
+    else if (wire == 5) { if (e - p < 4) ok = false; else p += 4; }
     else ok = false;
-    if (p > e) ok = false;
   }
 };
 string str_of(Reader r) { return string((const char*)r.p, (const char*)r.e); }
@@ -679,7 +685,9 @@ void decode_array(Reader r, string& name, vector<int>& dim, vector<float>& val) 
   if (!r.ok) THROW("bad format (Array)");
 }
 
-Network decode_net(Reader r) {  // net_of_proto clstm_proto.cc:100-137
+constexpr int kMaxNetDepth = 16;   // the deepest reference topology nests 4 levels; a corrupt file must not overflow the stack
+Network decode_net(Reader r, int depth = 0) {  // net_of_proto clstm_proto.cc:100-137
+  if (depth > kMaxNetDepth) return Network();
   string kind;
   int ninput = -1, noutput = -1;
   vector<int> icodec, codec;
@@ -737,7 +745,7 @@ Network decode_net(Reader r) {  // net_of_proto clstm_proto.cc:100-137
     }
   }
   for (size_t i = 0; i < subs.size(); i++) {
-    Network s = decode_net(subs[i]);
+    Network s = decode_net(subs[i], depth + 1);
     if (!s) return Network();
     net->add(s);
     net->sub[i]->attr.super = &net->attr;

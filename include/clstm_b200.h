@@ -144,7 +144,8 @@ int clstm_b200_synchronize(clstm_b200_net* net);
 /* Input pipeline for a training loop (the data-loader side of clstmocrtrain.cc:172-177): stage the NEXT batch into a
  * second input set on a copy stream while the step on the current batch is still running, then run the step on it.
  *   prefetch_batch(i+1) may be called as soon as step i has been launched (step_resident / step_prefetched return
- *   without waiting); the host buffers must stay valid until the following step_prefetched has been called and
+ *   without waiting); the copy is asynchronous, so the host buffers must stay valid (and unmodified) until the
+ *   first clstm_b200_fetch_decoded / clstm_b200_synchronize AFTER the step_prefetched that consumes the batch, and
  *   should be pinned (clstm_b200_alloc_pinned) for the copy to overlap.  step_prefetched makes the prefetched batch
  *   current and runs clstm_b200_step_resident on it.  fetch_decoded afterwards returns the results of that step.
  * If the prefetched batch needs larger device buffers than any batch before, the call waits for the running step and

@@ -1,0 +1,116 @@
+"""GPU tests of the batched tensor-core recurrence (clstm_b200/csrc/lstm_tc.cu: tcgen05 kind::f16 hi/lo products, TMA-streamed
+h tiles, TMEM accumulators).  Reference semantics: GenericNPLSTM::forward / backward, /root/reference/clstm.cc:600-653.
+Forced through CLSTM_B200_LSTM=tc (read when a net is created) so that small batches exercise it too; compared with the
+CPU oracle at the 1e-4 bar of BASELINE.json and, on the device, with the fp32 SIMT kernels."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from clstm_b200 import synth  # noqa: E402
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def ffi():
+    import clstm_b200
+    clstm_b200.lib()
+    return clstm_b200
+
+
+class forced_tc:
+    def __enter__(self):
+        self.old = os.environ.get("CLSTM_B200_LSTM")
+        os.environ["CLSTM_B200_LSTM"] = "tc"
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("CLSTM_B200_LSTM", None)
+        else:
+            os.environ["CLSTM_B200_LSTM"] = self.old
+
+
+def split(a, T):
+    offs = np.concatenate([[0], np.cumsum(T)])
+    return [a[offs[i]:offs[i + 1]] for i in range(len(T))]
+
+
+# nhidden, lines, tmin, tmax: forward row-slice widths 32 / 48 / 64, one and two line tiles, ragged down to T = 1,
+# resident and streamed backward weight chunks (nhidden 800)
+AB_CASES = [(64, 8, 5, 12), (64, 130, 3, 9), (104, 40, 1, 20), (200, 128, 20, 60), (256, 100, 17, 33), (400, 256, 20, 50),
+            (400, 32, 30, 40), (800, 128, 10, 30)]
+
+
+@pytest.mark.parametrize("no,B,t0,t1", AB_CASES)
+def test_tc_recurrence_matches_simt_kernels(ffi, no, B, t0, t1):
+    r = ffi.selftest_lstm(no, B, t0, t1, seed=7)
+    assert max(r["d_gates"], r["d_cell"], r["d_h"], r["d_hprev"]) < 2e-5, r
+    assert r["d_delta_rel"] < 1e-4, r
+
+
+PARITY = [
+    # ni, nh, nc, B, T, weights
+    (48, 200, 83, 5, (1, 60), "trained"),     # BASELINE config 3 width, ragged incl. T = 1
+    (48, 200, 83, 3, (30, 50), "init"),
+    (48, 400, 83, 3, (20, 45), "trained"),    # config 4 width
+    (48, 800, 83, 2, (10, 25), "trained"),    # config 5 top width: streamed backward weight chunks
+    (48, 64, 30, 140, (2, 12), "trained"),    # two line tiles (140 lines > 128 slots)
+]
+
+
+@pytest.mark.parametrize("ni,nh,nc,B,T,weights", PARITY)
+def test_tc_parity_with_oracle(ffi, oracle, ni, nh, nc, B, T, weights):
+    x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=3)
+    onet = oracle.BidiOracle(ni, nh, nc, seed=0.222)
+    if weights == "trained":
+        onet.set_params(synth.trained_like(onet.nparams, 0.3 if nh <= 200 else 0.3 * (200.0 / nh) ** 0.5, seed=7))
+    with forced_tc():
+        gnet = ffi.Net(ni, nh, nc)
+    gnet.set_params(onet.get_params())
+    out = gnet.forward(x, Ts)
+    assert gnet.lstm_variant == "tc"
+    xs, outs = split(x, Ts), split(out, Ts)
+    for b in range(B):
+        assert np.abs(onet.forward(xs[b]) - outs[b]).max() < TOL
+    # backward with injected deltas: input deltas and every parameter derivative
+    rng = np.random.default_rng(5)
+    deltas = (rng.standard_normal(out.shape) * 0.1).astype(np.float32)
+    gnet.clear_derivs()
+    din = gnet.backward(deltas)
+    gd = gnet.get_derivs()
+    onet.clear_derivs()
+    for b in range(B):
+        onet.forward(xs[b])
+        o_din = onet.backward(split(deltas, Ts)[b])
+        assert np.abs(o_din - split(din, Ts)[b]).max() < TOL * max(1.0, np.abs(o_din).max())
+    od = onet.get_derivs()
+    assert np.abs(od - gd).max() < TOL * max(1.0, np.abs(od).max())
+    # CTC on the tensor-core outputs: alignment indices bit-exact against the oracle run on the same outputs
+    al = gnet.ctc_align(labels, L)
+    amax = gnet.argmax(1)
+    dec = gnet.decode(1)
+    labs = split(labels, L)
+    for b in range(B):
+        o_al = oracle.ctc_align_labels(outs[b], labs[b])
+        assert np.abs(o_al - split(al, Ts)[b]).max() < 2e-5
+        assert np.array_equal(oracle.argmax_rows(o_al), split(amax, Ts)[b])
+        cs, locs = oracle.trivial_decode(o_al)
+        assert np.array_equal(cs, dec[b][0]) and np.array_equal(locs, dec[b][1])
+
+
+def test_tc_training_steps_track_oracle(ffi, oracle):
+    ni, nh, nc, B = 48, 200, 83, 6
+    x, Ts, labels, L = synth.make_lines(B, (30, 60), ni, nc, seed=11)
+    onet = oracle.BidiOracle(ni, nh, nc, seed=0.222)
+    onet.set_params(synth.trained_like(onet.nparams, 0.3, seed=7))
+    with forced_tc():
+        gnet = ffi.Net(ni, nh, nc)
+    gnet.set_params(onet.get_params())
+    for _ in range(3):   # the fp16 hi/lo weight copies must follow every update
+        gnet.train_step(x, Ts, labels, L, 1e-3, 0.9)
+        onet.train_lines(x, Ts, labels, L, 1e-3, 0.9, threads=1, reps=1)
+    assert gnet.lstm_variant == "tc"
+    assert np.abs(gnet.get_params() - onet.get_params()).max() < 1e-4

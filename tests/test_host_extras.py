@@ -112,3 +112,39 @@ def test_cli_train_and_recognise(host_bin, tmp_path):
     r3 = subprocess.run([os.path.join(BIN, "clstmocr"), str(tmp_path / "test.txt")], env=dict(os.environ, params="0"),
                         capture_output=True, text=True)
     assert r3.returncode == 1 and "must give load= parameter" in r3.stderr
+
+
+# ---------------------------------------------------------------------------------------------- the reference's own fixture
+OCR_FIX = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ocr")
+
+
+def test_reference_png_fixture_decodes_like_pil(host_bin, tmp_path):
+    """misc/textline.bin.png is an 819x88 RGBA file: the zlib-based decoder must produce what PIL produces."""
+    from PIL import Image
+    src = os.path.join(OCR_FIX, "textline.bin.png")
+    im = Image.open(src)
+    assert im.size == (819, 88)
+    out = subprocess.check_output([host_bin, "png", src], text=True).split("\n")
+    w, h = map(int, out[0].split())
+    got = np.array([[int(v) for v in row.split()] for row in out[1:1 + h]])
+    assert (w, h) == (819, 88)
+    assert np.array_equal(got, np.array(im).astype(int)[:, :, :3].sum(2))       # read_png: mean of R, G, B (extras.cc:416-431)
+
+
+@pytest.mark.gpu
+def test_reference_ocr_fixture(tmp_path):
+    """/root/reference/test-ocr.sh replayed with the drop-in CLIs: train 201 trials on the reference's text line, reload
+    the trial-200 checkpoint, recognise the line and find 'performance analysis' in the output."""
+    import shutil
+    for f in ("textline.bin.png", "textline.gt.txt"):
+        shutil.copy(os.path.join(OCR_FIX, f), tmp_path / f)
+    (tmp_path / "_ocrtest.txt").write_text(str(tmp_path / "textline.bin.png") + "\n")
+    env = dict(os.environ, ntrain="201", hidden="50", lrate="1e-2", save_name=str(tmp_path / "_ocrtest"), seed="0.222")
+    r = subprocess.run([os.path.join(BIN, "clstmocrtrain"), str(tmp_path / "_ocrtest.txt")], env=env, capture_output=True,
+                       text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert os.path.exists(tmp_path / "_ocrtest-200.clstm"), r.stdout[-1500:]
+    r2 = subprocess.run([os.path.join(BIN, "clstmocr"), str(tmp_path / "_ocrtest.txt")],
+                        env=dict(os.environ, load=str(tmp_path / "_ocrtest-200.clstm")), capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    assert "performance analysis" in r2.stdout, r2.stdout[-1000:]

@@ -1,8 +1,11 @@
 """A/B of the batched tensor-core recurrence (lstm_tc.cu) against the fp32 SIMT kernels on the device, for a list of
 (nhidden, lines, tmin, tmax) cases.  usage: python tools/tc_selftest.py [small|sizes|timing ...] ; one JSON line per case."""
 import json
+import os
 import sys
-import clstm_b200
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import clstm_b200  # noqa: E402
 
 CASES = {
     "small": [(64, 8, 5, 12), (64, 130, 3, 9), (200, 16, 10, 30), (104, 40, 1, 20)],
