@@ -57,6 +57,7 @@ constexpr float kScaleR = 16.f;        // weights      -> fp16 hi/lo of 16 R   (
 constexpr float kScaleD = 256.f;       // deltas       -> fp16 hi/lo of 256 d  (|d| < 256)
 constexpr unsigned kStageBytes = 2 * kTcLines * 128;   // one ring stage: hi tile + lo tile of [128 lines x 64 k] fp16
 constexpr int kBwdNR = 64;             // gate rows per CTA in the backward kernel (one 128-byte swizzle row of K)
+constexpr int kDbgStep = 64;           // the step whose event timestamps the debug counters record
 constexpr int kBwdChunk = 256;         // outputs per MMA chunk in the backward kernel (UMMA N)
 constexpr unsigned kBwdStageBytes = 2 * kBwdChunk * 128;
 
@@ -64,6 +65,7 @@ struct TcFwd {
   int no, no4;            // hidden units, gate rows
   int KC, nks;            // 64-wide k chunks / 16-wide k slices of h
   int NT, ntiles, nst;    // row slices per direction, line tiles in the batch, ring stages
+  int nsig;               // counter increments per step of a (tile, direction): 8 epilogue warps of every slice
   int d0, hstride, hoff[2];
   int rows_pad;           // rows per direction of the split weight copy (NT * NR)
   int KP;                 // row pitch (halves) of the h exchange buffer
@@ -75,6 +77,8 @@ struct TcFwd {
   __half* hx_hi;          // [direction slot][parity][tile][128][KP]
   __half* hx_lo;
   unsigned* flags;        // [direction slot][tile] steps published
+  long long* dbg;         // optional per-phase cycle counters of CTA (0,0,0) (self-test / tuning), nullptr otherwise
+  int opt;                // tuning switches (CLSTM_B200_TC_OPT): bit 0 fixed 32-row TMA boxes, bit 1 no writer-side proxy fence
 };
 
 struct TcBwd {
@@ -89,6 +93,8 @@ struct TcBwd {
   float* DG[2];
   float* part;            // [direction slot][tile][parity][dest slice][src slice][128][16]
   unsigned* flags;
+  long long* dbg;
+  int opt;
 };
 
 // vectorised per-thread stores of N consecutive floats (N % VW == 0, address VW-float aligned)
@@ -119,7 +125,9 @@ __device__ __forceinline__ void load_run(float* v, const float* src) {
 template <int NR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
-            const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo, Lines ln, TcFwd p) {
+            const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
+            const __grid_constant__ CUtensorMap tmH64_hi, const __grid_constant__ CUtensorMap tmH64_lo,
+            const __grid_constant__ CUtensorMap tmH128_hi, const __grid_constant__ CUtensorMap tmH128_lo, Lines ln, TcFwd p) {
   constexpr int NC = NR / 2;                      // accumulator columns (gate rows) per epilogue thread
   constexpr int NU = NR / 8;                      // hidden units per epilogue thread
   constexpr int VW = (NU % 4 == 0) ? 4 : 2;       // vector width of the per-unit runs
@@ -155,75 +163,115 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
   tc_fence_after();
   const unsigned tmem_d = tmem_base_s;
   unsigned* const flag_q = p.flags + (size_t)q * p.ntiles;
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  long long dt[4] = {0, 0, 0, 0};
+#define TC_T0 const long long t0_ = dbg ? clock64() : 0
+#define TC_T(i) if (dbg) { const long long t1_ = clock64(); dt[i] += t1_ - tlast_; tlast_ = t1_; }
 
+  // Roles 0 and 1 run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers / counters) and only the
+  // instruction that must come from one thread (TMA, tcgen05.mma, tcgen05.commit) sits under elect_one(): the loop
+  // bookkeeping then lives in uniform registers instead of being converted for every tensor-core instruction.
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    long long tlast_ = dbg ? clock64() : 0;
+    if (elect_one()) {
       mbar_expect_tx(rfull, (unsigned)p.KC * 2 * r_bytes);
       for (int kc = 0; kc < p.KC; kc++) {
         tma_load_2d(rs0 + kc * 2 * r_bytes, &tmR_hi, kc * 64, d * p.rows_pad + m * NR, rfull);
         tma_load_2d(rs0 + kc * 2 * r_bytes + r_bytes, &tmR_lo, kc * 64, d * p.rows_pad + m * NR, rfull);
       }
-      unsigned it = 0;
-      for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
-        const int l0 = tile * kTcLines;
-        const int nl = min(kTcLines, ln.B - l0);
-        const int Tt = ln.T[ln.order[l0]];
-        int act = nl;
-        for (int s = 1; s < Tt; s++) {
-          while (act > 0 && ln.T[ln.order[l0 + act - 1]] <= s) act--;      // lines still running at step s: a prefix
-          const int nb = (act + 31) >> 5;                                   // 32-row TMA boxes that hold them
-          wait_counter(flag_q + tile, (unsigned)p.NT * (unsigned)s);        // h_{s-1} of every row slice is in L2
-          fence_proxy_async();                                              // generic-proxy writes -> async-proxy reads
-          const int row0 = ((q * 2 + ((s - 1) & 1)) * p.ntiles + tile) * kTcLines;
-          for (int kc = 0; kc < p.KC; kc++, it++) {
-            const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
-            if (use > 0) mbar_wait(empty(st), (use - 1) & 1);
-            mbar_expect_tx(full(st), (unsigned)nb * 2 * 4096);
+    }
+    __syncwarp();
+    unsigned it = 0;
+    for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+      const int l0 = tile * kTcLines;
+      const int nl = min(kTcLines, ln.B - l0);
+      const int Tt = ln.T[ln.order[l0]];
+      int act = nl;
+      for (int s = 1; s < Tt; s++) {
+        while (act > 0 && ln.T[ln.order[l0 + act - 1]] <= s) act--;      // lines still running at step s: a prefix
+        // rows to fetch: the smallest box (32 / 64 / 128 rows) that holds the running lines
+        const int brows = (p.opt & 1) ? 32 : (act <= 32 ? 32 : (act <= 64 ? 64 : 128));
+        const int nb = (act + brows - 1) / brows;
+        const CUtensorMap* mh = brows == 32 ? &tmH_hi : (brows == 64 ? &tmH64_hi : &tmH128_hi);
+        const CUtensorMap* ml = brows == 32 ? &tmH_lo : (brows == 64 ? &tmH64_lo : &tmH128_lo);
+        TC_T(3);
+        wait_counter(flag_q + tile, (unsigned)p.nsig * (unsigned)s);      // h_{s-1} of every row slice is in L2
+        TC_T(0);
+        if (dbg && s == kDbgStep + 1) p.dbg[16 + 3] = clock64();
+        const int row0 = ((q * 2 + ((s - 1) & 1)) * p.ntiles + tile) * kTcLines;
+        for (int kc = 0; kc < p.KC; kc++, it++) {
+          const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
+          if (use > 0) mbar_wait(empty(st), (use - 1) & 1);
+          TC_T(1);
+          if (elect_one()) {
+            if (kc == 0) fence_proxy_async();                             // generic-proxy writes (other SMs) -> async-proxy reads
+            mbar_expect_tx(full(st), (unsigned)(nb * brows) * 256);
             const unsigned dst = ring0 + st * kStageBytes;
             for (int j = 0; j < nb; j++) {
-              tma_load_2d(dst + j * 4096, &tmH_hi, kc * 64, row0 + 32 * j, full(st));
-              tma_load_2d(dst + kTcLines * 128 + j * 4096, &tmH_lo, kc * 64, row0 + 32 * j, full(st));
+              tma_load_2d(dst + j * brows * 128, mh, kc * 64, row0 + brows * j, full(st));
+              tma_load_2d(dst + kTcLines * 128 + j * brows * 128, ml, kc * 64, row0 + brows * j, full(st));
             }
           }
+          __syncwarp();
+          TC_T(2);
+          if (dbg && s == kDbgStep + 1 && kc == 0) p.dbg[16 + 4] = clock64();
         }
+        if (dbg && s == kDbgStep + 1) p.dbg[16 + 5] = clock64();
       }
     }
+    if (dbg && lane == 0) for (int i = 0; i < 4; i++) p.dbg[i] = dt[i];     // flag wait | ring wait | TMA issue | other
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const unsigned idesc = make_idesc_f16(kTcLines, NR);
-      mbar_wait(rfull, 0);
-      unsigned it = 0;
-      for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
-        const int Tt = ln.T[ln.order[tile * kTcLines]];
-        for (int s = 1; s < Tt; s++) {
-          for (int kc = 0; kc < p.KC; kc++, it++) {
-            const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
-            mbar_wait(full(st), use & 1);
-            tc_fence_after();
-            const unsigned a_hi = ring0 + st * kStageBytes, a_lo = a_hi + kTcLines * 128;
-            const unsigned b_hi = rs0 + kc * 2 * r_bytes, b_lo = b_hi + r_bytes;
+    const unsigned idesc = make_idesc_f16(kTcLines, NR);
+    const unsigned long long dbase = make_desc(0);
+    auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
+    mbar_wait(rfull, 0);
+    unsigned it = 0;
+    long long tlast_ = dbg ? clock64() : 0;
+    for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+      const int Tt = ln.T[ln.order[tile * kTcLines]];
+      for (int s = 1; s < Tt; s++) {
+        for (int kc = 0; kc < p.KC; kc++, it++) {
+          const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
+          TC_T(2);
+          mbar_wait(full(st), use & 1);
+          tc_fence_after();
+          TC_T(0);
+          if (dbg && s == kDbgStep + 1 && kc == 0) p.dbg[16 + 6] = clock64();
+          if (dbg && s == kDbgStep + 1 && kc == p.KC - 1) p.dbg[16 + 7] = clock64();
+          const unsigned a_hi = ring0 + st * kStageBytes;
+          const unsigned b_hi = rs0 + kc * 2 * r_bytes;
+          // 16 k = 32 bytes along the swizzled row = +2 in the descriptor's address field
+          const unsigned long long ah = desc_of(a_hi), al = desc_of(a_hi + kTcLines * 128);
+          const unsigned long long bh = desc_of(b_hi), bl = desc_of(b_hi + r_bytes);
+          const int nk = min(4, p.nks - kc * 4);
+          if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
-              if (kc * 4 + ks < p.nks) {
-                const unsigned long long ah = make_desc(a_hi + ks * 32), al = make_desc(a_lo + ks * 32);
-                const unsigned long long bh = make_desc(b_hi + ks * 32), bl = make_desc(b_lo + ks * 32);
-                mma_f16(tmem_d, al, bh, idesc, (kc > 0 || ks > 0) ? 1u : 0u);   // small terms first
-                mma_f16(tmem_d, ah, bl, idesc, 1u);
-                mma_f16(tmem_d, ah, bh, idesc, 1u);
+              if (ks < nk) {
+                mma_f16(tmem_d, al + 2 * ks, bh + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);   // small terms first
+                mma_f16(tmem_d, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
+                mma_f16(tmem_d, ah + 2 * ks, bh + 2 * ks, idesc, 1u);
               }
             }
             mma_commit(empty(st));
+            if (kc == p.KC - 1) mma_commit(accfull);
           }
-          mma_commit(accfull);
+          __syncwarp();
+          TC_T(1);
         }
+        if (dbg && s == kDbgStep + 1) p.dbg[16 + 8] = clock64();
       }
     }
+    if (dbg && lane == 0) for (int i = 0; i < 3; i++) p.dbg[4 + i] = dt[i];   // full wait | MMA issue | other
   } else {
     // ------------------------------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;
     const int lq = warp & 3, ch = ew >> 2;                 // TMEM lane quadrant (fixed by the warp id), column half
+    long long tlast_ = dbg ? clock64() : 0;
+    long long de[6] = {0, 0, 0, 0, 0, 0};
+#define TC_E(i) if (dbg) { const long long t1_ = clock64(); de[i] += t1_ - tlast_; tlast_ = t1_; }
     const int pl = 32 * lq + lane;                         // line slot of this thread
     const unsigned taddr = tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * NC);
     const int ub = m * (NR / 4) + ch * NU;                 // first hidden unit of this thread
@@ -258,11 +306,16 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           }
         }
         float acc[NC];
+        TC_E(5);
         if (s > 0) {
           mbar_wait(accfull, accph);
           accph ^= 1;
           tc_fence_after();
+          TC_E(0);
+          if (dbg && s == kDbgStep) p.dbg[16 + 0] = clock64();
+          if (dbg && s == kDbgStep + 1) p.dbg[16 + 9] = clock64();
           tmem_ld<NC>(taddr, acc);
+          TC_E(1);
         } else {
 #pragma unroll
           for (int i = 0; i < NC; i++) acc[i] = 0.f;
@@ -300,14 +353,16 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
             }
           }
         }
-        // every epilogue thread has read its accumulators and written its h: publish the step
+        // this warp has read its accumulators and written its h: publish (release-increment per warp, no CTA barrier;
+        // the producer of every slice waits for all 8 warps of all slices, which also protects the accumulator)
+        TC_E(2);
+        if (dbg && s == kDbgStep) p.dbg[16 + 1] = clock64();
         tc_fence_before();
-        fence_proxy_async();
-        named_bar_sync(1, kEpiThreads);
-        if (ew == 0 && lane == 0) {
-          __threadfence();
-          atomicAdd(flag_q + tile, 1u);
-        }
+        if (p.opt & 2) fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) signal_counter(flag_q + tile);
+        TC_E(3);
+        if (dbg && s == kDbgStep) p.dbg[16 + 2] = clock64();
         if (active) {   // stash for the backward pass and the dense products, off the critical path
 #pragma unroll
           for (int u = 0; u < NU; u++)
@@ -334,8 +389,10 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
             }
           }
         }
+        TC_E(4);
       }
     }
+    if (dbg && ew == 0 && lane == 0) for (int i = 0; i < 6; i++) p.dbg[8 + i] = de[i];   // acc wait | tmem ld | math+h | publish | stash | xp issue
   }
   tc_fence_before();
   __syncthreads();
@@ -390,6 +447,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
   const unsigned tmem_d = tmem_base_s;
   unsigned* const flag_q = p.flags + (size_t)q * p.ntiles;
   const int row_t = d * p.kp_rows;                     // first row of this direction in the transposed split copy
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
   auto load_chunk = [&](unsigned st, int chunk) {      // B chunk: outputs [256*chunk, +256) x this CTA's 64 gate rows
     mbar_expect_tx(bfull(st), kBwdStageBytes);
@@ -419,15 +477,22 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------------------------------ MMA issuer (warp-uniform loop)
+    {
       unsigned it = 0, cnt = 0, aph = 0;
+      long long tlast_ = dbg ? clock64() : 0;
+      long long dt[4] = {0, 0, 0, 0};
+      const unsigned long long dbase = make_desc(0);
+      auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
+      const unsigned long long ah = desc_of(a_hi), al = desc_of(a_lo);
       for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
         const int Tt = ln.T[ln.order[tile * kTcLines]];
         for (int fs = Tt - 1; fs >= 1; fs--) {
+          TC_T(3);
           mbar_wait(afull, aph);                      // the deltas of this step are in shared memory
           aph ^= 1;
           tc_fence_after();
+          TC_T(0);
           for (int i = 0; i < p.nchunk; i++, it++, cnt++) {
             const unsigned buf = cnt & 1;
             if (cnt >= 2) mbar_wait(accempty(buf), ((cnt >> 1) - 1) & 1);   // the chunk that used this buffer is drained
@@ -435,23 +500,28 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
             if (p.resident) { st = i; if (it < (unsigned)p.nchunk) mbar_wait(bfull(st), 0); }
             else { st = it % (unsigned)p.nst; mbar_wait(bfull(st), (it / (unsigned)p.nst) & 1); }
             tc_fence_after();
+            TC_T(1);
             const int nw = min(kBwdChunk, p.nop16 - i * kBwdChunk);
             const unsigned idesc = make_idesc_f16(kTcLines, nw);
-            const unsigned b_hi = ring0 + st * kBwdStageBytes, b_lo = b_hi + kBwdChunk * 128;
+            const unsigned b_hi = ring0 + st * kBwdStageBytes;
+            const unsigned long long bh = desc_of(b_hi), bl = desc_of(b_hi + kBwdChunk * 128);
             const unsigned dcol = tmem_d + buf * kBwdChunk;
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kBwdNR / 16; ks++) {
-              const unsigned long long ah = make_desc(a_hi + ks * 32), al = make_desc(a_lo + ks * 32);
-              const unsigned long long bh = make_desc(b_hi + ks * 32), bl = make_desc(b_lo + ks * 32);
-              mma_f16(dcol, al, bh, idesc, ks > 0 ? 1u : 0u);
-              mma_f16(dcol, ah, bl, idesc, 1u);
-              mma_f16(dcol, ah, bh, idesc, 1u);
+              for (int ks = 0; ks < kBwdNR / 16; ks++) {
+                mma_f16(dcol, al + 2 * ks, bh + 2 * ks, idesc, ks > 0 ? 1u : 0u);
+                mma_f16(dcol, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
+                mma_f16(dcol, ah + 2 * ks, bh + 2 * ks, idesc, 1u);
+              }
+              if (!p.resident) mma_commit(bempty(st));
+              mma_commit(accfull(buf));
             }
-            if (!p.resident) mma_commit(bempty(st));
-            mma_commit(accfull(buf));
+            __syncwarp();
+            TC_T(2);
           }
         }
       }
+      if (dbg && lane == 0) for (int i = 0; i < 4; i++) p.dbg[i] = dt[i];   // delta wait | buffer / weight wait | MMA issue | other
     }
   } else {
     // ------------------------------------------------------------------------------------------ epilogue warps
@@ -468,6 +538,8 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
     constexpr float inv_scale = 1.0f / (kScaleD * kScaleR);
     const size_t slab = (size_t)NT * NT * (kTcLines * 16);     // floats of one [dest][src][128][16] exchange buffer
     unsigned cnt = 0;
+    long long tlast_ = dbg ? clock64() : 0;
+    long long de[6] = {0, 0, 0, 0, 0, 0};
     for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
       const int l0 = tile * kTcLines;
       const int nl = min(kTcLines, ln.B - l0);
@@ -491,9 +563,10 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
           if (fs > 0) load_run<NU, 4>(cp, Cd + (col + (d ? 1 : -1)) * (size_t)no + ub);
           load_run<NU, 4>(dh, dHd + col * p.hstride + ub);
         }
+        TC_E(0);
         if (it > 0) {                                      // partial products of the previous step, all slices
-          if (lane == 0) wait_counter(flag_q + tile, (unsigned)NT * (unsigned)it);
-          __syncwarp();
+          wait_counter(flag_q + tile, (unsigned)(NT * (kEpiThreads / 32)) * (unsigned)it);
+          TC_E(1);
           if (active && fs < Tp - 1) {
             const float* src = part_t + (size_t)((it - 1) & 1) * slab + (size_t)m * NT * (kTcLines * 16) + pl * 16 + ch * NU;
             float r[NU];
@@ -510,6 +583,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
             for (int u = 0; u < NU; u++) dh[u] += r[u];
           }
         }
+        TC_E(2);
         unsigned hi[2 * NU], lo[2 * NU];                    // packed half2: 4 gate rows of a unit = 2 words
         if (active) {
           float dl[4 * NU];
@@ -556,6 +630,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
         }
         fence_proxy_async_smem();
         mbar_arrive(afull);
+        TC_E(3);
         // drain the output chunks into the exchange buffer: group gq of 16 outputs belongs to slice (16 chunk + gq)
         float* const dst_par = part_t + (size_t)(it & 1) * slab + (size_t)m * (kTcLines * 16) + pl * 16;
         const bool wr = (li >= 0) && fs < Tp;              // rows of lines that are not running are never read
@@ -579,13 +654,13 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
           tc_fence_before();
           mbar_arrive(accempty(buf));
         }
-        named_bar_sync(1, kEpiThreads);
-        if (ew == 0 && lane == 0) {
-          __threadfence();
-          atomicAdd(flag_q + tile, 1u);
-        }
+        TC_E(4);
+        __syncwarp();
+        if (lane == 0) signal_counter(flag_q + tile);      // per warp: 8 increments per slice and step
+        TC_E(5);
       }
     }
+    if (dbg && ew == 0 && lane == 0) for (int i = 0; i < 6; i++) p.dbg[8 + i] = de[i];   // loads | flag wait | reduce | pointwise | drain | publish
   }
   tc_fence_before();
   __syncthreads();
@@ -657,8 +732,11 @@ struct LstmTcPlan {
   float* part = nullptr;
   unsigned* flags = nullptr;
   CUtensorMap tmR_hi[3], tmR_lo[3];   // box rows 32 / 48 / 64
-  CUtensorMap tmT_hi, tmT_lo, tmH_hi, tmH_lo;
+  CUtensorMap tmT_hi, tmT_lo, tmH_hi[3], tmH_lo[3];   // h exchange maps: box rows 32 / 64 / 128
   bool coop = true;
+  int opt = 0;                    // CLSTM_B200_TC_OPT tuning switches
+  long long* dbg = nullptr;       // 16 cycle counters + 16 event timestamps of step kDbgStep (CLSTM_B200_TC_DBG=1 or the self-test)
+  long long dbg_host[2][32] = {};
   char err[256] = {0};
 };
 
@@ -695,7 +773,7 @@ bool lstm_tc_supported(int no) {
 void lstm_tc_destroy(LstmTcPlan* p) {
   if (!p) return;
   cudaFree(p->rs_hi); cudaFree(p->rs_lo); cudaFree(p->rt_hi); cudaFree(p->rt_lo);
-  cudaFree(p->hx_hi); cudaFree(p->hx_lo); cudaFree(p->part); cudaFree(p->flags);
+  cudaFree(p->hx_hi); cudaFree(p->hx_lo); cudaFree(p->part); cudaFree(p->flags); cudaFree(p->dbg);
   delete p;
 }
 
@@ -722,8 +800,20 @@ LstmTcPlan* lstm_tc_create(int no, int num_sms) {
          make_map(&p->tmT_lo, p->rt_lo, (size_t)2 * p->kp_rows, p->RP, 64) == 0;
   }
   if (const char* e = getenv("CLSTM_B200_TC_COOP")) p->coop = atoi(e) != 0;
+  if (const char* e = getenv("CLSTM_B200_TC_OPT")) p->opt = atoi(e);
+  if (const char* e = getenv("CLSTM_B200_TC_DBG")) {
+    if (atoi(e) != 0 && cudaMalloc((void**)&p->dbg, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(p->dbg, 0, 32 * sizeof(long long));
+  }
   if (!ok) { lstm_tc_destroy(p); return nullptr; }
   return p;
+}
+
+// per-phase cycle counters of the last forward (which = 0) / backward (1) launch; the stream must be idle
+const long long* lstm_tc_debug_counters(LstmTcPlan* p, int which) {
+  if (!p || !p->dbg) return nullptr;
+  cudaMemcpy(p->dbg_host[which & 1], p->dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(p->dbg, 0, 32 * sizeof(long long));
+  return p->dbg_host[which & 1];
 }
 
 void lstm_tc_mark_stale(LstmTcPlan* p) { if (p) p->stale[0] = p->stale[1] = true; }
@@ -756,10 +846,11 @@ int ensure_exchange(LstmTcPlan* p, cudaStream_t st, int ntiles, int nt_b) {
   }
   cudaMemsetAsync(p->hx_hi, 0, hrows * p->KP * 2, st);
   cudaMemsetAsync(p->hx_lo, 0, hrows * p->KP * 2, st);
-  if (make_map(&p->tmH_hi, p->hx_hi, hrows, p->KP, 32) != 0 || make_map(&p->tmH_lo, p->hx_lo, hrows, p->KP, 32) != 0) {
-    snprintf(p->err, sizeof p->err, "cuTensorMapEncodeTiled failed for the h exchange buffer");
-    return 1;
-  }
+  for (int o = 0; o < 3; o++)
+    if (make_map(&p->tmH_hi[o], p->hx_hi, hrows, p->KP, 32 << o) != 0 || make_map(&p->tmH_lo[o], p->hx_lo, hrows, p->KP, 32 << o) != 0) {
+      snprintf(p->err, sizeof p->err, "cuTensorMapEncodeTiled failed for the h exchange buffer");
+      return 1;
+    }
   p->cap_tiles = ct; p->cap_nt_b = cn;
   return 0;
 }
@@ -797,16 +888,17 @@ int lstm_tc_forward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmF
   cudaMemsetAsync(p->flags, 0, (size_t)2 * p->cap_tiles * sizeof(unsigned), st);
   TcFwd f{};
   f.no = p->no; f.no4 = 4 * p->no; f.KC = p->KC; f.nks = p->nks; f.NT = NT; f.ntiles = ntiles; f.nst = nst;
+  f.nsig = NT * (kEpiThreads / 32);
   f.d0 = a.d0; f.hstride = a.hstride; f.hoff[0] = a.hoff[0]; f.hoff[1] = a.hoff[1];
   f.rows_pad = p->nr_max_rows; f.KP = p->KP;
   for (int d = 0; d < 2; d++) { f.XP[d] = a.XP[d]; f.G[d] = a.G[d]; f.C[d] = a.C[d]; f.Hprev[d] = a.Hprev[d]; }
-  f.H = a.H; f.hx_hi = p->hx_hi; f.hx_lo = p->hx_lo; f.flags = p->flags;
+  f.H = a.H; f.hx_hi = p->hx_hi; f.hx_lo = p->hx_lo; f.flags = p->flags; f.dbg = p->dbg; f.opt = p->opt;
   const dim3 grid(NT, tg, a.ndir);
   cudaError_t e;
   const int o = NR == 32 ? 0 : (NR == 48 ? 1 : 2);
-  if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi, p->tmH_lo, ln, f);
-  else if (NR == 48) e = launch_coop(lstm_tc_fwd<48>, grid, fwd_smem<48>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi, p->tmH_lo, ln, f);
-  else e = launch_coop(lstm_tc_fwd<64>, grid, fwd_smem<64>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi, p->tmH_lo, ln, f);
+  if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi[0], p->tmH_lo[0], p->tmH_hi[1], p->tmH_lo[1], p->tmH_hi[2], p->tmH_lo[2], ln, f);
+  else if (NR == 48) e = launch_coop(lstm_tc_fwd<48>, grid, fwd_smem<48>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi[0], p->tmH_lo[0], p->tmH_hi[1], p->tmH_lo[1], p->tmH_hi[2], p->tmH_lo[2], ln, f);
+  else e = launch_coop(lstm_tc_fwd<64>, grid, fwd_smem<64>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi[0], p->tmH_lo[0], p->tmH_hi[1], p->tmH_lo[1], p->tmH_hi[2], p->tmH_lo[2], ln, f);
   if (e != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "lstm_tc_fwd<%d> launch (grid %d x %d x %d, %d stages): %s", NR, NT, tg, a.ndir, nst, cudaGetErrorString(e));
     cudaGetLastError();
@@ -837,7 +929,7 @@ int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const Lstm
   b.d0 = a.d0; b.hstride = a.hstride; b.hoff[0] = a.hoff[0]; b.hoff[1] = a.hoff[1];
   b.kp_rows = p->kp_rows;
   for (int d = 0; d < 2; d++) { b.G[d] = a.G[d]; b.C[d] = a.C[d]; b.DG[d] = a.DG[d]; }
-  b.dH = a.dH; b.part = p->part; b.flags = p->flags;
+  b.dH = a.dH; b.part = p->part; b.flags = p->flags; b.dbg = p->dbg; b.opt = p->opt;
   const size_t smem = a_bytes + (size_t)nst * kBwdStageBytes + 1024;
   const dim3 grid(NT, tg, a.ndir);
   cudaError_t e = launch_coop(lstm_tc_bwd, grid, smem, st, p->coop, p->tmT_hi, p->tmT_lo, ln, b);
@@ -859,12 +951,20 @@ struct DevBuf {
   template <class T> T* as() { return reinterpret_cast<T*>(p); }
   bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16) == cudaSuccess; }
 };
-float max_abs_diff(const std::vector<float>& a, const std::vector<float>& b, float* maxref = nullptr) {
+float max_abs_diff(const char* what, const std::vector<float>& a, const std::vector<float>& b, float* maxref = nullptr) {
   float m = 0.f, r = 0.f;
+  size_t nan_a = 0, nan_b = 0, first = (size_t)-1;
   for (size_t i = 0; i < a.size(); i++) {
+    if (std::isnan(a[i])) nan_a++;
+    if (std::isnan(b[i])) { nan_b++; if (first == (size_t)-1) first = i; }
     const float d = std::fabs(a[i] - b[i]);
-    if (!(d <= m)) m = d;                 // NaN propagates into the result
-    r = std::max(r, std::fabs(a[i]));
+    if (d > m) m = d;
+    if (std::fabs(a[i]) > r) r = std::fabs(a[i]);
+  }
+  if (nan_a || nan_b) {
+    fprintf(stderr, "selftest_lstm %s: %zu NaN in the SIMT result, %zu NaN in the tensor-core result (first at %zu of %zu)\n", what,
+            nan_a, nan_b, first, a.size());
+    m = std::nanf("");
   }
   if (maxref) *maxref = r;
   return m;
@@ -883,6 +983,7 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   if (lstm_configure() != 0 || lstm_tc_configure() != 0) { say("configure failed"); return 1; }
   LstmTcPlan* plan = lstm_tc_create(no, prop.multiProcessorCount);
   if (!plan) { say("lstm_tc_create failed"); return 1; }
+  if (!plan->dbg && cudaMalloc((void**)&plan->dbg, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(plan->dbg, 0, 32 * sizeof(long long));
   unsigned long long rng = 0x9E3779B97F4A7C15ull ^ seed;
   auto uni = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (float)((rng >> 40) & 0xFFFFFF) / 16777216.f; };
   auto nrm = [&]() { float s = 0.f; for (int i = 0; i < 4; i++) s += uni(); return (s - 2.f) * 1.7320508f; };
@@ -919,6 +1020,7 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
     cudaMemset(dG[v].p, 0xff, 2 * n4 * 4); cudaMemset(dC[v].p, 0xff, 2 * n1 * 4); cudaMemset(dH[v].p, 0xff, n2 * 4);
     cudaMemset(dHp[v].p, 0xff, 2 * n1 * 4); cudaMemset(dDG[v].p, 0xff, 2 * n4 * 4);
   }
+  cudaDeviceSynchronize();   // the memsets above run on the legacy stream, the kernels below on a non-blocking stream
   Lines ln{};
   ln.B = B; ln.N = N; ln.Tmax = tmax; ln.T = dT.as<int>(); ln.off = dOff.as<int>(); ln.order = dOrd.as<int>();
   cudaStream_t st;
@@ -962,6 +1064,17 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) { char b2[200]; snprintf(b2, sizeof b2, "lstm_tc_fwd failed: %s", cudaGetErrorString(e)); say(b2); rc = 4; break; }
       cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+      if (const long long* c = lstm_tc_debug_counters(plan, 0))
+        if (rep == 1)
+          fprintf(stderr, "selftest_lstm fwd no=%d B=%d Tmax=%d %.3f ms | producer: flag %lld ring %lld issue %lld other %lld | mma: full %lld issue %lld "
+                  "other %lld | epilogue: accwait %lld tmemld %lld math %lld publish %lld stash %lld xp %lld (cycles, CTA 0)\n",
+                  no, B, tmax, ms[0], c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[8], c[9], c[10], c[11], c[12], c[13]);
+      if (const long long* c = plan->dbg_host[0])
+        if (rep == 1 && c[16])
+          fprintf(stderr, "selftest_lstm fwd timeline of step %d -> %d (cycles after the accumulator of step %d was ready): math done %lld, published %lld | "
+                  "producer: flag seen %lld, first TMA out %lld, last TMA out %lld | mma: first tile in %lld, last tile in %lld, last MMA issued %lld | "
+                  "next accumulator ready %lld\n", kDbgStep, kDbgStep + 1, kDbgStep, c[17] - c[16], c[18] - c[16], c[19] - c[16], c[20] - c[16],
+                  c[21] - c[16], c[22] - c[16], c[23] - c[16], c[24] - c[16], c[25] - c[16]);
     }
   }
   if (!rc) {
@@ -973,17 +1086,22 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) { char b2[200]; snprintf(b2, sizeof b2, "lstm_tc_bwd failed: %s", cudaGetErrorString(e)); say(b2); rc = 6; break; }
       cudaEventElapsedTime(&ms[1], ev[0], ev[1]);
+      if (const long long* c = lstm_tc_debug_counters(plan, 1))
+        if (rep == 1)
+          fprintf(stderr, "selftest_lstm bwd no=%d B=%d Tmax=%d %.3f ms | mma: deltawait %lld bufwait %lld issue %lld other %lld | epilogue: loads %lld "
+                  "flagwait %lld reduce %lld pointwise %lld drain %lld publish %lld (cycles, CTA 0)\n",
+                  no, B, tmax, ms[1], c[0], c[1], c[2], c[3], c[8], c[9], c[10], c[11], c[12], c[13]);
     }
   }
   if (rc == 0 || rc >= 5) {
     auto fetch = [&](DevBuf& b, size_t n) { std::vector<float> h(n); cudaMemcpy(h.data(), b.p, n * 4, cudaMemcpyDeviceToHost); return h; };
-    out[0] = max_abs_diff(fetch(dG[0], 2 * n4), fetch(dG[1], 2 * n4));
-    out[1] = max_abs_diff(fetch(dC[0], 2 * n1), fetch(dC[1], 2 * n1));
-    out[2] = max_abs_diff(fetch(dH[0], n2), fetch(dH[1], n2));
-    out[3] = max_abs_diff(fetch(dHp[0], 2 * n1), fetch(dHp[1], 2 * n1));
+    out[0] = max_abs_diff("gates", fetch(dG[0], 2 * n4), fetch(dG[1], 2 * n4));
+    out[1] = max_abs_diff("cell", fetch(dC[0], 2 * n1), fetch(dC[1], 2 * n1));
+    out[2] = max_abs_diff("h", fetch(dH[0], n2), fetch(dH[1], n2));
+    out[3] = max_abs_diff("hprev", fetch(dHp[0], 2 * n1), fetch(dHp[1], 2 * n1));
     if (rc == 0) {
       float ref = 0.f;
-      const float dd = max_abs_diff(fetch(dDG[0], 2 * n4), fetch(dDG[1], 2 * n4), &ref);
+      const float dd = max_abs_diff("deltas", fetch(dDG[0], 2 * n4), fetch(dDG[1], 2 * n4), &ref);
       out[4] = dd / std::max(ref, 1e-30f);
     }
   }

@@ -56,6 +56,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
+// one lane of a converged warp (the same lane every time)
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- fences
 // generic proxy <-> async proxy (TMA, tensor core operand reads), all state spaces
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -150,9 +157,23 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Poll with relaxed loads (an acquire load invalidates L1 on every iteration), then ONE acquire fence.  The data the
+// counter guards is read through L2 only (TMA, or ld.global.cg), never through a stale L1 line.
 __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
   SpinGuard g;
-  while (ld_acquire_gpu(p) < target) g.tick();
+  while (ld_relaxed_gpu(p) < target) g.tick();
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// release-increment: every write that happened-before (own writes, and the other threads' writes ordered by the
+// preceding CTA barrier) is visible at GPU scope before the counter moves.  Lighter than __threadfence() + atomicAdd,
+// which compiles to MEMBAR.SC + an L1 invalidation.
+__device__ __forceinline__ void signal_counter(unsigned* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 
 // ---------------------------------------------------------------- fast gate math (same approximations as lstm.cu)

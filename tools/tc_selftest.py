@@ -12,6 +12,9 @@ CASES = {
     "sizes": [(200, 128, 20, 60), (400, 256, 20, 50), (800, 128, 10, 30), (400, 32, 30, 40), (256, 100, 17, 33)],
     "timing": [(200, 128, 200, 2000), (400, 256, 200, 2000), (400, 32, 200, 2000)],
     "timing800": [(800, 128, 512, 512)],
+    "t3": [(200, 128, 200, 2000)],
+    "t4": [(400, 256, 200, 2000)],
+    "t4s": [(400, 32, 200, 2000)],
 }
 
 if __name__ == "__main__":
