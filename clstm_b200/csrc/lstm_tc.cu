@@ -57,9 +57,11 @@ constexpr float kScaleR = 16.f;        // weights      -> fp16 hi/lo of 16 R   (
 constexpr float kScaleD = 256.f;       // deltas       -> fp16 hi/lo of 256 d  (|d| < 256)
 constexpr unsigned kStageBytes = 2 * kTcLines * 128;   // one ring stage: hi tile + lo tile of [128 lines x 64 k] fp16
 constexpr int kBwdNR = 64;             // gate rows per CTA in the backward kernel (one 128-byte swizzle row of K)
+constexpr int kDbgCtas = 160;          // debug counter slots (one per CTA)
 constexpr int kDbgStep = 64;           // the step whose event timestamps the debug counters record
 constexpr int kBwdChunk = 256;         // outputs per MMA chunk in the backward kernel (UMMA N)
 constexpr unsigned kBwdStageBytes = 2 * kBwdChunk * 128;
+constexpr unsigned kBwdScratch = 8 * 32 * 32 * 4;   // row-transfer scratch of the 8 epilogue warps (rows of 32 floats)
 
 struct TcFwd {
   int no, no4;            // hidden units, gate rows
@@ -78,7 +80,8 @@ struct TcFwd {
   __half* hx_lo;
   unsigned* flags;        // [direction slot][tile] steps published
   long long* dbg;         // optional per-phase cycle counters of CTA (0,0,0) (self-test / tuning), nullptr otherwise
-  int opt;                // tuning switches (CLSTM_B200_TC_OPT): bit 0 fixed 32-row TMA boxes, bit 1 no writer-side proxy fence
+  int opt;                // tuning switches (CLSTM_B200_TC_OPT): 1 fixed 32-row TMA boxes, 2 writer-side proxy fence,
+                          // 4 no stash stores (timing experiment, wrong results), 8 no input-projection loads (ditto)
 };
 
 struct TcBwd {
@@ -121,6 +124,79 @@ __device__ __forceinline__ void load_run(float* v, const float* src) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- warp-cooperative rows
+// Every epilogue thread owns one text line, so its loads / stores of the line's current column go to a row of NF floats at
+// an address of its own: a lane-private vector access touches 32 different 128-byte lines per instruction (32 LSU
+// wavefronts for 512 bytes).  These helpers move the 32 rows of a warp through a per-warp shared-memory scratch instead,
+// so that consecutive lanes cover consecutive 16-byte chunks of the SAME row: an instruction then touches 32*16/(4 NF)
+// rows in full lines -- 8x fewer wavefronts for NF = 32.  Chunk c of row r sits at position c ^ (r mod CH) of the
+// row (conflict-free in both directions).  Rows of lanes without work are passed as nullptr.
+template <int NF> struct RowXfer {
+  static constexpr int CH = NF / 4;
+  static constexpr bool coop = (NF % 4 == 0) && CH >= 2 && (CH & (CH - 1)) == 0;
+};
+template <int NF>
+__device__ __forceinline__ void gather_rows(unsigned scr, const float* row, float* v, int lane) {
+  constexpr int CH = RowXfer<NF>::CH;
+  if constexpr (!RowXfer<NF>::coop) {
+    if (row) load_run<NF, (NF % 4 == 0) ? 4 : 2>(v, row);
+    else {
+#pragma unroll
+      for (int i = 0; i < NF; i++) v[i] = 0.f;
+    }
+  } else {
+    float4 t[CH];
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      const int f = i * 32 + lane, src = f / CH, c = f % CH;
+      const float* sp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(row), src));
+      t[i] = sp ? __ldg(reinterpret_cast<const float4*>(sp) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      const int f = i * 32 + lane, src = f / CH, c = f % CH;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scr + (unsigned)((src * CH + (c ^ (src % CH))) << 4)), "f"(t[i].x),
+                   "f"(t[i].y), "f"(t[i].z), "f"(t[i].w)
+                   : "memory");
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[4 * c]), "=f"(v[4 * c + 1]), "=f"(v[4 * c + 2]), "=f"(v[4 * c + 3])
+                   : "r"(scr + (unsigned)((lane * CH + (c ^ (lane % CH))) << 4))
+                   : "memory");
+    __syncwarp();
+  }
+}
+template <int NF>
+__device__ __forceinline__ void scatter_rows(unsigned scr, float* row, const float* v, int lane) {
+  constexpr int CH = RowXfer<NF>::CH;
+  if constexpr (!RowXfer<NF>::coop) {
+    if (row) store_run<NF, (NF % 4 == 0) ? 4 : 2>(row, v);
+  } else {
+#pragma unroll
+    for (int c = 0; c < CH; c++)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(scr + (unsigned)((lane * CH + (c ^ (lane % CH))) << 4)), "f"(v[4 * c]),
+                   "f"(v[4 * c + 1]), "f"(v[4 * c + 2]), "f"(v[4 * c + 3])
+                   : "memory");
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      const int f = i * 32 + lane, src = f / CH, c = f % CH;
+      float* dp = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(row), src));
+      float4 t;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                   : "r"(scr + (unsigned)((src * CH + (c ^ (src % CH))) << 4))
+                   : "memory");
+      if (dp) reinterpret_cast<float4*>(dp)[c] = t;
+    }
+    __syncwarp();
+  }
+}
+template <int NR> constexpr unsigned fwd_scratch_bytes() { return RowXfer<NR / 2>::coop ? 8u * 32u * (NR / 2) * 4u : 0u; }
+
 // ================================================================================================ forward
 template <int NR>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -141,6 +217,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
   const unsigned smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
   const unsigned rs0 = smem0;                                   // weight slice: chunk kc at rs0 + kc*2*r_bytes (hi | lo)
   const unsigned ring0 = rs0 + (unsigned)p.KC * 2 * r_bytes;    // stage st at ring0 + st*kStageBytes (hi | lo)
+  const unsigned scr0 = ring0 + (unsigned)p.nst * kStageBytes;  // per-warp row-transfer scratch of the epilogue warps
   const unsigned bar0 = smem_u32(&bars[0]);
   auto full = [&](unsigned st) { return bar0 + 8 * st; };
   auto empty = [&](unsigned st) { return bar0 + 8 * (kMaxStages + st); };
@@ -163,7 +240,8 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
   tc_fence_after();
   const unsigned tmem_d = tmem_base_s;
   unsigned* const flag_q = p.flags + (size_t)q * p.ntiles;
-  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool dbg = p.dbg != nullptr;
+  long long* const mydbg = p.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32;
   long long dt[4] = {0, 0, 0, 0};
 #define TC_T0 const long long t0_ = dbg ? clock64() : 0
 #define TC_T(i) if (dbg) { const long long t1_ = clock64(); dt[i] += t1_ - tlast_; tlast_ = t1_; }
@@ -198,11 +276,11 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
         TC_T(3);
         wait_counter(flag_q + tile, (unsigned)p.nsig * (unsigned)s);      // h_{s-1} of every row slice is in L2
         TC_T(0);
-        if (dbg && s == kDbgStep + 1) p.dbg[16 + 3] = clock64();
+        if (dbg && s == kDbgStep + 1) mydbg[16 + 3] = clock64();
         const int row0 = ((q * 2 + ((s - 1) & 1)) * p.ntiles + tile) * kTcLines;
         for (int kc = 0; kc < p.KC; kc++, it++) {
           const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
-          if (use > 0) mbar_wait(empty(st), (use - 1) & 1);
+          if (use > 0 && p.nst < p.KC) mbar_wait(empty(st), (use - 1) & 1);   // nst >= KC: the step counter already implies it
           TC_T(1);
           if (elect_one()) {
             if (kc == 0) fence_proxy_async();                             // generic-proxy writes (other SMs) -> async-proxy reads
@@ -215,12 +293,12 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           }
           __syncwarp();
           TC_T(2);
-          if (dbg && s == kDbgStep + 1 && kc == 0) p.dbg[16 + 4] = clock64();
+          if (dbg && s == kDbgStep + 1 && kc == 0) mydbg[16 + 4] = clock64();
         }
-        if (dbg && s == kDbgStep + 1) p.dbg[16 + 5] = clock64();
+        if (dbg && s == kDbgStep + 1) mydbg[16 + 5] = clock64();
       }
     }
-    if (dbg && lane == 0) for (int i = 0; i < 4; i++) p.dbg[i] = dt[i];     // flag wait | ring wait | TMA issue | other
+    if (dbg && lane == 0) for (int i = 0; i < 4; i++) mydbg[i] = dt[i];     // flag wait | ring wait | TMA issue | other
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
     const unsigned idesc = make_idesc_f16(kTcLines, NR);
@@ -238,8 +316,8 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           mbar_wait(full(st), use & 1);
           tc_fence_after();
           TC_T(0);
-          if (dbg && s == kDbgStep + 1 && kc == 0) p.dbg[16 + 6] = clock64();
-          if (dbg && s == kDbgStep + 1 && kc == p.KC - 1) p.dbg[16 + 7] = clock64();
+          if (dbg && s == kDbgStep + 1 && kc == 0) mydbg[16 + 6] = clock64();
+          if (dbg && s == kDbgStep + 1 && kc == p.KC - 1) mydbg[16 + 7] = clock64();
           const unsigned a_hi = ring0 + st * kStageBytes;
           const unsigned b_hi = rs0 + kc * 2 * r_bytes;
           // 16 k = 32 bytes along the swizzled row = +2 in the descriptor's address field
@@ -261,10 +339,10 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           __syncwarp();
           TC_T(1);
         }
-        if (dbg && s == kDbgStep + 1) p.dbg[16 + 8] = clock64();
+        if (dbg && s == kDbgStep + 1) mydbg[16 + 8] = clock64();
       }
     }
-    if (dbg && lane == 0) for (int i = 0; i < 3; i++) p.dbg[4 + i] = dt[i];   // full wait | MMA issue | other
+    if (dbg && lane == 0) for (int i = 0; i < 3; i++) mydbg[4 + i] = dt[i];   // full wait | MMA issue | other
   } else {
     // ------------------------------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;
@@ -276,6 +354,8 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
     const unsigned taddr = tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * NC);
     const int ub = m * (NR / 4) + ch * NU;                 // first hidden unit of this thread
     const int no = p.no, no4 = p.no4;
+    const unsigned scr = scr0 + (unsigned)ew * (32u * NC * 4u);
+    const bool mine = ub + NU <= no;                       // all of this thread's units are real (no % 8 == 0)
     const float* __restrict__ XPd = p.XP[d];
     float* __restrict__ Gd = p.G[d];
     float* __restrict__ Cd = p.C[d];
@@ -298,7 +378,9 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
         const int t = d ? Tp - 1 - s : s;
         const size_t col = (size_t)off + t;
         float xp[NC];
-        if (active) {
+        if (RowXfer<NC>::coop && NU % 4 == 0) {
+          gather_rows<NC>(scr, (active && mine && !(p.opt & 8)) ? XPd + col * no4 + 4 * ub : nullptr, xp, lane);
+        } else if (active) {
 #pragma unroll
           for (int u = 0; u < NU; u++) {
             if (ub + u < no) load_run<4, 4>(xp + 4 * u, XPd + col * no4 + 4 * (ub + u));
@@ -312,8 +394,8 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           accph ^= 1;
           tc_fence_after();
           TC_E(0);
-          if (dbg && s == kDbgStep) p.dbg[16 + 0] = clock64();
-          if (dbg && s == kDbgStep + 1) p.dbg[16 + 9] = clock64();
+          if (dbg && s == kDbgStep) mydbg[16 + 0] = clock64();
+          if (dbg && s == kDbgStep + 1) mydbg[16 + 9] = clock64();
           tmem_ld<NC>(taddr, acc);
           TC_E(1);
         } else {
@@ -356,14 +438,27 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
         // this warp has read its accumulators and written its h: publish (release-increment per warp, no CTA barrier;
         // the producer of every slice waits for all 8 warps of all slices, which also protects the accumulator)
         TC_E(2);
-        if (dbg && s == kDbgStep) p.dbg[16 + 1] = clock64();
+        if (dbg && s == kDbgStep) mydbg[16 + 1] = clock64();
         tc_fence_before();
         if (p.opt & 2) fence_proxy_async();
         __syncwarp();
         if (lane == 0) signal_counter(flag_q + tile);
         TC_E(3);
-        if (dbg && s == kDbgStep) p.dbg[16 + 2] = clock64();
-        if (active) {   // stash for the backward pass and the dense products, off the critical path
+        if (dbg && s == kDbgStep) mydbg[16 + 2] = clock64();
+        // stash for the backward pass and the dense products, off the critical path
+        if (RowXfer<NC>::coop && NU % 4 == 0) {
+          const bool st = active && mine && !(p.opt & 4);
+          scatter_rows<NC>(scr, st ? Gd + col * no4 + 4 * ub : nullptr, gv, lane);
+          scatter_rows<NU>(scr, st ? Cd + col * no + ub : nullptr, c, lane);
+          scatter_rows<NU>(scr, st ? Hd + col * p.hstride + ub : nullptr, hh, lane);
+          scatter_rows<NU>(scr, (st && s + 1 < Tp) ? Hpd + (col + (d ? -1 : 1)) * (size_t)no + ub : nullptr, hh, lane);
+          if (st && s == 0) {
+            float z[NU];
+#pragma unroll
+            for (int u = 0; u < NU; u++) z[u] = 0.f;
+            store_run<NU, VW>(Hpd + col * no + ub, z);
+          }
+        } else if (active && !(p.opt & 4)) {
 #pragma unroll
           for (int u = 0; u < NU; u++)
             if (ub + u < no) store_run<4, 4>(Gd + col * no4 + 4 * (ub + u), gv + 4 * u);
@@ -392,7 +487,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
         TC_E(4);
       }
     }
-    if (dbg && ew == 0 && lane == 0) for (int i = 0; i < 6; i++) p.dbg[8 + i] = de[i];   // acc wait | tmem ld | math+h | publish | stash | xp issue
+    if (dbg && ew == 0 && lane == 0) for (int i = 0; i < 6; i++) mydbg[8 + i] = de[i];   // acc wait | tmem ld | math+h | publish | stash | xp issue
   }
   tc_fence_before();
   __syncthreads();
@@ -414,7 +509,8 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
   const int m = blockIdx.x, q = blockIdx.z, d = p.d0 + q;
   const unsigned smem0 = (smem_u32(tc_smem) + 1023u) & ~1023u;
   const unsigned a_hi = smem0, a_lo = smem0 + kTcLines * 128;          // A operand: deltas of this CTA's 64 gate rows
-  const unsigned ring0 = smem0 + 2 * kTcLines * 128;                   // B stages (hi | lo), kBwdStageBytes each
+  const unsigned scr0 = smem0 + 2 * kTcLines * 128;                    // per-warp row-transfer scratch (8 x 4 KB)
+  const unsigned ring0 = scr0 + kBwdScratch;                           // B stages (hi | lo), kBwdStageBytes each
   const unsigned bar0 = smem_u32(&bars[0]);
   auto bfull = [&](unsigned st) { return bar0 + 8 * st; };
   auto bempty = [&](unsigned st) { return bar0 + 8 * (kMaxStages + st); };
@@ -447,7 +543,8 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
   const unsigned tmem_d = tmem_base_s;
   unsigned* const flag_q = p.flags + (size_t)q * p.ntiles;
   const int row_t = d * p.kp_rows;                     // first row of this direction in the transposed split copy
-  const bool dbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const bool dbg = p.dbg != nullptr;
+  long long* const mydbg = p.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32;
 
   auto load_chunk = [&](unsigned st, int chunk) {      // B chunk: outputs [256*chunk, +256) x this CTA's 64 gate rows
     mbar_expect_tx(bfull(st), kBwdStageBytes);
@@ -521,7 +618,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
           }
         }
       }
-      if (dbg && lane == 0) for (int i = 0; i < 4; i++) p.dbg[i] = dt[i];   // delta wait | buffer / weight wait | MMA issue | other
+      if (dbg && lane == 0) for (int i = 0; i < 4; i++) mydbg[i] = dt[i];   // delta wait | buffer / weight wait | MMA issue | other
     }
   } else {
     // ------------------------------------------------------------------------------------------ epilogue warps
@@ -557,25 +654,27 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
         const int t = d ? Tp - 1 - fs : fs;
         const size_t col = (size_t)off + t;
         float g[4 * NU], cc[NU], cp[NU], dh[NU];
-        if (active) {                                      // operands that do not depend on the exchange: issue first
-          load_run<4 * NU, 4>(g, Gd + col * no4 + 4 * ub);
-          load_run<NU, 4>(cc, Cd + col * no + ub);
-          if (fs > 0) load_run<NU, 4>(cp, Cd + (col + (d ? 1 : -1)) * (size_t)no + ub);
-          load_run<NU, 4>(dh, dHd + col * p.hstride + ub);
+        {                                                  // operands that do not depend on the exchange: fetch first
+          const unsigned scr = scr0 + (unsigned)ew * 4096u;
+          gather_rows<4 * NU>(scr, active ? Gd + col * no4 + 4 * ub : nullptr, g, lane);
+          gather_rows<NU>(scr, active ? Cd + col * no + ub : nullptr, cc, lane);
+          gather_rows<NU>(scr, (active && fs > 0) ? Cd + (col + (d ? 1 : -1)) * (size_t)no + ub : nullptr, cp, lane);
+          gather_rows<NU>(scr, active ? dHd + col * p.hstride + ub : nullptr, dh, lane);
         }
         TC_E(0);
         if (it > 0) {                                      // partial products of the previous step, all slices
           wait_counter(flag_q + tile, (unsigned)(NT * (kEpiThreads / 32)) * (unsigned)it);
           TC_E(1);
           if (active && fs < Tp - 1) {
-            const float* src = part_t + (size_t)((it - 1) & 1) * slab + (size_t)m * NT * (kTcLines * 16) + pl * 16 + ch * NU;
+            // exchange layout [dest slice][src slice][4 unit quads][128 lines][4 units]: a warp reads / writes 512 contiguous bytes
+            const float* src = part_t + (size_t)((it - 1) & 1) * slab + ((size_t)m * NT * 4 + 2 * ch) * (kTcLines * 4) + pl * 4;
             float r[NU];
 #pragma unroll
             for (int u = 0; u < NU; u++) r[u] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
             for (int sm = 0; sm < NT; sm++) {             // fixed order => deterministic
               const float4 x0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sm * (kTcLines * 16)));
-              const float4 x1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sm * (kTcLines * 16) + 4));
+              const float4 x1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)sm * (kTcLines * 16) + kTcLines * 4));
               r[0] += x0.x; r[1] += x0.y; r[2] += x0.z; r[3] += x0.w;
               r[4] += x1.x; r[5] += x1.y; r[6] += x1.z; r[7] += x1.w;
             }
@@ -602,7 +701,8 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
             dl[4 * u + 2] = go * (1.f - go) * dgo;
             dl[4 * u + 3] = (1.f - ci * ci) * dci;
           }
-          store_run<4 * NU, 4>(DGd + col * no4 + 4 * ub, dl);
+#pragma unroll
+          for (int i = 0; i < 4 * NU; i++) g[i] = dl[i];   // (the gate values are dead: reuse their registers for the DG rows)
 #pragma unroll
           for (int i = 0; i < 2 * NU; i++) {
             unsigned short h0, l0_, h1, l1_;
@@ -615,6 +715,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 2 * NU; i++) { hi[i] = 0u; lo[i] = 0u; }
         }
+        scatter_rows<4 * NU>(scr0 + (unsigned)ew * 4096u, active ? DGd + col * no4 + 4 * ub : nullptr, g, lane);
         if (fs == 0) break;                                // the first forward step has no predecessor: nothing to propagate
         // A operand row `pl`, k = 32*ch .. 32*ch+31: four 16-byte chunks of the 128-byte swizzled row
 #pragma unroll
@@ -632,7 +733,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
         mbar_arrive(afull);
         TC_E(3);
         // drain the output chunks into the exchange buffer: group gq of 16 outputs belongs to slice (16 chunk + gq)
-        float* const dst_par = part_t + (size_t)(it & 1) * slab + (size_t)m * (kTcLines * 16) + pl * 16;
+        float* const dst_par = part_t + (size_t)(it & 1) * slab + (size_t)m * (kTcLines * 16) + pl * 4;
         const bool wr = (li >= 0) && fs < Tp;              // rows of lines that are not running are never read
         for (int i = 0; i < p.nchunk; i++, cnt++) {
           const unsigned buf = cnt & 1;
@@ -647,7 +748,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
               float* o = dst_par + (size_t)(i * 16 + gq) * NT * (kTcLines * 16);
 #pragma unroll
               for (int e = 0; e < 16; e += 4)
-                __stcg(reinterpret_cast<float4*>(o + e),
+                __stcg(reinterpret_cast<float4*>(o + e * kTcLines),
                        make_float4(v[e] * inv_scale, v[e + 1] * inv_scale, v[e + 2] * inv_scale, v[e + 3] * inv_scale));
             }
           }
@@ -660,7 +761,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
         TC_E(5);
       }
     }
-    if (dbg && ew == 0 && lane == 0) for (int i = 0; i < 6; i++) p.dbg[8 + i] = de[i];   // loads | flag wait | reduce | pointwise | drain | publish
+    if (dbg && ew == 0 && lane == 0) for (int i = 0; i < 6; i++) mydbg[8 + i] = de[i];   // loads | flag wait | reduce | pointwise | drain | publish
   }
   tc_fence_before();
   __syncthreads();
@@ -715,7 +816,7 @@ int make_map(CUtensorMap* m, void* base, size_t rows, size_t cols, int box_rows)
 constexpr size_t kSmemLimit = 232448;     // 227 KB per CTA on sm_100
 constexpr size_t kSmemSlack = 1024 + 256; // alignment of the dynamic part + static barriers
 
-template <int NR> size_t fwd_smem(int KC, int nst) { return (size_t)KC * 2 * NR * 128 + (size_t)nst * kStageBytes + 1024; }
+template <int NR> size_t fwd_smem(int KC, int nst) { return (size_t)KC * 2 * NR * 128 + (size_t)nst * kStageBytes + fwd_scratch_bytes<NR>() + 1024; }
 
 }  // namespace
 
@@ -735,8 +836,10 @@ struct LstmTcPlan {
   CUtensorMap tmT_hi, tmT_lo, tmH_hi[3], tmH_lo[3];   // h exchange maps: box rows 32 / 64 / 128
   bool coop = true;
   int opt = 0;                    // CLSTM_B200_TC_OPT tuning switches
+  int last_ctas[2] = {0, 0};      // grid size of the last forward / backward launch (debug counters: one slot per CTA)
+  int last_gx[2] = {1, 1};
   long long* dbg = nullptr;       // 16 cycle counters + 16 event timestamps of step kDbgStep (CLSTM_B200_TC_DBG=1 or the self-test)
-  long long dbg_host[2][32] = {};
+  long long dbg_host[2][kDbgCtas * 32] = {};
   char err[256] = {0};
 };
 
@@ -751,7 +854,7 @@ bool pick_fwd(const LstmTcPlan* pl, int ndir, int ntiles, int* NR, int* NT, int*
       const int nr = fwd_nr_options[o];
       const int nt = (4 * pl->no + nr - 1) / nr;
       if (nt * ndir > pl->num_sms) continue;
-      const size_t base = (size_t)pl->KC * 2 * nr * 128 + kSmemSlack;
+      const size_t base = (size_t)pl->KC * 2 * nr * 128 + kSmemSlack + (nr == 32 ? fwd_scratch_bytes<32>() : (nr == 48 ? fwd_scratch_bytes<48>() : fwd_scratch_bytes<64>()));
       if (base + 2 * kStageBytes > kSmemLimit) continue;
       int st = (int)((kSmemLimit - base) / kStageBytes);
       st = std::min(st, std::min(kMaxStages, std::max(2, pl->KC)));
@@ -802,7 +905,7 @@ LstmTcPlan* lstm_tc_create(int no, int num_sms) {
   if (const char* e = getenv("CLSTM_B200_TC_COOP")) p->coop = atoi(e) != 0;
   if (const char* e = getenv("CLSTM_B200_TC_OPT")) p->opt = atoi(e);
   if (const char* e = getenv("CLSTM_B200_TC_DBG")) {
-    if (atoi(e) != 0 && cudaMalloc((void**)&p->dbg, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(p->dbg, 0, 32 * sizeof(long long));
+    if (atoi(e) != 0 && cudaMalloc((void**)&p->dbg, kDbgCtas * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(p->dbg, 0, kDbgCtas * 32 * sizeof(long long));
   }
   if (!ok) { lstm_tc_destroy(p); return nullptr; }
   return p;
@@ -811,8 +914,8 @@ LstmTcPlan* lstm_tc_create(int no, int num_sms) {
 // per-phase cycle counters of the last forward (which = 0) / backward (1) launch; the stream must be idle
 const long long* lstm_tc_debug_counters(LstmTcPlan* p, int which) {
   if (!p || !p->dbg) return nullptr;
-  cudaMemcpy(p->dbg_host[which & 1], p->dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
-  cudaMemset(p->dbg, 0, 32 * sizeof(long long));
+  cudaMemcpy(p->dbg_host[which & 1], p->dbg, kDbgCtas * 32 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(p->dbg, 0, kDbgCtas * 32 * sizeof(long long));
   return p->dbg_host[which & 1];
 }
 
@@ -894,6 +997,7 @@ int lstm_tc_forward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmF
   for (int d = 0; d < 2; d++) { f.XP[d] = a.XP[d]; f.G[d] = a.G[d]; f.C[d] = a.C[d]; f.Hprev[d] = a.Hprev[d]; }
   f.H = a.H; f.hx_hi = p->hx_hi; f.hx_lo = p->hx_lo; f.flags = p->flags; f.dbg = p->dbg; f.opt = p->opt;
   const dim3 grid(NT, tg, a.ndir);
+  p->last_ctas[0] = NT * tg * a.ndir; p->last_gx[0] = NT;
   cudaError_t e;
   const int o = NR == 32 ? 0 : (NR == 48 ? 1 : 2);
   if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi[0], p->tmH_lo[0], p->tmH_hi[1], p->tmH_lo[1], p->tmH_hi[2], p->tmH_lo[2], ln, f);
@@ -915,7 +1019,7 @@ int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const Lstm
   const int tg = std::min(ntiles, p->num_sms / (NT * a.ndir));
   const int nop16 = ((p->no + 15) / 16) * 16;
   const int nchunk = (nop16 + kBwdChunk - 1) / kBwdChunk;
-  const size_t a_bytes = 2 * kTcLines * 128;
+  const size_t a_bytes = 2 * kTcLines * 128 + kBwdScratch;
   const int max_st = (int)((kSmemLimit - kSmemSlack - a_bytes) / kBwdStageBytes);   // 3
   const bool resident = nchunk <= std::min(max_st, kMaxStages);
   const int nst = resident ? nchunk : std::min(max_st, kMaxStages);
@@ -932,6 +1036,7 @@ int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const Lstm
   b.dH = a.dH; b.part = p->part; b.flags = p->flags; b.dbg = p->dbg; b.opt = p->opt;
   const size_t smem = a_bytes + (size_t)nst * kBwdStageBytes + 1024;
   const dim3 grid(NT, tg, a.ndir);
+  p->last_ctas[1] = NT * tg * a.ndir; p->last_gx[1] = NT;
   cudaError_t e = launch_coop(lstm_tc_bwd, grid, smem, st, p->coop, p->tmT_hi, p->tmT_lo, ln, b);
   if (e != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "lstm_tc_bwd launch (grid %d x %d x %d, %d stages%s): %s", NT, tg, a.ndir, nst,
@@ -945,6 +1050,15 @@ int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const Lstm
 
 // ================================================================================================ self-test (device A/B)
 namespace {
+// min / median / max over the CTAs of one debug counter, and which CTA holds the minimum
+void spread(const char* name, const long long* c, int nctas, int idx, int gx) {
+  std::vector<std::pair<long long, int>> v;
+  for (int i = 0; i < nctas && i < kDbgCtas; i++) v.push_back({c[(size_t)i * 32 + idx], i});
+  if (v.empty()) return;
+  std::sort(v.begin(), v.end());
+  fprintf(stderr, "    %-10s min %lld (cta %d = slice %d) median %lld max %lld (cta %d = slice %d)\n", name, v.front().first, v.front().second,
+          v.front().second % gx, v[v.size() / 2].first, v.back().first, v.back().second, v.back().second % gx);
+}
 struct DevBuf {
   void* p = nullptr;
   ~DevBuf() { cudaFree(p); }
@@ -983,7 +1097,7 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   if (lstm_configure() != 0 || lstm_tc_configure() != 0) { say("configure failed"); return 1; }
   LstmTcPlan* plan = lstm_tc_create(no, prop.multiProcessorCount);
   if (!plan) { say("lstm_tc_create failed"); return 1; }
-  if (!plan->dbg && cudaMalloc((void**)&plan->dbg, 32 * sizeof(long long)) == cudaSuccess) cudaMemset(plan->dbg, 0, 32 * sizeof(long long));
+  if (!plan->dbg && cudaMalloc((void**)&plan->dbg, kDbgCtas * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(plan->dbg, 0, kDbgCtas * 32 * sizeof(long long));
   unsigned long long rng = 0x9E3779B97F4A7C15ull ^ seed;
   auto uni = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (float)((rng >> 40) & 0xFFFFFF) / 16777216.f; };
   auto nrm = [&]() { float s = 0.f; for (int i = 0; i < 4; i++) s += uni(); return (s - 2.f) * 1.7320508f; };
@@ -1069,6 +1183,11 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
           fprintf(stderr, "selftest_lstm fwd no=%d B=%d Tmax=%d %.3f ms | producer: flag %lld ring %lld issue %lld other %lld | mma: full %lld issue %lld "
                   "other %lld | epilogue: accwait %lld tmemld %lld math %lld publish %lld stash %lld xp %lld (cycles, CTA 0)\n",
                   no, B, tmax, ms[0], c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[8], c[9], c[10], c[11], c[12], c[13]);
+      if (rep == 1 && plan->dbg) {
+        const long long* c = plan->dbg_host[0];
+        const char* names[] = {"flagwait", "ringwait", "tmaissue", "p.other", "fullwait", "mmaissue", "m.other", "", "accwait", "tmemld", "math", "publish", "stash", "xp"};
+        for (int i : {0, 4, 5, 8, 10, 11, 12, 13}) spread(names[i], c, plan->last_ctas[0], i, plan->last_gx[0]);
+      }
       if (const long long* c = plan->dbg_host[0])
         if (rep == 1 && c[16])
           fprintf(stderr, "selftest_lstm fwd timeline of step %d -> %d (cycles after the accumulator of step %d was ready): math done %lld, published %lld | "
@@ -1091,6 +1210,11 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
           fprintf(stderr, "selftest_lstm bwd no=%d B=%d Tmax=%d %.3f ms | mma: deltawait %lld bufwait %lld issue %lld other %lld | epilogue: loads %lld "
                   "flagwait %lld reduce %lld pointwise %lld drain %lld publish %lld (cycles, CTA 0)\n",
                   no, B, tmax, ms[1], c[0], c[1], c[2], c[3], c[8], c[9], c[10], c[11], c[12], c[13]);
+      if (rep == 1 && plan->dbg) {
+        const long long* c = plan->dbg_host[1];
+        const char* names[] = {"deltawait", "bufwait", "mmaissue", "m.other", "", "", "", "", "loads", "flagwait", "reduce", "pointwise", "drain", "publish"};
+        for (int i : {0, 2, 8, 9, 10, 11, 12, 13}) spread(names[i], c, plan->last_ctas[1], i, plan->last_gx[1]);
+      }
     }
   }
   if (rc == 0 || rc >= 5) {
