@@ -80,7 +80,7 @@ struct TcFwd {
   __half* hx_lo;
   unsigned* flags;        // [direction slot][tile] steps published
   long long* dbg;         // optional per-phase cycle counters of CTA (0,0,0) (self-test / tuning), nullptr otherwise
-  int opt;                // tuning switches (CLSTM_B200_TC_OPT): 1 fixed 32-row TMA boxes, 2 writer-side proxy fence,
+  int opt;                // tuning switches (CLSTM_B200_TC_OPT): 2 writer-side proxy fence,
                           // 4 no stash stores (timing experiment, wrong results), 8 no input-projection loads (ditto)
 };
 
@@ -135,23 +135,30 @@ template <int NF> struct RowXfer {
   static constexpr int CH = NF / 4;
   static constexpr bool coop = (NF % 4 == 0) && CH >= 2 && (CH & (CH - 1)) == 0;
 };
+// issue: the global loads of a gather, results stay in registers (nothing waits for them here)
 template <int NF>
-__device__ __forceinline__ void gather_rows(unsigned scr, const float* row, float* v, int lane) {
+__device__ __forceinline__ void gather_issue(const float* row, float4* t, int lane) {
   constexpr int CH = RowXfer<NF>::CH;
   if constexpr (!RowXfer<NF>::coop) {
-    if (row) load_run<NF, (NF % 4 == 0) ? 4 : 2>(v, row);
-    else {
 #pragma unroll
-      for (int i = 0; i < NF; i++) v[i] = 0.f;
-    }
+    for (int i = 0; i < NF / 4; i++) t[i] = row ? __ldg(reinterpret_cast<const float4*>(row) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   } else {
-    float4 t[CH];
 #pragma unroll
     for (int i = 0; i < CH; i++) {
       const int f = i * 32 + lane, src = f / CH, c = f % CH;
       const float* sp = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(row), src));
       t[i] = sp ? __ldg(reinterpret_cast<const float4*>(sp) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+}
+// commit: through the scratch, every lane ends up with its own row in v
+template <int NF>
+__device__ __forceinline__ void gather_commit(unsigned scr, const float4* t, float* v, int lane) {
+  constexpr int CH = RowXfer<NF>::CH;
+  if constexpr (!RowXfer<NF>::coop) {
+#pragma unroll
+    for (int i = 0; i < NF / 4; i++) { v[4 * i] = t[i].x; v[4 * i + 1] = t[i].y; v[4 * i + 2] = t[i].z; v[4 * i + 3] = t[i].w; }
+  } else {
 #pragma unroll
     for (int i = 0; i < CH; i++) {
       const int f = i * 32 + lane, src = f / CH, c = f % CH;
@@ -201,9 +208,8 @@ template <int NR> constexpr unsigned fwd_scratch_bytes() { return RowXfer<NR / 2
 template <int NR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
-            const __grid_constant__ CUtensorMap tmH_hi, const __grid_constant__ CUtensorMap tmH_lo,
-            const __grid_constant__ CUtensorMap tmH64_hi, const __grid_constant__ CUtensorMap tmH64_lo,
-            const __grid_constant__ CUtensorMap tmH128_hi, const __grid_constant__ CUtensorMap tmH128_lo, Lines ln, TcFwd p) {
+            const __grid_constant__ CUtensorMap tmH32, const __grid_constant__ CUtensorMap tmH64,
+            const __grid_constant__ CUtensorMap tmH128, Lines ln, TcFwd p) {
   constexpr int NC = NR / 2;                      // accumulator columns (gate rows) per epilogue thread
   constexpr int NU = NR / 8;                      // hidden units per epilogue thread
   constexpr int VW = (NU % 4 == 0) ? 4 : 2;       // vector width of the per-unit runs
@@ -226,7 +232,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
   if (tid == 0) {
     for (int i = 0; i < 2 * kMaxStages + 2; i++) mbar_init(bar0 + 8 * i, 1);
     mbar_init_fence();
-    tma_prefetch_desc(&tmR_hi); tma_prefetch_desc(&tmR_lo); tma_prefetch_desc(&tmH_hi); tma_prefetch_desc(&tmH_lo);
+    tma_prefetch_desc(&tmR_hi); tma_prefetch_desc(&tmR_lo); tma_prefetch_desc(&tmH32); tma_prefetch_desc(&tmH64); tma_prefetch_desc(&tmH128);
   }
   __syncthreads();
   if (warp == 1) {
@@ -268,13 +274,12 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
       int act = nl;
       for (int s = 1; s < Tt; s++) {
         while (act > 0 && ln.T[ln.order[l0 + act - 1]] <= s) act--;      // lines still running at step s: a prefix
-        // rows to fetch: the smallest box (32 / 64 / 128 rows) that holds the running lines
-        const int brows = (p.opt & 1) ? 32 : (act <= 32 ? 32 : (act <= 64 ? 64 : 128));
-        const int nb = (act + brows - 1) / brows;
-        const CUtensorMap* mh = brows == 32 ? &tmH_hi : (brows == 64 ? &tmH64_hi : &tmH128_hi);
-        const CUtensorMap* ml = brows == 32 ? &tmH_lo : (brows == 64 ? &tmH64_lo : &tmH128_lo);
+        // rows to fetch: the smallest box (32 / 64 / 128 rows) that holds the running lines; ONE 3-D TMA per k chunk
+        // brings the hi and the lo plane ([2][brows][64 halves], lo tile right behind the hi tile)
+        const int brows = act <= 32 ? 32 : (act <= 64 ? 64 : 128);
+        const CUtensorMap* mh = brows == 32 ? &tmH32 : (brows == 64 ? &tmH64 : &tmH128);
         TC_T(3);
-        wait_counter(flag_q + tile, (unsigned)p.nsig * (unsigned)s);      // h_{s-1} of every row slice is in L2
+        wait_counter<false>(flag_q + tile, (unsigned)p.nsig * (unsigned)s);   // h_{s-1} of every row slice is in L2
         TC_T(0);
         if (dbg && s == kDbgStep + 1) mydbg[16 + 3] = clock64();
         const int row0 = ((q * 2 + ((s - 1) & 1)) * p.ntiles + tile) * kTcLines;
@@ -284,12 +289,8 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           TC_T(1);
           if (elect_one()) {
             if (kc == 0) fence_proxy_async();                             // generic-proxy writes (other SMs) -> async-proxy reads
-            mbar_expect_tx(full(st), (unsigned)(nb * brows) * 256);
-            const unsigned dst = ring0 + st * kStageBytes;
-            for (int j = 0; j < nb; j++) {
-              tma_load_2d(dst + j * brows * 128, mh, kc * 64, row0 + brows * j, full(st));
-              tma_load_2d(dst + kTcLines * 128 + j * brows * 128, ml, kc * 64, row0 + brows * j, full(st));
-            }
+            mbar_expect_tx(full(st), (unsigned)brows * 256);
+            tma_load_3d(ring0 + st * kStageBytes, mh, kc * 64, row0, 0, full(st));
           }
           __syncwarp();
           TC_T(2);
@@ -308,8 +309,12 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
     unsigned it = 0;
     long long tlast_ = dbg ? clock64() : 0;
     for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
-      const int Tt = ln.T[ln.order[tile * kTcLines]];
+      const int l0 = tile * kTcLines;
+      const int Tt = ln.T[ln.order[l0]];
+      int act = min(kTcLines, ln.B - l0);
       for (int s = 1; s < Tt; s++) {
+        while (act > 0 && ln.T[ln.order[l0 + act - 1]] <= s) act--;      // same row count as the producer: where the lo tile starts
+        const unsigned lo_off = (act <= 32 ? 32u : (act <= 64 ? 64u : 128u)) * 128u;
         for (int kc = 0; kc < p.KC; kc++, it++) {
           const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
           TC_T(2);
@@ -321,7 +326,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           const unsigned a_hi = ring0 + st * kStageBytes;
           const unsigned b_hi = rs0 + kc * 2 * r_bytes;
           // 16 k = 32 bytes along the swizzled row = +2 in the descriptor's address field
-          const unsigned long long ah = desc_of(a_hi), al = desc_of(a_hi + kTcLines * 128);
+          const unsigned long long ah = desc_of(a_hi), al = desc_of(a_hi + lo_off);
           const unsigned long long bh = desc_of(b_hi), bl = desc_of(b_hi + r_bytes);
           const int nk = min(4, p.nks - kc * 4);
           if (elect_one()) {
@@ -378,8 +383,9 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
         const int t = d ? Tp - 1 - s : s;
         const size_t col = (size_t)off + t;
         float xp[NC];
+        float4 xq[NC / 4];
         if (RowXfer<NC>::coop && NU % 4 == 0) {
-          gather_rows<NC>(scr, (active && mine && !(p.opt & 8)) ? XPd + col * no4 + 4 * ub : nullptr, xp, lane);
+          gather_issue<NC>((active && mine && !(p.opt & 8)) ? XPd + col * no4 + 4 * ub : nullptr, xq, lane);
         } else if (active) {
 #pragma unroll
           for (int u = 0; u < NU; u++) {
@@ -402,6 +408,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < NC; i++) acc[i] = 0.f;
         }
+        if (RowXfer<NC>::coop && NU % 4 == 0) gather_commit<NC>(scr, xq, xp, lane);
         float gv[NC], hh[NU];
         if (active) {
 #pragma unroll
@@ -654,21 +661,21 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
         const int t = d ? Tp - 1 - fs : fs;
         const size_t col = (size_t)off + t;
         float g[4 * NU], cc[NU], cp[NU], dh[NU];
-        {                                                  // operands that do not depend on the exchange: fetch first
-          const unsigned scr = scr0 + (unsigned)ew * 4096u;
-          gather_rows<4 * NU>(scr, active ? Gd + col * no4 + 4 * ub : nullptr, g, lane);
-          gather_rows<NU>(scr, active ? Cd + col * no + ub : nullptr, cc, lane);
-          gather_rows<NU>(scr, (active && fs > 0) ? Cd + (col + (d ? 1 : -1)) * (size_t)no + ub : nullptr, cp, lane);
-          gather_rows<NU>(scr, active ? dHd + col * p.hstride + ub : nullptr, dh, lane);
-        }
+        float4 gq4[NU], cq4[NU / 4], pq4[NU / 4], dq4[NU / 4];
+        // operands that do not depend on the exchange: their loads fly while the step counter is polled
+        gather_issue<4 * NU>(active ? Gd + col * no4 + 4 * ub : nullptr, gq4, lane);
+        gather_issue<NU>(active ? Cd + col * no + ub : nullptr, cq4, lane);
+        gather_issue<NU>((active && fs > 0) ? Cd + (col + (d ? 1 : -1)) * (size_t)no + ub : nullptr, pq4, lane);
+        gather_issue<NU>(active ? dHd + col * p.hstride + ub : nullptr, dq4, lane);
         TC_E(0);
+        float r[NU];
+        bool have_r = false;
         if (it > 0) {                                      // partial products of the previous step, all slices
           wait_counter(flag_q + tile, (unsigned)(NT * (kEpiThreads / 32)) * (unsigned)it);
           TC_E(1);
           if (active && fs < Tp - 1) {
             // exchange layout [dest slice][src slice][4 unit quads][128 lines][4 units]: a warp reads / writes 512 contiguous bytes
             const float* src = part_t + (size_t)((it - 1) & 1) * slab + ((size_t)m * NT * 4 + 2 * ch) * (kTcLines * 4) + pl * 4;
-            float r[NU];
 #pragma unroll
             for (int u = 0; u < NU; u++) r[u] = 0.f;
 #pragma unroll 8
@@ -678,9 +685,19 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
               r[0] += x0.x; r[1] += x0.y; r[2] += x0.z; r[3] += x0.w;
               r[4] += x1.x; r[5] += x1.y; r[6] += x1.z; r[7] += x1.w;
             }
-#pragma unroll
-            for (int u = 0; u < NU; u++) dh[u] += r[u];
+            have_r = true;
           }
+        }
+        {
+          const unsigned scr = scr0 + (unsigned)ew * 4096u;
+          gather_commit<4 * NU>(scr, gq4, g, lane);
+          gather_commit<NU>(scr, cq4, cc, lane);
+          gather_commit<NU>(scr, pq4, cp, lane);
+          gather_commit<NU>(scr, dq4, dh, lane);
+        }
+        if (have_r) {
+#pragma unroll
+          for (int u = 0; u < NU; u++) dh[u] += r[u];
         }
         TC_E(2);
         unsigned hi[2 * NU], lo[2 * NU];                    // packed half2: 4 gate rows of a unit = 2 words
@@ -813,6 +830,16 @@ int make_map(CUtensorMap* m, void* base, size_t rows, size_t cols, int box_rows)
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
              ? 0 : 1;
 }
+// 3-D view of two stacked [rows][cols] fp16 planes (hi, lo): box [2][box_rows][64 halves]
+int make_map3(CUtensorMap* m, void* base, size_t rows, size_t cols, int box_rows) {
+  const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  const cuuint64_t gstride[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+  const cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 2u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0 : 1;
+}
 constexpr size_t kSmemLimit = 232448;     // 227 KB per CTA on sm_100
 constexpr size_t kSmemSlack = 1024 + 256; // alignment of the dynamic part + static barriers
 
@@ -833,9 +860,10 @@ struct LstmTcPlan {
   float* part = nullptr;
   unsigned* flags = nullptr;
   CUtensorMap tmR_hi[3], tmR_lo[3];   // box rows 32 / 48 / 64
-  CUtensorMap tmT_hi, tmT_lo, tmH_hi[3], tmH_lo[3];   // h exchange maps: box rows 32 / 64 / 128
+  CUtensorMap tmT_hi, tmT_lo, tmH[3];   // h exchange maps (3-D: k, row, hi/lo plane): box rows 32 / 64 / 128
   bool coop = true;
   int opt = 0;                    // CLSTM_B200_TC_OPT tuning switches
+  int force_nr = 0;               // CLSTM_B200_TC_NR: forward row-slice width (tuning)
   int last_ctas[2] = {0, 0};      // grid size of the last forward / backward launch (debug counters: one slot per CTA)
   int last_gx[2] = {1, 1};
   long long* dbg = nullptr;       // 16 cycle counters + 16 event timestamps of step kDbgStep (CLSTM_B200_TC_DBG=1 or the self-test)
@@ -844,14 +872,16 @@ struct LstmTcPlan {
 };
 
 namespace {
-int fwd_nr_options[3] = {32, 48, 64};
+int fwd_nr_options[3] = {32, 48, 64};      // tensor-map order
+int fwd_nr_try[3] = {32, 64, 48};          // preference: the widths with cooperative row transfers first
 
 // choose the forward row-slice width: the smallest NR that lets every tile run concurrently and fits shared memory; if no
 // width does, the smallest that fits at all (tiles then run in groups)
 bool pick_fwd(const LstmTcPlan* pl, int ndir, int ntiles, int* NR, int* NT, int* tg, int* nst) {
   for (int pass = 0; pass < 2; pass++) {
     for (int o = 0; o < 3; o++) {
-      const int nr = fwd_nr_options[o];
+      const int nr = fwd_nr_try[o];
+      if (pl->force_nr && nr != pl->force_nr) continue;
       const int nt = (4 * pl->no + nr - 1) / nr;
       if (nt * ndir > pl->num_sms) continue;
       const size_t base = (size_t)pl->KC * 2 * nr * 128 + kSmemSlack + (nr == 32 ? fwd_scratch_bytes<32>() : (nr == 48 ? fwd_scratch_bytes<48>() : fwd_scratch_bytes<64>()));
@@ -876,7 +906,7 @@ bool lstm_tc_supported(int no) {
 void lstm_tc_destroy(LstmTcPlan* p) {
   if (!p) return;
   cudaFree(p->rs_hi); cudaFree(p->rs_lo); cudaFree(p->rt_hi); cudaFree(p->rt_lo);
-  cudaFree(p->hx_hi); cudaFree(p->hx_lo); cudaFree(p->part); cudaFree(p->flags); cudaFree(p->dbg);
+  cudaFree(p->hx_hi); cudaFree(p->part); cudaFree(p->flags); cudaFree(p->dbg);
   delete p;
 }
 
@@ -904,6 +934,7 @@ LstmTcPlan* lstm_tc_create(int no, int num_sms) {
   }
   if (const char* e = getenv("CLSTM_B200_TC_COOP")) p->coop = atoi(e) != 0;
   if (const char* e = getenv("CLSTM_B200_TC_OPT")) p->opt = atoi(e);
+  if (const char* e = getenv("CLSTM_B200_TC_NR")) p->force_nr = atoi(e);
   if (const char* e = getenv("CLSTM_B200_TC_DBG")) {
     if (atoi(e) != 0 && cudaMalloc((void**)&p->dbg, kDbgCtas * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(p->dbg, 0, kDbgCtas * 32 * sizeof(long long));
   }
@@ -936,21 +967,21 @@ int ensure_split(LstmTcPlan* p, cudaStream_t st, const float* const R[2], int d0
 int ensure_exchange(LstmTcPlan* p, cudaStream_t st, int ntiles, int nt_b) {
   if (ntiles <= p->cap_tiles && nt_b <= p->cap_nt_b) return 0;
   cudaStreamSynchronize(st);
-  cudaFree(p->hx_hi); cudaFree(p->hx_lo); cudaFree(p->part); cudaFree(p->flags);
+  cudaFree(p->hx_hi); cudaFree(p->part); cudaFree(p->flags);
   p->hx_hi = p->hx_lo = nullptr; p->part = nullptr; p->flags = nullptr;
   const int ct = std::max(ntiles, p->cap_tiles), cn = std::max(nt_b, p->cap_nt_b);
   const size_t hrows = (size_t)2 * 2 * ct * kTcLines;
   const size_t pf = (size_t)2 * ct * 2 * cn * cn * (kTcLines * 16);
-  if (cudaMalloc((void**)&p->hx_hi, hrows * p->KP * 2) != cudaSuccess || cudaMalloc((void**)&p->hx_lo, hrows * p->KP * 2) != cudaSuccess ||
+  if (cudaMalloc((void**)&p->hx_hi, 2 * hrows * p->KP * 2) != cudaSuccess ||
       cudaMalloc((void**)&p->part, pf * sizeof(float)) != cudaSuccess || cudaMalloc((void**)&p->flags, (size_t)2 * ct * sizeof(unsigned)) != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "out of memory for the exchange buffers (%d tiles)", ct);
     p->cap_tiles = 0; p->cap_nt_b = 0;
     return 1;
   }
-  cudaMemsetAsync(p->hx_hi, 0, hrows * p->KP * 2, st);
-  cudaMemsetAsync(p->hx_lo, 0, hrows * p->KP * 2, st);
+  p->hx_lo = p->hx_hi + hrows * p->KP;      // lo plane right behind the hi plane
+  cudaMemsetAsync(p->hx_hi, 0, 2 * hrows * p->KP * 2, st);
   for (int o = 0; o < 3; o++)
-    if (make_map(&p->tmH_hi[o], p->hx_hi, hrows, p->KP, 32 << o) != 0 || make_map(&p->tmH_lo[o], p->hx_lo, hrows, p->KP, 32 << o) != 0) {
+    if (make_map3(&p->tmH[o], p->hx_hi, hrows, p->KP, 32 << o) != 0) {
       snprintf(p->err, sizeof p->err, "cuTensorMapEncodeTiled failed for the h exchange buffer");
       return 1;
     }
@@ -1000,9 +1031,9 @@ int lstm_tc_forward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmF
   p->last_ctas[0] = NT * tg * a.ndir; p->last_gx[0] = NT;
   cudaError_t e;
   const int o = NR == 32 ? 0 : (NR == 48 ? 1 : 2);
-  if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi[0], p->tmH_lo[0], p->tmH_hi[1], p->tmH_lo[1], p->tmH_hi[2], p->tmH_lo[2], ln, f);
-  else if (NR == 48) e = launch_coop(lstm_tc_fwd<48>, grid, fwd_smem<48>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi[0], p->tmH_lo[0], p->tmH_hi[1], p->tmH_lo[1], p->tmH_hi[2], p->tmH_lo[2], ln, f);
-  else e = launch_coop(lstm_tc_fwd<64>, grid, fwd_smem<64>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH_hi[0], p->tmH_lo[0], p->tmH_hi[1], p->tmH_lo[1], p->tmH_hi[2], p->tmH_lo[2], ln, f);
+  if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], ln, f);
+  else if (NR == 48) e = launch_coop(lstm_tc_fwd<48>, grid, fwd_smem<48>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], ln, f);
+  else e = launch_coop(lstm_tc_fwd<64>, grid, fwd_smem<64>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], ln, f);
   if (e != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "lstm_tc_fwd<%d> launch (grid %d x %d x %d, %d stages): %s", NR, NT, tg, a.ndir, nst, cudaGetErrorString(e));
     cudaGetLastError();

@@ -80,6 +80,12 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -164,10 +170,11 @@ __device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
 }
 // Poll with relaxed loads (an acquire load invalidates L1 on every iteration), then ONE acquire fence.  The data the
 // counter guards is read through L2 only (TMA, or ld.global.cg), never through a stale L1 line.
+template <bool ACQUIRE = true>
 __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
   SpinGuard g;
   while (ld_relaxed_gpu(p) < target) g.tick();
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  if (ACQUIRE) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // (a TMA consumer issues fence.proxy.async instead)
 }
 // release-increment: every write that happened-before (own writes, and the other threads' writes ordered by the
 // preceding CTA barrier) is visible at GPU scope before the counter moves.  Lighter than __threadfence() + atomicAdd,
