@@ -61,7 +61,7 @@ constexpr int kDbgCtas = 160;          // debug counter slots (one per CTA)
 constexpr int kDbgStep = 64;           // the step whose event timestamps the debug counters record
 constexpr int kBwdChunk = 256;         // outputs per MMA chunk in the backward kernel (UMMA N)
 constexpr unsigned kBwdStageBytes = 2 * kBwdChunk * 128;
-constexpr unsigned kBwdScratch = 8 * 32 * 32 * 4;   // row-transfer scratch of the 8 epilogue warps (rows of 32 floats)
+constexpr unsigned kBwdScratch = 8 * 32 * 16 * 4;   // row-transfer scratch of the 8 epilogue warps (rows go in 64-byte pieces)
 
 struct TcFwd {
   int no, no4;            // hidden units, gate rows
@@ -202,7 +202,30 @@ __device__ __forceinline__ void scatter_rows(unsigned scr, float* row, const flo
     __syncwarp();
   }
 }
-template <int NR> constexpr unsigned fwd_scratch_bytes() { return RowXfer<NR / 2>::coop ? 8u * 32u * (NR / 2) * 4u : 0u; }
+// Rows wider than 16 floats go in 64-byte pieces, so the scratch is 2 KB per warp (16 KB per CTA) whatever the width.
+constexpr unsigned kWarpScratch = 32 * 16 * 4;
+template <int NF>
+__device__ __forceinline__ void gather_issue_w(const float* row, float4* t, int lane) {
+  if constexpr (NF > 16 && NF % 16 == 0) {
+#pragma unroll
+    for (int h = 0; h < NF / 16; h++) gather_issue<16>(row ? row + 16 * h : nullptr, t + 4 * h, lane);
+  } else gather_issue<NF>(row, t, lane);
+}
+template <int NF>
+__device__ __forceinline__ void gather_commit_w(unsigned scr, const float4* t, float* v, int lane) {
+  if constexpr (NF > 16 && NF % 16 == 0) {
+#pragma unroll
+    for (int h = 0; h < NF / 16; h++) gather_commit<16>(scr, t + 4 * h, v + 16 * h, lane);
+  } else gather_commit<NF>(scr, t, v, lane);
+}
+template <int NF>
+__device__ __forceinline__ void scatter_rows_w(unsigned scr, float* row, const float* v, int lane) {
+  if constexpr (NF > 16 && NF % 16 == 0) {
+#pragma unroll
+    for (int h = 0; h < NF / 16; h++) scatter_rows<16>(scr, row ? row + 16 * h : nullptr, v + 16 * h, lane);
+  } else scatter_rows<NF>(scr, row, v, lane);
+}
+template <int NR> constexpr unsigned fwd_scratch_bytes() { return RowXfer<NR / 2>::coop ? 8u * kWarpScratch : 0u; }
 
 // ================================================================================================ forward
 template <int NR>
@@ -359,7 +382,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
     const unsigned taddr = tmem_d + ((unsigned)(32 * lq) << 16) + (unsigned)(ch * NC);
     const int ub = m * (NR / 4) + ch * NU;                 // first hidden unit of this thread
     const int no = p.no, no4 = p.no4;
-    const unsigned scr = scr0 + (unsigned)ew * (32u * NC * 4u);
+    const unsigned scr = scr0 + (unsigned)ew * kWarpScratch;
     const bool mine = ub + NU <= no;                       // all of this thread's units are real (no % 8 == 0)
     const float* __restrict__ XPd = p.XP[d];
     float* __restrict__ Gd = p.G[d];
@@ -385,7 +408,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
         float xp[NC];
         float4 xq[NC / 4];
         if (RowXfer<NC>::coop && NU % 4 == 0) {
-          gather_issue<NC>((active && mine && !(p.opt & 8)) ? XPd + col * no4 + 4 * ub : nullptr, xq, lane);
+          gather_issue_w<NC>((active && mine && !(p.opt & 8)) ? XPd + col * no4 + 4 * ub : nullptr, xq, lane);
         } else if (active) {
 #pragma unroll
           for (int u = 0; u < NU; u++) {
@@ -408,7 +431,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < NC; i++) acc[i] = 0.f;
         }
-        if (RowXfer<NC>::coop && NU % 4 == 0) gather_commit<NC>(scr, xq, xp, lane);
+        if (RowXfer<NC>::coop && NU % 4 == 0) gather_commit_w<NC>(scr, xq, xp, lane);
         float gv[NC], hh[NU];
         if (active) {
 #pragma unroll
@@ -455,7 +478,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
         // stash for the backward pass and the dense products, off the critical path
         if (RowXfer<NC>::coop && NU % 4 == 0) {
           const bool st = active && mine && !(p.opt & 4);
-          scatter_rows<NC>(scr, st ? Gd + col * no4 + 4 * ub : nullptr, gv, lane);
+          scatter_rows_w<NC>(scr, st ? Gd + col * no4 + 4 * ub : nullptr, gv, lane);
           scatter_rows<NU>(scr, st ? Cd + col * no + ub : nullptr, c, lane);
           scatter_rows<NU>(scr, st ? Hd + col * p.hstride + ub : nullptr, hh, lane);
           scatter_rows<NU>(scr, (st && s + 1 < Tp) ? Hpd + (col + (d ? -1 : 1)) * (size_t)no + ub : nullptr, hh, lane);
@@ -663,7 +686,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
         float g[4 * NU], cc[NU], cp[NU], dh[NU];
         float4 gq4[NU], cq4[NU / 4], pq4[NU / 4], dq4[NU / 4];
         // operands that do not depend on the exchange: their loads fly while the step counter is polled
-        gather_issue<4 * NU>(active ? Gd + col * no4 + 4 * ub : nullptr, gq4, lane);
+        gather_issue_w<4 * NU>(active ? Gd + col * no4 + 4 * ub : nullptr, gq4, lane);
         gather_issue<NU>(active ? Cd + col * no + ub : nullptr, cq4, lane);
         gather_issue<NU>((active && fs > 0) ? Cd + (col + (d ? 1 : -1)) * (size_t)no + ub : nullptr, pq4, lane);
         gather_issue<NU>(active ? dHd + col * p.hstride + ub : nullptr, dq4, lane);
@@ -689,8 +712,8 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
           }
         }
         {
-          const unsigned scr = scr0 + (unsigned)ew * 4096u;
-          gather_commit<4 * NU>(scr, gq4, g, lane);
+          const unsigned scr = scr0 + (unsigned)ew * kWarpScratch;
+          gather_commit_w<4 * NU>(scr, gq4, g, lane);
           gather_commit<NU>(scr, cq4, cc, lane);
           gather_commit<NU>(scr, pq4, cp, lane);
           gather_commit<NU>(scr, dq4, dh, lane);
@@ -732,7 +755,7 @@ lstm_tc_bwd(const __grid_constant__ CUtensorMap tmT_hi, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 2 * NU; i++) { hi[i] = 0u; lo[i] = 0u; }
         }
-        scatter_rows<4 * NU>(scr0 + (unsigned)ew * 4096u, active ? DGd + col * no4 + 4 * ub : nullptr, g, lane);
+        scatter_rows_w<4 * NU>(scr0 + (unsigned)ew * kWarpScratch, active ? DGd + col * no4 + 4 * ub : nullptr, g, lane);
         if (fs == 0) break;                                // the first forward step has no predecessor: nothing to propagate
         // A operand row `pl`, k = 32*ch .. 32*ch+31: four 16-byte chunks of the 128-byte swizzled row
 #pragma unroll
