@@ -237,7 +237,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
   constexpr int NU = NR / 8;                      // hidden units per epilogue thread
   constexpr int VW = (NU % 4 == 0) ? 4 : 2;       // vector width of the per-unit runs
   constexpr unsigned r_bytes = NR * 128;          // hi (or lo) part of one k chunk of the weight slice
-  constexpr int TMEM_COLS = 64;
+  constexpr int TMEM_COLS = (2 * NR <= 64) ? 64 : 128;
   extern __shared__ __align__(1024) unsigned char tc_smem[];
   __shared__ __align__(8) unsigned long long bars[2 * kMaxStages + 2];
   __shared__ unsigned tmem_base_s;
@@ -311,7 +311,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           if (use > 0 && p.nst < p.KC) mbar_wait(empty(st), (use - 1) & 1);   // nst >= KC: the step counter already implies it
           TC_T(1);
           if (elect_one()) {
-            if (kc == 0) fence_proxy_async();                             // generic-proxy writes (other SMs) -> async-proxy reads
+            if (kc == 0) fence_proxy_async_global();                      // generic-proxy writes (other SMs) -> async-proxy reads
             mbar_expect_tx(full(st), (unsigned)brows * 256);
             tma_load_3d(ring0 + st * kStageBytes, mh, kc * 64, row0, 0, full(st));
           }
@@ -325,7 +325,10 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
     if (dbg && lane == 0) for (int i = 0; i < 4; i++) mydbg[i] = dt[i];     // flag wait | ring wait | TMA issue | other
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------------------ MMA issuer
-    const unsigned idesc = make_idesc_f16(kTcLines, NR);
+    // Per 16 k: TWO instructions instead of three.  The hi and lo tiles of the weight slice are adjacent in shared memory,
+    // so one MMA with N = 2 NR multiplies h_hi with [R_hi ; R_lo] (columns [0,NR) collect hi*hi, [NR,2NR) hi*lo), a second
+    // one adds h_lo * R_hi to columns [0,NR); the epilogue adds the two column ranges.
+    const unsigned idesc2 = make_idesc_f16(kTcLines, 2 * NR), idesc1 = make_idesc_f16(kTcLines, NR);
     const unsigned long long dbase = make_desc(0);
     auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
     mbar_wait(rfull, 0);
@@ -350,15 +353,14 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           const unsigned b_hi = rs0 + kc * 2 * r_bytes;
           // 16 k = 32 bytes along the swizzled row = +2 in the descriptor's address field
           const unsigned long long ah = desc_of(a_hi), al = desc_of(a_hi + lo_off);
-          const unsigned long long bh = desc_of(b_hi), bl = desc_of(b_hi + r_bytes);
+          const unsigned long long bh = desc_of(b_hi);
           const int nk = min(4, p.nks - kc * 4);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
               if (ks < nk) {
-                mma_f16(tmem_d, al + 2 * ks, bh + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);   // small terms first
-                mma_f16(tmem_d, ah + 2 * ks, bl + 2 * ks, idesc, 1u);
-                mma_f16(tmem_d, ah + 2 * ks, bh + 2 * ks, idesc, 1u);
+                mma_f16(tmem_d, ah + 2 * ks, bh + 2 * ks, idesc2, (kc > 0 || ks > 0) ? 1u : 0u);
+                mma_f16(tmem_d, al + 2 * ks, bh + 2 * ks, idesc1, 1u);
               }
             }
             mma_commit(empty(st));
@@ -425,7 +427,11 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           TC_E(0);
           if (dbg && s == kDbgStep) mydbg[16 + 0] = clock64();
           if (dbg && s == kDbgStep + 1) mydbg[16 + 9] = clock64();
+          float acc2[NC];
           tmem_ld<NC>(taddr, acc);
+          tmem_ld<NC>(taddr + NR, acc2);
+#pragma unroll
+          for (int i = 0; i < NC; i++) acc[i] += acc2[i];
           TC_E(1);
         } else {
 #pragma unroll

@@ -66,6 +66,8 @@ __device__ __forceinline__ bool elect_one() {
 // ---------------------------------------------------------------- fences
 // generic proxy <-> async proxy (TMA, tensor core operand reads), all state spaces
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// global state space only: FENCE.VIEW.ASYNC.G, no MEMBAR (the plain form drags a MEMBAR.ALL.GPU along)
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
