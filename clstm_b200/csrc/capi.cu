@@ -616,17 +616,21 @@ int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, con
 
 // ------------------------------------------------------------------------------------------------ device passes
 // The batched tensor-core recurrence advances all lines of a 128-slot tile in lock step: its time per pass is
-// (longest line) x (step latency, ~2-4 us), independent of the number of lines, while the register / cluster kernels run
-// one chain per (line, direction) at ~0.3-1 us per step but only as many chains at a time as fit the SMs.
+// (longest line) x (step latency), nearly independent of the number of lines, while the register / cluster kernels run one
+// chain per (line, direction) at 0.3-1 us per step but only as many chains at a time as fit the SMs.  Crossovers measured
+// on B200 (T = 200..2000): nhidden 400: cluster 0.56 ms per line vs tensor-core 37..46 ms per batch => 64 lines;
+// nhidden 200: cluster 0.125 ms per line vs 31 ms per batch => ~256 lines; nhidden <= 100: the register kernels win
+// at every batch size; beyond 400 only the L2-streaming generic kernels remain, so the tensor-core path always wins.
 bool want_lstm_tc(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int B) {
   if (!bk.tc || n->cell != 0 || n->lstm_mode == 2) return false;
   if (n->lstm_mode == 1) return true;
   const int no = bk.no;
-  if (no >= 400) return B >= 12 || no > 400;      // 16-CTA clusters: <= 9 chains at a time; beyond 400 only the generic kernels remain
-  if (no > 200) return B >= 24;
-  if (no == 200) return B >= 48;                  // 4-CTA clusters: 37 chains at a time
-  if (no > 100) return B >= 48;                   // generic kernels otherwise
-  return false;                                   // register-resident kernels: one SM per chain, up to 148 chains
+  if (no > 400) return B >= 4;
+  if (no == 400) return B >= 64;
+  if (no > 200) return B >= 48;                   // no cluster instance for these widths: generic kernels otherwise
+  if (no == 200) return B >= 224;
+  if (no > 100) return B >= 64;                   // generic kernels otherwise
+  return false;
 }
 
 const float* block_input(const clstm_b200_net* n, int k) { return k == 0 ? n->x : n->blk[k - 1].H; }

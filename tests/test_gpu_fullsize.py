@@ -26,6 +26,26 @@ def split(a, T):
     return [a[offs[i]:offs[i + 1]] for i in range(len(T))]
 
 
+def check_indices(oracle, o_al, g_al, g_amax, g_dec, b, margin=1e-3):
+    """argmax(aligned) per column and trivial_decode(aligned) of the device against the oracle's on the same outputs.
+    Returns the number of near-tie decisions (top-2 / best-frame margin below `margin`) that came out differently;
+    any other difference fails."""
+    ties = 0
+    o_amax = oracle.argmax_rows(o_al)
+    for t in np.nonzero(o_amax != g_amax)[0]:
+        top2 = np.sort(o_al[t])[-2:]
+        assert top2[1] - top2[0] < margin, (b, int(t), top2)
+        ties += 1
+    cs, locs = oracle.trivial_decode(o_al)
+    if ties == 0:
+        assert np.array_equal(cs, g_dec[0]), b
+        for k in np.nonzero(locs != g_dec[1])[0]:            # same run, another frame: only if the two frames tie
+            c = cs[k]
+            assert abs(o_al[locs[k], c] - o_al[g_dec[1][k], c]) < margin, (b, int(k))
+            ties += 1
+    return ties
+
+
 def test_cfg2_full_size_values(ffi, oracle):
     ni, nh, nc, B, T = 48, 100, 83, 32, 500
     x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=4)
@@ -48,7 +68,12 @@ def test_cfg2_full_size_values(ffi, oracle):
     assert np.abs(od - gd).max() < TOL * max(1.0, np.abs(od).max())
 
 
-def test_cfg3_full_size_alignment_indices(ffi, oracle):
+@pytest.mark.parametrize("recurrence", ["auto", "tc"])
+def test_cfg3_full_size_alignment_indices(ffi, oracle, monkeypatch, recurrence):
+    # "auto": the variant the library picks for 128 lines of nhidden 200 (thread-block cluster kernels);
+    # "tc": the batched tensor-core recurrence forced through CLSTM_B200_LSTM=tc (read when the net is created)
+    if recurrence == "tc":
+        monkeypatch.setenv("CLSTM_B200_LSTM", "tc")
     ni, nh, nc, B = 48, 200, 83, 128
     x, Ts, labels, L = synth.make_lines(B, (200, 2000), ni, nc, seed=1000)
     onet = oracle.BidiOracle(ni, nh, nc, seed=0.222)
@@ -56,18 +81,20 @@ def test_cfg3_full_size_alignment_indices(ffi, oracle):
     gnet = ffi.Net(ni, nh, nc)
     gnet.set_params(onet.get_params())
     out = gnet.forward(x, Ts)
-    assert gnet.lstm_variant == "tc"              # 128 lines per GPU: the batched tensor-core recurrence
+    assert gnet.lstm_variant == ("tc" if recurrence == "tc" else "cluster")
     aligned = gnet.ctc_align(labels, L)
     amax = gnet.argmax(1)
     dec = gnet.decode(1)
     outs, als, ams, labs = split(out, Ts), split(aligned, Ts), split(amax, Ts), split(labels, L)
+    near_ties = 0
     for b in range(B):
         o_al = oracle.ctc_align_labels(outs[b], labs[b])      # the oracle aligner on the device's own outputs
         # lattice values reach several thousand for T ~ 2000, where one Float ulp is ~5e-4 (see test_long_lines_wide_net)
         assert np.abs(o_al - als[b]).max() < 5e-4, b
-        assert np.array_equal(oracle.argmax_rows(o_al), ams[b]), b
-        cs, locs = oracle.trivial_decode(o_al)
-        assert np.array_equal(cs, dec[b][0]) and np.array_equal(locs, dec[b][1]), b
+        near_ties += check_indices(oracle, o_al, als[b], ams[b], dec[b], b)
+    # indices are bit-exact wherever the reference's own Float arithmetic defines them: the only admissible differences are
+    # decisions between two posteriors that differ by less than the 5e-4 resolution above; they must be very rare
+    assert near_ties <= max(2, int(2e-5 * Ts.sum())), near_ties
     # every line through the oracle net: outputs, then input deltas and parameter derivatives for identical injected deltas
     rng = np.random.default_rng(5)
     deltas = (rng.standard_normal(out.shape) * 0.1).astype(np.float32)
@@ -105,3 +132,26 @@ def test_prefetch_of_a_larger_batch_keeps_pending_results(ffi):
         for (c0, l0), (c1, l1) in zip(ref, got):
             assert np.array_equal(c0, c1) and np.array_equal(l0, l1)
     assert np.array_equal(seq.get_params(), pipe.get_params())
+
+
+def test_cfg4_width_large_batch_uses_tensor_core_recurrence(ffi, oracle):
+    # BASELINE config 4 width (nhidden 400) with 96 ragged lines: the library picks the batched tcgen05 recurrence by itself;
+    # outputs of every line and the alignment indices against the oracle
+    ni, nh, nc, B = 48, 400, 83, 96
+    x, Ts, labels, L = synth.make_lines(B, (60, 240), ni, nc, seed=21)
+    onet = oracle.BidiOracle(ni, nh, nc, seed=0.222)
+    onet.set_params(synth.trained_like(onet.nparams, 0.15, seed=7))
+    gnet = ffi.Net(ni, nh, nc)
+    gnet.set_params(onet.get_params())
+    out = gnet.forward(x, Ts)
+    assert gnet.lstm_variant == "tc"
+    aligned = gnet.ctc_align(labels, L)
+    amax = gnet.argmax(1)
+    dec = gnet.decode(1)
+    for b, (xx, oo, aa, am, ll) in enumerate(zip(split(x, Ts), split(out, Ts), split(aligned, Ts), split(amax, Ts), split(labels, L))):
+        assert np.abs(onet.forward(xx) - oo).max() < TOL, b
+        o_al = oracle.ctc_align_labels(oo, ll)
+        assert np.abs(o_al - aa).max() < 1e-4, b
+        assert np.array_equal(oracle.argmax_rows(o_al), am), b
+        cs, locs = oracle.trivial_decode(o_al)
+        assert np.array_equal(cs, dec[b][0]) and np.array_equal(locs, dec[b][1]), b
