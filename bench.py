@@ -339,6 +339,8 @@ def run_b200(a):
     step_res = lambda: net.step_resident(LR, MOM, CLIP)  # noqa: E731
     warm = max(3, a.warmup)
     est = float(np.median(timed(step_res, warm)))         # warm-up, also calibrates the inner iteration count
+    if dp_mode == "p2p-fused":
+        net.peer_stats()                                  # arm the in-kernel counters of the fused all-reduce + update
     inner = a.inner if a.inner > 0 else int(min(10, max(1, round(20.0 / max(est, 1e-3)))))
     iters = a.steps * inner
     net.synchronize()
@@ -350,6 +352,7 @@ def run_b200(a):
     clocks = sampler.stop(t0, t1)
     ms_step = float(np.median(ms_it))
     value = px_per_step / (ms_step / 1000.0)
+    peer = net.peer_stats() if dp_mode == "p2p-fused" else None
     # second pass with per-phase CUDA events for the kernel table / roofline (everything on one stream)
     net.profile(True)
     prof_iters = min(iters, max(3, a.steps))
@@ -488,6 +491,11 @@ def run_b200(a):
            "allreduce_ms_per_step": (stats.get("allreduce", (0.0, 0))[0] / prof_iters) if world > 1 else 0.0}
     if dp_check is not None:
         out["dp_check"] = dp_check
+    if peer is not None and peer["launches"] > 0:
+        peer["nvlink_read_gbs"] = peer["nvlink_bytes_per_launch"] / max(peer["data_us"], 1e-9) / 1e3
+        peer["note"] = ("peer_allreduce_update_kernel, rank 0, in-kernel %globaltimer: wait_us = arrive-flag spin until the slowest rank "
+                        "published its derivatives, data_us = peer reads over NVLink + clip + update (block 0's share of the grid-stride loop)")
+        out["fused_allreduce"] = peer
     if world == 1 and not a.no_extras:
         out["normalizer"] = normalizer_leg(net, a)
     if world == 1 and not a.no_cpu_baseline:

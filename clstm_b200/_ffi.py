@@ -76,6 +76,7 @@ EXPORTS = {
     "clstm_b200_stream": (C.c_void_p, [C.c_void_p]),
     "clstm_b200_lstm_variant": (C.c_char_p, [C.c_void_p]),
     "clstm_b200_selftest_gemm": (C.c_int, [C.c_void_p, f32p, C.c_int]),
+    "clstm_b200_peer_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "clstm_b200_selftest_lstm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_float, f32p]),
     "clstm_b200_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "clstm_b200_free_pinned": (None, [C.c_void_p]),
@@ -376,6 +377,13 @@ class Net:
         cnt = np.zeros(n, np.int64)
         _chk(L.clstm_b200_phase_stats(self.h, ms.ctypes.data_as(f32p), cnt.ctypes.data_as(i64p), n))
         return {L.clstm_b200_phase_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
+    def peer_stats(self, reset=True):
+        """{launches, wait_us, data_us, nvlink_bytes} of the fused NVLink all-reduce + update kernel since the last reset
+        (the first call only arms the counters)."""
+        out = (C.c_double * 4)()
+        _chk(lib().clstm_b200_peer_stats(self.h, out, 1 if reset else 0))
+        return {"launches": int(out[0]), "wait_us": float(out[1]), "data_us": float(out[2]), "nvlink_bytes_per_launch": float(out[3])}
 
     def selftest_gemm(self):
         err = np.zeros(16, np.float32)

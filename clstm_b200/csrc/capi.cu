@@ -210,6 +210,7 @@ struct clstm_b200_net {
   float* peer_buf[kMaxPeers] = {};
   bool p2p = false;
   unsigned epoch = 0;
+  unsigned long long* peer_stats = nullptr;   // device: {ns waiting for peers, ns data phase, launches} of the fused update kernel
 };
 
 namespace {
@@ -828,6 +829,7 @@ int run_peer_update(clstm_b200_net* n, float lr, float mom, float clip) {
   for (int r = 0; r < n->world; r++) a.comm[r] = n->peer_buf[r];
   a.rank = n->rank; a.world = n->world; a.epoch = ++n->epoch;
   a.v = n->v; a.d = n->d; a.n = n->P; a.lr = lr; a.mom = mom; a.clip = clip;
+  a.stats = n->peer_stats;
   peer_allreduce_update(n->st, a);
   n->g_pending = false;
   join_dx(n);              // see run_update
@@ -1034,7 +1036,7 @@ void clstm_b200_destroy(clstm_b200_net* n) {
     n->blk[k].tc = nullptr;
     for (int d = 0; d < 2; d++) { dev_free(n->blk[k].Rt[d]); dev_free(n->blk[k].WxT[d]); }
   }
-  dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->status);
+  dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->status); dev_free(n->peer_stats);
   dev_free(n->ws); dev_free(n->tot); dev_free(n->mx_part); dev_free(n->ws2);
   dev_free(n->n_raw); dev_free(n->n_tmp); dev_free(n->n_smooth); dev_free(n->n_a); dev_free(n->n_center);
   dev_free(n->n_r); dev_free(n->n_scale); dev_free(n->n_masks); dev_free(n->n_ym); dev_free(n->n_yd); dev_free(n->n_meta);
@@ -1558,6 +1560,25 @@ const char* clstm_b200_lstm_variant(const clstm_b200_net* n) { return n ? n->var
 
 // Self-test of the tcgen05 (3xTF32) dense products against the fp32 SIMT tiles on random data, same shapes/strides
 // as the products of the path.  err[i] = max |tc - simt| / max|simt| for case i.  Returns the number of cases.
+int clstm_b200_peer_stats(clstm_b200_net* n, double* out4, int reset) {
+  if (!n || !out4) return fail("null argument");
+  CU(cudaSetDevice(n->cfg.device));
+  if (!n->peer_stats) {
+    TRY(dev_alloc(&n->peer_stats, 3));
+    CU(cudaMemsetAsync(n->peer_stats, 0, 3 * sizeof(unsigned long long), n->st));
+  }
+  unsigned long long h[3] = {0, 0, 0};
+  CU(cudaMemcpyAsync(h, n->peer_stats, sizeof h, cudaMemcpyDeviceToHost, n->st));
+  CU(cudaStreamSynchronize(n->st));
+  const double k = h[2] ? 1.0 / (double)h[2] : 0.0;
+  out4[0] = (double)h[2];
+  out4[1] = 1e-3 * (double)h[0] * k;                                   // us per launch waiting for the slowest rank
+  out4[2] = 1e-3 * (double)h[1] * k;                                   // us per launch reading the peers + updating
+  out4[3] = (double)(n->world > 1 ? n->world - 1 : 0) * 4.0 * (double)n->P;   // bytes read over NVLink per launch
+  if (reset) CU(cudaMemsetAsync(n->peer_stats, 0, 3 * sizeof(unsigned long long), n->st));
+  return 0;
+}
+
 int clstm_b200_selftest_lstm(int device, int nhidden, int nlines, int tmin, int tmax, unsigned seed, float wscale, float* out9) {
   if (!out9) return fail("null argument");
   if (nhidden <= 0 || nlines <= 0 || tmin <= 0 || tmax < tmin) return fail("bad self-test geometry");

@@ -176,6 +176,7 @@ struct PeerArgs {
   float *v, *d;
   size_t n;
   float lr, mom, clip;
+  unsigned long long* stats;   // optional device counters {ns spent waiting for the peers, ns in the data phase, launches} (block 0)
 };
 void peer_allreduce_update(cudaStream_t st, const PeerArgs& a);   // 2 launches
 

@@ -200,8 +200,16 @@ __device__ __forceinline__ void spin_until(const unsigned* p, unsigned epoch) {
   }
 }
 
+__device__ __forceinline__ unsigned long long global_ns_() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(PeerArgs a) {
   unsigned* hdr = reinterpret_cast<unsigned*>(a.comm[a.rank]);
+  const bool rec = a.stats != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const unsigned long long t_start = rec ? global_ns_() : 0;
   // ---- all ranks' g complete?
   if (blockIdx.x == 0 && threadIdx.x < a.world) {
     __threadfence_system();
@@ -209,6 +217,7 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(PeerArgs a) 
   }
   if (threadIdx.x < a.world) spin_until(hdr + kPeerArrive + threadIdx.x, a.epoch);
   __syncthreads();
+  const unsigned long long t_data = rec ? global_ns_() : 0;
   // ---- sum over ranks in rank order, fold, clip, update (clstm_compute.cc:553-563)
   const size_t n4 = a.n / 4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -239,6 +248,12 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(PeerArgs a) 
       a.v[i] = __fadd_rn(a.v[i], __fmul_rn(di, a.lr));
       a.d[i] = di * a.mom;
     }
+  if (rec) {   // time spent waiting for the slowest rank vs. time in the NVLink read + update loop (this block's share)
+    const unsigned long long t_end = global_ns_();
+    atomicAdd(a.stats + 0, t_data - t_start);
+    atomicAdd(a.stats + 1, t_end - t_data);
+    atomicAdd(a.stats + 2, 1ull);
+  }
   // ---- last block of this rank announces "done reading" to every rank
   __threadfence();
   __syncthreads();

@@ -197,6 +197,11 @@ const char* clstm_b200_lstm_variant(const clstm_b200_net* net);
  * this net; err[i] = max|difference| / max|reference| per case; returns the number of cases (<0 on error). */
 int clstm_b200_selftest_gemm(clstm_b200_net* net, float* err, int max_cases);
 
+/* Measurement hook of the fused NVLink all-reduce + update kernel (share_deltas + sgd_update, clstm.cc:731-744, 201-217):
+ * the first call arms device counters, later calls return out4 = {launches, mean us a launch waited for the slowest rank,
+ * mean us of the peer-read + update phase, bytes read over NVLink per launch = (world-1) * 4 * nparams}. */
+int clstm_b200_peer_stats(clstm_b200_net* net, double* out4, int reset);
+
 /* device self-test of the batched tensor-core recurrence (no net needed): random bidirectional problem with `nlines`
  * lines of tmin..tmax columns; out9[0..3] = max |difference| of gates, cell states, outputs and previous outputs against
  * the fp32 SIMT kernels, out9[4] = max |difference| of the backward deltas relative to their maximum,
