@@ -221,11 +221,16 @@ __global__ void __launch_bounds__(256) peer_allreduce_update_kernel(PeerArgs a) 
   // ---- sum over ranks in rank order, fold, clip, update (clstm_compute.cc:553-563)
   const size_t n4 = a.n / 4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    // all peers' loads of this element in flight before the first add (NVLink latency ~2 us: memory-level parallelism is
+    // what buys bandwidth here); summation stays in rank order => bit-identical on every rank
+    float4 gq[kMaxPeers];
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; r++)
+      if (r < a.world) gq[r] = reinterpret_cast<const float4*>(a.comm[r] + kPeerHeaderFloats)[i];
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < a.world; r++) {
-      const float4 g = reinterpret_cast<const float4*>(a.comm[r] + kPeerHeaderFloats)[i];
-      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
-    }
+#pragma unroll
+    for (int r = 0; r < kMaxPeers; r++)
+      if (r < a.world) { s.x += gq[r].x; s.y += gq[r].y; s.z += gq[r].z; s.w += gq[r].w; }
     float4 d = reinterpret_cast<float4*>(a.d)[i];
     float4 v = reinterpret_cast<float4*>(a.v)[i];
     float dd[4] = {d.x + s.x, d.y + s.y, d.z + s.z, d.w + s.w};
@@ -278,7 +283,10 @@ __global__ void __launch_bounds__(256) peer_zero_kernel(PeerArgs a) {
 }  // namespace
 
 void peer_allreduce_update(cudaStream_t st, const PeerArgs& a) {
-  peer_allreduce_update_kernel<<<64, 256, 0, st>>>(a);
+  // enough CTAs to keep ~1 MB of peer loads in flight for large nets, never more than one float4 per thread needs
+  int blocks = (int)((a.n / 4 + 255) / 256);
+  blocks = blocks < 64 ? 64 : (blocks > 592 ? 592 : blocks);
+  peer_allreduce_update_kernel<<<blocks, 256, 0, st>>>(a);
   peer_zero_kernel<<<32, 256, 0, st>>>(a);
 }
 
