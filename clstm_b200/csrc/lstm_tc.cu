@@ -232,7 +232,8 @@ template <int NR>
 __global__ void __launch_bounds__(kTcThreads, 1)
 lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
             const __grid_constant__ CUtensorMap tmH32, const __grid_constant__ CUtensorMap tmH64,
-            const __grid_constant__ CUtensorMap tmH128, Lines ln, TcFwd p) {
+            const __grid_constant__ CUtensorMap tmH128, const __grid_constant__ CUtensorMap tmHm_hi,
+            const __grid_constant__ CUtensorMap tmHm_lo, Lines ln, TcFwd p) {
   constexpr int NC = NR / 2;                      // accumulator columns (gate rows) per epilogue thread
   constexpr int NU = NR / 8;                      // hidden units per epilogue thread
   constexpr int VW = (NU % 4 == 0) ? 4 : 2;       // vector width of the per-unit runs
@@ -252,12 +253,21 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
   auto empty = [&](unsigned st) { return bar0 + 8 * (kMaxStages + st); };
   const unsigned rfull = bar0 + 8 * (2 * kMaxStages), accfull = rfull + 8;
 
+  // Thread-block cluster along the row slices (all of them read the SAME h tile): with CS > 1 every CTA fetches a share of
+  // the rows and TMA-multicasts it into all CS shared memories -- one L2 read instead of CS, and CS request streams in
+  // parallel.  A ring stage is then free only when ALL CS tensor cores are done with it: the MMA warps commit to the
+  // `empty` barrier of every CTA of the cluster.
+  const unsigned CS = cluster_nctarank(), crank = cluster_ctarank();
+  const unsigned short cmask = (unsigned short)((1u << CS) - 1u);
   if (tid == 0) {
-    for (int i = 0; i < 2 * kMaxStages + 2; i++) mbar_init(bar0 + 8 * i, 1);
+    for (int i = 0; i < 2 * kMaxStages + 2; i++)
+      mbar_init(bar0 + 8 * i, (i >= kMaxStages && i < 2 * kMaxStages) ? CS : 1u);
     mbar_init_fence();
     tma_prefetch_desc(&tmR_hi); tma_prefetch_desc(&tmR_lo); tma_prefetch_desc(&tmH32); tma_prefetch_desc(&tmH64); tma_prefetch_desc(&tmH128);
+    tma_prefetch_desc(&tmHm_hi); tma_prefetch_desc(&tmHm_lo);
   }
   __syncthreads();
+  if (CS > 1) cluster_sync_all();      // no remote arrive / multicast write may meet an uninitialised barrier
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
                  "n"(TMEM_COLS)
@@ -312,8 +322,17 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
           TC_T(1);
           if (elect_one()) {
             if (kc == 0) fence_proxy_async_global();                      // generic-proxy writes (other SMs) -> async-proxy reads
-            mbar_expect_tx(full(st), (unsigned)brows * 256);
-            tma_load_3d(ring0 + st * kStageBytes, mh, kc * 64, row0, 0, full(st));
+            if (CS == 1) {
+              mbar_expect_tx(full(st), (unsigned)brows * 256);
+              tma_load_3d(ring0 + st * kStageBytes, mh, kc * 64, row0, 0, full(st));
+            } else {             // 32-row boxes dealt round-robin to the CTAs of the cluster, each multicast to all of them
+              const int nb32 = (act + 31) >> 5;
+              mbar_expect_tx(full(st), (unsigned)nb32 * 2 * 4096);
+              for (int j = (int)crank; j < nb32; j += (int)CS) {
+                tma_load_2d_mc(ring0 + st * kStageBytes + j * 4096, &tmHm_hi, kc * 64, row0 + 32 * j, full(st), cmask);
+                tma_load_2d_mc(ring0 + st * kStageBytes + kTcLines * 128 + j * 4096, &tmHm_lo, kc * 64, row0 + 32 * j, full(st), cmask);
+              }
+            }
           }
           __syncwarp();
           TC_T(2);
@@ -340,7 +359,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
       int act = min(kTcLines, ln.B - l0);
       for (int s = 1; s < Tt; s++) {
         while (act > 0 && ln.T[ln.order[l0 + act - 1]] <= s) act--;      // same row count as the producer: where the lo tile starts
-        const unsigned lo_off = (act <= 32 ? 32u : (act <= 64 ? 64u : 128u)) * 128u;
+        const unsigned lo_off = (CS > 1) ? kTcLines * 128u : (act <= 32 ? 32u : (act <= 64 ? 64u : 128u)) * 128u;
         for (int kc = 0; kc < p.KC; kc++, it++) {
           const unsigned st = it % (unsigned)p.nst, use = it / (unsigned)p.nst;
           TC_T(2);
@@ -363,7 +382,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
                 mma_f16(tmem_d, al + 2 * ks, bh + 2 * ks, idesc1, 1u);
               }
             }
-            mma_commit(empty(st));
+            if (CS == 1) mma_commit(empty(st)); else mma_commit_mc(empty(st), cmask);
             if (kc == p.KC - 1) mma_commit(accfull);
           }
           __syncwarp();
@@ -527,6 +546,7 @@ lstm_tc_fwd(const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();      // the last commits of the other CTAs still arrive on this CTA's barriers
   if (warp == 1) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TMEM_COLS) : "memory");
@@ -890,11 +910,14 @@ struct LstmTcPlan {
   unsigned* flags = nullptr;
   CUtensorMap tmR_hi[3], tmR_lo[3];   // box rows 32 / 48 / 64
   CUtensorMap tmT_hi, tmT_lo, tmH[3];   // h exchange maps (3-D: k, row, hi/lo plane): box rows 32 / 64 / 128
+  CUtensorMap tmHm[2];                  // 2-D 32-row maps of the hi / lo plane (cluster multicast path)
+  int cluster = -1;                     // CLSTM_B200_TC_CLUSTER: -1 auto (largest divisor <= 8 of the slice count), 0/1 off
   bool coop = true;
   int opt = 0;                    // CLSTM_B200_TC_OPT tuning switches
   int force_nr = 0;               // CLSTM_B200_TC_NR: forward row-slice width (tuning)
   int last_ctas[2] = {0, 0};      // grid size of the last forward / backward launch (debug counters: one slot per CTA)
   int last_gx[2] = {1, 1};
+  int last_cluster = 1;
   long long* dbg = nullptr;       // 16 cycle counters + 16 event timestamps of step kDbgStep (CLSTM_B200_TC_DBG=1 or the self-test)
   long long dbg_host[2][kDbgCtas * 32] = {};
   char err[256] = {0};
@@ -964,6 +987,7 @@ LstmTcPlan* lstm_tc_create(int no, int num_sms) {
   if (const char* e = getenv("CLSTM_B200_TC_COOP")) p->coop = atoi(e) != 0;
   if (const char* e = getenv("CLSTM_B200_TC_OPT")) p->opt = atoi(e);
   if (const char* e = getenv("CLSTM_B200_TC_NR")) p->force_nr = atoi(e);
+  if (const char* e = getenv("CLSTM_B200_TC_CLUSTER")) p->cluster = atoi(e);
   if (const char* e = getenv("CLSTM_B200_TC_DBG")) {
     if (atoi(e) != 0 && cudaMalloc((void**)&p->dbg, kDbgCtas * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(p->dbg, 0, kDbgCtas * 32 * sizeof(long long));
   }
@@ -1014,19 +1038,35 @@ int ensure_exchange(LstmTcPlan* p, cudaStream_t st, int ntiles, int nt_b) {
       snprintf(p->err, sizeof p->err, "cuTensorMapEncodeTiled failed for the h exchange buffer");
       return 1;
     }
+  if (make_map(&p->tmHm[0], p->hx_hi, hrows, p->KP, 32) != 0 || make_map(&p->tmHm[1], p->hx_lo, hrows, p->KP, 32) != 0) {
+    snprintf(p->err, sizeof p->err, "cuTensorMapEncodeTiled failed for the h exchange buffer (multicast maps)");
+    return 1;
+  }
   p->cap_tiles = ct; p->cap_nt_b = cn;
   return 0;
 }
 
 template <class K, class... Args>
-cudaError_t launch_coop(K kernel, dim3 grid, size_t smem, cudaStream_t st, bool coop, Args... args) {
+cudaError_t launch_coop(K kernel, dim3 grid, size_t smem, cudaStream_t st, bool coop, int cluster_x, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;
-  at[0].val.cooperative = 1;
-  cfg.attrs = at; cfg.numAttrs = coop ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (coop) { at[na].id = cudaLaunchAttributeCooperative; at[na].val.cooperative = 1; na++; }
+  if (cluster_x > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = (unsigned)cluster_x; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    na++;
+  }
+  cfg.attrs = at; cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+int pick_cluster(const LstmTcPlan* p, int NT) {
+  if (p->cluster == 0 || p->cluster == 1) return 1;
+  if (p->cluster > 1) return (NT % p->cluster == 0) ? p->cluster : 1;
+  for (int c = 8; c > 1; c--)
+    if (NT % c == 0) return c;
+  return 1;
 }
 }  // namespace
 
@@ -1058,11 +1098,18 @@ int lstm_tc_forward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmF
   f.H = a.H; f.hx_hi = p->hx_hi; f.hx_lo = p->hx_lo; f.flags = p->flags; f.dbg = p->dbg; f.opt = p->opt;
   const dim3 grid(NT, tg, a.ndir);
   p->last_ctas[0] = NT * tg * a.ndir; p->last_gx[0] = NT;
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
   const int o = NR == 32 ? 0 : (NR == 48 ? 1 : 2);
-  if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], ln, f);
-  else if (NR == 48) e = launch_coop(lstm_tc_fwd<48>, grid, fwd_smem<48>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], ln, f);
-  else e = launch_coop(lstm_tc_fwd<64>, grid, fwd_smem<64>(p->KC, nst), st, p->coop, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], ln, f);
+  int cs = pick_cluster(p, NT);
+  for (int attempt = 0; attempt < 2; attempt++) {        // a cluster shape the device cannot place falls back to unicast
+    if (NR == 32) e = launch_coop(lstm_tc_fwd<32>, grid, fwd_smem<32>(p->KC, nst), st, p->coop, cs, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], p->tmHm[0], p->tmHm[1], ln, f);
+    else if (NR == 48) e = launch_coop(lstm_tc_fwd<48>, grid, fwd_smem<48>(p->KC, nst), st, p->coop, cs, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], p->tmHm[0], p->tmHm[1], ln, f);
+    else e = launch_coop(lstm_tc_fwd<64>, grid, fwd_smem<64>(p->KC, nst), st, p->coop, cs, p->tmR_hi[o], p->tmR_lo[o], p->tmH[0], p->tmH[1], p->tmH[2], p->tmHm[0], p->tmHm[1], ln, f);
+    if (e == cudaSuccess || cs == 1) break;
+    cudaGetLastError();
+    cs = 1;
+  }
+  p->last_cluster = cs;
   if (e != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "lstm_tc_fwd<%d> launch (grid %d x %d x %d, %d stages): %s", NR, NT, tg, a.ndir, nst, cudaGetErrorString(e));
     cudaGetLastError();
@@ -1097,7 +1144,7 @@ int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const Lstm
   const size_t smem = a_bytes + (size_t)nst * kBwdStageBytes + 1024;
   const dim3 grid(NT, tg, a.ndir);
   p->last_ctas[1] = NT * tg * a.ndir; p->last_gx[1] = NT;
-  cudaError_t e = launch_coop(lstm_tc_bwd, grid, smem, st, p->coop, p->tmT_hi, p->tmT_lo, ln, b);
+  cudaError_t e = launch_coop(lstm_tc_bwd, grid, smem, st, p->coop, 1, p->tmT_hi, p->tmT_lo, ln, b);
   if (e != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "lstm_tc_bwd launch (grid %d x %d x %d, %d stages%s): %s", NT, tg, a.ndir, nst,
              resident ? ", resident" : "", cudaGetErrorString(e));
@@ -1240,9 +1287,9 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
       cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
       if (const long long* c = lstm_tc_debug_counters(plan, 0))
         if (rep == 1)
-          fprintf(stderr, "selftest_lstm fwd no=%d B=%d Tmax=%d %.3f ms | producer: flag %lld ring %lld issue %lld other %lld | mma: full %lld issue %lld "
+          fprintf(stderr, "selftest_lstm fwd cluster=%d no=%d B=%d Tmax=%d %.3f ms | producer: flag %lld ring %lld issue %lld other %lld | mma: full %lld issue %lld "
                   "other %lld | epilogue: accwait %lld tmemld %lld math %lld publish %lld stash %lld xp %lld (cycles, CTA 0)\n",
-                  no, B, tmax, ms[0], c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[8], c[9], c[10], c[11], c[12], c[13]);
+                  plan->last_cluster, no, B, tmax, ms[0], c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[8], c[9], c[10], c[11], c[12], c[13]);
       if (rep == 1 && plan->dbg) {
         const long long* c = plan->dbg_host[0];
         const char* names[] = {"flagwait", "ringwait", "tmaissue", "p.other", "fullwait", "mmaissue", "m.other", "", "accwait", "tmemld", "math", "publish", "stash", "xp"};
