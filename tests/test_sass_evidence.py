@@ -49,3 +49,17 @@ def test_cluster_kernels_use_dsmem_async_stores_and_mbarriers():
 def test_fused_peer_update_uses_system_scope_flags():
     s = sass("misc.o")
     assert ".SYS" in s                        # st.release.sys / ld.acquire.sys on the NVLink peer flags
+
+
+def test_batched_recurrence_is_tcgen05_with_tma_and_tmem():
+    # the north-star formulation of the recurrence (lstm_tc.cu): tcgen05.mma on TMA-staged operands, TMEM accumulators,
+    # cluster multicast of the shared h tile, release-increments for the per-step exchange
+    s = sass("lstm_tc.o")
+    assert "sm_100a" in s
+    assert s.count("UTCHMMA") >= 30           # forward (3 widths): 2 MMAs x 4 k slices per chunk; backward: 3 x 4 per chunk
+    assert s.count("UTMALDG") >= 20           # cp.async.bulk.tensor: weight slices, h tiles (2-D multicast and 3-D), backward weight chunks
+    assert "UTMALDG.3D" in s and "UTMALDG.2D.MULTICAST" in s
+    assert "LDTM" in s and "UTCBAR" in s      # tcgen05.ld / tcgen05.commit
+    assert "REDG.E.ADD.STRONG.GPU" in s       # red.release.gpu on the step counters
+    assert "HMMA" not in s.replace("UTCHMMA", "")
+    assert "FENCE.VIEW.ASYNC" in s            # proxy fences between generic-proxy writes and TMA / tensor-core reads
