@@ -114,3 +114,34 @@ def test_tc_training_steps_track_oracle(ffi, oracle):
         onet.train_lines(x, Ts, labels, L, 1e-3, 0.9, threads=1, reps=1)
     assert gnet.lstm_variant == "tc"
     assert np.abs(gnet.get_params() - onet.get_params()).max() < 1e-4
+
+
+# the tensor-core recurrence under the other prefab wirings (clstm_prefab.cc:22-129): one direction only (lstm1 / revlstm1: the
+# launch covers direction slot 0 or 1 alone, H rows are nhidden wide) and two stacked blocks of different widths (bidi2)
+PREFABS = [("lstm1", 64, 0), ("revlstm1", 64, 0), ("bidi2", 64, 96)]
+
+
+@pytest.mark.parametrize("prefab,nh,nh2", PREFABS)
+def test_tc_recurrence_in_other_topologies(ffi, oracle, prefab, nh, nh2):
+    ni, nc = 12, 9
+    rng = np.random.default_rng(5)
+    onet = oracle.PrefabOracle(prefab, ni, nh, nc, nh2=nh2, cell="NPLSTM", output="SoftmaxLayer", seed=0.21)
+    with forced_tc():
+        gnet = ffi.Net(ni, nh, nc, prefab=prefab, nhidden2=nh2)
+    p = rng.normal(0, 0.25, onet.nparams).astype(np.float32)
+    onet.set_params(p); gnet.set_params(p)
+    T = np.array([11, 1, 23, 7, 16], np.int32)
+    x = rng.uniform(-1, 1, (int(T.sum()), ni)).astype(np.float32)
+    out = gnet.forward(x, T)
+    assert gnet.lstm_variant == "tc"
+    probe = rng.normal(0, 1, out.shape).astype(np.float32)
+    gnet.clear_derivs()
+    din = gnet.backward(probe)
+    gd = gnet.get_derivs()
+    onet.clear_derivs()
+    for xx, oo, pp, dd in zip(split(x, T), split(out, T), split(probe, T), split(din, T)):
+        assert np.abs(onet.forward(xx) - oo).max() < TOL
+        o_din = onet.backward(pp)
+        assert np.abs(o_din - dd).max() < 2e-4 * max(1.0, np.abs(o_din).max())
+    od = onet.get_derivs()
+    assert np.abs(od - gd).max() < 3e-4 * max(1.0, np.abs(od).max())
