@@ -78,6 +78,7 @@ EXPORTS = {
     "clstm_b200_selftest_gemm": (C.c_int, [C.c_void_p, f32p, C.c_int]),
     "clstm_b200_peer_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "clstm_b200_selftest_lstm": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_float, f32p]),
+    "clstm_b200_selftest_lstm_x": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_float, f32p]),
     "clstm_b200_alloc_pinned": (C.c_void_p, [C.c_size_t]),
     "clstm_b200_free_pinned": (None, [C.c_void_p]),
     "clstm_b200_last_error": (C.c_char_p, []),
@@ -120,13 +121,14 @@ def _i32(a):
     return a, a.ctypes.data_as(i32p)
 
 
-def selftest_lstm(nhidden, nlines, tmin, tmax, seed=1, wscale=None, device=0):
+def selftest_lstm(nhidden, nlines, tmin, tmax, seed=1, wscale=None, device=0, cluster_resident=False):
     """Device A/B of the batched tensor-core recurrence against the fp32 SIMT kernels (clstm_b200_selftest_lstm).
     Returns dict(d_gates, d_cell, d_h, d_hprev, d_delta_rel, ms_tc_fwd, ms_tc_bwd, ms_simt_fwd, ms_simt_bwd)."""
     out = np.zeros(9, np.float32)
     if wscale is None:
         wscale = 0.5 / np.sqrt(nhidden)
-    _chk(lib().clstm_b200_selftest_lstm(device, nhidden, nlines, tmin, tmax, seed, float(wscale), out.ctypes.data_as(f32p)))
+    fn = lib().clstm_b200_selftest_lstm_x if cluster_resident else lib().clstm_b200_selftest_lstm
+    _chk(fn(device, nhidden, nlines, tmin, tmax, seed, float(wscale), out.ctypes.data_as(f32p)))
     keys = ["d_gates", "d_cell", "d_h", "d_hprev", "d_delta_rel", "ms_tc_fwd", "ms_tc_bwd", "ms_simt_fwd", "ms_simt_bwd"]
     return dict(zip(keys, (float(v) for v in out)))
 

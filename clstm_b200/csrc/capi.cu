@@ -1579,6 +1579,19 @@ int clstm_b200_peer_stats(clstm_b200_net* n, double* out4, int reset) {
   return 0;
 }
 
+int clstm_b200_selftest_lstm_x(int device, int nhidden, int nlines, int tmin, int tmax, unsigned seed, float wscale, float* out9) {
+  if (!out9) return fail("null argument");
+  if (nhidden <= 0 || nlines <= 0 || tmin <= 0 || tmax < tmin) return fail("bad self-test geometry");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail("no CUDA device %d; clstm_b200 has no CPU fallback", device);
+  CU(cudaSetDevice(device));
+  char msg[256];
+  const int rc = lstm_tc_selftest(nhidden, nlines, tmin, tmax, seed, wscale, out9, msg, (int)sizeof msg, 1);
+  if (rc != 0) return fail("selftest_lstm_x (nhidden %d, %d lines): %s", nhidden, nlines, msg);
+  return 0;
+}
+
 int clstm_b200_selftest_lstm(int device, int nhidden, int nlines, int tmin, int tmax, unsigned seed, float wscale, float* out9) {
   if (!out9) return fail("null argument");
   if (nhidden <= 0 || nlines <= 0 || tmin <= 0 || tmax < tmin) return fail("bad self-test geometry");

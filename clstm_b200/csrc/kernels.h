@@ -109,7 +109,18 @@ int lstm_tc_forward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmF
 int lstm_tc_backward(LstmTcPlan* p, cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
 // device-side A/B of the tensor-core recurrence against the generic kernels on random data; out[0..4] = max abs
 // difference of gates, cell, h, h_prev and (relative) deltas, out[5..8] = ms of tc fwd, tc bwd, generic fwd, generic bwd
-int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wscale, float* out, char* msg, int msglen);
+// variant 0: lstm_tc.cu (lock-step tiles, L2 exchange), 1: lstm_tcx.cu (cluster-resident, DSMEM exchange)
+int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wscale, float* out, char* msg, int msglen, int variant = 0);
+
+// ---------------------------------------------------------------- lstm_tcx.cu (cluster-resident tcgen05 recurrence, DSMEM exchange)
+struct LstmTcxPlan;
+bool lstm_tcx_supported(int no);                     // nhidden <= 256, divisible into <= 8 CTAs of <= 32 units
+LstmTcxPlan* lstm_tcx_create(int no, int num_sms);
+void lstm_tcx_destroy(LstmTcxPlan* p);
+void lstm_tcx_mark_stale(LstmTcxPlan* p);
+const char* lstm_tcx_error(const LstmTcxPlan* p);
+int lstm_tcx_forward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const LstmFwdArgs& a);    // 0 / -1 n.a. / > 0 error
+int lstm_tcx_backward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
 
 // ---------------------------------------------------------------- lstm_cluster.cu (thread-block clusters + DSMEM)
 bool lstm_cluster_supported(int no);

@@ -1192,11 +1192,11 @@ float max_abs_diff(const char* what, const std::vector<float>& a, const std::vec
 }
 }  // namespace
 
-int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wscale, float* out, char* msg, int msglen) {
+int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wscale, float* out, char* msg, int msglen, int variant) {
   auto say = [&](const char* m) { if (msg && msglen > 0) snprintf(msg, msglen, "%s", m); };
   say("");
   for (int i = 0; i < 9; i++) out[i] = -1.f;
-  if (!lstm_tc_supported(no)) { say("size not supported"); return 1; }
+  if (variant == 1 ? !lstm_tcx_supported(no) : !lstm_tc_supported(no)) { say("size not supported"); return 1; }
   cudaDeviceProp prop;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -1204,6 +1204,8 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   if (lstm_configure() != 0 || lstm_tc_configure() != 0) { say("configure failed"); return 1; }
   LstmTcPlan* plan = lstm_tc_create(no, prop.multiProcessorCount);
   if (!plan) { say("lstm_tc_create failed"); return 1; }
+  LstmTcxPlan* xplan = (variant == 1) ? lstm_tcx_create(no, prop.multiProcessorCount) : nullptr;
+  if (variant == 1 && !xplan) { say("lstm_tcx_create failed"); lstm_tc_destroy(plan); return 1; }
   if (!plan->dbg && cudaMalloc((void**)&plan->dbg, kDbgCtas * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(plan->dbg, 0, kDbgCtas * 32 * sizeof(long long));
   unsigned long long rng = 0x9E3779B97F4A7C15ull ^ seed;
   auto uni = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (float)((rng >> 40) & 0xFFFFFF) / 16777216.f; };
@@ -1279,24 +1281,24 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   if (!rc) {
     for (int rep = 0; rep < 2 && !rc; rep++) {    // second repetition = warm timing
       cudaEventRecord(ev[0], st);
-      int r = lstm_tc_forward(plan, st, ln, fargs(1));
+      int r = xplan ? lstm_tcx_forward(xplan, st, ln, fargs(1)) : lstm_tc_forward(plan, st, ln, fargs(1));
       cudaEventRecord(ev[1], st);
-      if (r != 0) { say(r < 0 ? "lstm_tc_forward: not applicable" : lstm_tc_error(plan)); rc = 3; break; }
+      if (r != 0) { say(r < 0 ? "tensor-core forward: not applicable" : (xplan ? lstm_tcx_error(xplan) : lstm_tc_error(plan))); rc = 3; break; }
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) { char b2[200]; snprintf(b2, sizeof b2, "lstm_tc_fwd failed: %s", cudaGetErrorString(e)); say(b2); rc = 4; break; }
       cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
-      if (const long long* c = lstm_tc_debug_counters(plan, 0))
+      if (const long long* c = xplan ? nullptr : lstm_tc_debug_counters(plan, 0))
         if (rep == 1)
           fprintf(stderr, "selftest_lstm fwd cluster=%d no=%d B=%d Tmax=%d %.3f ms | producer: flag %lld ring %lld issue %lld other %lld | mma: full %lld issue %lld "
                   "other %lld | epilogue: accwait %lld tmemld %lld math %lld publish %lld stash %lld xp %lld (cycles, CTA 0)\n",
                   plan->last_cluster, no, B, tmax, ms[0], c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[8], c[9], c[10], c[11], c[12], c[13]);
-      if (rep == 1 && plan->dbg) {
+      if (rep == 1 && plan->dbg && !xplan) {
         const long long* c = plan->dbg_host[0];
         const char* names[] = {"flagwait", "ringwait", "tmaissue", "p.other", "fullwait", "mmaissue", "m.other", "", "accwait", "tmemld", "math", "publish", "stash", "xp"};
         for (int i : {0, 4, 5, 8, 10, 11, 12, 13}) spread(names[i], c, plan->last_ctas[0], i, plan->last_gx[0]);
       }
       if (const long long* c = plan->dbg_host[0])
-        if (rep == 1 && c[16])
+        if (rep == 1 && c[16] && !xplan)
           fprintf(stderr, "selftest_lstm fwd timeline of step %d -> %d (cycles after the accumulator of step %d was ready): math done %lld, published %lld | "
                   "producer: flag seen %lld, first TMA out %lld, last TMA out %lld | mma: first tile in %lld, last tile in %lld, last MMA issued %lld | "
                   "next accumulator ready %lld\n", kDbgStep, kDbgStep + 1, kDbgStep, c[17] - c[16], c[18] - c[16], c[19] - c[16], c[20] - c[16],
@@ -1306,18 +1308,18 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   if (!rc) {
     for (int rep = 0; rep < 2 && !rc; rep++) {
       cudaEventRecord(ev[0], st);
-      int r = lstm_tc_backward(plan, st, ln, bargs(1));
+      int r = xplan ? lstm_tcx_backward(xplan, st, ln, bargs(1)) : lstm_tc_backward(plan, st, ln, bargs(1));
       cudaEventRecord(ev[1], st);
-      if (r != 0) { say(r < 0 ? "lstm_tc_backward: not applicable" : lstm_tc_error(plan)); rc = 5; break; }
+      if (r != 0) { say(r < 0 ? "tensor-core backward: not applicable" : (xplan ? lstm_tcx_error(xplan) : lstm_tc_error(plan))); rc = 5; break; }
       cudaError_t e = cudaStreamSynchronize(st);
       if (e != cudaSuccess) { char b2[200]; snprintf(b2, sizeof b2, "lstm_tc_bwd failed: %s", cudaGetErrorString(e)); say(b2); rc = 6; break; }
       cudaEventElapsedTime(&ms[1], ev[0], ev[1]);
-      if (const long long* c = lstm_tc_debug_counters(plan, 1))
+      if (const long long* c = xplan ? nullptr : lstm_tc_debug_counters(plan, 1))
         if (rep == 1)
           fprintf(stderr, "selftest_lstm bwd no=%d B=%d Tmax=%d %.3f ms | mma: deltawait %lld bufwait %lld issue %lld other %lld | epilogue: loads %lld "
                   "flagwait %lld reduce %lld pointwise %lld drain %lld publish %lld (cycles, CTA 0)\n",
                   no, B, tmax, ms[1], c[0], c[1], c[2], c[3], c[8], c[9], c[10], c[11], c[12], c[13]);
-      if (rep == 1 && plan->dbg) {
+      if (rep == 1 && plan->dbg && !xplan) {
         const long long* c = plan->dbg_host[1];
         const char* names[] = {"deltawait", "bufwait", "mmaissue", "m.other", "", "", "", "", "loads", "flagwait", "reduce", "pointwise", "drain", "publish"};
         for (int i : {0, 2, 8, 9, 10, 11, 12, 13}) spread(names[i], c, plan->last_ctas[1], i, plan->last_gx[1]);
@@ -1340,6 +1342,7 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   for (auto& e : ev) cudaEventDestroy(e);
   cudaStreamDestroy(st);
   lstm_tc_destroy(plan);
+  lstm_tcx_destroy(xplan);
   return rc;
 }
 

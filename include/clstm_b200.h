@@ -208,6 +208,9 @@ int clstm_b200_peer_stats(clstm_b200_net* net, double* out4, int reset);
  * out9[5..8] = milliseconds of tensor-core forward / backward and SIMT forward / backward.
  * Replaces nothing in the reference; it checks GenericNPLSTM::forward/backward (clstm.cc:600-653) computed two ways. */
 int clstm_b200_selftest_lstm(int device, int nhidden, int nlines, int tmin, int tmax, unsigned seed, float wscale, float* out9);
+/* the same A/B for the cluster-resident tensor-core recurrence (lstm_tcx.cu: 16 lines per thread-block cluster, h exchanged
+ * through distributed shared memory); nhidden <= 256 */
+int clstm_b200_selftest_lstm_x(int device, int nhidden, int nlines, int tmin, int tmax, unsigned seed, float wscale, float* out9);
 
 /* page-locked host memory for batches that are copied every step (cudaHostAlloc) */
 void* clstm_b200_alloc_pinned(size_t bytes);

@@ -13,16 +13,18 @@ CASES = {
     "timing": [(200, 128, 200, 2000), (400, 256, 200, 2000), (400, 32, 200, 2000)],
     "timing800": [(800, 128, 512, 512)],
     "t3": [(200, 128, 200, 2000)],
+    "xsmall": [(200, 16, 3, 8), (200, 40, 1, 20), (100, 20, 5, 12), (256, 33, 4, 9), (128, 128, 10, 30)],
     "t4": [(400, 256, 200, 2000)],
     "t4s": [(400, 32, 200, 2000)],
 }
 
 if __name__ == "__main__":
-    groups = sys.argv[1:] or ["small"]
+    xmode = "--x" in sys.argv                # the cluster-resident variant (lstm_tcx.cu)
+    groups = [a for a in sys.argv[1:] if a != "--x"] or ["small"]
     for g in groups:
         for (no, B, t0, t1) in CASES[g]:
             try:
-                r = clstm_b200.selftest_lstm(no, B, t0, t1, seed=7)
+                r = clstm_b200.selftest_lstm(no, B, t0, t1, seed=7, cluster_resident=xmode)
                 r.update(case=[no, B, t0, t1], ok=bool(max(r["d_gates"], r["d_cell"], r["d_h"], r["d_hprev"]) < 2e-5 and r["d_delta_rel"] < 1e-4))
             except Exception as e:  # noqa: BLE001
                 r = dict(case=[no, B, t0, t1], ok=False, error=str(e))
