@@ -92,7 +92,12 @@ __device__ __forceinline__ void quad_transpose(const float* a, float* b, int g) 
   const float ra = __shfl_xor_sync(0xffffffffu, lo ? own0 : own1, 1);   // lane g^1's gate for my line
   const float rb = __shfl_xor_sync(0xffffffffu, lo ? r0 : r1, 1);       // lane g^3's gate for my line
   const float mine = lo ? own1 : own0, par = lo ? r1 : r0;              // gates g and g^2 of line 4i+g
-  b[g] = mine; b[g ^ 2] = par; b[g ^ 1] = ra; b[g ^ 3] = rb;
+  // b[k] = value of gate k: k^g = 0 mine, 1 ra, 2 par, 3 rb  (selects with static k: no local-memory indexing)
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const bool xl = ((k & 1) != 0) != lo, xh = ((k & 2) != 0) != hi;
+    b[k] = xh ? (xl ? rb : par) : (xl ? ra : mine);
+  }
 }
 
 // ================================================================================================ forward
@@ -144,7 +149,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
   const int groups_per_cluster_stride = cl_per_dir;
   const int my_first_group = cluster_id - q * cl_per_dir;
-  unsigned hph[2] = {0, 0}, accph = 0;
+  unsigned hph0 = 0, hph1 = 0, accph = 0;
 
   for (int group = my_first_group; group < p.ngroups; group += groups_per_cluster_stride) {
     const int l0 = group * kXL;
@@ -167,8 +172,8 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         const unsigned hb = b ? hbar1 : hbar0;
         if (elect_one()) mbar_expect_tx(hb, hbytes);
         __syncwarp();
-        mbar_wait_cluster(hb, hph[b]);
-        hph[b] ^= 1;
+        mbar_wait_cluster(hb, b ? hph1 : hph0);
+        if (b) hph1 ^= 1; else hph0 ^= 1;
         fence_proxy_async_smem();                               // remote generic-proxy stores -> tensor-core reads
         tc_fence_after();
         if (elect_one()) {
@@ -347,7 +352,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   cluster_sync_all();
   const unsigned tmem_d = tmem_base_s;
   const int my_first_group = cluster_id - q * cl_per_dir;
-  unsigned pph[2] = {0, 0}, accph = 0, bph = 0;
+  unsigned pph0 = 0, pph1 = 0, accph = 0, bph = 0;
   const unsigned pbytes = CS * 32u * kXL * 4u;                  // bytes a CTA receives per step (= one reduce buffer)
 
   for (int group = my_first_group; group < p.ngroups; group += cl_per_dir) {
@@ -428,8 +433,8 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           const unsigned b = (unsigned)(it - 1) & 1u;
           const unsigned pb = b ? pbar1 : pbar0;
           if (tid == 0) mbar_expect_tx(pb, pbytes);
-          mbar_wait_cluster(pb, pph[b]);
-          pph[b] ^= 1;
+          mbar_wait_cluster(pb, b ? pph1 : pph0);
+          if (b) pph1 ^= 1; else pph0 ^= 1;
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             const int l = 4 * i + g;
