@@ -117,6 +117,8 @@ struct clstm_b200_net {
     float *H = nullptr, *dH = nullptr;     // [N][ndir*no]
     LstmTcPlan* tc = nullptr;              // batched tensor-core recurrence (lstm_tc.cu), nullptr if the size is not covered
     bool tc_used = false;                  // the forward pass of the current batch ran on it (backward follows suit)
+    LstmTcxPlan* tcx = nullptr;            // cluster-resident tensor-core recurrence (lstm_tcx.cu), nullptr if the size is not covered
+    bool tcx_used = false;
     int nout() const { return ndir * no; }
   } blk[2];
   int nblk = 1;
@@ -131,7 +133,7 @@ struct clstm_b200_net {
   float* W1T = nullptr;                    // W1^T [nfeat][nc]
   bool g_pending = false;
   bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
-  int lstm_mode = 0;            // recurrence: 0 auto (by size and batch), 1 always the tensor-core kernels, 2 never
+  int lstm_mode = 0;            // recurrence: 0 auto (by size and batch), 1 always the lock-step tensor-core kernels, 2 never, 3 always the cluster-resident ones
 
   // ---- batch capacity and buffers.  The INPUT SET (x, metadata, tiles, their pinned staging, host geometry, Lines view)
   // exists twice: the members below are the current set, `spare` holds the other one, swap_sets() exchanges them.
@@ -558,6 +560,7 @@ void prepare_weights(clstm_b200_net* n) {   // after every change of v
   for (int k = 0; k < n->nblk; k++) {
     auto& bk = n->blk[k];
     lstm_tc_mark_stale(bk.tc);
+    lstm_tcx_mark_stale(bk.tcx);
     for (int d = bk.d0; d < bk.d0 + bk.ndir; d++) {
       j.job[j.n++] = {n->v + bk.oR[d], bk.Rt[d], 4 * bk.no, bk.no};
       j.job[j.n++] = {n->v + bk.oWx[d], bk.WxT[d], 4 * bk.no, bk.ni};
@@ -623,7 +626,7 @@ int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, con
 // nhidden 200: cluster 0.125 ms per line vs 31 ms per batch => ~256 lines; nhidden <= 100: the register kernels win
 // at every batch size; beyond 400 only the L2-streaming generic kernels remain, so the tensor-core path always wins.
 bool want_lstm_tc(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int B) {
-  if (!bk.tc || n->cell != 0 || n->lstm_mode == 2) return false;
+  if (!bk.tc || n->cell != 0 || n->lstm_mode == 2 || n->lstm_mode == 3) return false;
   if (n->lstm_mode == 1) return true;
   const int no = bk.no;
   if (no > 400) return B >= 4;
@@ -631,6 +634,13 @@ bool want_lstm_tc(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int 
   if (no > 200) return B >= 48;                   // no cluster instance for these widths: generic kernels otherwise
   if (no == 200) return B >= 224;
   if (no > 100) return B >= 64;                   // generic kernels otherwise
+  return false;
+}
+
+// The cluster-resident tensor-core recurrence (16 lines per cluster, DSMEM exchange): nhidden 104..256.
+bool want_lstm_tcx(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int B) {
+  if (!bk.tcx || n->cell != 0 || n->lstm_mode == 1 || n->lstm_mode == 2) return false;
+  if (n->lstm_mode == 3) return true;
   return false;
 }
 
@@ -657,8 +667,13 @@ int run_forward(clstm_b200_net* n) {
       }
       a.H = bk.H;
       const char* var = nullptr;
-      bk.tc_used = false;
-      if (want_lstm_tc(n, bk, ln.B)) {
+      bk.tc_used = bk.tcx_used = false;
+      if (want_lstm_tcx(n, bk, ln.B)) {
+        const int r = lstm_tcx_forward(bk.tcx, n->st, ln, a);
+        if (r > 0) return fail("%s", lstm_tcx_error(bk.tcx));
+        if (r == 0) { var = "tcx"; bk.tcx_used = true; s.launches(1); }
+      }
+      if (!var && want_lstm_tc(n, bk, ln.B)) {
         const int r = lstm_tc_forward(bk.tc, n->st, ln, a);
         if (r > 0) return fail("%s", lstm_tc_error(bk.tc));
         if (r == 0) { var = "tc"; bk.tc_used = true; s.launches(1); }
@@ -739,7 +754,13 @@ int run_backward(clstm_b200_net* n, bool defer_dx = false) {
         a.R[d] = n->v + bk.oR[d]; a.G[d] = bk.G[d]; a.C[d] = bk.C[d]; a.DG[d] = bk.DG[d];
       }
       bool done = false;
-      if (bk.tc_used) {
+      if (bk.tcx_used) {
+        const int r = lstm_tcx_backward(bk.tcx, n->st, ln, a);
+        if (r > 0) return fail("%s", lstm_tcx_error(bk.tcx));
+        done = (r == 0);
+        if (done) s.launches(1);
+      }
+      if (!done && bk.tc_used) {
         const int r = lstm_tc_backward(bk.tc, n->st, ln, a);
         if (r > 0) return fail("%s", lstm_tc_error(bk.tc));
         done = (r == 0);
@@ -994,12 +1015,15 @@ int clstm_b200_create_ex(const clstm_b200_cfg_ex* cfg, clstm_b200_net** out) {
   }
   {
     const char* e = getenv("CLSTM_B200_LSTM");   // "tc": always the batched tensor-core recurrence; "simt": never
-    n->lstm_mode = (e && strcmp(e, "tc") == 0) ? 1 : ((e && strcmp(e, "simt") == 0) ? 2 : 0);
+    n->lstm_mode = (e && strcmp(e, "tc") == 0) ? 1 : ((e && strcmp(e, "simt") == 0) ? 2 : ((e && strcmp(e, "tcx") == 0) ? 3 : 0));
   }
   if (lstm_tc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   if (n->cell == 0 && n->lstm_mode != 2)
     for (int k = 0; k < n->nblk; k++)
+    {
       if (lstm_tc_supported(n->blk[k].no)) n->blk[k].tc = lstm_tc_create(n->blk[k].no, n->num_sms);
+      if (lstm_tcx_supported(n->blk[k].no)) n->blk[k].tcx = lstm_tcx_create(n->blk[k].no, n->num_sms);
+    }
   if (lstm_configure() != 0 || ctc_configure() != 0 || gemm_tc_configure() != 0 || norm_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   n->variant = n->cell == 0 ? lstm_variant_for(n->no) : "generic";
   if (cudaStreamSynchronize(n->st) != cudaSuccess) { clstm_b200_destroy(n); return fail("device initialisation failed"); }
@@ -1034,6 +1058,8 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   for (int k = 0; k < 2; k++) {
     lstm_tc_destroy(n->blk[k].tc);
     n->blk[k].tc = nullptr;
+    lstm_tcx_destroy(n->blk[k].tcx);
+    n->blk[k].tcx = nullptr;
     for (int d = 0; d < 2; d++) { dev_free(n->blk[k].Rt[d]); dev_free(n->blk[k].WxT[d]); }
   }
   dev_free(n->lm); dev_free(n->lr); dev_free(n->rl); dev_free(n->status); dev_free(n->peer_stats);

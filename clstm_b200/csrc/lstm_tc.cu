@@ -1206,11 +1206,11 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   cudaGetDevice(&dev);
   cudaGetDeviceProperties(&prop, dev);
   if (lstm_configure() != 0 || lstm_tc_configure() != 0) { say("configure failed"); return 1; }
-  LstmTcPlan* plan = lstm_tc_create(no, prop.multiProcessorCount);
-  if (!plan) { say("lstm_tc_create failed"); return 1; }
+  LstmTcPlan* plan = (variant == 1) ? nullptr : lstm_tc_create(no, prop.multiProcessorCount);
+  if (variant != 1 && !plan) { say("lstm_tc_create failed"); return 1; }
   LstmTcxPlan* xplan = (variant == 1) ? lstm_tcx_create(no, prop.multiProcessorCount) : nullptr;
   if (variant == 1 && !xplan) { say("lstm_tcx_create failed"); lstm_tc_destroy(plan); return 1; }
-  if (!plan->dbg && cudaMalloc((void**)&plan->dbg, kDbgCtas * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(plan->dbg, 0, kDbgCtas * 32 * sizeof(long long));
+  if (plan && !plan->dbg && cudaMalloc((void**)&plan->dbg, kDbgCtas * 32 * sizeof(long long)) == cudaSuccess) cudaMemset(plan->dbg, 0, kDbgCtas * 32 * sizeof(long long));
   unsigned long long rng = 0x9E3779B97F4A7C15ull ^ seed;
   auto uni = [&]() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (float)((rng >> 40) & 0xFFFFFF) / 16777216.f; };
   auto nrm = [&]() { float s = 0.f; for (int i = 0; i < 4; i++) s += uni(); return (s - 2.f) * 1.7320508f; };
@@ -1298,13 +1298,13 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
           fprintf(stderr, "selftest_lstm fwd cluster=%d no=%d B=%d Tmax=%d %.3f ms | producer: flag %lld ring %lld issue %lld other %lld | mma: full %lld issue %lld "
                   "other %lld | epilogue: accwait %lld tmemld %lld math %lld publish %lld stash %lld xp %lld (cycles, CTA 0)\n",
                   plan->last_cluster, no, B, tmax, ms[0], c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[8], c[9], c[10], c[11], c[12], c[13]);
-      if (rep == 1 && plan->dbg && !xplan) {
+      if (rep == 1 && !xplan && plan->dbg) {
         const long long* c = plan->dbg_host[0];
         const char* names[] = {"flagwait", "ringwait", "tmaissue", "p.other", "fullwait", "mmaissue", "m.other", "", "accwait", "tmemld", "math", "publish", "stash", "xp"};
         for (int i : {0, 4, 5, 8, 10, 11, 12, 13}) spread(names[i], c, plan->last_ctas[0], i, plan->last_gx[0]);
       }
-      if (const long long* c = plan->dbg_host[0])
-        if (rep == 1 && c[16] && !xplan)
+      if (const long long* c = xplan ? nullptr : plan->dbg_host[0])
+        if (rep == 1 && c[16])
           fprintf(stderr, "selftest_lstm fwd timeline of step %d -> %d (cycles after the accumulator of step %d was ready): math done %lld, published %lld | "
                   "producer: flag seen %lld, first TMA out %lld, last TMA out %lld | mma: first tile in %lld, last tile in %lld, last MMA issued %lld | "
                   "next accumulator ready %lld\n", kDbgStep, kDbgStep + 1, kDbgStep, c[17] - c[16], c[18] - c[16], c[19] - c[16], c[20] - c[16],
@@ -1325,7 +1325,7 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
           fprintf(stderr, "selftest_lstm bwd no=%d B=%d Tmax=%d %.3f ms | mma: deltawait %lld bufwait %lld issue %lld other %lld | epilogue: loads %lld "
                   "flagwait %lld reduce %lld pointwise %lld drain %lld publish %lld (cycles, CTA 0)\n",
                   no, B, tmax, ms[1], c[0], c[1], c[2], c[3], c[8], c[9], c[10], c[11], c[12], c[13]);
-      if (rep == 1 && plan->dbg && !xplan) {
+      if (rep == 1 && !xplan && plan->dbg) {
         const long long* c = plan->dbg_host[1];
         const char* names[] = {"deltawait", "bufwait", "mmaissue", "m.other", "", "", "", "", "loads", "flagwait", "reduce", "pointwise", "drain", "publish"};
         for (int i : {0, 2, 8, 9, 10, 11, 12, 13}) spread(names[i], c, plan->last_ctas[1], i, plan->last_gx[1]);

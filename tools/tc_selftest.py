@@ -16,6 +16,10 @@ CASES = {
     "xsmall": [(200, 16, 3, 8), (200, 40, 1, 20), (100, 20, 5, 12), (256, 33, 4, 9), (128, 128, 10, 30)],
     "t4": [(400, 256, 200, 2000)],
     "t4s": [(400, 32, 200, 2000)],
+    "t2": [(100, 32, 500, 500)],
+    "t2b": [(100, 128, 500, 500)],
+    "t3s": [(200, 32, 512, 512)],
+    "xrest": [(100, 20, 5, 12), (256, 33, 4, 9), (128, 128, 10, 30), (96, 7, 2, 15), (160, 50, 1, 25), (200, 700, 2, 6)],
 }
 
 if __name__ == "__main__":
