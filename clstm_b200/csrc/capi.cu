@@ -637,7 +637,7 @@ bool want_lstm_tc(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int 
   return false;
 }
 
-// The cluster-resident tensor-core recurrence (16 lines per cluster, DSMEM exchange): nhidden 104..256.
+// The cluster-resident tensor-core recurrence (16 lines per cluster, DSMEM exchange): nhidden 33..480.
 bool want_lstm_tcx(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int B) {
   if (!bk.tcx || n->cell != 0 || n->lstm_mode == 1 || n->lstm_mode == 2) return false;
   if (n->lstm_mode == 3) return true;

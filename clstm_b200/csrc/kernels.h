@@ -114,7 +114,7 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
 
 // ---------------------------------------------------------------- lstm_tcx.cu (cluster-resident tcgen05 recurrence, DSMEM exchange)
 struct LstmTcxPlan;
-bool lstm_tcx_supported(int no);                     // nhidden <= 256, divisible into <= 8 CTAs of <= 32 units
+bool lstm_tcx_supported(int no);                     // nhidden 33..480: clusters of ceil(nhidden / 32) <= 15 CTAs
 LstmTcxPlan* lstm_tcx_create(int no, int num_sms);
 void lstm_tcx_destroy(LstmTcxPlan* p);
 void lstm_tcx_mark_stale(LstmTcxPlan* p);

@@ -1,26 +1,32 @@
-// lstm_tcx.cu -- the recurrence of the NPLSTM for mid-size nets (nhidden <= 256) as a CLUSTER-RESIDENT tensor-core kernel:
+// lstm_tcx.cu -- the recurrence of the NPLSTM as a CLUSTER-RESIDENT tensor-core kernel (nhidden 33..480):
 // a thread-block cluster owns a group of 16 text lines of one direction for the whole sequence, the recurrent matrix is
-// split over the CTAs' shared memories, the per-step products run on tcgen05 (lines on the UMMA N dimension, accumulators
-// in TMEM) and h travels between the CTAs through DISTRIBUTED SHARED MEMORY (st.async + mbarrier complete_tx) -- no L2 round
-// trip inside a step, which is what bounds the lock-step kernels of lstm_tc.cu at ~5 us per step.
+// split over the CTAs (32 hidden units = 128 gate rows each; the slice stays in shared memory or -- wide nets -- in TENSOR
+// MEMORY for the whole sequence), the per-step products run on tcgen05 (lines on the UMMA N dimension, accumulators in TMEM)
+// and h travels between the CTAs through DISTRIBUTED SHARED MEMORY (st.async + mbarrier complete_tx) -- no L2 round trip
+// inside a step, which is what bounds the lock-step kernels of lstm_tc.cu at ~5 us per step.
 //
 // Reference semantics (paths relative to /root/reference), identical to lstm.cu / lstm_tc.cu:
 //   GenericNPLSTM<SIG,TANH,TANH>::forward   clstm.cc:600-621 (loop body :612-620), forward_lin1 clstm_compute.cc:286
 //   GenericNPLSTM::backward                 clstm.cc:622-653 (loop body :629-650), backward_lin1 clstm_compute.cc:296
 //
-// Geometry.  CS CTAs per cluster, each owns UPC = nhidden / CS hidden units (<= 32) = 4 UPC gate rows (gate-interleaved,
-// row 4j+g) as ONE UMMA M tile of 128 rows (rows beyond 4 UPC are zero).  The K dimension is laid out in "slots":
-// k' = 32 c + j addresses unit j of CTA c (slots UPC..31 of a CTA are zero padding), KQ = 32 CS slots in all, so the 8 units a
-// warp of CTA c produces form exactly one 16-byte chunk of the K-major operand row.
-//   forward :  pre[128 rows x 16 lines] = R_slice[128 x KQ] (A, resident, TMA-loaded once) * h_{s-1}[16 lines x KQ]^T (B)
-//   backward:  part[k' tile of 128 x 16 lines] = Rt_slice[KQ x 128 rows] (A, resident) * delta[16 lines x 128 rows]^T (B, local)
+// Geometry.  CS = ceil(nhidden / 32) CTAs per cluster; CTA c owns hidden units 32c .. 32c+31 = gate rows 128c .. 128c+127
+// (gate-interleaved, row 4j+g) as ONE UMMA M tile of 128 rows (rows of units >= nhidden are zero).  K index = hidden unit,
+// KQ = 32 CS, so the 8 units a warp quadrant of CTA c produces form exactly one 16-byte chunk of the K-major operand row.
+//   forward :  pre[128 rows x 16 lines] = R_slice[128 x KQ] (A, resident) * h_{s-1}[16 lines x KQ]^T (B, all-gathered per step)
+//   backward:  part[128 outputs x 16 lines] (per 128-output tile) = Rt_slice[KQ x 128 rows] (A, resident) * delta[16 x 128]^T (B, local)
 // Operands are fp16 hi/lo pairs (tc_common.cuh::split_f16); B stacks the hi rows (0..15) over the lo rows (16..31), so one
 // MMA with N = 32 gives A_hi*[B_hi ; B_lo] and a second one with N = 16 adds A_lo*B_hi: two tcgen05.mma per 16 k.
-// TMEM lane = gate row: the four gates of a unit sit in four adjacent lanes; a 4x4 register transpose inside the quad
-// (4 shuffles per 4 lines) hands lane g the four gates of lines 4i+g, whose cell state it keeps in registers.
-// Exchange: every warp packs its 8 units x 16 lines into 16-byte chunks (32 shuffles) and st.async's them into the B buffer
-// of every CTA of the cluster; the stores complete bytes on the destination's mbarrier, the MMA warp of each CTA waits on
-// its own barrier only.  Two B buffers; safe by data flow (a CTA sends step s only after it received all of step s-1).
+// A operand: shared memory (SWIZZLE_128B tiles loaded once by TMA) while it fits (KQ <= 256); beyond that the slice lives in
+// TMEM (tcgen05.st once, then `tcgen05.mma [d], [a], b-desc`: no shared-memory read of the weights at all) -- forward both
+// planes, backward the hi plane (the lo plane stays in shared memory: 512 TMEM columns hold D + one plane of four tiles).
+// Threads: 16 epilogue warps (TMEM lane quadrant q = warp & 3 -> 8 units, line quad lg = warp >> 2 -> lines 4lg..4lg+3)
+// + 1 loader / MMA warp.  TMEM lane = gate row: the four gates of a unit sit in four adjacent lanes; a 4x4 register transpose
+// inside the lane quad (4 shuffles) hands lane g the four gates of line 4lg+g, whose cell state it keeps in a register.
+// Exchange: every warp packs its 8 units x 4 lines into 16-byte chunks (8 shuffles) and st.async's them into the B buffer of
+// every CTA of the cluster; the stores complete bytes on a per-64-k-chunk mbarrier of the destination, so its MMA warp starts
+// on a chunk as soon as the two CTAs that feed it have delivered.  Two B buffers; safe by data flow (a CTA sends step s only
+// after it received all of step s-1).  Streamed operands (input projection; gates / cell / upstream deltas) are prefetched
+// one step ahead into registers.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -36,13 +42,15 @@ namespace cb200 {
 namespace {
 using namespace tc;
 
-constexpr int kXL = 16;            // lines per cluster
-constexpr int kXThreads = 160;     // warps 0..3: epilogue (TMEM lane = gate row), warp 4: loader / MMA issuer
-constexpr int kXSlots = 32;        // unit slots per CTA in the K layout
+constexpr int kXL = 16;                      // lines per cluster
+constexpr int kXEW = 16;                     // epilogue warps
+constexpr int kXThreads = 32 * (kXEW + 1);   // + the loader / MMA warp
+constexpr int kXMaxKc = 8;                   // 64-wide K chunks (KQ <= 512)
+constexpr int kXMaxCS = 15;                  // CTAs per cluster (KQ = 480: D + both A planes fill the 512 TMEM columns)
 constexpr float kXScaleH = 16.f, kXScaleR = 16.f, kXScaleD = 256.f;
 
 struct TcxArgs {
-  int no, no4, UPC, CS, KQ, nkc;   // hidden units, gate rows, units per CTA, CTAs per cluster, K slots, 64-wide K chunks
+  int no, no4, CS, KQ, nks, nkc, nmt;   // hidden units, gate rows, CTAs per cluster, K slots, 16-wide k steps, 64-wide K chunks, 128-output tiles
   int ngroups, d0, ndir, hstride, hoff[2];
   const float* XP[2];
   float* G[2];
@@ -52,6 +60,8 @@ struct TcxArgs {
   // backward
   const float* dH;
   float* DG[2];
+  // the weight copies (for the TMEM-resident form, which loads them with plain loads)
+  const __half *w_hi, *w_lo;
 };
 
 __device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned rank) {
@@ -59,10 +69,8 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-// 16-byte store into CTA `rank`'s shared memory that also completes 16 bytes on that CTA's mbarrier
-__device__ __forceinline__ void st_async_v4(unsigned local_addr, unsigned local_bar, unsigned rank, unsigned a, unsigned b, unsigned c,
-                                            unsigned d) {
-  const unsigned raddr = mapa_u32(local_addr, rank), rbar = mapa_u32(local_bar, rank);
+// 16-byte store into a peer CTA's shared memory (cluster address) that also completes 16 bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(unsigned raddr, unsigned rbar, unsigned a, unsigned b, unsigned c, unsigned d) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(a),
                "r"(b), "r"(c), "r"(d), "r"(rbar)
                : "memory");
@@ -83,7 +91,7 @@ __device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity)
     g.tick();
   }
 }
-// 4x4 transpose inside a quad of lanes: in a[m] = value of THIS lane's gate for line 4i+m; out b[k] = gate k of line 4i+g
+// 4x4 transpose inside a quad of lanes: in a[m] = value of THIS lane's gate for line m; out b[k] = gate k of line g
 __device__ __forceinline__ void quad_transpose(const float* a, float* b, int g) {
   const bool hi = (g & 2) != 0, lo = (g & 1) != 0;
   const float r0 = __shfl_xor_sync(0xffffffffu, hi ? a[0] : a[2], 2);
@@ -91,7 +99,7 @@ __device__ __forceinline__ void quad_transpose(const float* a, float* b, int g) 
   const float own0 = hi ? a[2] : a[0], own1 = hi ? a[3] : a[1];        // my gate, lines 2hi, 2hi+1
   const float ra = __shfl_xor_sync(0xffffffffu, lo ? own0 : own1, 1);   // lane g^1's gate for my line
   const float rb = __shfl_xor_sync(0xffffffffu, lo ? r0 : r1, 1);       // lane g^3's gate for my line
-  const float mine = lo ? own1 : own0, par = lo ? r1 : r0;              // gates g and g^2 of line 4i+g
+  const float mine = lo ? own1 : own0, par = lo ? r1 : r0;              // gates g and g^2 of line g
   // b[k] = value of gate k: k^g = 0 mine, 1 ra, 2 par, 3 rb  (selects with static k: no local-memory indexing)
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -99,42 +107,77 @@ __device__ __forceinline__ void quad_transpose(const float* a, float* b, int g) 
     b[k] = xh ? (xl ? rb : par) : (xl ? ra : mine);
   }
 }
+// A operand from tensor memory (K-major, lane = row, 32-bit column = two consecutive k)
+__device__ __forceinline__ void mma_f16_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(unsigned taddr, uint4 v) {   // 4 consecutive columns of this thread's TMEM lane
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4_nowait(unsigned taddr, unsigned* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_alloc(unsigned dst_smem, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ unsigned pow2_cols(unsigned need) {
+  unsigned c = 32;
+  while (c < need) c <<= 1;
+  return c;
+}
+__device__ __forceinline__ float ldg_f32(const float* p) { return __ldg(p); }
 
 // ================================================================================================ forward
+// smem (dynamic, 1024-aligned): [A hi: nkc x 16 KB | A lo: nkc x 16 KB] (shared-memory form only) | B buffers 2 x nkc x 4 KB
+// (chunk kc of a buffer: [32 rows = 16 lines hi, 16 lines lo][128 B = 64 k], SWIZZLE_128B)
+// TMEM: D 32 columns | (TMEM form) A hi KQ/2 columns | A lo KQ/2 columns
+template <bool A_TMEM>
 __global__ void __launch_bounds__(kXThreads, 1)
 lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, Lines ln, TcxArgs p) {
   extern __shared__ __align__(1024) unsigned char xs[];
-  __shared__ __align__(8) unsigned long long bars[4];          // hbar[2] (h tiles), accbar, abar (weights)
+  __shared__ __align__(8) unsigned long long bars[2 * kXMaxKc + 2];   // hbar[2][kXMaxKc] (h chunks), accbar, abar (weights)
   __shared__ unsigned tmem_base_s;
   __shared__ int lineT[kXL], lineOff[kXL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned CS = cluster_nctarank(), c = cluster_ctarank();
   const int cluster_id = blockIdx.x / (int)CS, nclusters = gridDim.x / (int)CS;
   const int cl_per_dir = nclusters / p.ndir;                   // clusters are bound to one direction (one weight slice)
-  const int q = cluster_id / cl_per_dir, d = p.d0 + q;
+  const int dq = cluster_id / cl_per_dir, d = p.d0 + dq;
+  const int nkc = p.nkc;
   const unsigned smem0 = (smem_u32(xs) + 1023u) & ~1023u;
-  const unsigned a_hi0 = smem0, a_lo0 = smem0 + (unsigned)p.nkc * 16384u;       // A: chunk kc at +kc*16384 ([128 rows][128 B])
-  const unsigned b0 = a_lo0 + (unsigned)p.nkc * 16384u;                        // B buffer b at b0 + b*(nkc*4096): chunk kc [32 rows][128 B]
-  const unsigned bbytes = (unsigned)p.nkc * 4096u;
+  const unsigned a_bytes = A_TMEM ? 0u : (unsigned)nkc * 16384u;
+  const unsigned a_hi0 = smem0, a_lo0 = smem0 + a_bytes;       // A: chunk kc at +kc*16384 ([128 rows][128 B])
+  const unsigned b0 = a_lo0 + a_bytes;                         // B buffer b at b0 + b*bbytes, chunk kc at +kc*4096
+  const unsigned bbytes = (unsigned)nkc * 4096u;
   const unsigned bar0 = smem_u32(&bars[0]);
-  const unsigned hbar0 = bar0, hbar1 = bar0 + 8, accbar = bar0 + 16, abar = bar0 + 24;
-  const unsigned hbytes = CS * 4u * kXL * 2u * 16u;           // bytes a CTA receives per step: CS x 4 warps x 16 lines x 2 planes x 16 B
+  const unsigned accbar = bar0 + 8u * (2 * kXMaxKc), abar = accbar + 8u;
+  const unsigned tcols = pow2_cols(32u + (A_TMEM ? (unsigned)p.KQ : 0u));
+  const unsigned acol_hi = 32u, acol_lo = 32u + (unsigned)p.KQ / 2u;
 
   if (tid == 0) {
-    mbar_init(hbar0, 1); mbar_init(hbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1);
+    for (int i = 0; i < 2 * kXMaxKc + 2; i++) mbar_init(bar0 + 8u * i, 1);
     mbar_init_fence();
-    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
+    if (!A_TMEM) { tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); }
   }
-  // the B buffers must never hold NaN patterns (slots of padding units are never written)
+  // the B buffers must never hold NaN patterns (k slots beyond KQ inside the last chunk are never written)
   for (unsigned i = tid; i < 2 * bbytes / 16; i += blockDim.x)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(b0 + 16 * i), "r"(0u) : "memory");
   __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(32) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    if (elect_one()) {       // this CTA's weight slice, once: rows [(d*CS + c)*128, +128) of the slot-ordered copy
-      mbar_expect_tx(abar, (unsigned)p.nkc * 2u * 16384u);
-      for (int kc = 0; kc < p.nkc; kc++) {
+  if (warp == kXEW) {
+    tmem_alloc(smem_u32(&tmem_base_s), tcols);
+    if (!A_TMEM && elect_one()) {       // this CTA's weight slice, once: rows [(d*CS + c)*128, +128) of the padded copy
+      mbar_expect_tx(abar, (unsigned)nkc * 2u * 16384u);
+      for (int kc = 0; kc < nkc; kc++) {
         tma_load_2d(a_hi0 + kc * 16384, &tmA_hi, kc * 64, (d * (int)CS + (int)c) * 128, abar);
         tma_load_2d(a_lo0 + kc * 16384, &tmA_lo, kc * 64, (d * (int)CS + (int)c) * 128, abar);
       }
@@ -144,14 +187,28 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   fence_proxy_async_smem();
   __syncthreads();
   tc_fence_after();
-  cluster_sync_all();                                           // barriers of every CTA initialised before any remote store
   const unsigned tmem_d = tmem_base_s;
+  if (A_TMEM && warp < kXEW) {          // weight slice -> tensor memory: lane = gate row, column = k pair; warp lg takes a quarter of K
+    const int row = 32 * (warp & 3) + lane, lg = warp >> 2;
+    const size_t base = ((size_t)(d * (int)CS + (int)c) * 128 + row) * p.KQ;
+    const int kq4 = p.KQ / 4;            // = 8 CS halfs
+    const unsigned trow = tmem_d + ((unsigned)(32 * (warp & 3)) << 16);
+    for (int k = lg * kq4; k < (lg + 1) * kq4; k += 8) {
+      const uint4 vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
+      const uint4 vl = *reinterpret_cast<const uint4*>(p.w_lo + base + k);
+      tmem_st4(trow + acol_hi + (unsigned)k / 2u, vh);
+      tmem_st4(trow + acol_lo + (unsigned)k / 2u, vl);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+  }
+  if (A_TMEM) { __syncthreads(); tc_fence_after(); }
+  cluster_sync_all();                                           // barriers of every CTA initialised before any remote store
 
-  const int groups_per_cluster_stride = cl_per_dir;
-  const int my_first_group = cluster_id - q * cl_per_dir;
-  unsigned hph0 = 0, hph1 = 0, accph = 0;
+  const int my_first_group = cluster_id - dq * cl_per_dir;
+  unsigned hph = 0, accph = 0;                                  // hph bit b: phase of the chunk barriers of buffer b
 
-  for (int group = my_first_group; group < p.ngroups; group += groups_per_cluster_stride) {
+  for (int group = my_first_group; group < p.ngroups; group += cl_per_dir) {
     const int l0 = group * kXL;
     if (tid < kXL) {
       const int li = (l0 + tid < ln.B) ? ln.order[l0 + tid] : -1;
@@ -161,102 +218,128 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     __syncthreads();
     const int Tg = lineT[0];
 
-    if (warp == 4) {
+    if (warp == kXEW) {
       // ------------------------------------------------------------------------------------------ MMA issuer
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      mbar_wait(abar, 0);
-      for (int s = 1; s < Tg; s++) {
+      if (!A_TMEM) mbar_wait(abar, 0);
+      const int own_kc = (int)c >> 1;                           // start with the chunk this CTA feeds: once it is complete, every
+      for (int s = 1; s < Tg; s++) {                            // epilogue warp of this CTA has read the accumulator of step s-1
         const unsigned b = (unsigned)(s - 1) & 1u;              // h_{s-1} sits in buffer (s-1)&1
-        const unsigned hb = b ? hbar1 : hbar0;
-        if (elect_one()) mbar_expect_tx(hb, hbytes);
+        const unsigned hb0 = bar0 + 8u * (b * kXMaxKc);
+        if (elect_one())
+          for (int kc = 0; kc < nkc; kc++) mbar_expect_tx(hb0 + 8u * kc, (unsigned)min(2, (int)CS - 2 * kc) * 2048u);
         __syncwarp();
-        mbar_wait_cluster(hb, b ? hph1 : hph0);
-        if (b) hph1 ^= 1; else hph0 ^= 1;
-        fence_proxy_async_smem();                               // remote generic-proxy stores -> tensor-core reads
-        tc_fence_after();
-        if (elect_one()) {
-          for (int kc = 0; kc < p.nkc; kc++) {
-            const unsigned long long ah = desc_of(a_hi0 + kc * 16384), al = desc_of(a_lo0 + kc * 16384);
+        const unsigned ph = (hph >> b) & 1u;
+        for (int i = 0; i < nkc; i++) {
+          int kc = own_kc + i;
+          if (kc >= nkc) kc -= nkc;
+          mbar_wait_cluster(hb0 + 8u * kc, ph);
+          fence_proxy_async_smem();                             // remote generic-proxy stores -> tensor-core reads
+          tc_fence_after();
+          if (elect_one()) {
             const unsigned long long bh = desc_of(b0 + b * bbytes + kc * 4096);
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
-              mma_f16(tmem_d, ah + 2 * ks, bh + 2 * ks, idesc32, (kc > 0 || ks > 0) ? 1u : 0u);   // R_hi [h_hi ; h_lo]
-              mma_f16(tmem_d, al + 2 * ks, bh + 2 * ks, idesc16, 1u);                             // + R_lo h_hi
+              const int kk = 4 * kc + ks;
+              if (kk < p.nks) {
+                const unsigned acc = (i > 0 || ks > 0) ? 1u : 0u;
+                if (A_TMEM) {
+                  mma_f16_ts(tmem_d, tmem_d + acol_hi + 8u * kk, bh + 2 * ks, idesc32, acc);      // R_hi [h_hi ; h_lo]
+                  mma_f16_ts(tmem_d, tmem_d + acol_lo + 8u * kk, bh + 2 * ks, idesc16, 1u);       // + R_lo h_hi
+                } else {
+                  mma_f16(tmem_d, desc_of(a_hi0 + kc * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);
+                  mma_f16(tmem_d, desc_of(a_lo0 + kc * 16384) + 2 * ks, bh + 2 * ks, idesc16, 1u);
+                }
+              }
             }
+            if (i == nkc - 1) mma_commit(accbar);
           }
-          mma_commit(accbar);
+          __syncwarp();
         }
-        __syncwarp();
+        hph ^= 1u << b;
       }
     } else {
       // ------------------------------------------------------------------------------------------ epilogue warps
-      const int j = tid >> 2, g = tid & 3;                      // unit slot of this CTA, gate
-      const bool real = j < p.UPC;
-      const int unit = (int)c * p.UPC + j;                      // hidden unit
-      const int grow = 4 * unit + g;                            // gate row
+      const int q = warp & 3, lg = warp >> 2;
+      const int row = 32 * q + lane;                            // TMEM lane = gate row of this CTA
+      const int j = row >> 2, g = row & 3;                      // unit slot, gate
+      const int unit = 32 * (int)c + j;
+      const bool real = unit < p.no;
+      const int grow = 4 * unit + g;
       const int no = p.no, no4 = p.no4;
       const float* __restrict__ XPd = p.XP[d];
       float* __restrict__ Gd = p.G[d];
       float* __restrict__ Cd = p.C[d];
       float* __restrict__ Hpd = p.Hprev[d];
       float* __restrict__ Hd = p.H + p.hoff[d];
-      const unsigned taddr = tmem_d + ((unsigned)(32 * warp) << 16);
+      const unsigned taddr = tmem_d + ((unsigned)(32 * q) << 16) + 4u * (unsigned)lg;
       constexpr float inv_scale = 1.0f / (kXScaleH * kXScaleR);
-      float cst[4] = {0.f, 0.f, 0.f, 0.f};                      // cell state of unit j for lines 4i+g
-      // where this lane's 16-byte chunk goes in a B buffer: line = lane % 16, plane = lane / 16 (0 hi, 1 lo)
-      const int xl = lane & 15, plane = lane >> 4;
-      const unsigned xrow = (unsigned)(xl + 16 * plane);
-      const unsigned xoff = (unsigned)((int)c >> 1) * 4096u + xrow * 128u + ((((unsigned)(4 * ((int)c & 1) + warp)) ^ (xrow & 7u)) << 4);
-      for (int s = 0; s < Tg; s++) {
-        float xp[kXL];
+      // the four lines of this warp: lengths and the element offset of (current column, this gate row)
+      int Tl[4];
+      long long eo[4];
 #pragma unroll
-        for (int l = 0; l < kXL; l++) {
-          const int Tl = lineT[l];
-          xp[l] = (real && s < Tl) ? XPd[((size_t)lineOff[l] + (d ? Tl - 1 - s : s)) * no4 + grow] : 0.f;
-        }
-        float act[kXL];
+      for (int i = 0; i < 4; i++) {
+        Tl[i] = lineT[4 * lg + i];
+        eo[i] = ((long long)lineOff[4 * lg + i] + (d ? Tl[i] - 1 : 0)) * no4 + grow;
+      }
+      const long long estep = d ? -(long long)no4 : (long long)no4;
+      const int myT = lineT[4 * lg + g];                         // the line whose cell state this lane keeps
+      long long co = (long long)lineOff[4 * lg + g] + (d ? myT - 1 : 0);
+      const int cstep = d ? -1 : 1;
+      float cst = 0.f;
+      // exchange: lane = r + 8 dg: 16-byte chunk r = (line ll = r & 3, plane = r >> 2) goes to CTAs dg, dg+4, dg+8, dg+12
+      const int ll = lane & 3, plane = (lane >> 2) & 1;
+      const unsigned xrow = (unsigned)(4 * lg + ll + 16 * plane);
+      const unsigned xoff = (unsigned)((int)c >> 1) * 4096u + xrow * 128u + ((((unsigned)(4 * ((int)c & 1) + q)) ^ (xrow & 7u)) << 4);
+      unsigned rdst[4], rbar[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const unsigned dst = (unsigned)(lane >> 3) + 4u * i;
+        rdst[i] = mapa_u32(b0 + xoff, dst < CS ? dst : 0u);
+        rbar[i] = mapa_u32(bar0 + 8u * (unsigned)((int)c >> 1), dst < CS ? dst : 0u);
+      }
+      float xp[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) xp[i] = (real && 0 < Tl[i]) ? ldg_f32(XPd + eo[i]) : 0.f;
+      for (int s = 0; s < Tg; s++) {
+        float xpn[4];                                           // next step's input projection: in flight during this step
+#pragma unroll
+        for (int i = 0; i < 4; i++) xpn[i] = (real && s + 1 < Tl[i]) ? ldg_f32(XPd + eo[i] + estep) : 0.f;
+        float act[4];
         if (s > 0) {
           mbar_wait(accbar, accph);
           accph ^= 1;
           tc_fence_after();
-          float acc[32];
-          tmem_ld<32>(taddr, acc);
+          unsigned ra[4], rb[4];
+          tmem_ld4_nowait(taddr, ra);
+          tmem_ld4_nowait(taddr + 16u, rb);
+          tmem_wait_ld();
 #pragma unroll
-          for (int l = 0; l < kXL; l++) act[l] = fmaf(acc[l] + acc[kXL + l], inv_scale, xp[l]);
+          for (int i = 0; i < 4; i++) act[i] = fmaf(__uint_as_float(ra[i]) + __uint_as_float(rb[i]), inv_scale, xp[i]);
         } else {
 #pragma unroll
-          for (int l = 0; l < kXL; l++) act[l] = xp[l];
+          for (int i = 0; i < 4; i++) act[i] = xp[i];
         }
 #pragma unroll
-        for (int l = 0; l < kXL; l++) act[l] = (g == 3) ? tanh_fast(act[l]) : sigmoid_fast(act[l]);   // forward_full1 clstm.cc:614-617
-        float hh[4];
-        unsigned hp[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          float gt[4];
-          quad_transpose(act + 4 * i, gt, g);                   // gi, gf, go, ci of line 4i+g
-          const bool on = real && s < lineT[4 * i + g];
-          if (on) {
-            cst[i] = fmaf(gt[1], cst[i], gt[3] * gt[0]);        // forward_statemem clstm_compute.cc:504-508
-            hh[i] = tanh_fast(cst[i]) * gt[2];                  // forward_nonlingate :530-537
-          } else hh[i] = 0.f;
-          unsigned short h16, l16;
-          split_f16(hh[i] * kXScaleH, h16, l16);
-          hp[i] = pack_h2(h16, l16);
+        for (int i = 0; i < 4; i++) act[i] = (g == 3) ? tanh_fast(act[i]) : sigmoid_fast(act[i]);   // forward_full1 clstm.cc:614-617
+        float gt[4];
+        quad_transpose(act, gt, g);                             // gi, gf, go, ci of line 4lg+g
+        const bool on = real && s < myT;
+        float hh = 0.f;
+        if (on) {
+          cst = fmaf(gt[1], cst, gt[3] * gt[0]);                // forward_statemem clstm_compute.cc:504-508
+          hh = tanh_fast(cst) * gt[2];                          // forward_nonlingate :530-537
         }
         if (s + 1 < Tg) {
-          // this warp's 8 units x 16 lines as 16-byte chunks: lane (line xl, plane) collects unit k's value from lane 4k + xl%4
+          unsigned short h16, l16;
+          split_f16(hh * kXScaleH, h16, l16);
+          const unsigned hp = pack_h2(h16, l16);
+          // this warp's 8 units x 4 lines as 16-byte chunks: lane (line ll, plane) collects unit k's value from lane 4k + ll
           unsigned v[8];
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-              const unsigned t = __shfl_sync(0xffffffffu, hp[i], 4 * k + (xl & 3));
-              if ((xl >> 2) == i) v[k] = t;
-            }
-          }
+          for (int k = 0; k < 8; k++) v[k] = __shfl_sync(0xffffffffu, hp, 4 * k + ll);
           unsigned w4[4];
 #pragma unroll
           for (int e = 0; e < 4; e++) {
@@ -265,27 +348,24 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             w4[e] = x0 | (x1 << 16);
           }
           tc_fence_before();                                    // (the accumulator has been read: tcgen05.wait::ld above)
-          const unsigned dstb = b0 + ((unsigned)s & 1u) * bbytes + xoff;
-          const unsigned hb = (s & 1) ? hbar1 : hbar0;
-          for (unsigned r = 0; r < CS; r++) st_async_v4(dstb, hb, r, w4[0], w4[1], w4[2], w4[3]);
+          const unsigned boff = ((unsigned)s & 1u) * bbytes, hoff = ((unsigned)s & 1u) * (8u * kXMaxKc);
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if ((unsigned)(lane >> 3) + 4u * i < CS) st_async_v4(rdst[i] + boff, rbar[i] + hoff, w4[0], w4[1], w4[2], w4[3]);
         }
         // ---- stash for the backward pass and the dense products
 #pragma unroll
-        for (int l = 0; l < kXL; l++) {
-          const int Tl = lineT[l];
-          if (real && s < Tl) Gd[((size_t)lineOff[l] + (d ? Tl - 1 - s : s)) * no4 + grow] = act[l];
+        for (int i = 0; i < 4; i++)
+          if (real && s < Tl[i]) Gd[eo[i]] = act[i];
+        if (on) {
+          Cd[co * no + unit] = cst;
+          Hd[co * p.hstride + unit] = hh;
+          if (s + 1 < myT) Hpd[(co + cstep) * no + unit] = hh;
+          if (s == 0) Hpd[co * no + unit] = 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int l = 4 * i + g, Tl = lineT[l];
-          if (real && s < Tl) {
-            const size_t col = (size_t)lineOff[l] + (d ? Tl - 1 - s : s);
-            Cd[col * no + unit] = cst[i];
-            Hd[col * p.hstride + unit] = hh[i];
-            if (s + 1 < Tl) Hpd[(col + (d ? -1 : 1)) * (size_t)no + unit] = hh[i];
-            if (s == 0) Hpd[col * no + unit] = 0.f;
-          }
-        }
+        for (int i = 0; i < 4; i++) { eo[i] += estep; xp[i] = xpn[i]; }
+        co += cstep;
       }
     }
     __syncthreads();
@@ -293,16 +373,18 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kXEW) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(32) : "memory");
+    tmem_dealloc(tmem_d, tcols);
   }
 }
 
 
 // ================================================================================================ backward
-// smem: A (Rt slice) [mt][kc] chunks of [128 k' rows][64 r'] hi, then lo | B = delta tile [2 kc][32 rows][128 B] | reduce
-// buffers [2][CS src][32 slots][16 lines] fp32
+// smem: A (Rt slice) chunks (mt, kc) of [128 output rows][64 gate rows] hi (shared-memory form only), then lo | B = delta tile
+// [2 kc][32 rows][128 B] | reduce buffers [2][CS src][32 slots][16 lines] fp32
+// TMEM: D nmt x 32 columns | (TMEM form) A hi nmt x 64 columns
+template <bool AHI_TMEM>
 __global__ void __launch_bounds__(kXThreads, 1)
 lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, Lines ln, TcxArgs p) {
   extern __shared__ __align__(1024) unsigned char xs[];
@@ -313,35 +395,36 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const unsigned CS = cluster_nctarank(), c = cluster_ctarank();
   const int cluster_id = blockIdx.x / (int)CS, nclusters = gridDim.x / (int)CS;
   const int cl_per_dir = nclusters / p.ndir;
-  const int q = cluster_id / cl_per_dir, d = p.d0 + q;
-  const int nmt = p.KQ / 128 > 0 ? p.KQ / 128 : 1;             // M tiles of outputs (k' slots)
-  const int mrows = p.KQ < 128 ? p.KQ : 128;                   // (KQ = 64: one partial tile)
+  const int dq = cluster_id / cl_per_dir, d = p.d0 + dq;
+  const int nmt = p.nmt;                                       // 128-row tiles of output slots (the last one may reach beyond KQ)
   const unsigned smem0 = (smem_u32(xs) + 1023u) & ~1023u;
-  const unsigned a_hi0 = smem0, a_lo0 = smem0 + (unsigned)nmt * 2u * 16384u;     // chunk (mt, kc) at +(mt*2+kc)*16384
-  const unsigned b0 = a_lo0 + (unsigned)nmt * 2u * 16384u;                      // delta tile: chunk kc at +kc*4096
-  const unsigned r0 = b0 + 8192u;                                               // reduce buffers
+  const unsigned aplane = (unsigned)nmt * 2u * 16384u;         // chunk (mt, kc) at +(mt*2+kc)*16384
+  const unsigned a_hi0 = smem0, a_lo0 = smem0 + (AHI_TMEM ? 0u : aplane);
+  const unsigned b0 = a_lo0 + aplane;                          // delta tile: chunk kc at +kc*4096
+  const unsigned r0 = b0 + 8192u;                              // reduce buffers
   const unsigned rbytes = CS * 32u * kXL * 4u;
   const unsigned bar0 = smem_u32(&bars[0]);
   const unsigned pbar0 = bar0, pbar1 = bar0 + 8, accbar = bar0 + 16, abar = bar0 + 24, bbar = bar0 + 32;
+  const unsigned tcols = pow2_cols((unsigned)nmt * (AHI_TMEM ? 96u : 32u));
+  const unsigned acol_hi = 32u * (unsigned)nmt;
 
   if (tid == 0) {
-    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, 128);
+    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, 32 * kXEW);
     mbar_init_fence();
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
   }
   for (unsigned i = tid; i < 8192 / 16; i += blockDim.x)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(b0 + 16 * i), "r"(0u) : "memory");
   __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(64) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == kXEW) {
+    tmem_alloc(smem_u32(&tmem_base_s), tcols);
     if (elect_one()) {       // Rt slice of this CTA: rows = output slots k', columns = this CTA's 128 gate rows
-      mbar_expect_tx(abar, (unsigned)nmt * 2u * 2u * 16384u);
+      mbar_expect_tx(abar, (unsigned)nmt * 2u * (AHI_TMEM ? 1u : 2u) * 16384u);
       for (int mt = 0; mt < nmt; mt++)
         for (int kc = 0; kc < 2; kc++) {
-          const int row = (d * (int)CS + (int)c) * p.KQ + mt * 128;
-          tma_load_2d(a_hi0 + (mt * 2 + kc) * 16384, &tmA_hi, kc * 64, row, abar);
-          tma_load_2d(a_lo0 + (mt * 2 + kc) * 16384, &tmA_lo, kc * 64, row, abar);
+          const int rw = (d * (int)CS + (int)c) * p.KQ + mt * 128;
+          if (!AHI_TMEM) tma_load_2d(a_hi0 + (mt * 2 + kc) * 16384, &tmA_hi, kc * 64, rw, abar);
+          tma_load_2d(a_lo0 + (mt * 2 + kc) * 16384, &tmA_lo, kc * 64, rw, abar);
         }
     }
   }
@@ -349,9 +432,27 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   fence_proxy_async_smem();
   __syncthreads();
   tc_fence_after();
-  cluster_sync_all();
   const unsigned tmem_d = tmem_base_s;
-  const int my_first_group = cluster_id - q * cl_per_dir;
+  if (AHI_TMEM && warp < kXEW) {        // hi plane -> tensor memory: lane = output slot of the tile, column = gate-row pair
+    const int rowl = 32 * (warp & 3) + lane, lg = warp >> 2;
+    const unsigned trow = tmem_d + ((unsigned)(32 * (warp & 3)) << 16);
+    for (int mt = 0; mt < nmt; mt++) {
+      const int slot = mt * 128 + rowl;
+      const size_t base = ((size_t)(d * (int)CS + (int)c) * p.KQ + slot) * 128;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {       // this warp's quarter of the 128 gate rows: 32 halfs = 4 x 16 bytes
+        const int k = 32 * lg + 8 * e;
+        uint4 vh = make_uint4(0u, 0u, 0u, 0u);
+        if (slot < p.KQ) vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
+        tmem_st4(trow + acol_hi + 64u * (unsigned)mt + (unsigned)k / 2u, vh);
+      }
+    }
+    tmem_wait_st();
+    tc_fence_before();
+  }
+  if (AHI_TMEM) { __syncthreads(); tc_fence_after(); }
+  cluster_sync_all();
+  const int my_first_group = cluster_id - dq * cl_per_dir;
   unsigned pph0 = 0, pph1 = 0, accph = 0, bph = 0;
   const unsigned pbytes = CS * 32u * kXL * 4u;                  // bytes a CTA receives per step (= one reduce buffer)
 
@@ -365,7 +466,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     __syncthreads();
     const int Tg = lineT[0];
 
-    if (warp == 4) {
+    if (warp == kXEW) {
       // ------------------------------------------------------------------------------------------ MMA issuer
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
@@ -378,12 +479,14 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (elect_one()) {
           for (int mt = 0; mt < nmt; mt++)
             for (int kc = 0; kc < 2; kc++) {
-              const unsigned long long ah = desc_of(a_hi0 + (mt * 2 + kc) * 16384), al = desc_of(a_lo0 + (mt * 2 + kc) * 16384);
+              const unsigned long long al = desc_of(a_lo0 + (mt * 2 + kc) * 16384);
               const unsigned long long bh = desc_of(b0 + kc * 4096);
 #pragma unroll
               for (int ks = 0; ks < 4; ks++) {
-                mma_f16(tmem_d + 32 * mt, ah + 2 * ks, bh + 2 * ks, idesc32, (kc > 0 || ks > 0) ? 1u : 0u);   // Rt_hi [d_hi ; d_lo]
-                mma_f16(tmem_d + 32 * mt, al + 2 * ks, bh + 2 * ks, idesc16, 1u);                             // + Rt_lo d_hi
+                const unsigned acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                if (AHI_TMEM) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_hi + 64u * mt + 8u * (4 * kc + ks), bh + 2 * ks, idesc32, acc);
+                else mma_f16(tmem_d + 32 * mt, desc_of(a_hi0 + (mt * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);   // Rt_hi [d_hi ; d_lo]
+                mma_f16(tmem_d + 32 * mt, al + 2 * ks, bh + 2 * ks, idesc16, 1u);                                              // + Rt_lo d_hi
               }
             }
           mma_commit(accbar);
@@ -392,41 +495,56 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
     } else {
       // ------------------------------------------------------------------------------------------ epilogue warps
-      const int j = tid >> 2, g = tid & 3;
-      const bool real = j < p.UPC;
-      const int unit = (int)c * p.UPC + j;
+      const int q = warp & 3, lg = warp >> 2;
+      const int row = 32 * q + lane;
+      const int j = row >> 2, g = row & 3;
+      const int unit = 32 * (int)c + j;
+      const bool real = unit < p.no;
       const int grow = 4 * unit + g;
       const int no = p.no, no4 = p.no4;
       const float* __restrict__ Gd = p.G[d];
       const float* __restrict__ Cd = p.C[d];
       const float* __restrict__ dHd = p.dH + p.hoff[d];
       float* __restrict__ DGd = p.DG[d];
-      const unsigned taddr = tmem_d + ((unsigned)(32 * warp) << 16);
+      const unsigned taddr = tmem_d + ((unsigned)(32 * q) << 16) + 4u * (unsigned)lg;
       constexpr float inv_scale = 1.0f / (kXScaleD * kXScaleR);
-      float dcc[4] = {0.f, 0.f, 0.f, 0.f};                      // carried cell derivative of unit j for lines 4i+g
-      // where this thread's deltas (gate row r' = tid, line l, plane) go in the delta tile
-      const unsigned boff = (unsigned)(tid >> 6) * 4096u + 2u * (unsigned)(tid & 7);
-      const unsigned bchunk = (unsigned)((tid & 63) >> 3);
+      // the four lines of this warp; forward step fs of line l sits in column off + (d ? T-1-fs : fs)
+      const int fs0 = Tg - 1;
+      int Tl[4];
+      long long eo[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        Tl[i] = lineT[4 * lg + i];
+        eo[i] = ((long long)lineOff[4 * lg + i] + (d ? Tl[i] - 1 - fs0 : fs0)) * no4 + grow;
+      }
+      const long long estep = d ? (long long)no4 : -(long long)no4;   // fs -> fs - 1
+      const int myT = lineT[4 * lg + g];
+      long long co = (long long)lineOff[4 * lg + g] + (d ? myT - 1 - fs0 : fs0);
+      const int cstep = d ? 1 : -1;
+      float dcc = 0.f;                                          // carried cell derivative of (unit j, line 4lg+g)
+      // where this thread's deltas (gate row r' = row) go in the delta tile
+      const unsigned boff = (unsigned)(row >> 6) * 4096u + 2u * (unsigned)(row & 7);
+      const unsigned bchunk = (unsigned)((row & 63) >> 3);
+      // operands of the first step
+      float gact[4], cc = 0.f, cp = 0.f, dh = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; i++) gact[i] = (real && fs0 < Tl[i]) ? ldg_f32(Gd + eo[i]) : 0.f;
+      if (real && fs0 < myT) {
+        cc = ldg_f32(Cd + co * no + unit);
+        if (fs0 > 0) cp = ldg_f32(Cd + (co + cstep) * no + unit);
+        dh = ldg_f32(dHd + co * p.hstride + unit);
+      }
       for (int it = 0; it < Tg; it++) {
         const int fs = Tg - 1 - it;
-        // ---- operands that do not depend on the exchange
-        float gact[kXL];
+        // ---- next step's operands: in flight during this step (they do not depend on the exchange)
+        float gactn[4], ccn = 0.f, cpn = 0.f, dhn = 0.f;
 #pragma unroll
-        for (int l = 0; l < kXL; l++) {
-          const int Tl = lineT[l];
-          gact[l] = (real && fs < Tl) ? Gd[((size_t)lineOff[l] + (d ? Tl - 1 - fs : fs)) * no4 + grow] : 0.f;
-        }
-        float cc[4], cp[4], dh[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int l = 4 * i + g, Tl = lineT[l];
-          cc[i] = cp[i] = dh[i] = 0.f;
-          if (real && fs < Tl) {
-            const size_t col = (size_t)lineOff[l] + (d ? Tl - 1 - fs : fs);
-            cc[i] = Cd[col * no + unit];
-            if (fs > 0) cp[i] = Cd[(col + (d ? 1 : -1)) * (size_t)no + unit];
-            dh[i] = dHd[col * p.hstride + unit];
-          }
+        for (int i = 0; i < 4; i++) gactn[i] = (real && fs >= 1 && fs - 1 < Tl[i]) ? ldg_f32(Gd + eo[i] + estep) : 0.f;
+        if (real && fs >= 1 && fs - 1 < myT) {
+          const long long cn = co + cstep;
+          ccn = ldg_f32(Cd + cn * no + unit);
+          if (fs - 1 > 0) cpn = ldg_f32(Cd + (cn + cstep) * no + unit);
+          dhn = ldg_f32(dHd + cn * p.hstride + unit);
         }
         // ---- recurrent part of dh: the CS partial products of the previous step, fixed order
         if (it > 0) {
@@ -435,78 +553,74 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if (tid == 0) mbar_expect_tx(pb, pbytes);
           mbar_wait_cluster(pb, b ? pph1 : pph0);
           if (b) pph1 ^= 1; else pph0 ^= 1;
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int l = 4 * i + g;
-            if (real && fs < lineT[l] - 1) {
-              float r = 0.f;
-              for (unsigned sc = 0; sc < CS; sc++) {
-                float x;
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(r0 + b * rbytes + ((sc * 32u + (unsigned)j) * kXL + (unsigned)l) * 4u) : "memory");
-                r += x;
-              }
-              dh[i] += r;
+          if (real && fs < myT - 1) {
+            float r = 0.f;
+            const unsigned ra = r0 + b * rbytes + ((unsigned)j * kXL + (unsigned)(4 * lg + g)) * 4u;
+            for (unsigned sc = 0; sc < CS; sc++) {
+              float x;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(ra + sc * (32u * kXL * 4u)) : "memory");
+              r += x;
             }
+            dh += r;
           }
         }
         // ---- pointwise (backward_nonlingate / statemem / nonlin0, clstm_compute.cc:539-547, 509-515, 231-267)
-        float dl[kXL];
+        float gt[4], dq4[4], dl[4];
+        quad_transpose(gact, gt, g);                            // gi, gf, go, ci of line 4lg+g
+        const bool on = real && fs < myT;
+        if (on) {
+          const float th = tanh_fast(cc);
+          const float dgo = th * dh;
+          const float dc = fmaf(1.f - th * th, gt[2] * dh, dcc);
+          float dgf = 0.f, carry = 0.f;
+          if (fs > 0) { dgf = dc * cp; carry = dc * gt[1]; }
+          dcc = carry;
+          dq4[0] = gt[0] * (1.f - gt[0]) * (dc * gt[3]);
+          dq4[1] = gt[1] * (1.f - gt[1]) * dgf;
+          dq4[2] = gt[2] * (1.f - gt[2]) * dgo;
+          dq4[3] = (1.f - gt[3] * gt[3]) * (dc * gt[0]);
+        } else { dq4[0] = dq4[1] = dq4[2] = dq4[3] = 0.f; }
+        quad_transpose(dq4, dl, g);                             // back: this lane's gate for lines 4lg..4lg+3
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          float gt[4], dq[4];
-          quad_transpose(gact + 4 * i, gt, g);                  // gi, gf, go, ci of line 4i+g
-          const bool on = real && fs < lineT[4 * i + g];
-          if (on) {
-            const float th = tanh_fast(cc[i]);
-            const float dgo = th * dh[i];
-            const float dc = fmaf(1.f - th * th, gt[2] * dh[i], dcc[i]);
-            float dgf = 0.f, carry = 0.f;
-            if (fs > 0) { dgf = dc * cp[i]; carry = dc * gt[1]; }
-            dcc[i] = carry;
-            dq[0] = gt[0] * (1.f - gt[0]) * (dc * gt[3]);
-            dq[1] = gt[1] * (1.f - gt[1]) * dgf;
-            dq[2] = gt[2] * (1.f - gt[2]) * dgo;
-            dq[3] = (1.f - gt[3] * gt[3]) * (dc * gt[0]);
-          } else { dq[0] = dq[1] = dq[2] = dq[3] = 0.f; }
-          quad_transpose(dq, dl + 4 * i, g);                    // back: this lane's gate for lines 4i..4i+3
-        }
-#pragma unroll
-        for (int l = 0; l < kXL; l++) {
-          const int Tl = lineT[l];
-          if (real && fs < Tl) DGd[((size_t)lineOff[l] + (d ? Tl - 1 - fs : fs)) * no4 + grow] = dl[l];
-        }
+        for (int i = 0; i < 4; i++)
+          if (real && fs < Tl[i]) DGd[eo[i]] = dl[i];
         if (fs == 0) break;
         // ---- delta tile (B operand): row = line (+16 for the lo plane), k = this thread's gate row
 #pragma unroll
-        for (int l = 0; l < kXL; l++) {
+        for (int i = 0; i < 4; i++) {
           unsigned short h16, l16;
-          split_f16(dl[l] * kXScaleD, h16, l16);
-          const unsigned rh = (unsigned)l, rl = (unsigned)l + 16u;
+          split_f16(dl[i] * kXScaleD, h16, l16);
+          const unsigned rh = (unsigned)(4 * lg + i), rl = rh + 16u;
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(b0 + boff + rh * 128u + ((bchunk ^ (rh & 7u)) << 4)), "h"(h16) : "memory");
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(b0 + boff + rl * 128u + ((bchunk ^ (rl & 7u)) << 4)), "h"(l16) : "memory");
         }
         fence_proxy_async_smem();
         mbar_arrive(bbar);
-        // ---- partial products of this CTA's gate rows for ALL output slots: send each slot's 16 lines to its owner
+        // ---- partial products of this CTA's gate rows for ALL output slots: send each slot's lines to its owner
         mbar_wait(accbar, accph);
         accph ^= 1;
         tc_fence_after();
         for (int mt = 0; mt < nmt; mt++) {
-          float acc[32];
-          tmem_ld<32>(taddr + 32 * mt, acc);
-          const unsigned owner = (unsigned)(4 * mt + warp);     // slots 128 mt + 32 warp .. +31 belong to this CTA of the cluster
-          if (owner < CS && (mt * 128 + tid) < mrows * nmt) {
-            const unsigned dst = r0 + ((unsigned)it & 1u) * rbytes + ((c * 32u + (unsigned)lane) * kXL) * 4u;
+          unsigned ra[4], rb[4];
+          tmem_ld4_nowait(taddr + 32u * mt, ra);
+          tmem_ld4_nowait(taddr + 32u * mt + 16u, rb);
+          tmem_wait_ld();
+          const unsigned owner = (unsigned)(4 * mt + q);        // slots 128 mt + 32 q .. +31 belong to this CTA of the cluster
+          if (owner < CS) {
+            const unsigned dst = r0 + ((unsigned)it & 1u) * rbytes + ((c * 32u + (unsigned)lane) * kXL + 4u * (unsigned)lg) * 4u;
             const unsigned pb = (it & 1) ? pbar1 : pbar0;
-#pragma unroll
-            for (int e = 0; e < 4; e++)
-              st_async_v4(dst + 16 * e, pb, owner, __float_as_uint((acc[4 * e] + acc[16 + 4 * e]) * inv_scale),
-                          __float_as_uint((acc[4 * e + 1] + acc[16 + 4 * e + 1]) * inv_scale),
-                          __float_as_uint((acc[4 * e + 2] + acc[16 + 4 * e + 2]) * inv_scale),
-                          __float_as_uint((acc[4 * e + 3] + acc[16 + 4 * e + 3]) * inv_scale));
+            st_async_v4(mapa_u32(dst, owner), mapa_u32(pb, owner),
+                        __float_as_uint((__uint_as_float(ra[0]) + __uint_as_float(rb[0])) * inv_scale),
+                        __float_as_uint((__uint_as_float(ra[1]) + __uint_as_float(rb[1])) * inv_scale),
+                        __float_as_uint((__uint_as_float(ra[2]) + __uint_as_float(rb[2])) * inv_scale),
+                        __float_as_uint((__uint_as_float(ra[3]) + __uint_as_float(rb[3])) * inv_scale));
           }
         }
         tc_fence_before();
+#pragma unroll
+        for (int i = 0; i < 4; i++) { eo[i] += estep; gact[i] = gactn[i]; }
+        co += cstep;
+        cc = ccn; cp = cpn; dh = dhn;
       }
     }
     __syncthreads();
@@ -514,29 +628,27 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kXEW) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(64) : "memory");
+    tmem_dealloc(tmem_d, tcols);
   }
 }
 
 // ================================================================================================ weight layouts
-// R [4no x no] fp32 -> slot-ordered fp16 hi/lo copy for the forward kernel: row (c*128 + 4j+g) = gate row 4(c*UPC+j)+g of CTA c,
-// column k' = 32 c' + j' = unit c'*UPC + j'.  Padding stays zero from the allocation.
-// Backward copy: for CTA c a [KQ output slots][128 gate rows of c] matrix, element (k', 4j+g) = the same weight.
-__global__ void lstm_tcx_split_kernel(const float* __restrict__ R, int no, int UPC, int KQ, __half* __restrict__ a_hi,
+// R [4no x no] fp32 -> fp16 hi/lo copies.  Forward: the matrix padded to [CS*128 rows][KQ] (row = gate row, column = unit).
+// Backward: for CTA c a [KQ output slots][128 gate rows of c] matrix, element (k', r') = R[128c + r'][k'].  Padding stays
+// zero from the allocation.
+__global__ void lstm_tcx_split_kernel(const float* __restrict__ R, int no, int KQ, __half* __restrict__ a_hi,
                                       __half* __restrict__ a_lo, __half* __restrict__ t_hi, __half* __restrict__ t_lo) {
   const size_t total = (size_t)4 * no * no;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / no), k = (int)(i % no);
-    const int unit = r >> 2, g = r & 3;
-    const int c = unit / UPC, j = unit % UPC, c2 = k / UPC, j2 = k % UPC;
     unsigned short hi, lo;
     split_f16(R[i] * kXScaleR, hi, lo);
-    const size_t o = (size_t)(c * 128 + 4 * j + g) * KQ + (32 * c2 + j2);
+    const size_t o = (size_t)r * KQ + k;
     reinterpret_cast<unsigned short*>(a_hi)[o] = hi;
     reinterpret_cast<unsigned short*>(a_lo)[o] = lo;
-    const size_t ot = ((size_t)c * KQ + (32 * c2 + j2)) * 128 + (4 * j + g);
+    const size_t ot = ((size_t)(r >> 7) * KQ + k) * 128 + (r & 127);
     reinterpret_cast<unsigned short*>(t_hi)[ot] = hi;
     reinterpret_cast<unsigned short*>(t_lo)[ot] = lo;
   }
@@ -566,8 +678,9 @@ int make_map_x(CUtensorMap* m, void* base, size_t rows, size_t cols, int box_row
 }  // namespace
 
 struct LstmTcxPlan {
-  int no = 0, num_sms = 148, UPC = 0, CS = 0, KQ = 0, nkc = 0;
-  __half *a_hi = nullptr, *a_lo = nullptr;       // forward weight slices [2 dirs][CS][128][KQ]
+  int no = 0, num_sms = 148, CS = 0, KQ = 0, nks = 0, nkc = 0, nmt = 0;
+  bool tmem = false;                             // weight slice in tensor memory (forward: both planes, backward: the hi plane)
+  __half *a_hi = nullptr, *a_lo = nullptr;       // forward weight slices [2 dirs][CS*128][KQ]
   __half *t_hi = nullptr, *t_lo = nullptr;       // backward weight slices [2 dirs][CS][KQ][128]
   bool stale[2] = {true, true};
   CUtensorMap tmA_hi, tmA_lo, tmT_hi, tmT_lo;
@@ -576,10 +689,8 @@ struct LstmTcxPlan {
 };
 
 bool lstm_tcx_supported(int no) {
-  if (no < 32 || no > 256 || no % 4 != 0) return false;
-  for (int cs = 3; cs <= 8; cs++)          // (at least 3 CTAs: 128 output slots, one full partial-sum tile in the backward kernel)
-    if (no % cs == 0 && no / cs <= kXSlots) return true;
-  return false;
+  const int cs = (no + 31) / 32;
+  return cs >= 2 && cs <= kXMaxCS;
 }
 void lstm_tcx_destroy(LstmTcxPlan* p) {
   if (!p) return;
@@ -590,10 +701,9 @@ const char* lstm_tcx_error(const LstmTcxPlan* p) { return p ? p->err : "no plan"
 void lstm_tcx_mark_stale(LstmTcxPlan* p) { if (p) p->stale[0] = p->stale[1] = true; }
 
 namespace {
-size_t tcx_fwd_smem(int nkc) { return (size_t)nkc * 2 * 16384 + (size_t)2 * nkc * 4096 + 1024; }
-size_t tcx_bwd_smem(int KQ, int CS) {
-  const int nmt = KQ / 128 > 0 ? KQ / 128 : 1;
-  return (size_t)nmt * 2 * 2 * 16384 + 8192 + (size_t)2 * CS * 32 * kXL * 4 + 1024;
+size_t tcx_fwd_smem(const LstmTcxPlan* p) { return (p->tmem ? 0 : (size_t)p->nkc * 2 * 16384) + (size_t)2 * p->nkc * 4096 + 1024; }
+size_t tcx_bwd_smem(const LstmTcxPlan* p) {
+  return (size_t)p->nmt * 2 * 16384 * (p->tmem ? 1 : 2) + 8192 + (size_t)2 * p->CS * 32 * kXL * 4 + 1024;
 }
 int ensure_split_x(LstmTcxPlan* p, cudaStream_t st, const float* const R[2], int d0, int ndir) {
   for (int d = d0; d < d0 + ndir; d++) {
@@ -601,10 +711,27 @@ int ensure_split_x(LstmTcxPlan* p, cudaStream_t st, const float* const R[2], int
     const size_t off = (size_t)d * p->CS * 128 * p->KQ;
     const size_t total = (size_t)4 * p->no * p->no;
     const int nb = (int)std::min<size_t>((total + 255) / 256, (size_t)p->num_sms * 8);
-    lstm_tcx_split_kernel<<<nb, 256, 0, st>>>(R[d], p->no, p->UPC, p->KQ, p->a_hi + off, p->a_lo + off, p->t_hi + off, p->t_lo + off);
+    lstm_tcx_split_kernel<<<nb, 256, 0, st>>>(R[d], p->no, p->KQ, p->a_hi + off, p->a_lo + off, p->t_hi + off, p->t_lo + off);
     p->stale[d] = false;
   }
   return (int)cudaGetLastError();
+}
+template <class K>
+cudaError_t tcx_attrs(K kern, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  return e;
+}
+void tcx_launch_cfg(const LstmTcxPlan* p, cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int nclusters, size_t smem, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(nclusters * p->CS); cfg.blockDim = dim3(kXThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)p->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+}
+void tcx_fill(const LstmTcxPlan* p, TcxArgs& x, int B, int d0, int ndir, int hstride, const int* hoff) {
+  x.no = p->no; x.no4 = 4 * p->no; x.CS = p->CS; x.KQ = p->KQ; x.nks = p->nks; x.nkc = p->nkc; x.nmt = p->nmt;
+  x.ngroups = (B + kXL - 1) / kXL; x.d0 = d0; x.ndir = ndir; x.hstride = hstride; x.hoff[0] = hoff[0]; x.hoff[1] = hoff[1];
 }
 }
 
@@ -612,33 +739,34 @@ LstmTcxPlan* lstm_tcx_create(int no, int num_sms) {
   if (!lstm_tcx_supported(no) || load_encode_x() != 0) return nullptr;
   auto* p = new LstmTcxPlan;
   p->no = no; p->num_sms = num_sms;
-  for (int cs = 3; cs <= 8; cs++)
-    if (no % cs == 0 && no / cs <= kXSlots) { p->CS = cs; break; }       // the smallest cluster that holds the units
-  p->UPC = no / p->CS; p->KQ = ((kXSlots * p->CS + 63) / 64) * 64; p->nkc = p->KQ / 64;
+  p->CS = (no + 31) / 32; p->KQ = 32 * p->CS; p->nks = p->KQ / 16; p->nkc = (p->KQ + 63) / 64; p->nmt = (p->KQ + 127) / 128;
+  p->tmem = p->KQ > 256;                                   // the slice no longer fits shared memory next to the h buffers
+  if (const char* e = getenv("CLSTM_B200_TCX_TMEM")) p->tmem = (atoi(e) != 0) || p->KQ > 256;
   const size_t elems = (size_t)2 * p->CS * 128 * p->KQ;
   bool ok = cudaMalloc((void**)&p->a_hi, elems * 2) == cudaSuccess && cudaMalloc((void**)&p->a_lo, elems * 2) == cudaSuccess &&
             cudaMalloc((void**)&p->t_hi, elems * 2) == cudaSuccess && cudaMalloc((void**)&p->t_lo, elems * 2) == cudaSuccess;
   if (ok) {
     cudaMemset(p->a_hi, 0, elems * 2); cudaMemset(p->a_lo, 0, elems * 2);
     cudaMemset(p->t_hi, 0, elems * 2); cudaMemset(p->t_lo, 0, elems * 2);
-    const int trows = p->KQ < 128 ? p->KQ : 128;
     ok = make_map_x(&p->tmA_hi, p->a_hi, (size_t)2 * p->CS * 128, p->KQ, 128) == 0 &&
          make_map_x(&p->tmA_lo, p->a_lo, (size_t)2 * p->CS * 128, p->KQ, 128) == 0 &&
-         make_map_x(&p->tmT_hi, p->t_hi, (size_t)2 * p->CS * p->KQ, 128, trows) == 0 &&
-         make_map_x(&p->tmT_lo, p->t_lo, (size_t)2 * p->CS * p->KQ, 128, trows) == 0;
+         make_map_x(&p->tmT_hi, p->t_hi, (size_t)2 * p->CS * p->KQ, 128, 128) == 0 &&
+         make_map_x(&p->tmT_lo, p->t_lo, (size_t)2 * p->CS * p->KQ, 128, 128) == 0;
   }
-  if (ok) ok = cudaFuncSetAttribute(lstm_tcx_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcx_fwd_smem(p->nkc)) == cudaSuccess &&
-               cudaFuncSetAttribute(lstm_tcx_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tcx_bwd_smem(p->KQ, p->CS)) == cudaSuccess;
+  if (ok) ok = p->tmem ? (tcx_attrs(lstm_tcx_fwd<true>, tcx_fwd_smem(p)) == cudaSuccess && tcx_attrs(lstm_tcx_bwd<true>, tcx_bwd_smem(p)) == cudaSuccess)
+                       : (tcx_attrs(lstm_tcx_fwd<false>, tcx_fwd_smem(p)) == cudaSuccess && tcx_attrs(lstm_tcx_bwd<false>, tcx_bwd_smem(p)) == cudaSuccess);
   if (ok) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p->CS * 32); cfg.blockDim = dim3(kXThreads); cfg.dynamicSmemBytes = tcx_fwd_smem(p->nkc);
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)p->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, lstm_tcx_fwd, &cfg) != cudaSuccess || nc < 1) ok = false;
-    p->max_clusters = nc;
+    int nf = 0, nb = 0;
+    tcx_launch_cfg(p, cfg, at, 16, tcx_fwd_smem(p), nullptr);
+    cudaError_t e = p->tmem ? cudaOccupancyMaxActiveClusters(&nf, lstm_tcx_fwd<true>, &cfg) : cudaOccupancyMaxActiveClusters(&nf, lstm_tcx_fwd<false>, &cfg);
+    tcx_launch_cfg(p, cfg, at, 16, tcx_bwd_smem(p), nullptr);
+    if (e == cudaSuccess) e = p->tmem ? cudaOccupancyMaxActiveClusters(&nb, lstm_tcx_bwd<true>, &cfg) : cudaOccupancyMaxActiveClusters(&nb, lstm_tcx_bwd<false>, &cfg);
+    if (e != cudaSuccess || nf < 1 || nb < 1) ok = false;
+    p->max_clusters = std::min(nf, nb);
+    if (getenv("CLSTM_B200_TC_DBG")) fprintf(stderr, "lstm_tcx: nhidden %d -> clusters of %d CTAs, KQ %d, %s weights, resident clusters fwd %d bwd %d, smem fwd %zu bwd %zu\n",
+                                             no, p->CS, p->KQ, p->tmem ? "TMEM" : "smem", nf, nb, tcx_fwd_smem(p), tcx_bwd_smem(p));
   }
   if (!ok) { cudaGetLastError(); lstm_tcx_destroy(p); return nullptr; }
   return p;
@@ -648,22 +776,17 @@ LstmTcxPlan* lstm_tcx_create(int no, int num_sms) {
 int lstm_tcx_forward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const LstmFwdArgs& a) {
   if (!p || a.cell != 0 || a.no != p->no) return -1;
   if (ensure_split_x(p, st, a.R, a.d0, a.ndir) != 0) { snprintf(p->err, sizeof p->err, "weight split launch failed"); return 1; }
-  const int ngroups = (ln.B + kXL - 1) / kXL;
-  int cl_per_dir = std::min(ngroups, p->max_clusters / a.ndir);
-  if (cl_per_dir < 1) return -1;
   TcxArgs x{};
-  x.no = p->no; x.no4 = 4 * p->no; x.UPC = p->UPC; x.CS = p->CS; x.KQ = p->KQ; x.nkc = p->nkc;
-  x.ngroups = ngroups; x.d0 = a.d0; x.ndir = a.ndir; x.hstride = a.hstride; x.hoff[0] = a.hoff[0]; x.hoff[1] = a.hoff[1];
+  tcx_fill(p, x, ln.B, a.d0, a.ndir, a.hstride, a.hoff);
+  const int cl_per_dir = std::min(x.ngroups, p->max_clusters / a.ndir);
+  if (cl_per_dir < 1) return -1;
   for (int d = 0; d < 2; d++) { x.XP[d] = a.XP[d]; x.G[d] = a.G[d]; x.C[d] = a.C[d]; x.Hprev[d] = a.Hprev[d]; }
-  x.H = a.H;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cl_per_dir * a.ndir * p->CS); cfg.blockDim = dim3(kXThreads); cfg.dynamicSmemBytes = tcx_fwd_smem(p->nkc);
-  cfg.stream = st;
+  x.H = a.H; x.w_hi = p->a_hi; x.w_lo = p->a_lo;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)p->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tcx_fwd, p->tmA_hi, p->tmA_lo, ln, x);
+  tcx_launch_cfg(p, cfg, at, cl_per_dir * a.ndir, tcx_fwd_smem(p), st);
+  cudaError_t e = p->tmem ? cudaLaunchKernelEx(&cfg, lstm_tcx_fwd<true>, p->tmA_hi, p->tmA_lo, ln, x)
+                          : cudaLaunchKernelEx(&cfg, lstm_tcx_fwd<false>, p->tmA_hi, p->tmA_lo, ln, x);
   if (e != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "lstm_tcx_fwd launch (%d clusters of %d): %s", cl_per_dir * a.ndir, p->CS, cudaGetErrorString(e));
     cudaGetLastError();
@@ -675,22 +798,17 @@ int lstm_tcx_forward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const Lst
 int lstm_tcx_backward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const LstmBwdArgs& a) {
   if (!p || a.cell != 0 || a.no != p->no) return -1;
   if (ensure_split_x(p, st, a.R, a.d0, a.ndir) != 0) { snprintf(p->err, sizeof p->err, "weight split launch failed"); return 1; }
-  const int ngroups = (ln.B + kXL - 1) / kXL;
-  const int cl_per_dir = std::min(ngroups, p->max_clusters / a.ndir);
-  if (cl_per_dir < 1) return -1;
   TcxArgs x{};
-  x.no = p->no; x.no4 = 4 * p->no; x.UPC = p->UPC; x.CS = p->CS; x.KQ = p->KQ; x.nkc = p->nkc;
-  x.ngroups = ngroups; x.d0 = a.d0; x.ndir = a.ndir; x.hstride = a.hstride; x.hoff[0] = a.hoff[0]; x.hoff[1] = a.hoff[1];
+  tcx_fill(p, x, ln.B, a.d0, a.ndir, a.hstride, a.hoff);
+  const int cl_per_dir = std::min(x.ngroups, p->max_clusters / a.ndir);
+  if (cl_per_dir < 1) return -1;
   for (int d = 0; d < 2; d++) { x.G[d] = const_cast<float*>(a.G[d]); x.C[d] = const_cast<float*>(a.C[d]); x.DG[d] = a.DG[d]; }
-  x.dH = a.dH;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cl_per_dir * a.ndir * p->CS); cfg.blockDim = dim3(kXThreads); cfg.dynamicSmemBytes = tcx_bwd_smem(p->KQ, p->CS);
-  cfg.stream = st;
+  x.dH = a.dH; x.w_hi = p->t_hi; x.w_lo = p->t_lo;
+  cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)p->CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_tcx_bwd, p->tmT_hi, p->tmT_lo, ln, x);
+  tcx_launch_cfg(p, cfg, at, cl_per_dir * a.ndir, tcx_bwd_smem(p), st);
+  cudaError_t e = p->tmem ? cudaLaunchKernelEx(&cfg, lstm_tcx_bwd<true>, p->tmT_hi, p->tmT_lo, ln, x)
+                          : cudaLaunchKernelEx(&cfg, lstm_tcx_bwd<false>, p->tmT_hi, p->tmT_lo, ln, x);
   if (e != cudaSuccess) {
     snprintf(p->err, sizeof p->err, "lstm_tcx_bwd launch (%d clusters of %d): %s", cl_per_dir * a.ndir, p->CS, cudaGetErrorString(e));
     cudaGetLastError();

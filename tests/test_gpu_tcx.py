@@ -43,10 +43,11 @@ def split(a, T):
     return [a[offs[i]:offs[i + 1]] for i in range(len(T))]
 
 
-# nhidden, lines, tmin, tmax: clusters of 8 (200, 256), 4 (100, 128, 64), 3 (96) and 5 (160) CTAs; fewer lines than one group,
-# several groups per cluster (more groups than resident clusters), ragged down to T = 1
+# nhidden, lines, tmin, tmax: clusters of 2..15 CTAs (32 units each, the last one partly filled), weight slice in shared memory
+# (nhidden <= 256) and in tensor memory (wider), fewer lines than one group, several groups per cluster (more groups than
+# resident clusters), ragged down to T = 1
 AB_CASES = [(200, 16, 3, 8), (200, 40, 1, 20), (100, 20, 5, 12), (256, 33, 4, 9), (128, 128, 10, 30), (96, 7, 2, 15),
-            (160, 50, 1, 25), (200, 700, 2, 6), (64, 130, 3, 9)]
+            (160, 50, 1, 25), (200, 700, 2, 6), (64, 130, 3, 9), (400, 40, 1, 20), (320, 33, 4, 9), (480, 17, 2, 7), (288, 16, 5, 9)]
 
 
 @pytest.mark.parametrize("no,B,t0,t1", AB_CASES)
@@ -62,6 +63,7 @@ PARITY = [
     (48, 200, 83, 35, (30, 50), "init"),      # three line groups
     (48, 100, 83, 20, (20, 45), "trained"),   # config 2 width
     (48, 256, 83, 3, (10, 25), "trained"),
+    (48, 400, 83, 5, (20, 45), "trained"),    # config 4 width: weight slice in tensor memory
 ]
 
 
@@ -70,7 +72,7 @@ def test_tcx_parity_with_oracle(ffi, oracle, ni, nh, nc, B, T, weights):
     x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=3)
     onet = oracle.BidiOracle(ni, nh, nc, seed=0.222)
     if weights == "trained":
-        onet.set_params(synth.trained_like(onet.nparams, 0.3, seed=7))
+        onet.set_params(synth.trained_like(onet.nparams, 0.3 if nh <= 200 else 0.3 * (200.0 / nh) ** 0.5, seed=7))
     with forced("tcx"):
         gnet = ffi.Net(ni, nh, nc)
     gnet.set_params(onet.get_params())

@@ -4,6 +4,6 @@
 mkdir -p gpurun_out
 G="${@:-xsmall}"
 for only in fwd bwd; do
-  CLSTM_B200_SELFTEST_ONLY=$only timeout 180 python tools/tc_selftest.py --x $G > gpurun_out/tcx_$only.log 2>&1
+  CLSTM_B200_SELFTEST_ONLY=$only timeout 300 python tools/tc_selftest.py --x $G > gpurun_out/tcx_$only.log 2>&1
   echo "== $only exit $?"; tail -12 gpurun_out/tcx_$only.log
 done

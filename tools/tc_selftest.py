@@ -16,6 +16,7 @@ CASES = {
     "xsmall": [(200, 16, 3, 8), (200, 40, 1, 20), (100, 20, 5, 12), (256, 33, 4, 9), (128, 128, 10, 30)],
     "t4": [(400, 256, 200, 2000)],
     "t4s": [(400, 32, 200, 2000)],
+    "xwide": [(400, 20, 3, 9), (400, 40, 1, 20), (320, 33, 4, 9), (480, 17, 2, 7), (288, 16, 5, 9)],
     "t2": [(100, 32, 500, 500)],
     "t2b": [(100, 128, 500, 500)],
     "t3s": [(200, 32, 512, 512)],
