@@ -119,6 +119,7 @@ LstmTcxPlan* lstm_tcx_create(int no, int num_sms);
 void lstm_tcx_destroy(LstmTcxPlan* p);
 void lstm_tcx_mark_stale(LstmTcxPlan* p);
 const char* lstm_tcx_error(const LstmTcxPlan* p);
+const long long* lstm_tcx_debug(LstmTcxPlan* p);       // clock stamps of one step of CTA 0 (CLSTM_B200_TC_DBG), else nullptr
 int lstm_tcx_forward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const LstmFwdArgs& a);    // 0 / -1 n.a. / > 0 error
 int lstm_tcx_backward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const LstmBwdArgs& a);
 

@@ -2,7 +2,7 @@
 // a thread-block cluster owns a group of 16 text lines of one direction for the whole sequence, the recurrent matrix is
 // split over the CTAs (32 hidden units = 128 gate rows each; the slice stays in shared memory or -- wide nets -- in TENSOR
 // MEMORY for the whole sequence), the per-step products run on tcgen05 (lines on the UMMA N dimension, accumulators in TMEM)
-// and h travels between the CTAs through DISTRIBUTED SHARED MEMORY (st.async + mbarrier complete_tx) -- no L2 round trip
+// and h travels between the CTAs through DISTRIBUTED SHARED MEMORY (bulk copies + mbarrier complete_tx) -- no L2 round trip
 // inside a step, which is what bounds the lock-step kernels of lstm_tc.cu at ~5 us per step.
 //
 // Reference semantics (paths relative to /root/reference), identical to lstm.cu / lstm_tc.cu:
@@ -22,11 +22,14 @@
 // Threads: 16 epilogue warps (TMEM lane quadrant q = warp & 3 -> 8 units, line quad lg = warp >> 2 -> lines 4lg..4lg+3)
 // + 1 loader / MMA warp.  TMEM lane = gate row: the four gates of a unit sit in four adjacent lanes; a 4x4 register transpose
 // inside the lane quad (4 shuffles) hands lane g the four gates of line 4lg+g, whose cell state it keeps in a register.
-// Exchange: every warp packs its 8 units x 4 lines into 16-byte chunks (8 shuffles) and st.async's them into the B buffer of
-// every CTA of the cluster; the stores complete bytes on a per-64-k-chunk mbarrier of the destination, so its MMA warp starts
-// on a chunk as soon as the two CTAs that feed it have delivered.  Two B buffers; safe by data flow (a CTA sends step s only
-// after it received all of step s-1).  Streamed operands (input projection; gates / cell / upstream deltas) are prefetched
-// one step ahead into registers.
+// Exchange: every warp packs its 8 units x 4 lines into 16-byte chunks (8 shuffles) and writes them into a 2 KB staging block
+// of its OWN shared memory; the block ([32 rows = 16 lines hi / lo][32 k], SWIZZLE_64B, exactly one K chunk of the B operand)
+// then travels with ONE bulk copy per destination CTA (cp.async.bulk shared::cta -> shared::cluster) that completes its bytes
+// on a per-source mbarrier of the destination, whose MMA warp starts on a chunk as soon as it has landed.  (The first version
+// pushed 16-byte st.async stores: ~3.6 cycles per store and destination, 4900 cycles per step at nhidden 200.)  Two B buffers
+// and two staging blocks; safe by data flow (a CTA sends step s only after it received all of step s-1).  The backward
+// partial sums travel the same way (2 KB per owner CTA).  Streamed operands (input projection; gates / cell / upstream
+// deltas) are prefetched one step ahead into registers.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -45,7 +48,7 @@ using namespace tc;
 constexpr int kXL = 16;                      // lines per cluster
 constexpr int kXEW = 16;                     // epilogue warps
 constexpr int kXThreads = 32 * (kXEW + 1);   // + the loader / MMA warp
-constexpr int kXMaxKc = 8;                   // 64-wide K chunks (KQ <= 512)
+constexpr int kXDbgStep = 64;                // step whose timeline CTA 0 records when a debug buffer is given
 constexpr int kXMaxCS = 15;                  // CTAs per cluster (KQ = 480: D + both A planes fill the 512 TMEM columns)
 constexpr float kXScaleH = 16.f, kXScaleR = 16.f, kXScaleD = 256.f;
 
@@ -62,6 +65,8 @@ struct TcxArgs {
   float* DG[2];
   // the weight copies (for the TMEM-resident form, which loads them with plain loads)
   const __half *w_hi, *w_lo;
+  int nlt;                 // backward, TMEM form: lo-plane tiles that live in tensor memory (the others stay in shared memory)
+  long long* dbg;          // optional: timeline of one step of CTA 0 (clock64 stamps)
 };
 
 __device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned rank) {
@@ -69,11 +74,23 @@ __device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
-// 16-byte store into a peer CTA's shared memory (cluster address) that also completes 16 bytes on that CTA's mbarrier
-__device__ __forceinline__ void st_async_v4(unsigned raddr, unsigned rbar, unsigned a, unsigned b, unsigned c, unsigned d) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr), "r"(a),
-               "r"(b), "r"(c), "r"(d), "r"(rbar)
+// one contiguous block of this CTA's shared memory -> a peer CTA's shared memory; completes `bytes` on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(unsigned rdst, unsigned src, unsigned bytes, unsigned rbar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rdst), "r"(src),
+               "r"(bytes), "r"(rbar)
                : "memory");
+}
+// K-major SWIZZLE_64B tile: rows of 64 bytes (32 halfs), 16-byte chunk c of row r at c ^ ((r >> 1) & 3), 8-row groups 512 B apart
+__device__ __forceinline__ unsigned long long make_desc64(unsigned saddr) {
+  unsigned long long d = 0;
+  d |= (unsigned long long)((saddr & 0x3FFFF) >> 4);
+  d |= (unsigned long long)(512 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;
+  return d;
+}
+__device__ __forceinline__ void sts_v4(unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 // wait on a barrier whose bytes arrive from other CTAs of the cluster
 __device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
@@ -137,15 +154,20 @@ __device__ __forceinline__ unsigned pow2_cols(unsigned need) {
 }
 __device__ __forceinline__ float ldg_f32(const float* p) { return __ldg(p); }
 
+__device__ __forceinline__ void dbg_stamp(long long* dbg, int slot) {
+  if (dbg) dbg[slot] = clock64();
+}
+
 // ================================================================================================ forward
-// smem (dynamic, 1024-aligned): [A hi: nkc x 16 KB | A lo: nkc x 16 KB] (shared-memory form only) | B buffers 2 x nkc x 4 KB
-// (chunk kc of a buffer: [32 rows = 16 lines hi, 16 lines lo][128 B = 64 k], SWIZZLE_128B)
+// smem (dynamic, 1024-aligned): [A hi: nkc x 16 KB | A lo: nkc x 16 KB] (shared-memory form only; SWIZZLE_128B chunks of 64 k) |
+// B buffers 2 x CS x 2 KB (chunk cc of a buffer = the units of CTA cc: [32 rows = 16 lines hi, 16 lines lo][64 B = 32 k],
+// SWIZZLE_64B) | staging 2 x 2 KB (this CTA's own chunk of the step, same layout)
 // TMEM: D 32 columns | (TMEM form) A hi KQ/2 columns | A lo KQ/2 columns
 template <bool A_TMEM>
 __global__ void __launch_bounds__(kXThreads, 1)
 lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, Lines ln, TcxArgs p) {
   extern __shared__ __align__(1024) unsigned char xs[];
-  __shared__ __align__(8) unsigned long long bars[2 * kXMaxKc + 2];   // hbar[2][kXMaxKc] (h chunks), accbar, abar (weights)
+  __shared__ __align__(8) unsigned long long bars[2 * kXMaxCS + 3];   // hbar[2][kXMaxCS] (h chunks by source CTA), accbar, abar (weights), stagebar
   __shared__ unsigned tmem_base_s;
   __shared__ int lineT[kXL], lineOff[kXL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -157,21 +179,21 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const unsigned smem0 = (smem_u32(xs) + 1023u) & ~1023u;
   const unsigned a_bytes = A_TMEM ? 0u : (unsigned)nkc * 16384u;
   const unsigned a_hi0 = smem0, a_lo0 = smem0 + a_bytes;       // A: chunk kc at +kc*16384 ([128 rows][128 B])
-  const unsigned b0 = a_lo0 + a_bytes;                         // B buffer b at b0 + b*bbytes, chunk kc at +kc*4096
-  const unsigned bbytes = (unsigned)nkc * 4096u;
+  const unsigned b0 = a_lo0 + a_bytes;                         // B buffer b at b0 + b*bbytes, chunk of CTA cc at +cc*2048
+  const unsigned bbytes = CS * 2048u;
+  const unsigned stg0 = b0 + 2u * bbytes;                      // staging block s&1 at stg0 + (s&1)*2048
   const unsigned bar0 = smem_u32(&bars[0]);
-  const unsigned accbar = bar0 + 8u * (2 * kXMaxKc), abar = accbar + 8u;
+  const unsigned accbar = bar0 + 8u * (2 * kXMaxCS), abar = accbar + 8u, stagebar = accbar + 16u;
   const unsigned tcols = pow2_cols(32u + (A_TMEM ? (unsigned)p.KQ : 0u));
   const unsigned acol_hi = 32u, acol_lo = 32u + (unsigned)p.KQ / 2u;
+  long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
 
   if (tid == 0) {
-    for (int i = 0; i < 2 * kXMaxKc + 2; i++) mbar_init(bar0 + 8u * i, 1);
+    for (int i = 0; i < 2 * kXMaxCS + 2; i++) mbar_init(bar0 + 8u * i, 1);
+    mbar_init(stagebar, kXEW);
     mbar_init_fence();
     if (!A_TMEM) { tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); }
   }
-  // the B buffers must never hold NaN patterns (k slots beyond KQ inside the last chunk are never written)
-  for (unsigned i = tid; i < 2 * bbytes / 16; i += blockDim.x)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(b0 + 16 * i), "r"(0u) : "memory");
   __syncthreads();
   if (warp == kXEW) {
     tmem_alloc(smem_u32(&tmem_base_s), tcols);
@@ -184,7 +206,6 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   }
   tc_fence_before();
-  fence_proxy_async_smem();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_d = tmem_base_s;
@@ -203,10 +224,10 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     tc_fence_before();
   }
   if (A_TMEM) { __syncthreads(); tc_fence_after(); }
-  cluster_sync_all();                                           // barriers of every CTA initialised before any remote store
+  cluster_sync_all();                                           // barriers of every CTA initialised before any remote copy
 
   const int my_first_group = cluster_id - dq * cl_per_dir;
-  unsigned hph = 0, accph = 0;                                  // hph bit b: phase of the chunk barriers of buffer b
+  unsigned hph = 0, accph = 0, stph = 0;                        // hph bit b: phase of the chunk barriers of buffer b
 
   for (int group = my_first_group; group < p.ngroups; group += cl_per_dir) {
     const int l0 = group * kXL;
@@ -219,46 +240,58 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const int Tg = lineT[0];
 
     if (warp == kXEW) {
-      // ------------------------------------------------------------------------------------------ MMA issuer
+      // ------------------------------------------------------------------------------------------ copy + MMA issuer
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
       if (!A_TMEM) mbar_wait(abar, 0);
-      const int own_kc = (int)c >> 1;                           // start with the chunk this CTA feeds: once it is complete, every
-      for (int s = 1; s < Tg; s++) {                            // epilogue warp of this CTA has read the accumulator of step s-1
-        const unsigned b = (unsigned)(s - 1) & 1u;              // h_{s-1} sits in buffer (s-1)&1
-        const unsigned hb0 = bar0 + 8u * (b * kXMaxKc);
-        if (elect_one())
-          for (int kc = 0; kc < nkc; kc++) mbar_expect_tx(hb0 + 8u * kc, (unsigned)min(2, (int)CS - 2 * kc) * 2048u);
-        __syncwarp();
-        const unsigned ph = (hph >> b) & 1u;
-        for (int i = 0; i < nkc; i++) {
-          int kc = own_kc + i;
-          if (kc >= nkc) kc -= nkc;
-          mbar_wait_cluster(hb0 + 8u * kc, ph);
-          fence_proxy_async_smem();                             // remote generic-proxy stores -> tensor-core reads
-          tc_fence_after();
-          if (elect_one()) {
-            const unsigned long long bh = desc_of(b0 + b * bbytes + kc * 4096);
+      // lane X < CS sends this CTA's chunk to CTA X
+      const unsigned peer = (unsigned)lane < CS ? (unsigned)lane : 0u;
+      const unsigned rdst0 = mapa_u32(b0 + c * 2048u, peer), rbar0 = mapa_u32(bar0 + 8u * c, peer);
+      for (int s = 0; s < Tg; s++) {
+        const bool rec = dbg && s == kXDbgStep;
+        if (s >= 1) {
+          const unsigned b = (unsigned)(s - 1) & 1u;            // h_{s-1} sits in buffer (s-1)&1
+          const unsigned hb0 = bar0 + 8u * (b * kXMaxCS);
+          if ((unsigned)lane < CS) mbar_expect_tx(hb0 + 8u * lane, 2048u);
+          __syncwarp();
+          const unsigned ph = (hph >> b) & 1u;
+          for (unsigned i = 0; i < CS; i++) {                   // own chunk first: once it is here, every epilogue warp of this
+            unsigned cc = c + i;                                // CTA has read the accumulator of step s-1
+            if (cc >= CS) cc -= CS;
+            mbar_wait_cluster(hb0 + 8u * cc, ph);
+            if (rec && i == 0) dbg_stamp(dbg, 8);
+            tc_fence_after();
+            if (elect_one()) {
+              const unsigned long long bh = make_desc64(b0 + b * bbytes + cc * 2048u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-              const int kk = 4 * kc + ks;
-              if (kk < p.nks) {
+              for (int ks = 0; ks < 2; ks++) {
+                const unsigned kk = 2u * cc + ks;
                 const unsigned acc = (i > 0 || ks > 0) ? 1u : 0u;
                 if (A_TMEM) {
                   mma_f16_ts(tmem_d, tmem_d + acol_hi + 8u * kk, bh + 2 * ks, idesc32, acc);      // R_hi [h_hi ; h_lo]
                   mma_f16_ts(tmem_d, tmem_d + acol_lo + 8u * kk, bh + 2 * ks, idesc16, 1u);       // + R_lo h_hi
                 } else {
-                  mma_f16(tmem_d, desc_of(a_hi0 + kc * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);
-                  mma_f16(tmem_d, desc_of(a_lo0 + kc * 16384) + 2 * ks, bh + 2 * ks, idesc16, 1u);
+                  mma_f16(tmem_d, desc_of(a_hi0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc32, acc);
+                  mma_f16(tmem_d, desc_of(a_lo0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc16, 1u);
                 }
               }
+              if (i == CS - 1) mma_commit(accbar);
             }
-            if (i == nkc - 1) mma_commit(accbar);
+            __syncwarp();
           }
-          __syncwarp();
+          if (rec) dbg_stamp(dbg, 9);
+          hph ^= 1u << b;
         }
-        hph ^= 1u << b;
+        if (s + 1 < Tg) {                                       // h_s is staged: one bulk copy per destination CTA
+          mbar_wait(stagebar, stph);
+          stph ^= 1;
+          if (rec) dbg_stamp(dbg, 10);
+          const unsigned sb = (unsigned)s & 1u;
+          if ((unsigned)lane < CS) bulk_copy_to_peer(rdst0 + sb * bbytes, stg0 + sb * 2048u, 2048u, rbar0 + sb * (8u * kXMaxCS));
+          __syncwarp();
+          if (rec) dbg_stamp(dbg, 11);
+        }
       }
     } else {
       // ------------------------------------------------------------------------------------------ epilogue warps
@@ -289,21 +322,16 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       long long co = (long long)lineOff[4 * lg + g] + (d ? myT - 1 : 0);
       const int cstep = d ? -1 : 1;
       float cst = 0.f;
-      // exchange: lane = r + 8 dg: 16-byte chunk r = (line ll = r & 3, plane = r >> 2) goes to CTAs dg, dg+4, dg+8, dg+12
+      // staging: lanes 0..7 hold the warp's eight 16-byte chunks: (line ll = lane & 3, plane = lane >> 2), 8 units of quadrant q
       const int ll = lane & 3, plane = (lane >> 2) & 1;
       const unsigned xrow = (unsigned)(4 * lg + ll + 16 * plane);
-      const unsigned xoff = (unsigned)((int)c >> 1) * 4096u + xrow * 128u + ((((unsigned)(4 * ((int)c & 1) + q)) ^ (xrow & 7u)) << 4);
-      unsigned rdst[4], rbar[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const unsigned dst = (unsigned)(lane >> 3) + 4u * i;
-        rdst[i] = mapa_u32(b0 + xoff, dst < CS ? dst : 0u);
-        rbar[i] = mapa_u32(bar0 + 8u * (unsigned)((int)c >> 1), dst < CS ? dst : 0u);
-      }
+      const unsigned xoff = xrow * 64u + ((((unsigned)q) ^ ((xrow >> 1) & 3u)) << 4);
+      const bool rec0 = dbg && warp == 0 && lane == 0;
       float xp[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) xp[i] = (real && 0 < Tl[i]) ? ldg_f32(XPd + eo[i]) : 0.f;
       for (int s = 0; s < Tg; s++) {
+        const bool rec = rec0 && s == kXDbgStep;
         float xpn[4];                                           // next step's input projection: in flight during this step
 #pragma unroll
         for (int i = 0; i < 4; i++) xpn[i] = (real && s + 1 < Tl[i]) ? ldg_f32(XPd + eo[i] + estep) : 0.f;
@@ -311,11 +339,13 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (s > 0) {
           mbar_wait(accbar, accph);
           accph ^= 1;
+          if (rec) dbg_stamp(dbg, 0);
           tc_fence_after();
           unsigned ra[4], rb[4];
           tmem_ld4_nowait(taddr, ra);
           tmem_ld4_nowait(taddr + 16u, rb);
           tmem_wait_ld();
+          if (rec) dbg_stamp(dbg, 1);
 #pragma unroll
           for (int i = 0; i < 4; i++) act[i] = fmaf(__uint_as_float(ra[i]) + __uint_as_float(rb[i]), inv_scale, xp[i]);
         } else {
@@ -347,11 +377,13 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             const unsigned x1 = plane ? (v[2 * e + 1] >> 16) : (v[2 * e + 1] & 0xffffu);
             w4[e] = x0 | (x1 << 16);
           }
+          if (rec) dbg_stamp(dbg, 2);
           tc_fence_before();                                    // (the accumulator has been read: tcgen05.wait::ld above)
-          const unsigned boff = ((unsigned)s & 1u) * bbytes, hoff = ((unsigned)s & 1u) * (8u * kXMaxKc);
-#pragma unroll
-          for (int i = 0; i < 4; i++)
-            if ((unsigned)(lane >> 3) + 4u * i < CS) st_async_v4(rdst[i] + boff, rbar[i] + hoff, w4[0], w4[1], w4[2], w4[3]);
+          if (lane < 8) sts_v4(stg0 + ((unsigned)s & 1u) * 2048u + xoff, w4[0], w4[1], w4[2], w4[3]);
+          fence_proxy_async_smem();                             // generic-proxy stores -> the bulk copy's reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stagebar);
+          if (rec) dbg_stamp(dbg, 3);
         }
         // ---- stash for the backward pass and the dense products
 #pragma unroll
@@ -366,6 +398,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 4; i++) { eo[i] += estep; xp[i] = xpn[i]; }
         co += cstep;
+        if (rec) dbg_stamp(dbg, 4);
       }
     }
     __syncthreads();
@@ -381,14 +414,15 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 
 
 // ================================================================================================ backward
-// smem: A (Rt slice) chunks (mt, kc) of [128 output rows][64 gate rows] hi (shared-memory form only), then lo | B = delta tile
-// [2 kc][32 rows][128 B] | reduce buffers [2][CS src][32 slots][16 lines] fp32
-// TMEM: D nmt x 32 columns | (TMEM form) A hi nmt x 64 columns
-template <bool AHI_TMEM>
+// smem: A (Rt slice) chunks (mt, kc) of [128 output rows][64 gate rows], SWIZZLE_128B: hi plane then lo plane (shared-memory
+// form), or only the lo tiles nlt .. nmt-1 (TMEM form) | B = delta tile [2 kc][32 rows][128 B] | reduce buffers
+// [2][CS src][32 slots][16 lines] fp32 | staging [2][CS owners][32 slots][16 lines] fp32 (16-byte chunks XOR-swizzled by slot)
+// TMEM: D nmt x 32 columns | (TMEM form) A hi nmt x 64 columns | A lo nlt x 64 columns
+template <bool A_TMEM>
 __global__ void __launch_bounds__(kXThreads, 1)
 lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, Lines ln, TcxArgs p) {
   extern __shared__ __align__(1024) unsigned char xs[];
-  __shared__ __align__(8) unsigned long long bars[5];          // pbar[2] (partial sums), accbar, abar (weights), bbar (delta tile)
+  __shared__ __align__(8) unsigned long long bars[6];          // pbar[2] (partial sums), accbar, abar (weights), bbar (delta tile), stagebar
   __shared__ unsigned tmem_base_s;
   __shared__ int lineT[kXL], lineOff[kXL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -397,34 +431,37 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int cl_per_dir = nclusters / p.ndir;
   const int dq = cluster_id / cl_per_dir, d = p.d0 + dq;
   const int nmt = p.nmt;                                       // 128-row tiles of output slots (the last one may reach beyond KQ)
+  const int nlt = A_TMEM ? p.nlt : 0;                          // lo tiles in tensor memory
   const unsigned smem0 = (smem_u32(xs) + 1023u) & ~1023u;
-  const unsigned aplane = (unsigned)nmt * 2u * 16384u;         // chunk (mt, kc) at +(mt*2+kc)*16384
-  const unsigned a_hi0 = smem0, a_lo0 = smem0 + (AHI_TMEM ? 0u : aplane);
-  const unsigned b0 = a_lo0 + aplane;                          // delta tile: chunk kc at +kc*4096
+  const unsigned a_hi0 = smem0;                                // chunk (mt, kc) at +(mt*2+kc)*16384 (shared-memory form)
+  const unsigned a_lo0 = smem0 + (A_TMEM ? 0u : (unsigned)nmt * 32768u);   // lo tile mt at +((mt - nlt)*2 + kc)*16384
+  const unsigned b0 = a_lo0 + (unsigned)(nmt - nlt) * 32768u;  // delta tile: chunk kc at +kc*4096
   const unsigned r0 = b0 + 8192u;                              // reduce buffers
-  const unsigned rbytes = CS * 32u * kXL * 4u;
+  const unsigned rbytes = CS * 2048u;
+  const unsigned stg0 = r0 + 2u * rbytes;                      // staging
   const unsigned bar0 = smem_u32(&bars[0]);
-  const unsigned pbar0 = bar0, pbar1 = bar0 + 8, accbar = bar0 + 16, abar = bar0 + 24, bbar = bar0 + 32;
-  const unsigned tcols = pow2_cols((unsigned)nmt * (AHI_TMEM ? 96u : 32u));
-  const unsigned acol_hi = 32u * (unsigned)nmt;
+  const unsigned pbar0 = bar0, pbar1 = bar0 + 8, accbar = bar0 + 16, abar = bar0 + 24, bbar = bar0 + 32, stagebar = bar0 + 40;
+  const unsigned tcols = pow2_cols((unsigned)nmt * (A_TMEM ? 96u : 32u) + (unsigned)nlt * 64u);
+  const unsigned acol_hi = 32u * (unsigned)nmt, acol_lo = 96u * (unsigned)nmt;
+  long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg + 32 : nullptr;
 
   if (tid == 0) {
-    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, 32 * kXEW);
+    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, 32 * kXEW); mbar_init(stagebar, kXEW);
     mbar_init_fence();
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
   }
-  for (unsigned i = tid; i < 8192 / 16; i += blockDim.x)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(b0 + 16 * i), "r"(0u) : "memory");
+  for (unsigned i = tid; i < 8192 / 16; i += blockDim.x) sts_v4(b0 + 16 * i, 0u, 0u, 0u, 0u);
   __syncthreads();
+  const unsigned a_loads = (unsigned)(A_TMEM ? (nmt - nlt) : 2 * nmt) * 2u;   // 16 KB TMA boxes
   if (warp == kXEW) {
     tmem_alloc(smem_u32(&tmem_base_s), tcols);
-    if (elect_one()) {       // Rt slice of this CTA: rows = output slots k', columns = this CTA's 128 gate rows
-      mbar_expect_tx(abar, (unsigned)nmt * 2u * (AHI_TMEM ? 1u : 2u) * 16384u);
+    if (a_loads && elect_one()) {       // Rt slice of this CTA: rows = output slots k', columns = this CTA's 128 gate rows
+      mbar_expect_tx(abar, a_loads * 16384u);
       for (int mt = 0; mt < nmt; mt++)
         for (int kc = 0; kc < 2; kc++) {
           const int rw = (d * (int)CS + (int)c) * p.KQ + mt * 128;
-          if (!AHI_TMEM) tma_load_2d(a_hi0 + (mt * 2 + kc) * 16384, &tmA_hi, kc * 64, rw, abar);
-          tma_load_2d(a_lo0 + (mt * 2 + kc) * 16384, &tmA_lo, kc * 64, rw, abar);
+          if (!A_TMEM) tma_load_2d(a_hi0 + (mt * 2 + kc) * 16384, &tmA_hi, kc * 64, rw, abar);
+          if (mt >= nlt) tma_load_2d(a_lo0 + ((mt - nlt) * 2 + kc) * 16384, &tmA_lo, kc * 64, rw, abar);
         }
     }
   }
@@ -433,7 +470,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_d = tmem_base_s;
-  if (AHI_TMEM && warp < kXEW) {        // hi plane -> tensor memory: lane = output slot of the tile, column = gate-row pair
+  if (A_TMEM && warp < kXEW) {          // weight planes -> tensor memory: lane = output slot of the tile, column = gate-row pair
     const int rowl = 32 * (warp & 3) + lane, lg = warp >> 2;
     const unsigned trow = tmem_d + ((unsigned)(32 * (warp & 3)) << 16);
     for (int mt = 0; mt < nmt; mt++) {
@@ -442,19 +479,23 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
 #pragma unroll
       for (int e = 0; e < 4; e++) {       // this warp's quarter of the 128 gate rows: 32 halfs = 4 x 16 bytes
         const int k = 32 * lg + 8 * e;
-        uint4 vh = make_uint4(0u, 0u, 0u, 0u);
-        if (slot < p.KQ) vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
+        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
+        if (slot < p.KQ) {
+          vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
+          if (mt < nlt) vl = *reinterpret_cast<const uint4*>(p.w_lo + base + k);
+        }
         tmem_st4(trow + acol_hi + 64u * (unsigned)mt + (unsigned)k / 2u, vh);
+        if (mt < nlt) tmem_st4(trow + acol_lo + 64u * (unsigned)mt + (unsigned)k / 2u, vl);
       }
     }
     tmem_wait_st();
     tc_fence_before();
   }
-  if (AHI_TMEM) { __syncthreads(); tc_fence_after(); }
+  if (A_TMEM) { __syncthreads(); tc_fence_after(); }
   cluster_sync_all();
   const int my_first_group = cluster_id - dq * cl_per_dir;
-  unsigned pph0 = 0, pph1 = 0, accph = 0, bph = 0;
-  const unsigned pbytes = CS * 32u * kXL * 4u;                  // bytes a CTA receives per step (= one reduce buffer)
+  unsigned pph0 = 0, pph1 = 0, accph = 0, bph = 0, stph = 0;
+  const unsigned pbytes = CS * 2048u;                           // bytes a CTA receives per step (= one reduce buffer)
 
   for (int group = my_first_group; group < p.ngroups; group += cl_per_dir) {
     const int l0 = group * kXL;
@@ -467,31 +508,45 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     const int Tg = lineT[0];
 
     if (warp == kXEW) {
-      // ------------------------------------------------------------------------------------------ MMA issuer
+      // ------------------------------------------------------------------------------------------ MMA + copy issuer
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      mbar_wait(abar, 0);
-      for (int fs = Tg - 1; fs >= 1; fs--) {
+      if (a_loads) mbar_wait(abar, 0);
+      // lane X < CS sends the partial sums of X's 32 output slots to CTA X (slot c of X's reduce buffer)
+      const unsigned peer = (unsigned)lane < CS ? (unsigned)lane : 0u;
+      const unsigned rdst0 = mapa_u32(r0 + c * 2048u, peer), rbar0 = mapa_u32(pbar0, peer);
+      for (int it = 0; it + 1 < Tg; it++) {
+        const bool rec = dbg && it == kXDbgStep;
         mbar_wait(bbar, bph);                                   // the deltas of this step are in shared memory
         bph ^= 1;
+        if (rec) dbg_stamp(dbg, 8);
         tc_fence_after();
         if (elect_one()) {
           for (int mt = 0; mt < nmt; mt++)
             for (int kc = 0; kc < 2; kc++) {
-              const unsigned long long al = desc_of(a_lo0 + (mt * 2 + kc) * 16384);
               const unsigned long long bh = desc_of(b0 + kc * 4096);
 #pragma unroll
               for (int ks = 0; ks < 4; ks++) {
                 const unsigned acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                if (AHI_TMEM) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_hi + 64u * mt + 8u * (4 * kc + ks), bh + 2 * ks, idesc32, acc);
-                else mma_f16(tmem_d + 32 * mt, desc_of(a_hi0 + (mt * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);   // Rt_hi [d_hi ; d_lo]
-                mma_f16(tmem_d + 32 * mt, al + 2 * ks, bh + 2 * ks, idesc16, 1u);                                              // + Rt_lo d_hi
+                const unsigned kcol = 64u * mt + 8u * (4 * kc + ks);
+                if (A_TMEM) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_hi + kcol, bh + 2 * ks, idesc32, acc);                 // Rt_hi [d_hi ; d_lo]
+                else mma_f16(tmem_d + 32 * mt, desc_of(a_hi0 + (mt * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);
+                if (mt < nlt) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_lo + kcol, bh + 2 * ks, idesc16, 1u);                 // + Rt_lo d_hi
+                else mma_f16(tmem_d + 32 * mt, desc_of(a_lo0 + ((mt - nlt) * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc16, 1u);
               }
             }
           mma_commit(accbar);
         }
         __syncwarp();
+        if (rec) dbg_stamp(dbg, 9);
+        mbar_wait(stagebar, stph);                              // the partial sums are staged: one bulk copy per owner CTA
+        stph ^= 1;
+        if (rec) dbg_stamp(dbg, 10);
+        const unsigned sb = (unsigned)it & 1u;
+        if ((unsigned)lane < CS) bulk_copy_to_peer(rdst0 + sb * rbytes, stg0 + sb * rbytes + (unsigned)lane * 2048u, 2048u, rbar0 + sb * 8u);
+        __syncwarp();
+        if (rec) dbg_stamp(dbg, 11);
       }
     } else {
       // ------------------------------------------------------------------------------------------ epilogue warps
@@ -525,6 +580,10 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       // where this thread's deltas (gate row r' = row) go in the delta tile
       const unsigned boff = (unsigned)(row >> 6) * 4096u + 2u * (unsigned)(row & 7);
       const unsigned bchunk = (unsigned)((row & 63) >> 3);
+      // reduce buffer: element (source sc, slot j, line 4lg+g); staging: (owner, slot lane, lines 4lg..4lg+3); chunks swizzled by slot
+      const unsigned red_off = (unsigned)j * 64u + ((((unsigned)lg) ^ (((unsigned)j >> 1) & 3u)) << 4) + (unsigned)g * 4u;
+      const unsigned stg_off = (unsigned)lane * 64u + ((((unsigned)lg) ^ (((unsigned)lane >> 1) & 3u)) << 4);
+      const bool rec0 = dbg && warp == 0 && lane == 0;
       // operands of the first step
       float gact[4], cc = 0.f, cp = 0.f, dh = 0.f;
 #pragma unroll
@@ -536,6 +595,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       }
       for (int it = 0; it < Tg; it++) {
         const int fs = Tg - 1 - it;
+        const bool rec = rec0 && it == kXDbgStep;
         // ---- next step's operands: in flight during this step (they do not depend on the exchange)
         float gactn[4], ccn = 0.f, cpn = 0.f, dhn = 0.f;
 #pragma unroll
@@ -553,12 +613,13 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if (tid == 0) mbar_expect_tx(pb, pbytes);
           mbar_wait_cluster(pb, b ? pph1 : pph0);
           if (b) pph1 ^= 1; else pph0 ^= 1;
+          if (rec) dbg_stamp(dbg, 0);
           if (real && fs < myT - 1) {
             float r = 0.f;
-            const unsigned ra = r0 + b * rbytes + ((unsigned)j * kXL + (unsigned)(4 * lg + g)) * 4u;
+            const unsigned ra = r0 + b * rbytes + red_off;
             for (unsigned sc = 0; sc < CS; sc++) {
               float x;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(ra + sc * (32u * kXL * 4u)) : "memory");
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(ra + sc * 2048u) : "memory");
               r += x;
             }
             dh += r;
@@ -596,9 +657,11 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         fence_proxy_async_smem();
         mbar_arrive(bbar);
-        // ---- partial products of this CTA's gate rows for ALL output slots: send each slot's lines to its owner
+        if (rec) dbg_stamp(dbg, 1);
+        // ---- partial products of this CTA's gate rows for ALL output slots: stage each owner's slots x lines block
         mbar_wait(accbar, accph);
         accph ^= 1;
+        if (rec) dbg_stamp(dbg, 2);
         tc_fence_after();
         for (int mt = 0; mt < nmt; mt++) {
           unsigned ra[4], rb[4];
@@ -606,17 +669,18 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           tmem_ld4_nowait(taddr + 32u * mt + 16u, rb);
           tmem_wait_ld();
           const unsigned owner = (unsigned)(4 * mt + q);        // slots 128 mt + 32 q .. +31 belong to this CTA of the cluster
-          if (owner < CS) {
-            const unsigned dst = r0 + ((unsigned)it & 1u) * rbytes + ((c * 32u + (unsigned)lane) * kXL + 4u * (unsigned)lg) * 4u;
-            const unsigned pb = (it & 1) ? pbar1 : pbar0;
-            st_async_v4(mapa_u32(dst, owner), mapa_u32(pb, owner),
-                        __float_as_uint((__uint_as_float(ra[0]) + __uint_as_float(rb[0])) * inv_scale),
-                        __float_as_uint((__uint_as_float(ra[1]) + __uint_as_float(rb[1])) * inv_scale),
-                        __float_as_uint((__uint_as_float(ra[2]) + __uint_as_float(rb[2])) * inv_scale),
-                        __float_as_uint((__uint_as_float(ra[3]) + __uint_as_float(rb[3])) * inv_scale));
-          }
+          if (owner < CS)
+            sts_v4(stg0 + ((unsigned)it & 1u) * rbytes + owner * 2048u + stg_off,
+                   __float_as_uint((__uint_as_float(ra[0]) + __uint_as_float(rb[0])) * inv_scale),
+                   __float_as_uint((__uint_as_float(ra[1]) + __uint_as_float(rb[1])) * inv_scale),
+                   __float_as_uint((__uint_as_float(ra[2]) + __uint_as_float(rb[2])) * inv_scale),
+                   __float_as_uint((__uint_as_float(ra[3]) + __uint_as_float(rb[3])) * inv_scale));
         }
         tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stagebar);
+        if (rec) dbg_stamp(dbg, 3);
 #pragma unroll
         for (int i = 0; i < 4; i++) { eo[i] += estep; gact[i] = gactn[i]; }
         co += cstep;
@@ -685,6 +749,9 @@ struct LstmTcxPlan {
   bool stale[2] = {true, true};
   CUtensorMap tmA_hi, tmA_lo, tmT_hi, tmT_lo;
   int max_clusters = 0;
+  int nlt = 0;                                   // backward, TMEM form: lo tiles that fit into tensor memory next to D and the hi plane
+  long long* dbg = nullptr;                      // 64 clock stamps (forward 0..31, backward 32..63) when CLSTM_B200_TC_DBG is set
+  long long dbg_host[64] = {0};
   char err[256] = {0};
 };
 
@@ -694,16 +761,23 @@ bool lstm_tcx_supported(int no) {
 }
 void lstm_tcx_destroy(LstmTcxPlan* p) {
   if (!p) return;
-  cudaFree(p->a_hi); cudaFree(p->a_lo); cudaFree(p->t_hi); cudaFree(p->t_lo);
+  cudaFree(p->a_hi); cudaFree(p->a_lo); cudaFree(p->t_hi); cudaFree(p->t_lo); cudaFree(p->dbg);
   delete p;
 }
 const char* lstm_tcx_error(const LstmTcxPlan* p) { return p ? p->err : "no plan"; }
 void lstm_tcx_mark_stale(LstmTcxPlan* p) { if (p) p->stale[0] = p->stale[1] = true; }
+// timeline of step kXDbgStep of CTA 0 (after a synchronize): [0..15] forward, [32..47] backward; nullptr without CLSTM_B200_TC_DBG
+const long long* lstm_tcx_debug(LstmTcxPlan* p) {
+  if (!p || !p->dbg) return nullptr;
+  cudaMemcpy(p->dbg_host, p->dbg, sizeof p->dbg_host, cudaMemcpyDeviceToHost);
+  return p->dbg_host;
+}
 
 namespace {
-size_t tcx_fwd_smem(const LstmTcxPlan* p) { return (p->tmem ? 0 : (size_t)p->nkc * 2 * 16384) + (size_t)2 * p->nkc * 4096 + 1024; }
+size_t tcx_fwd_smem(const LstmTcxPlan* p) { return (p->tmem ? 0 : (size_t)p->nkc * 2 * 16384) + (size_t)2 * p->CS * 2048 + 2 * 2048 + 1024; }
 size_t tcx_bwd_smem(const LstmTcxPlan* p) {
-  return (size_t)p->nmt * 2 * 16384 * (p->tmem ? 1 : 2) + 8192 + (size_t)2 * p->CS * 32 * kXL * 4 + 1024;
+  const size_t a = p->tmem ? (size_t)(p->nmt - p->nlt) * 32768 : (size_t)p->nmt * 65536;
+  return a + 8192 + (size_t)4 * p->CS * 2048 + 1024;
 }
 int ensure_split_x(LstmTcxPlan* p, cudaStream_t st, const float* const R[2], int d0, int ndir) {
   for (int d = d0; d < d0 + ndir; d++) {
@@ -732,6 +806,7 @@ void tcx_launch_cfg(const LstmTcxPlan* p, cudaLaunchConfig_t& cfg, cudaLaunchAtt
 void tcx_fill(const LstmTcxPlan* p, TcxArgs& x, int B, int d0, int ndir, int hstride, const int* hoff) {
   x.no = p->no; x.no4 = 4 * p->no; x.CS = p->CS; x.KQ = p->KQ; x.nks = p->nks; x.nkc = p->nkc; x.nmt = p->nmt;
   x.ngroups = (B + kXL - 1) / kXL; x.d0 = d0; x.ndir = ndir; x.hstride = hstride; x.hoff[0] = hoff[0]; x.hoff[1] = hoff[1];
+  x.nlt = p->nlt; x.dbg = p->dbg;
 }
 }
 
@@ -742,6 +817,8 @@ LstmTcxPlan* lstm_tcx_create(int no, int num_sms) {
   p->CS = (no + 31) / 32; p->KQ = 32 * p->CS; p->nks = p->KQ / 16; p->nkc = (p->KQ + 63) / 64; p->nmt = (p->KQ + 127) / 128;
   p->tmem = p->KQ > 256;                                   // the slice no longer fits shared memory next to the h buffers
   if (const char* e = getenv("CLSTM_B200_TCX_TMEM")) p->tmem = (atoi(e) != 0) || p->KQ > 256;
+  p->nlt = p->tmem ? std::min(p->nmt, (512 - 96 * p->nmt) / 64) : 0;
+  if (getenv("CLSTM_B200_TC_DBG") && cudaMalloc((void**)&p->dbg, sizeof p->dbg_host) == cudaSuccess) cudaMemset(p->dbg, 0, sizeof p->dbg_host);
   const size_t elems = (size_t)2 * p->CS * 128 * p->KQ;
   bool ok = cudaMalloc((void**)&p->a_hi, elems * 2) == cudaSuccess && cudaMalloc((void**)&p->a_lo, elems * 2) == cudaSuccess &&
             cudaMalloc((void**)&p->t_hi, elems * 2) == cudaSuccess && cudaMalloc((void**)&p->t_lo, elems * 2) == cudaSuccess;
