@@ -92,22 +92,9 @@ __device__ __forceinline__ unsigned long long make_desc64(unsigned saddr) {
 __device__ __forceinline__ void sts_v4(unsigned addr, unsigned a, unsigned b, unsigned c, unsigned d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-// wait on a barrier whose bytes arrive from other CTAs of the cluster
-__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
-  unsigned done = 0;
-  SpinGuard g;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    g.tick();
-  }
-}
+// Barriers whose bytes arrive through bulk copies issued by other CTAs are waited on with the plain CTA-scope try_wait of
+// tc_common.cuh (as for TMA loads): a cluster-scope acquire compiles to TRYWAIT + CCTL.IVALL, an L1 invalidate per wait that
+// cost ~350 cycles per chunk and threw away the prefetched operands.
 // 4x4 transpose inside a quad of lanes: in a[m] = value of THIS lane's gate for line m; out b[k] = gate k of line g
 __device__ __forceinline__ void quad_transpose(const float* a, float* b, int g) {
   const bool hi = (g & 2) != 0, lo = (g & 1) != 0;
@@ -173,8 +160,6 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned CS = cluster_nctarank(), c = cluster_ctarank();
   const int cluster_id = blockIdx.x / (int)CS, nclusters = gridDim.x / (int)CS;
-  const int cl_per_dir = nclusters / p.ndir;                   // clusters are bound to one direction (one weight slice)
-  const int dq = cluster_id / cl_per_dir, d = p.d0 + dq;
   const int nkc = p.nkc;
   const unsigned smem0 = (smem_u32(xs) + 1023u) & ~1023u;
   const unsigned a_bytes = A_TMEM ? 0u : (unsigned)nkc * 16384u;
@@ -195,41 +180,56 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     if (!A_TMEM) { tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); }
   }
   __syncthreads();
-  if (warp == kXEW) {
-    tmem_alloc(smem_u32(&tmem_base_s), tcols);
-    if (!A_TMEM && elect_one()) {       // this CTA's weight slice, once: rows [(d*CS + c)*128, +128) of the padded copy
-      mbar_expect_tx(abar, (unsigned)nkc * 2u * 16384u);
-      for (int kc = 0; kc < nkc; kc++) {
-        tma_load_2d(a_hi0 + kc * 16384, &tmA_hi, kc * 64, (d * (int)CS + (int)c) * 128, abar);
-        tma_load_2d(a_lo0 + kc * 16384, &tmA_lo, kc * 64, (d * (int)CS + (int)c) * 128, abar);
-      }
-    }
-  }
+  if (warp == kXEW) tmem_alloc(smem_u32(&tmem_base_s), tcols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_d = tmem_base_s;
-  if (A_TMEM && warp < kXEW) {          // weight slice -> tensor memory: lane = gate row, column = k pair; warp lg takes a quarter of K
-    const int row = 32 * (warp & 3) + lane, lg = warp >> 2;
-    const size_t base = ((size_t)(d * (int)CS + (int)c) * 128 + row) * p.KQ;
-    const int kq4 = p.KQ / 4;            // = 8 CS halfs
-    const unsigned trow = tmem_d + ((unsigned)(32 * (warp & 3)) << 16);
-    for (int k = lg * kq4; k < (lg + 1) * kq4; k += 8) {
-      const uint4 vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
-      const uint4 vl = *reinterpret_cast<const uint4*>(p.w_lo + base + k);
-      tmem_st4(trow + acol_hi + (unsigned)k / 2u, vh);
-      tmem_st4(trow + acol_lo + (unsigned)k / 2u, vl);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-  }
-  if (A_TMEM) { __syncthreads(); tc_fence_after(); }
   cluster_sync_all();                                           // barriers of every CTA initialised before any remote copy
+  // this CTA's weight slice of direction d: gate rows [(d*CS + c)*128, +128) of the padded copy (called by all threads)
+  unsigned aph = 0;
+  auto load_weights = [&](int d) {
+    if (!A_TMEM) {
+      if (warp == kXEW && elect_one()) {
+        mbar_expect_tx(abar, (unsigned)nkc * 2u * 16384u);
+        for (int kc = 0; kc < nkc; kc++) {
+          tma_load_2d(a_hi0 + kc * 16384, &tmA_hi, kc * 64, (d * (int)CS + (int)c) * 128, abar);
+          tma_load_2d(a_lo0 + kc * 16384, &tmA_lo, kc * 64, (d * (int)CS + (int)c) * 128, abar);
+        }
+      }
+      if (warp == kXEW) { mbar_wait(abar, aph); }
+      aph ^= 1;
+    } else {
+      tc_fence_after();
+      if (warp < kXEW) {                  // -> tensor memory: lane = gate row, column = k pair; warp lg takes a quarter of K
+        const int row = 32 * (warp & 3) + lane, lg = warp >> 2;
+        const size_t base = ((size_t)(d * (int)CS + (int)c) * 128 + row) * p.KQ;
+        const int kq4 = p.KQ / 4;          // = 8 CS halfs
+        const unsigned trow = tmem_d + ((unsigned)(32 * (warp & 3)) << 16);
+        for (int k = lg * kq4; k < (lg + 1) * kq4; k += 8) {
+          const uint4 vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
+          const uint4 vl = *reinterpret_cast<const uint4*>(p.w_lo + base + k);
+          tmem_st4(trow + acol_hi + (unsigned)k / 2u, vh);
+          tmem_st4(trow + acol_lo + (unsigned)k / 2u, vl);
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+  };
 
-  const int my_first_group = cluster_id - dq * cl_per_dir;
   unsigned hph = 0, accph = 0, stph = 0;                        // hph bit b: phase of the chunk barriers of buffer b
-
-  for (int group = my_first_group; group < p.ngroups; group += cl_per_dir) {
+  // work items = (line group, direction), longest first (the groups are cut from the length-sorted line order); round r hands
+  // item r*nclusters + i to cluster i, odd rounds in reverse (snake), so every cluster gets a similar number of steps
+  const int nitems = p.ngroups * p.ndir;
+  int cur_d = -1;
+  for (int r = 0; r * nclusters < nitems; r++) {
+    const int item = r * nclusters + ((r & 1) ? nclusters - 1 - cluster_id : cluster_id);
+    if (item >= nitems) continue;
+    const int group = item / p.ndir, d = p.d0 + item % p.ndir;
+    if (d != cur_d) { load_weights(d); cur_d = d; }
     const int l0 = group * kXL;
     if (tid < kXL) {
       const int li = (l0 + tid < ln.B) ? ln.order[l0 + tid] : -1;
@@ -244,7 +244,6 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      if (!A_TMEM) mbar_wait(abar, 0);
       // lane X < CS sends this CTA's chunk to CTA X
       const unsigned peer = (unsigned)lane < CS ? (unsigned)lane : 0u;
       const unsigned rdst0 = mapa_u32(b0 + c * 2048u, peer), rbar0 = mapa_u32(bar0 + 8u * c, peer);
@@ -259,7 +258,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (unsigned i = 0; i < CS; i++) {                   // own chunk first: once it is here, every epilogue warp of this
             unsigned cc = c + i;                                // CTA has read the accumulator of step s-1
             if (cc >= CS) cc -= CS;
-            mbar_wait_cluster(hb0 + 8u * cc, ph);
+            mbar_wait(hb0 + 8u * cc, ph);
             if (rec && i == 0) dbg_stamp(dbg, 8);
             tc_fence_after();
             if (elect_one()) {
@@ -309,6 +308,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       float* __restrict__ Hd = p.H + p.hoff[d];
       const unsigned taddr = tmem_d + ((unsigned)(32 * q) << 16) + 4u * (unsigned)lg;
       constexpr float inv_scale = 1.0f / (kXScaleH * kXScaleR);
+      const float gsc = (g == 3) ? -2.f * kLog2e : -kLog2e;
       // the four lines of this warp: lengths and the element offset of (current column, this gate row)
       int Tl[4];
       long long eo[4];
@@ -353,7 +353,10 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           for (int i = 0; i < 4; i++) act[i] = xp[i];
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) act[i] = (g == 3) ? tanh_fast(act[i]) : sigmoid_fast(act[i]);   // forward_full1 clstm.cc:614-617
+        for (int i = 0; i < 4; i++) {                            // forward_full1 clstm.cc:614-617: sigmoid for gi, gf, go; tanh(x) = 2 sigmoid(2x) - 1 for ci
+          const float y = rcp_approx(1.0f + ex2_approx(gsc * act[i]));
+          act[i] = (g == 3) ? fmaf(2.f, y, -1.f) : y;
+        }
         float gt[4];
         quad_transpose(act, gt, g);                             // gi, gf, go, ci of line 4lg+g
         const bool on = real && s < myT;
@@ -428,8 +431,6 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned CS = cluster_nctarank(), c = cluster_ctarank();
   const int cluster_id = blockIdx.x / (int)CS, nclusters = gridDim.x / (int)CS;
-  const int cl_per_dir = nclusters / p.ndir;
-  const int dq = cluster_id / cl_per_dir, d = p.d0 + dq;
   const int nmt = p.nmt;                                       // 128-row tiles of output slots (the last one may reach beyond KQ)
   const int nlt = A_TMEM ? p.nlt : 0;                          // lo tiles in tensor memory
   const unsigned smem0 = (smem_u32(xs) + 1023u) & ~1023u;
@@ -453,51 +454,65 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   for (unsigned i = tid; i < 8192 / 16; i += blockDim.x) sts_v4(b0 + 16 * i, 0u, 0u, 0u, 0u);
   __syncthreads();
   const unsigned a_loads = (unsigned)(A_TMEM ? (nmt - nlt) : 2 * nmt) * 2u;   // 16 KB TMA boxes
-  if (warp == kXEW) {
-    tmem_alloc(smem_u32(&tmem_base_s), tcols);
-    if (a_loads && elect_one()) {       // Rt slice of this CTA: rows = output slots k', columns = this CTA's 128 gate rows
-      mbar_expect_tx(abar, a_loads * 16384u);
-      for (int mt = 0; mt < nmt; mt++)
-        for (int kc = 0; kc < 2; kc++) {
-          const int rw = (d * (int)CS + (int)c) * p.KQ + mt * 128;
-          if (!A_TMEM) tma_load_2d(a_hi0 + (mt * 2 + kc) * 16384, &tmA_hi, kc * 64, rw, abar);
-          if (mt >= nlt) tma_load_2d(a_lo0 + ((mt - nlt) * 2 + kc) * 16384, &tmA_lo, kc * 64, rw, abar);
-        }
-    }
-  }
+  if (warp == kXEW) tmem_alloc(smem_u32(&tmem_base_s), tcols);
   tc_fence_before();
   fence_proxy_async_smem();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_d = tmem_base_s;
-  if (A_TMEM && warp < kXEW) {          // weight planes -> tensor memory: lane = output slot of the tile, column = gate-row pair
-    const int rowl = 32 * (warp & 3) + lane, lg = warp >> 2;
-    const unsigned trow = tmem_d + ((unsigned)(32 * (warp & 3)) << 16);
-    for (int mt = 0; mt < nmt; mt++) {
-      const int slot = mt * 128 + rowl;
-      const size_t base = ((size_t)(d * (int)CS + (int)c) * p.KQ + slot) * 128;
-#pragma unroll
-      for (int e = 0; e < 4; e++) {       // this warp's quarter of the 128 gate rows: 32 halfs = 4 x 16 bytes
-        const int k = 32 * lg + 8 * e;
-        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
-        if (slot < p.KQ) {
-          vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
-          if (mt < nlt) vl = *reinterpret_cast<const uint4*>(p.w_lo + base + k);
-        }
-        tmem_st4(trow + acol_hi + 64u * (unsigned)mt + (unsigned)k / 2u, vh);
-        if (mt < nlt) tmem_st4(trow + acol_lo + 64u * (unsigned)mt + (unsigned)k / 2u, vl);
-      }
-    }
-    tmem_wait_st();
-    tc_fence_before();
-  }
-  if (A_TMEM) { __syncthreads(); tc_fence_after(); }
   cluster_sync_all();
-  const int my_first_group = cluster_id - dq * cl_per_dir;
+  // Rt slice of this CTA for direction d: rows = output slots k', columns = this CTA's 128 gate rows (called by all threads)
+  unsigned aph = 0;
+  auto load_weights = [&](int d) {
+    if (a_loads) {
+      if (warp == kXEW && elect_one()) {
+        mbar_expect_tx(abar, a_loads * 16384u);
+        for (int mt = 0; mt < nmt; mt++)
+          for (int kc = 0; kc < 2; kc++) {
+            const int rw = (d * (int)CS + (int)c) * p.KQ + mt * 128;
+            if (!A_TMEM) tma_load_2d(a_hi0 + (mt * 2 + kc) * 16384, &tmA_hi, kc * 64, rw, abar);
+            if (mt >= nlt) tma_load_2d(a_lo0 + ((mt - nlt) * 2 + kc) * 16384, &tmA_lo, kc * 64, rw, abar);
+          }
+      }
+      if (warp == kXEW) mbar_wait(abar, aph);
+      aph ^= 1;
+    }
+    if (A_TMEM) {
+      tc_fence_after();
+      if (warp < kXEW) {                  // -> tensor memory: lane = output slot of the tile, column = gate-row pair
+        const int rowl = 32 * (warp & 3) + lane, lg = warp >> 2;
+        const unsigned trow = tmem_d + ((unsigned)(32 * (warp & 3)) << 16);
+        for (int mt = 0; mt < nmt; mt++) {
+          const int slot = mt * 128 + rowl;
+          const size_t base = ((size_t)(d * (int)CS + (int)c) * p.KQ + slot) * 128;
+#pragma unroll
+          for (int e = 0; e < 4; e++) {   // this warp's quarter of the 128 gate rows: 32 halfs = 4 x 16 bytes
+            const int k = 32 * lg + 8 * e;
+            uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = make_uint4(0u, 0u, 0u, 0u);
+            if (slot < p.KQ) {
+              vh = *reinterpret_cast<const uint4*>(p.w_hi + base + k);
+              if (mt < nlt) vl = *reinterpret_cast<const uint4*>(p.w_lo + base + k);
+            }
+            tmem_st4(trow + acol_hi + 64u * (unsigned)mt + (unsigned)k / 2u, vh);
+            if (mt < nlt) tmem_st4(trow + acol_lo + 64u * (unsigned)mt + (unsigned)k / 2u, vl);
+          }
+        }
+        tmem_wait_st();
+      }
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+  };
   unsigned pph0 = 0, pph1 = 0, accph = 0, bph = 0, stph = 0;
   const unsigned pbytes = CS * 2048u;                           // bytes a CTA receives per step (= one reduce buffer)
-
-  for (int group = my_first_group; group < p.ngroups; group += cl_per_dir) {
+  const int nitems = p.ngroups * p.ndir;                        // work items as in the forward kernel
+  int cur_d = -1;
+  for (int r = 0; r * nclusters < nitems; r++) {
+    const int item = r * nclusters + ((r & 1) ? nclusters - 1 - cluster_id : cluster_id);
+    if (item >= nitems) continue;
+    const int group = item / p.ndir, d = p.d0 + item % p.ndir;
+    if (d != cur_d) { load_weights(d); cur_d = d; }
     const int l0 = group * kXL;
     if (tid < kXL) {
       const int li = (l0 + tid < ln.B) ? ln.order[l0 + tid] : -1;
@@ -512,7 +527,6 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      if (a_loads) mbar_wait(abar, 0);
       // lane X < CS sends the partial sums of X's 32 output slots to CTA X (slot c of X's reduce buffer)
       const unsigned peer = (unsigned)lane < CS ? (unsigned)lane : 0u;
       const unsigned rdst0 = mapa_u32(r0 + c * 2048u, peer), rbar0 = mapa_u32(pbar0, peer);
@@ -611,7 +625,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           const unsigned b = (unsigned)(it - 1) & 1u;
           const unsigned pb = b ? pbar1 : pbar0;
           if (tid == 0) mbar_expect_tx(pb, pbytes);
-          mbar_wait_cluster(pb, b ? pph1 : pph0);
+          mbar_wait(pb, b ? pph1 : pph0);
           if (b) pph1 ^= 1; else pph0 ^= 1;
           if (rec) dbg_stamp(dbg, 0);
           if (real && fs < myT - 1) {
@@ -855,17 +869,17 @@ int lstm_tcx_forward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const Lst
   if (ensure_split_x(p, st, a.R, a.d0, a.ndir) != 0) { snprintf(p->err, sizeof p->err, "weight split launch failed"); return 1; }
   TcxArgs x{};
   tcx_fill(p, x, ln.B, a.d0, a.ndir, a.hstride, a.hoff);
-  const int cl_per_dir = std::min(x.ngroups, p->max_clusters / a.ndir);
-  if (cl_per_dir < 1) return -1;
+  const int ncl = std::min(x.ngroups * a.ndir, p->max_clusters);
+  if (ncl < 1) return -1;
   for (int d = 0; d < 2; d++) { x.XP[d] = a.XP[d]; x.G[d] = a.G[d]; x.C[d] = a.C[d]; x.Hprev[d] = a.Hprev[d]; }
   x.H = a.H; x.w_hi = p->a_hi; x.w_lo = p->a_lo;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
-  tcx_launch_cfg(p, cfg, at, cl_per_dir * a.ndir, tcx_fwd_smem(p), st);
+  tcx_launch_cfg(p, cfg, at, ncl, tcx_fwd_smem(p), st);
   cudaError_t e = p->tmem ? cudaLaunchKernelEx(&cfg, lstm_tcx_fwd<true>, p->tmA_hi, p->tmA_lo, ln, x)
                           : cudaLaunchKernelEx(&cfg, lstm_tcx_fwd<false>, p->tmA_hi, p->tmA_lo, ln, x);
   if (e != cudaSuccess) {
-    snprintf(p->err, sizeof p->err, "lstm_tcx_fwd launch (%d clusters of %d): %s", cl_per_dir * a.ndir, p->CS, cudaGetErrorString(e));
+    snprintf(p->err, sizeof p->err, "lstm_tcx_fwd launch (%d clusters of %d): %s", ncl, p->CS, cudaGetErrorString(e));
     cudaGetLastError();
     return (int)e;
   }
@@ -877,17 +891,17 @@ int lstm_tcx_backward(LstmTcxPlan* p, cudaStream_t st, const Lines& ln, const Ls
   if (ensure_split_x(p, st, a.R, a.d0, a.ndir) != 0) { snprintf(p->err, sizeof p->err, "weight split launch failed"); return 1; }
   TcxArgs x{};
   tcx_fill(p, x, ln.B, a.d0, a.ndir, a.hstride, a.hoff);
-  const int cl_per_dir = std::min(x.ngroups, p->max_clusters / a.ndir);
-  if (cl_per_dir < 1) return -1;
+  const int ncl = std::min(x.ngroups * a.ndir, p->max_clusters);
+  if (ncl < 1) return -1;
   for (int d = 0; d < 2; d++) { x.G[d] = const_cast<float*>(a.G[d]); x.C[d] = const_cast<float*>(a.C[d]); x.DG[d] = a.DG[d]; }
   x.dH = a.dH; x.w_hi = p->t_hi; x.w_lo = p->t_lo;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute at[1];
-  tcx_launch_cfg(p, cfg, at, cl_per_dir * a.ndir, tcx_bwd_smem(p), st);
+  tcx_launch_cfg(p, cfg, at, ncl, tcx_bwd_smem(p), st);
   cudaError_t e = p->tmem ? cudaLaunchKernelEx(&cfg, lstm_tcx_bwd<true>, p->tmT_hi, p->tmT_lo, ln, x)
                           : cudaLaunchKernelEx(&cfg, lstm_tcx_bwd<false>, p->tmT_hi, p->tmT_lo, ln, x);
   if (e != cudaSuccess) {
-    snprintf(p->err, sizeof p->err, "lstm_tcx_bwd launch (%d clusters of %d): %s", cl_per_dir * a.ndir, p->CS, cudaGetErrorString(e));
+    snprintf(p->err, sizeof p->err, "lstm_tcx_bwd launch (%d clusters of %d): %s", ncl, p->CS, cudaGetErrorString(e));
     cudaGetLastError();
     return (int)e;
   }
