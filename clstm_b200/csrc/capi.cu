@@ -637,11 +637,15 @@ bool want_lstm_tc(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int 
   return false;
 }
 
-// The cluster-resident tensor-core recurrence (16 lines per cluster, DSMEM exchange): nhidden 33..480.
+// The cluster-resident tensor-core recurrence (lstm_tcx.cu: 16 lines per cluster, weights in shared / tensor memory, DSMEM
+// exchange): nhidden 33..480.  Measured on B200 (forward + backward): nhidden 200, 128 lines, T 200..2000: 9.1 ms against
+// 15.2 ms for the 4-CTA cluster kernels; 32 lines x 512 steps: 2 ms against 7.4 ms; nhidden 400, 256 lines: 39.5 ms against
+// 44 ms for the lock-step kernels of lstm_tc.cu, 32 lines x 512 steps: 4 ms against 11.7 ms.  At nhidden <= 100 the register
+// kernels (one SM per chain, 0.6-0.8 us per step) stay ahead at every batch size (32 lines x 500 steps: 0.69 ms vs 1.8 ms).
 bool want_lstm_tcx(const clstm_b200_net* n, const clstm_b200_net::Block& bk, int B) {
   if (!bk.tcx || n->cell != 0 || n->lstm_mode == 1 || n->lstm_mode == 2) return false;
   if (n->lstm_mode == 3) return true;
-  return false;
+  return bk.no > 100;
 }
 
 const float* block_input(const clstm_b200_net* n, int k) { return k == 0 ? n->x : n->blk[k - 1].H; }

@@ -68,12 +68,13 @@ def test_cfg2_full_size_values(ffi, oracle):
     assert np.abs(od - gd).max() < TOL * max(1.0, np.abs(od).max())
 
 
-@pytest.mark.parametrize("recurrence", ["auto", "tc"])
+@pytest.mark.parametrize("recurrence", ["auto", "tc", "simt"])
 def test_cfg3_full_size_alignment_indices(ffi, oracle, monkeypatch, recurrence):
-    # "auto": the variant the library picks for 128 lines of nhidden 200 (thread-block cluster kernels);
-    # "tc": the batched tensor-core recurrence forced through CLSTM_B200_LSTM=tc (read when the net is created)
-    if recurrence == "tc":
-        monkeypatch.setenv("CLSTM_B200_LSTM", "tc")
+    # "auto": the variant the library picks for 128 lines of nhidden 200 (the cluster-resident tensor-core recurrence, lstm_tcx.cu);
+    # "tc": the lock-step tensor-core recurrence forced through CLSTM_B200_LSTM=tc (read when the net is created);
+    # "simt": the fp32 thread-block cluster kernels (CLSTM_B200_LSTM=simt)
+    if recurrence != "auto":
+        monkeypatch.setenv("CLSTM_B200_LSTM", recurrence)
     ni, nh, nc, B = 48, 200, 83, 128
     x, Ts, labels, L = synth.make_lines(B, (200, 2000), ni, nc, seed=1000)
     onet = oracle.BidiOracle(ni, nh, nc, seed=0.222)
@@ -81,7 +82,7 @@ def test_cfg3_full_size_alignment_indices(ffi, oracle, monkeypatch, recurrence):
     gnet = ffi.Net(ni, nh, nc)
     gnet.set_params(onet.get_params())
     out = gnet.forward(x, Ts)
-    assert gnet.lstm_variant == ("tc" if recurrence == "tc" else "cluster")
+    assert gnet.lstm_variant == {"auto": "tcx", "tc": "tc", "simt": "cluster"}[recurrence]
     aligned = gnet.ctc_align(labels, L)
     amax = gnet.argmax(1)
     dec = gnet.decode(1)
@@ -135,7 +136,7 @@ def test_prefetch_of_a_larger_batch_keeps_pending_results(ffi):
 
 
 def test_cfg4_width_large_batch_uses_tensor_core_recurrence(ffi, oracle):
-    # BASELINE config 4 width (nhidden 400) with 96 ragged lines: the library picks the batched tcgen05 recurrence by itself;
+    # BASELINE config 4 width (nhidden 400) with 96 ragged lines: the library picks the cluster-resident tcgen05 recurrence by itself;
     # outputs of every line and the alignment indices against the oracle
     ni, nh, nc, B = 48, 400, 83, 96
     x, Ts, labels, L = synth.make_lines(B, (60, 240), ni, nc, seed=21)
@@ -144,7 +145,7 @@ def test_cfg4_width_large_batch_uses_tensor_core_recurrence(ffi, oracle):
     gnet = ffi.Net(ni, nh, nc)
     gnet.set_params(onet.get_params())
     out = gnet.forward(x, Ts)
-    assert gnet.lstm_variant == "tc"
+    assert gnet.lstm_variant == "tcx"
     aligned = gnet.ctc_align(labels, L)
     amax = gnet.argmax(1)
     dec = gnet.decode(1)

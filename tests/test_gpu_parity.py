@@ -254,6 +254,7 @@ def test_cluster_exchange_variants_parity(ffi, oracle, monkeypatch, nh, B, T, mo
     # the cluster kernels exchange through mbarrier + st.async, one line per cluster by default (covered by CASES above) or
     # two lines software pipelined ("pair"); the cluster-barrier variants of both stay selectable for A/B runs and stay
     # tested: odd line counts and very different lengths inside a pair included
+    monkeypatch.setenv("CLSTM_B200_LSTM", "simt")      # (the library itself prefers the tensor-core recurrence at these widths)
     if mode.startswith("pair"):
         monkeypatch.setenv("CLSTM_B200_CLUSTER_PAIR", "1")
     else:
@@ -263,8 +264,8 @@ def test_cluster_exchange_variants_parity(ffi, oracle, monkeypatch, nh, B, T, mo
     ni, nc = 48, 83
     x, Ts, labels, L = synth.make_lines(B, T, ni, nc, seed=77)
     onet, gnet = make_pair(ffi, oracle, ni, nh, nc, "trained")
-    assert gnet.lstm_variant == "cluster"
     out = gnet.forward(x, Ts)
+    assert gnet.lstm_variant == "cluster"
     probe = np.random.default_rng(3).normal(0, 1, out.shape).astype(np.float32)
     gnet.clear_derivs()
     din = gnet.backward(probe)
