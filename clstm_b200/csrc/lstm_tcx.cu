@@ -244,8 +244,10 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      // lane X < CS sends this CTA's chunk to CTA X
-      const unsigned peer = (unsigned)lane < CS ? (unsigned)lane : 0u;
+      // lane i < CS sends this CTA's chunk to CTA (c + i) mod CS: the copies are issued in lane order, so at any time every CTA
+      // of the cluster is the destination of ONE copy (all CTAs sending to CTA 0 first, then to CTA 1, ... serialises on the
+      // destination's port), and the own chunk goes first
+      const unsigned peer = (unsigned)lane < CS ? (c + (unsigned)lane) % CS : 0u;
       const unsigned rdst0 = mapa_u32(b0 + c * 2048u, peer), rbar0 = mapa_u32(bar0 + 8u * c, peer);
       for (int s = 0; s < Tg; s++) {
         const bool rec = dbg && s == kXDbgStep;
@@ -255,9 +257,8 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if ((unsigned)lane < CS) mbar_expect_tx(hb0 + 8u * lane, 2048u);
           __syncwarp();
           const unsigned ph = (hph >> b) & 1u;
-          for (unsigned i = 0; i < CS; i++) {                   // own chunk first: once it is here, every epilogue warp of this
-            unsigned cc = c + i;                                // CTA has read the accumulator of step s-1
-            if (cc >= CS) cc -= CS;
+          for (unsigned i = 0; i < CS; i++) {                   // own chunk first (once it is here, every epilogue warp of this CTA
+            const unsigned cc = (c + CS - i) % CS;              // has read the accumulator of step s-1), then in arrival order
             mbar_wait(hb0 + 8u * cc, ph);
             if (rec && i == 0) dbg_stamp(dbg, 8);
             tc_fence_after();
@@ -527,8 +528,9 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      // lane X < CS sends the partial sums of X's 32 output slots to CTA X (slot c of X's reduce buffer)
-      const unsigned peer = (unsigned)lane < CS ? (unsigned)lane : 0u;
+      // lane i < CS sends the partial sums of the 32 output slots of CTA (c + i) mod CS to that CTA (slot c of its reduce
+      // buffer); staggered like the forward exchange
+      const unsigned peer = (unsigned)lane < CS ? (c + (unsigned)lane) % CS : 0u;
       const unsigned rdst0 = mapa_u32(r0 + c * 2048u, peer), rbar0 = mapa_u32(pbar0, peer);
       for (int it = 0; it + 1 < Tg; it++) {
         const bool rec = dbg && it == kXDbgStep;
@@ -558,7 +560,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         stph ^= 1;
         if (rec) dbg_stamp(dbg, 10);
         const unsigned sb = (unsigned)it & 1u;
-        if ((unsigned)lane < CS) bulk_copy_to_peer(rdst0 + sb * rbytes, stg0 + sb * rbytes + (unsigned)lane * 2048u, 2048u, rbar0 + sb * 8u);
+        if ((unsigned)lane < CS) bulk_copy_to_peer(rdst0 + sb * rbytes, stg0 + sb * rbytes + peer * 2048u, 2048u, rbar0 + sb * 8u);
         __syncwarp();
         if (rec) dbg_stamp(dbg, 11);
       }
@@ -829,7 +831,10 @@ LstmTcxPlan* lstm_tcx_create(int no, int num_sms) {
   auto* p = new LstmTcxPlan;
   p->no = no; p->num_sms = num_sms;
   p->CS = (no + 31) / 32; p->KQ = 32 * p->CS; p->nks = p->KQ / 16; p->nkc = (p->KQ + 63) / 64; p->nmt = (p->KQ + 127) / 128;
-  p->tmem = p->KQ > 256;                                   // the slice no longer fits shared memory next to the h buffers
+  // weights in tensor memory: measured faster at every width (nhidden 200, 128 lines: 4.9 + 4.2 ms against 5.7 + 5.5 ms with
+  // the slice in shared memory, whose 128 x 16 A tile costs 32 cycles of shared-memory bandwidth per MMA); the shared-memory
+  // form stays selectable for A/B runs (CLSTM_B200_TCX_TMEM=0) where it fits
+  p->tmem = true;
   if (const char* e = getenv("CLSTM_B200_TCX_TMEM")) p->tmem = (atoi(e) != 0) || p->KQ > 256;
   p->nlt = p->tmem ? std::min(p->nmt, (512 - 96 * p->nmt) / 64) : 0;
   if (getenv("CLSTM_B200_TC_DBG") && cudaMalloc((void**)&p->dbg, sizeof p->dbg_host) == cudaSuccess) cudaMemset(p->dbg, 0, sizeof p->dbg_host);
