@@ -1335,13 +1335,12 @@ int lstm_tc_selftest(int no, int B, int Tmin, int Tmax, unsigned seed, float wsc
   if (rc == 0 && xplan)
     if (const long long* t = lstm_tcx_debug(xplan)) {
       if (run_fwd && t[0])
-        fprintf(stderr, "selftest_lstm_x fwd no=%d timeline of one step (cycles after the accumulator was ready): tmem read %lld, packed %lld, staged %lld, stash done %lld | "
-                "copy warp: staged seen %lld, copies issued %lld | next step: own chunk in %lld, last MMA issued %lld\n", no, t[1] - t[0], t[2] - t[0],
-                t[3] - t[0], t[4] - t[0], t[10] - t[0], t[11] - t[0], t[8] - t[0], t[9] - t[0]);
+        fprintf(stderr, "selftest_lstm_x fwd no=%d timeline of one step (cycles after the accumulator was ready): tmem read %lld, packed %lld, staged + epilogue barrier %lld, "
+                "copy issued %lld, stash done %lld | next step: own chunk in + MMAs issued %lld, last but one %lld, last MMA issued %lld\n", no, t[1] - t[0], t[2] - t[0],
+                t[3] - t[0], t[10] - t[0], t[4] - t[0], t[8] - t[0], t[12] - t[0], t[9] - t[0]);
       if (run_bwd && t[32])
-        fprintf(stderr, "selftest_lstm_x bwd no=%d timeline of one step (cycles after the partial sums arrived): deltas in smem %lld, accumulator ready %lld, staged %lld | "
-                "mma warp: deltas seen %lld, MMAs issued %lld, staged seen %lld, copies issued %lld\n", no, t[33] - t[32], t[34] - t[32], t[35] - t[32],
-                t[40] - t[32], t[41] - t[32], t[42] - t[32], t[43] - t[32]);
+        fprintf(stderr, "selftest_lstm_x bwd no=%d timeline of one step (cycles after the partial sums arrived): deltas in smem %lld, accumulator ready %lld, staged + epilogue "
+                "barrier %lld, copy issued %lld | mma warp: MMAs issued %lld\n", no, t[33] - t[32], t[34] - t[32], t[35] - t[32], t[42] - t[32], t[41] - t[32]);
     }
   if ((rc == 0 || rc >= 5) && !run_fwd) { out[0] = out[1] = out[2] = out[3] = 0.f; }
   if ((rc == 0 || rc >= 5) && run_fwd) {

@@ -67,6 +67,9 @@ struct TcxArgs {
   const __half *w_hi, *w_lo;
   int nlt;                 // backward, TMEM form: lo-plane tiles that live in tensor memory (the others stay in shared memory)
   long long* dbg;          // optional: timeline of one step of CTA 0 (clock64 stamps)
+  int flags;               // tuning switches (CLSTM_B200_TCX_FLAGS): 1 epilogue waits by one lane per warp, 2 MMA-warp waits by one lane,
+                           // 4 bulk copies issued by the epilogue warps (one each) instead of the MMA warp, 8 MMAs issued chunk by chunk
+                           // as the chunks arrive instead of after the last one, 16 backward: output tiles innermost
 };
 
 __device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned rank) {
@@ -95,6 +98,17 @@ __device__ __forceinline__ void sts_v4(unsigned addr, unsigned a, unsigned b, un
 // Barriers whose bytes arrive through bulk copies issued by other CTAs are waited on with the plain CTA-scope try_wait of
 // tc_common.cuh (as for TMA loads): a cluster-scope acquire compiles to TRYWAIT + CCTL.IVALL, an L1 invalidate per wait that
 // cost ~350 cycles per chunk and threw away the prefetched operands.
+// One lane polls, the warp follows: a warp-wide try_wait is 32 requests to the barrier unit (measured ~350 cycles per wait of
+// the MMA warp, and 512 polling threads per accumulator barrier); __syncwarp orders the other lanes behind the acquire.
+__device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity) {
+  if (elect_one()) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void mbar_wait_sel(unsigned bar, unsigned parity, bool one_lane) {
+  if (one_lane) mbar_wait_warp(bar, parity);
+  else mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void epi_bar_sync() { named_bar_sync(1, 32 * 16); }   // the 16 epilogue warps
 // 4x4 transpose inside a quad of lanes: in a[m] = value of THIS lane's gate for line m; out b[k] = gate k of line g
 __device__ __forceinline__ void quad_transpose(const float* a, float* b, int g) {
   const bool hi = (g & 2) != 0, lo = (g & 1) != 0;
@@ -244,11 +258,9 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      // lane i < CS sends this CTA's chunk to CTA (c + i) mod CS: the copies are issued in lane order, so at any time every CTA
-      // of the cluster is the destination of ONE copy (all CTAs sending to CTA 0 first, then to CTA 1, ... serialises on the
-      // destination's port), and the own chunk goes first
-      const unsigned peer = (unsigned)lane < CS ? (c + (unsigned)lane) % CS : 0u;
-      const unsigned rdst0 = mapa_u32(b0 + c * 2048u, peer), rbar0 = mapa_u32(bar0 + 8u * c, peer);
+      const bool w1 = (p.flags & 2) != 0, per_chunk = (p.flags & 8) != 0, epi_copies = (p.flags & 4) != 0;
+      const unsigned cpeer = (unsigned)lane < CS ? (unsigned)lane : 0u;    // lane X < CS sends this CTA's chunk to CTA X
+      const unsigned crdst0 = mapa_u32(b0 + c * 2048u, cpeer), crbar0 = mapa_u32(bar0 + 8u * c, cpeer);
       for (int s = 0; s < Tg; s++) {
         const bool rec = dbg && s == kXDbgStep;
         if (s >= 1) {
@@ -257,38 +269,66 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if ((unsigned)lane < CS) mbar_expect_tx(hb0 + 8u * lane, 2048u);
           __syncwarp();
           const unsigned ph = (hph >> b) & 1u;
-          for (unsigned i = 0; i < CS; i++) {                   // own chunk first (once it is here, every epilogue warp of this CTA
-            const unsigned cc = (c + CS - i) % CS;              // has read the accumulator of step s-1), then in arrival order
-            mbar_wait(hb0 + 8u * cc, ph);
-            if (rec && i == 0) dbg_stamp(dbg, 8);
+          if (per_chunk) {
+            mbar_wait(hb0 + 8u * c, ph);                        // own chunk: every epilogue warp of this CTA has read the accumulator
+            tc_fence_after();                                   // of step s-1; then the chunks in UNIFORM order (MMA operands that
+            for (int cc = 0; cc < p.CS; cc++) {                 // depend on the CTA rank leave the uniform datapath: ~85 cycles per MMA)
+              mbar_wait(hb0 + 8u * cc, ph);
+              if (elect_one()) {
+                const unsigned long long bh = make_desc64(b0 + b * bbytes + cc * 2048u);
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++) {
+                  const unsigned kk = 2u * cc + ks;
+                  const unsigned acc = (cc > 0 || ks > 0) ? 1u : 0u;
+                  if (A_TMEM) {
+                    mma_f16_ts(tmem_d, tmem_d + acol_hi + 8u * kk, bh + 2 * ks, idesc32, acc);    // R_hi [h_hi ; h_lo]
+                    mma_f16_ts(tmem_d, tmem_d + acol_lo + 8u * kk, bh + 2 * ks, idesc16, 1u);     // + R_lo h_hi
+                  } else {
+                    mma_f16(tmem_d, desc_of(a_hi0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc32, acc);
+                    mma_f16(tmem_d, desc_of(a_lo0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc16, 1u);
+                  }
+                }
+                if (cc == p.CS - 1) mma_commit(accbar);
+              }
+              __syncwarp();
+              if (rec && cc == 0) dbg_stamp(dbg, 8);
+              if (rec && cc == p.CS - 2) dbg_stamp(dbg, 12);
+            }
+          } else {                                              // every chunk first, then all MMAs of the step back to back
+            for (int i = 0; i < p.CS; i++) {
+              mbar_wait_sel(hb0 + 8u * i, ph, w1);
+              if (rec && i == 0) dbg_stamp(dbg, 8);
+            }
+            if (rec) dbg_stamp(dbg, 12);
             tc_fence_after();
             if (elect_one()) {
-              const unsigned long long bh = make_desc64(b0 + b * bbytes + cc * 2048u);
+              for (int cc = 0; cc < p.CS; cc++) {
+                const unsigned long long bh = make_desc64(b0 + b * bbytes + cc * 2048u);
 #pragma unroll
-              for (int ks = 0; ks < 2; ks++) {
-                const unsigned kk = 2u * cc + ks;
-                const unsigned acc = (i > 0 || ks > 0) ? 1u : 0u;
-                if (A_TMEM) {
-                  mma_f16_ts(tmem_d, tmem_d + acol_hi + 8u * kk, bh + 2 * ks, idesc32, acc);      // R_hi [h_hi ; h_lo]
-                  mma_f16_ts(tmem_d, tmem_d + acol_lo + 8u * kk, bh + 2 * ks, idesc16, 1u);       // + R_lo h_hi
-                } else {
-                  mma_f16(tmem_d, desc_of(a_hi0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc32, acc);
-                  mma_f16(tmem_d, desc_of(a_lo0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc16, 1u);
+                for (int ks = 0; ks < 2; ks++) {
+                  const unsigned kk = 2u * cc + ks;
+                  const unsigned acc = (cc > 0 || ks > 0) ? 1u : 0u;
+                  if (A_TMEM) {
+                    mma_f16_ts(tmem_d, tmem_d + acol_hi + 8u * kk, bh + 2 * ks, idesc32, acc);
+                    mma_f16_ts(tmem_d, tmem_d + acol_lo + 8u * kk, bh + 2 * ks, idesc16, 1u);
+                  } else {
+                    mma_f16(tmem_d, desc_of(a_hi0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc32, acc);
+                    mma_f16(tmem_d, desc_of(a_lo0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc16, 1u);
+                  }
                 }
               }
-              if (i == CS - 1) mma_commit(accbar);
+              mma_commit(accbar);
             }
             __syncwarp();
           }
           if (rec) dbg_stamp(dbg, 9);
           hph ^= 1u << b;
         }
-        if (s + 1 < Tg) {                                       // h_s is staged: one bulk copy per destination CTA
-          mbar_wait(stagebar, stph);
+        if (!epi_copies && s + 1 < Tg) {                        // h_s is staged: one bulk copy per destination CTA
+          mbar_wait_sel(stagebar, stph, w1);
           stph ^= 1;
-          if (rec) dbg_stamp(dbg, 10);
           const unsigned sb = (unsigned)s & 1u;
-          if ((unsigned)lane < CS) bulk_copy_to_peer(rdst0 + sb * bbytes, stg0 + sb * 2048u, 2048u, rbar0 + sb * (8u * kXMaxCS));
+          if ((unsigned)lane < CS) bulk_copy_to_peer(crdst0 + sb * bbytes, stg0 + sb * 2048u, 2048u, crbar0 + sb * (8u * kXMaxCS));
           __syncwarp();
           if (rec) dbg_stamp(dbg, 11);
         }
@@ -328,6 +368,8 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned xrow = (unsigned)(4 * lg + ll + 16 * plane);
       const unsigned xoff = xrow * 64u + ((((unsigned)q) ^ ((xrow >> 1) & 3u)) << 4);
       const bool rec0 = dbg && warp == 0 && lane == 0;
+      const unsigned peer = (unsigned)warp < CS ? (unsigned)warp : 0u;
+      const unsigned rdst0 = mapa_u32(b0 + c * 2048u, peer), rbar0 = mapa_u32(bar0 + 8u * c, peer);
       float xp[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) xp[i] = (real && 0 < Tl[i]) ? ldg_f32(XPd + eo[i]) : 0.f;
@@ -338,7 +380,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         for (int i = 0; i < 4; i++) xpn[i] = (real && s + 1 < Tl[i]) ? ldg_f32(XPd + eo[i] + estep) : 0.f;
         float act[4];
         if (s > 0) {
-          mbar_wait(accbar, accph);
+          mbar_wait_sel(accbar, accph, (p.flags & 1) != 0);
           accph ^= 1;
           if (rec) dbg_stamp(dbg, 0);
           tc_fence_after();
@@ -383,11 +425,20 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           }
           if (rec) dbg_stamp(dbg, 2);
           tc_fence_before();                                    // (the accumulator has been read: tcgen05.wait::ld above)
-          if (lane < 8) sts_v4(stg0 + ((unsigned)s & 1u) * 2048u + xoff, w4[0], w4[1], w4[2], w4[3]);
-          fence_proxy_async_smem();                             // generic-proxy stores -> the bulk copy's reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(stagebar);
-          if (rec) dbg_stamp(dbg, 3);
+          const unsigned sb = (unsigned)s & 1u;
+          if (lane < 8) sts_v4(stg0 + sb * 2048u + xoff, w4[0], w4[1], w4[2], w4[3]);
+          fence_proxy_async_smem();                             // generic-proxy stores -> the bulk copies' reads
+          if (p.flags & 4) {
+            epi_bar_sync();                                     // h_s is staged: warp X < CS sends the block to CTA X (one copy each)
+            if (rec) dbg_stamp(dbg, 3);
+            if ((unsigned)warp < CS && elect_one())
+              bulk_copy_to_peer(rdst0 + sb * bbytes, stg0 + sb * 2048u, 2048u, rbar0 + sb * (8u * kXMaxCS));
+            if (rec) dbg_stamp(dbg, 10);
+          } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stagebar);               // the MMA warp sends the block once all 16 warps have staged
+            if (rec) dbg_stamp(dbg, 3);
+          }
         }
         // ---- stash for the backward pass and the dense products
 #pragma unroll
@@ -448,7 +499,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg + 32 : nullptr;
 
   if (tid == 0) {
-    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, 32 * kXEW); mbar_init(stagebar, kXEW);
+    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, (p.flags & 1) ? kXEW : 32 * kXEW); mbar_init(stagebar, kXEW);
     mbar_init_fence();
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
   }
@@ -528,41 +579,57 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      // lane i < CS sends the partial sums of the 32 output slots of CTA (c + i) mod CS to that CTA (slot c of its reduce
-      // buffer); staggered like the forward exchange
-      const unsigned peer = (unsigned)lane < CS ? (c + (unsigned)lane) % CS : 0u;
-      const unsigned rdst0 = mapa_u32(r0 + c * 2048u, peer), rbar0 = mapa_u32(pbar0, peer);
+      const bool w1 = (p.flags & 2) != 0, epi_copies = (p.flags & 4) != 0, tiles_inner = (p.flags & 16) != 0;
+      const unsigned cpeer = (unsigned)lane < CS ? (unsigned)lane : 0u;    // lane X < CS sends owner X's partial sums to CTA X
+      const unsigned crdst0 = mapa_u32(r0 + c * 2048u, cpeer), crbar0 = mapa_u32(pbar0, cpeer);
       for (int it = 0; it + 1 < Tg; it++) {
         const bool rec = dbg && it == kXDbgStep;
-        mbar_wait(bbar, bph);                                   // the deltas of this step are in shared memory
+        mbar_wait_sel(bbar, bph, w1);                           // the deltas of this step are in shared memory
         bph ^= 1;
-        if (rec) dbg_stamp(dbg, 8);
         tc_fence_after();
         if (elect_one()) {
-          for (int mt = 0; mt < nmt; mt++)
+          if (tiles_inner) {                                    // consecutive MMAs go to different accumulators
             for (int kc = 0; kc < 2; kc++) {
               const unsigned long long bh = desc_of(b0 + kc * 4096);
 #pragma unroll
               for (int ks = 0; ks < 4; ks++) {
                 const unsigned acc = (kc > 0 || ks > 0) ? 1u : 0u;
-                const unsigned kcol = 64u * mt + 8u * (4 * kc + ks);
-                if (A_TMEM) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_hi + kcol, bh + 2 * ks, idesc32, acc);                 // Rt_hi [d_hi ; d_lo]
-                else mma_f16(tmem_d + 32 * mt, desc_of(a_hi0 + (mt * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);
-                if (mt < nlt) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_lo + kcol, bh + 2 * ks, idesc16, 1u);                 // + Rt_lo d_hi
-                else mma_f16(tmem_d + 32 * mt, desc_of(a_lo0 + ((mt - nlt) * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc16, 1u);
+                for (int mt = 0; mt < nmt; mt++) {
+                  const unsigned kcol = 64u * mt + 8u * (4 * kc + ks);
+                  if (A_TMEM) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_hi + kcol, bh + 2 * ks, idesc32, acc);
+                  else mma_f16(tmem_d + 32 * mt, desc_of(a_hi0 + (mt * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);
+                  if (mt < nlt) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_lo + kcol, bh + 2 * ks, idesc16, 1u);
+                  else mma_f16(tmem_d + 32 * mt, desc_of(a_lo0 + ((mt - nlt) * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc16, 1u);
+                }
               }
             }
+          } else {
+            for (int mt = 0; mt < nmt; mt++)
+              for (int kc = 0; kc < 2; kc++) {
+                const unsigned long long bh = desc_of(b0 + kc * 4096);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                  const unsigned acc = (kc > 0 || ks > 0) ? 1u : 0u;
+                  const unsigned kcol = 64u * mt + 8u * (4 * kc + ks);
+                  if (A_TMEM) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_hi + kcol, bh + 2 * ks, idesc32, acc);               // Rt_hi [d_hi ; d_lo]
+                  else mma_f16(tmem_d + 32 * mt, desc_of(a_hi0 + (mt * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc32, acc);
+                  if (mt < nlt) mma_f16_ts(tmem_d + 32 * mt, tmem_d + acol_lo + kcol, bh + 2 * ks, idesc16, 1u);               // + Rt_lo d_hi
+                  else mma_f16(tmem_d + 32 * mt, desc_of(a_lo0 + ((mt - nlt) * 2 + kc) * 16384) + 2 * ks, bh + 2 * ks, idesc16, 1u);
+                }
+              }
+          }
           mma_commit(accbar);
         }
         __syncwarp();
         if (rec) dbg_stamp(dbg, 9);
-        mbar_wait(stagebar, stph);                              // the partial sums are staged: one bulk copy per owner CTA
-        stph ^= 1;
-        if (rec) dbg_stamp(dbg, 10);
-        const unsigned sb = (unsigned)it & 1u;
-        if ((unsigned)lane < CS) bulk_copy_to_peer(rdst0 + sb * rbytes, stg0 + sb * rbytes + peer * 2048u, 2048u, rbar0 + sb * 8u);
-        __syncwarp();
-        if (rec) dbg_stamp(dbg, 11);
+        if (!epi_copies) {
+          mbar_wait_sel(stagebar, stph, w1);                    // the partial sums are staged: one bulk copy per owner CTA
+          stph ^= 1;
+          const unsigned sb = (unsigned)it & 1u;
+          if ((unsigned)lane < CS) bulk_copy_to_peer(crdst0 + sb * rbytes, stg0 + sb * rbytes + (unsigned)lane * 2048u, 2048u, crbar0 + sb * 8u);
+          __syncwarp();
+          if (rec) dbg_stamp(dbg, 11);
+        }
       }
     } else {
       // ------------------------------------------------------------------------------------------ epilogue warps
@@ -600,6 +667,8 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned red_off = (unsigned)j * 64u + ((((unsigned)lg) ^ (((unsigned)j >> 1) & 3u)) << 4) + (unsigned)g * 4u;
       const unsigned stg_off = (unsigned)lane * 64u + ((((unsigned)lg) ^ (((unsigned)lane >> 1) & 3u)) << 4);
       const bool rec0 = dbg && warp == 0 && lane == 0;
+      const unsigned peer = (unsigned)warp < CS ? (unsigned)warp : 0u;
+      const unsigned rdst0 = mapa_u32(r0 + c * 2048u, peer), rbar0 = mapa_u32(pbar0, peer);
       // operands of the first step
       float gact[4], cc = 0.f, cp = 0.f, dh = 0.f;
 #pragma unroll
@@ -627,7 +696,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           const unsigned b = (unsigned)(it - 1) & 1u;
           const unsigned pb = b ? pbar1 : pbar0;
           if (tid == 0) mbar_expect_tx(pb, pbytes);
-          mbar_wait(pb, b ? pph1 : pph0);
+          mbar_wait_sel(pb, b ? pph1 : pph0, (p.flags & 1) != 0);
           if (b) pph1 ^= 1; else pph0 ^= 1;
           if (rec) dbg_stamp(dbg, 0);
           if (real && fs < myT - 1) {
@@ -672,10 +741,13 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(b0 + boff + rl * 128u + ((bchunk ^ (rl & 7u)) << 4)), "h"(l16) : "memory");
         }
         fence_proxy_async_smem();
-        mbar_arrive(bbar);
+        if (p.flags & 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bbar);
+        } else mbar_arrive(bbar);
         if (rec) dbg_stamp(dbg, 1);
         // ---- partial products of this CTA's gate rows for ALL output slots: stage each owner's slots x lines block
-        mbar_wait(accbar, accph);
+        mbar_wait_sel(accbar, accph, (p.flags & 1) != 0);
         accph ^= 1;
         if (rec) dbg_stamp(dbg, 2);
         tc_fence_after();
@@ -694,9 +766,19 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         tc_fence_before();
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(stagebar);
-        if (rec) dbg_stamp(dbg, 3);
+        if (p.flags & 4) {
+          epi_bar_sync();                                       // staged: warp X < CS sends the block of owner X (slot c of its reduce buffer)
+          if (rec) dbg_stamp(dbg, 3);
+          if ((unsigned)warp < CS && elect_one()) {
+            const unsigned sb = (unsigned)it & 1u;
+            bulk_copy_to_peer(rdst0 + sb * rbytes, stg0 + sb * rbytes + (unsigned)warp * 2048u, 2048u, rbar0 + sb * 8u);
+          }
+          if (rec) dbg_stamp(dbg, 10);
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stagebar);
+          if (rec) dbg_stamp(dbg, 3);
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) { eo[i] += estep; gact[i] = gactn[i]; }
         co += cstep;
@@ -768,6 +850,7 @@ struct LstmTcxPlan {
   int nlt = 0;                                   // backward, TMEM form: lo tiles that fit into tensor memory next to D and the hi plane
   long long* dbg = nullptr;                      // 64 clock stamps (forward 0..31, backward 32..63) when CLSTM_B200_TC_DBG is set
   long long dbg_host[64] = {0};
+  int flags = 0;                                 // see TcxArgs::flags
   char err[256] = {0};
 };
 
@@ -822,7 +905,7 @@ void tcx_launch_cfg(const LstmTcxPlan* p, cudaLaunchConfig_t& cfg, cudaLaunchAtt
 void tcx_fill(const LstmTcxPlan* p, TcxArgs& x, int B, int d0, int ndir, int hstride, const int* hoff) {
   x.no = p->no; x.no4 = 4 * p->no; x.CS = p->CS; x.KQ = p->KQ; x.nks = p->nks; x.nkc = p->nkc; x.nmt = p->nmt;
   x.ngroups = (B + kXL - 1) / kXL; x.d0 = d0; x.ndir = ndir; x.hstride = hstride; x.hoff[0] = hoff[0]; x.hoff[1] = hoff[1];
-  x.nlt = p->nlt; x.dbg = p->dbg;
+  x.nlt = p->nlt; x.dbg = p->dbg; x.flags = p->flags;
 }
 }
 
@@ -837,6 +920,7 @@ LstmTcxPlan* lstm_tcx_create(int no, int num_sms) {
   p->tmem = true;
   if (const char* e = getenv("CLSTM_B200_TCX_TMEM")) p->tmem = (atoi(e) != 0) || p->KQ > 256;
   p->nlt = p->tmem ? std::min(p->nmt, (512 - 96 * p->nmt) / 64) : 0;
+  if (const char* e = getenv("CLSTM_B200_TCX_FLAGS")) p->flags = atoi(e);
   if (getenv("CLSTM_B200_TC_DBG") && cudaMalloc((void**)&p->dbg, sizeof p->dbg_host) == cudaSuccess) cudaMemset(p->dbg, 0, sizeof p->dbg_host);
   const size_t elems = (size_t)2 * p->CS * 128 * p->KQ;
   bool ok = cudaMalloc((void**)&p->a_hi, elems * 2) == cudaSuccess && cudaMalloc((void**)&p->a_lo, elems * 2) == cudaSuccess &&
