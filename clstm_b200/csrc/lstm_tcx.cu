@@ -48,6 +48,20 @@ using namespace tc;
 constexpr int kXL = 16;                      // lines per cluster
 constexpr int kXEW = 16;                     // epilogue warps
 constexpr int kXThreads = 32 * (kXEW + 1);   // + the loader / MMA warp
+// Build-time tuning switches (make TCX_FLAGS=n, measured on B200 with tools/tcx_flag_sweep.sh; nhidden 400 x 256 lines, forward / backward ms):
+//  0  all-lane barrier waits, the MMA warp issues the bulk copies, MMAs of a step back to back after the last chunk   18.6 / 18.2
+//  1  epilogue waits by one lane per warp                                                                            19.9 / 34.3
+//  2  MMA-warp waits by one lane                                                                                     22.9 / 32.2
+//  4  bulk copies issued by the epilogue warps, one each, behind a named barrier                                     18.0 / 29.9 -> no gain
+//  8  MMAs issued chunk by chunk as the chunks arrive (uniform chunk order)                                          22.5 / --
+// 16  backward: output tiles innermost (consecutive MMAs to different accumulators)                                   -- / 21.5
+// 32  pull form: the CTAs signal "staged", every CTA fetches the peers' blocks with ld.shared::cluster               17.8 / 25.0
+// (bits combine).  None of the alternatives beat the plain form: the exchange runs at ~5 B/clk per SM whichever way the bytes
+// move (st.async stores, bulk copies, remote loads), so the step is bound by the all-gather itself.
+#ifndef CB200_TCX_FLAGS
+#define CB200_TCX_FLAGS 0
+#endif
+constexpr int kXFlags = CB200_TCX_FLAGS;
 constexpr int kXDbgStep = 64;                // step whose timeline CTA 0 records when a debug buffer is given
 constexpr int kXMaxCS = 15;                  // CTAs per cluster (KQ = 480: D + both A planes fill the 512 TMEM columns)
 constexpr float kXScaleH = 16.f, kXScaleR = 16.f, kXScaleD = 256.f;
@@ -67,9 +81,6 @@ struct TcxArgs {
   const __half *w_hi, *w_lo;
   int nlt;                 // backward, TMEM form: lo-plane tiles that live in tensor memory (the others stay in shared memory)
   long long* dbg;          // optional: timeline of one step of CTA 0 (clock64 stamps)
-  int flags;               // tuning switches (CLSTM_B200_TCX_FLAGS): 1 epilogue waits by one lane per warp, 2 MMA-warp waits by one lane,
-                           // 4 bulk copies issued by the epilogue warps (one each) instead of the MMA warp, 8 MMAs issued chunk by chunk
-                           // as the chunks arrive instead of after the last one, 16 backward: output tiles innermost
 };
 
 __device__ __forceinline__ unsigned mapa_u32(unsigned local_addr, unsigned rank) {
@@ -103,6 +114,46 @@ __device__ __forceinline__ void sts_v4(unsigned addr, unsigned a, unsigned b, un
 __device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity) {
   if (elect_one()) mbar_wait(bar, parity);
   __syncwarp();
+}
+// cluster-scope signalling for the pull form of the exchange: a release-arrive on a PEER's barrier, an acquire wait on one's own
+__device__ __forceinline__ void mbar_arrive_remote_release(unsigned rbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  SpinGuard g;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    g.tick();
+  }
+}
+__device__ __forceinline__ uint4 ld_cluster_v4(unsigned raddr) {
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(raddr) : "memory");
+  return v;
+}
+// Pull form: every CTA copies the CS staged 2 KB blocks (block cc from CTA cc's shared memory at `src_off`) into its own buffer
+// at dst0 + cc*2048 with 16-byte distributed-shared-memory loads spread over the 512 epilogue threads.
+__device__ __forceinline__ void pull_blocks(unsigned dst0, unsigned src_local, int CS, int etid) {
+  const int npieces = CS * 128;
+  uint4 v[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int idx = etid + 512 * r;
+    if (idx < npieces) v[r] = ld_cluster_v4(mapa_u32(src_local + (unsigned)(idx & 127) * 16u, (unsigned)(idx >> 7)));
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int idx = etid + 512 * r;
+    if (idx < npieces) sts_v4(dst0 + (unsigned)idx * 16u, v[r].x, v[r].y, v[r].z, v[r].w);
+  }
 }
 __device__ __forceinline__ void mbar_wait_sel(unsigned bar, unsigned parity, bool one_lane) {
   if (one_lane) mbar_wait_warp(bar, parity);
@@ -168,7 +219,7 @@ template <bool A_TMEM>
 __global__ void __launch_bounds__(kXThreads, 1)
 lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, Lines ln, TcxArgs p) {
   extern __shared__ __align__(1024) unsigned char xs[];
-  __shared__ __align__(8) unsigned long long bars[2 * kXMaxCS + 3];   // hbar[2][kXMaxCS] (h chunks by source CTA), accbar, abar (weights), stagebar
+  __shared__ __align__(8) unsigned long long bars[2 * kXMaxCS + 6];   // hbar[2][kXMaxCS] (h chunks by source CTA), accbar, abar (weights), stagebar, readybar[2], fullbar
   __shared__ unsigned tmem_base_s;
   __shared__ int lineT[kXL], lineOff[kXL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,7 +233,8 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const unsigned bbytes = CS * 2048u;
   const unsigned stg0 = b0 + 2u * bbytes;                      // staging block s&1 at stg0 + (s&1)*2048
   const unsigned bar0 = smem_u32(&bars[0]);
-  const unsigned accbar = bar0 + 8u * (2 * kXMaxCS), abar = accbar + 8u, stagebar = accbar + 16u;
+  const unsigned accbar = bar0 + 8u * (2 * kXMaxCS), abar = accbar + 8u, stagebar = accbar + 16u, readybar0 = accbar + 24u, fullbar = accbar + 40u;
+  const bool pull = (kXFlags & 32) != 0;
   const unsigned tcols = pow2_cols(32u + (A_TMEM ? (unsigned)p.KQ : 0u));
   const unsigned acol_hi = 32u, acol_lo = 32u + (unsigned)p.KQ / 2u;
   long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
@@ -190,6 +242,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   if (tid == 0) {
     for (int i = 0; i < 2 * kXMaxCS + 2; i++) mbar_init(bar0 + 8u * i, 1);
     mbar_init(stagebar, kXEW);
+    mbar_init(readybar0, CS); mbar_init(readybar0 + 8u, CS); mbar_init(fullbar, kXEW);
     mbar_init_fence();
     if (!A_TMEM) { tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); }
   }
@@ -234,7 +287,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
     }
   };
 
-  unsigned hph = 0, accph = 0, stph = 0;                        // hph bit b: phase of the chunk barriers of buffer b
+  unsigned hph = 0, accph = 0, stph = 0, fph = 0, rph = 0;      // hph bit b: phase of the chunk barriers of buffer b
   // work items = (line group, direction), longest first (the groups are cut from the length-sorted line order); round r hands
   // item r*nclusters + i to cluster i, odd rounds in reverse (snake), so every cluster gets a similar number of steps
   const int nitems = p.ngroups * p.ndir;
@@ -258,7 +311,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      const bool w1 = (p.flags & 2) != 0, per_chunk = (p.flags & 8) != 0, epi_copies = (p.flags & 4) != 0;
+      const bool w1 = (kXFlags & 2) != 0, per_chunk = (kXFlags & 8) != 0, epi_copies = (kXFlags & 4) != 0;
       const unsigned cpeer = (unsigned)lane < CS ? (unsigned)lane : 0u;    // lane X < CS sends this CTA's chunk to CTA X
       const unsigned crdst0 = mapa_u32(b0 + c * 2048u, cpeer), crbar0 = mapa_u32(bar0 + 8u * c, cpeer);
       for (int s = 0; s < Tg; s++) {
@@ -266,10 +319,34 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (s >= 1) {
           const unsigned b = (unsigned)(s - 1) & 1u;            // h_{s-1} sits in buffer (s-1)&1
           const unsigned hb0 = bar0 + 8u * (b * kXMaxCS);
-          if ((unsigned)lane < CS) mbar_expect_tx(hb0 + 8u * lane, 2048u);
+          if (!pull && (unsigned)lane < CS) mbar_expect_tx(hb0 + 8u * lane, 2048u);
           __syncwarp();
           const unsigned ph = (hph >> b) & 1u;
-          if (per_chunk) {
+          if (pull) {                                           // the epilogue warps have fetched every block of h_{s-1}
+            mbar_wait(fullbar, fph);
+            fph ^= 1;
+            if (rec) dbg_stamp(dbg, 12);
+            tc_fence_after();
+            if (elect_one()) {
+              for (int cc = 0; cc < p.CS; cc++) {
+                const unsigned long long bh = make_desc64(b0 + b * bbytes + cc * 2048u);
+#pragma unroll
+                for (int ks = 0; ks < 2; ks++) {
+                  const unsigned kk = 2u * cc + ks;
+                  const unsigned acc = (cc > 0 || ks > 0) ? 1u : 0u;
+                  if (A_TMEM) {
+                    mma_f16_ts(tmem_d, tmem_d + acol_hi + 8u * kk, bh + 2 * ks, idesc32, acc);
+                    mma_f16_ts(tmem_d, tmem_d + acol_lo + 8u * kk, bh + 2 * ks, idesc16, 1u);
+                  } else {
+                    mma_f16(tmem_d, desc_of(a_hi0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc32, acc);
+                    mma_f16(tmem_d, desc_of(a_lo0 + (kk >> 2) * 16384u) + 2 * (kk & 3u), bh + 2 * ks, idesc16, 1u);
+                  }
+                }
+              }
+              mma_commit(accbar);
+            }
+            __syncwarp();
+          } else if (per_chunk) {
             mbar_wait(hb0 + 8u * c, ph);                        // own chunk: every epilogue warp of this CTA has read the accumulator
             tc_fence_after();                                   // of step s-1; then the chunks in UNIFORM order (MMA operands that
             for (int cc = 0; cc < p.CS; cc++) {                 // depend on the CTA rank leave the uniform datapath: ~85 cycles per MMA)
@@ -324,7 +401,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if (rec) dbg_stamp(dbg, 9);
           hph ^= 1u << b;
         }
-        if (!epi_copies && s + 1 < Tg) {                        // h_s is staged: one bulk copy per destination CTA
+        if (!pull && !epi_copies && s + 1 < Tg) {               // h_s is staged: one bulk copy per destination CTA
           mbar_wait_sel(stagebar, stph, w1);
           stph ^= 1;
           const unsigned sb = (unsigned)s & 1u;
@@ -380,7 +457,7 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         for (int i = 0; i < 4; i++) xpn[i] = (real && s + 1 < Tl[i]) ? ldg_f32(XPd + eo[i] + estep) : 0.f;
         float act[4];
         if (s > 0) {
-          mbar_wait_sel(accbar, accph, (p.flags & 1) != 0);
+          mbar_wait_sel(accbar, accph, (kXFlags & 1) != 0);
           accph ^= 1;
           if (rec) dbg_stamp(dbg, 0);
           tc_fence_after();
@@ -427,8 +504,14 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           tc_fence_before();                                    // (the accumulator has been read: tcgen05.wait::ld above)
           const unsigned sb = (unsigned)s & 1u;
           if (lane < 8) sts_v4(stg0 + sb * 2048u + xoff, w4[0], w4[1], w4[2], w4[3]);
+          if (pull) {
+            epi_bar_sync();                                     // h_s is staged here: tell every CTA of the cluster
+            if (warp == 0 && (unsigned)lane < CS) mbar_arrive_remote_release(mapa_u32(readybar0 + 8u * sb, (unsigned)lane));
+            if (rec) dbg_stamp(dbg, 3);
+          } else
           fence_proxy_async_smem();                             // generic-proxy stores -> the bulk copies' reads
-          if (p.flags & 4) {
+          if (pull) {
+          } else if (kXFlags & 4) {
             epi_bar_sync();                                     // h_s is staged: warp X < CS sends the block to CTA X (one copy each)
             if (rec) dbg_stamp(dbg, 3);
             if ((unsigned)warp < CS && elect_one())
@@ -454,6 +537,18 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         for (int i = 0; i < 4; i++) { eo[i] += estep; xp[i] = xpn[i]; }
         co += cstep;
         if (rec) dbg_stamp(dbg, 4);
+        if (pull && s + 1 < Tg) {                               // every CTA has staged h_s: fetch the CS blocks into B buffer s&1
+          const unsigned sb = (unsigned)s & 1u;
+          if (warp == 0) mbar_wait_acq_cluster(readybar0 + 8u * sb, (rph >> sb) & 1u);
+          rph ^= 1u << sb;
+          epi_bar_sync();
+          if (rec) dbg_stamp(dbg, 10);
+          pull_blocks(b0 + sb * bbytes, stg0 + sb * 2048u, p.CS, tid);
+          fence_proxy_async_smem();                             // generic-proxy stores -> tensor-core reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(fullbar);
+          if (rec) dbg_stamp(dbg, 11);
+        }
       }
     }
     __syncthreads();
@@ -477,7 +572,7 @@ template <bool A_TMEM>
 __global__ void __launch_bounds__(kXThreads, 1)
 lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo, Lines ln, TcxArgs p) {
   extern __shared__ __align__(1024) unsigned char xs[];
-  __shared__ __align__(8) unsigned long long bars[6];          // pbar[2] (partial sums), accbar, abar (weights), bbar (delta tile), stagebar
+  __shared__ __align__(8) unsigned long long bars[8];          // pbar[2] (partial sums), accbar, abar (weights), bbar (delta tile), stagebar, readybar[2]
   __shared__ unsigned tmem_base_s;
   __shared__ int lineT[kXL], lineOff[kXL];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -493,13 +588,14 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   const unsigned rbytes = CS * 2048u;
   const unsigned stg0 = r0 + 2u * rbytes;                      // staging
   const unsigned bar0 = smem_u32(&bars[0]);
-  const unsigned pbar0 = bar0, pbar1 = bar0 + 8, accbar = bar0 + 16, abar = bar0 + 24, bbar = bar0 + 32, stagebar = bar0 + 40;
+  const unsigned pbar0 = bar0, pbar1 = bar0 + 8, accbar = bar0 + 16, abar = bar0 + 24, bbar = bar0 + 32, stagebar = bar0 + 40, readybar0 = bar0 + 48;
+  const bool pull = (kXFlags & 32) != 0;
   const unsigned tcols = pow2_cols((unsigned)nmt * (A_TMEM ? 96u : 32u) + (unsigned)nlt * 64u);
   const unsigned acol_hi = 32u * (unsigned)nmt, acol_lo = 96u * (unsigned)nmt;
   long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg + 32 : nullptr;
 
   if (tid == 0) {
-    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, (p.flags & 1) ? kXEW : 32 * kXEW); mbar_init(stagebar, kXEW);
+    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, (kXFlags & 1) ? kXEW : 32 * kXEW); mbar_init(stagebar, kXEW); mbar_init(readybar0, CS); mbar_init(readybar0 + 8u, CS);
     mbar_init_fence();
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
   }
@@ -556,7 +652,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       tc_fence_after();
     }
   };
-  unsigned pph0 = 0, pph1 = 0, accph = 0, bph = 0, stph = 0;
+  unsigned pph0 = 0, pph1 = 0, accph = 0, bph = 0, stph = 0, rph = 0;
   const unsigned pbytes = CS * 2048u;                           // bytes a CTA receives per step (= one reduce buffer)
   const int nitems = p.ngroups * p.ndir;                        // work items as in the forward kernel
   int cur_d = -1;
@@ -579,7 +675,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
       const unsigned idesc32 = make_idesc_f16(128, 32), idesc16 = make_idesc_f16(128, 16);
       const unsigned long long dbase = make_desc(0);
       auto desc_of = [&](unsigned addr) { return dbase | (unsigned long long)((addr & 0x3FFFF) >> 4); };
-      const bool w1 = (p.flags & 2) != 0, epi_copies = (p.flags & 4) != 0, tiles_inner = (p.flags & 16) != 0;
+      const bool w1 = (kXFlags & 2) != 0, epi_copies = (kXFlags & 4) != 0, tiles_inner = (kXFlags & 16) != 0;
       const unsigned cpeer = (unsigned)lane < CS ? (unsigned)lane : 0u;    // lane X < CS sends owner X's partial sums to CTA X
       const unsigned crdst0 = mapa_u32(r0 + c * 2048u, cpeer), crbar0 = mapa_u32(pbar0, cpeer);
       for (int it = 0; it + 1 < Tg; it++) {
@@ -622,7 +718,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         }
         __syncwarp();
         if (rec) dbg_stamp(dbg, 9);
-        if (!epi_copies) {
+        if (!pull && !epi_copies) {
           mbar_wait_sel(stagebar, stph, w1);                    // the partial sums are staged: one bulk copy per owner CTA
           stph ^= 1;
           const unsigned sb = (unsigned)it & 1u;
@@ -695,9 +791,17 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (it > 0) {
           const unsigned b = (unsigned)(it - 1) & 1u;
           const unsigned pb = b ? pbar1 : pbar0;
-          if (tid == 0) mbar_expect_tx(pb, pbytes);
-          mbar_wait_sel(pb, b ? pph1 : pph0, (p.flags & 1) != 0);
-          if (b) pph1 ^= 1; else pph0 ^= 1;
+          if (pull) {                                           // every CTA has staged its partial sums: fetch the blocks of MY slots
+            if (warp == 0) mbar_wait_acq_cluster(readybar0 + 8u * b, (rph >> b) & 1u);
+            rph ^= 1u << b;
+            epi_bar_sync();
+            pull_blocks(r0 + b * rbytes, stg0 + b * rbytes + c * 2048u, p.CS, tid);
+            epi_bar_sync();
+          } else {
+            if (tid == 0) mbar_expect_tx(pb, pbytes);
+            mbar_wait_sel(pb, b ? pph1 : pph0, (kXFlags & 1) != 0);
+            if (b) pph1 ^= 1; else pph0 ^= 1;
+          }
           if (rec) dbg_stamp(dbg, 0);
           if (real && fs < myT - 1) {
             float r = 0.f;
@@ -741,13 +845,13 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           asm volatile("st.shared.b16 [%0], %1;" ::"r"(b0 + boff + rl * 128u + ((bchunk ^ (rl & 7u)) << 4)), "h"(l16) : "memory");
         }
         fence_proxy_async_smem();
-        if (p.flags & 1) {
+        if (kXFlags & 1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bbar);
         } else mbar_arrive(bbar);
         if (rec) dbg_stamp(dbg, 1);
         // ---- partial products of this CTA's gate rows for ALL output slots: stage each owner's slots x lines block
-        mbar_wait_sel(accbar, accph, (p.flags & 1) != 0);
+        mbar_wait_sel(accbar, accph, (kXFlags & 1) != 0);
         accph ^= 1;
         if (rec) dbg_stamp(dbg, 2);
         tc_fence_after();
@@ -765,8 +869,14 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
                    __float_as_uint((__uint_as_float(ra[3]) + __uint_as_float(rb[3])) * inv_scale));
         }
         tc_fence_before();
+        if (pull) {
+          epi_bar_sync();                                       // staged: tell every CTA of the cluster
+          if (warp == 0 && (unsigned)lane < CS) mbar_arrive_remote_release(mapa_u32(readybar0 + 8u * ((unsigned)it & 1u), (unsigned)lane));
+          if (rec) dbg_stamp(dbg, 3);
+        } else
         fence_proxy_async_smem();
-        if (p.flags & 4) {
+        if (pull) {
+        } else if (kXFlags & 4) {
           epi_bar_sync();                                       // staged: warp X < CS sends the block of owner X (slot c of its reduce buffer)
           if (rec) dbg_stamp(dbg, 3);
           if ((unsigned)warp < CS && elect_one()) {
@@ -850,7 +960,6 @@ struct LstmTcxPlan {
   int nlt = 0;                                   // backward, TMEM form: lo tiles that fit into tensor memory next to D and the hi plane
   long long* dbg = nullptr;                      // 64 clock stamps (forward 0..31, backward 32..63) when CLSTM_B200_TC_DBG is set
   long long dbg_host[64] = {0};
-  int flags = 0;                                 // see TcxArgs::flags
   char err[256] = {0};
 };
 
@@ -905,7 +1014,7 @@ void tcx_launch_cfg(const LstmTcxPlan* p, cudaLaunchConfig_t& cfg, cudaLaunchAtt
 void tcx_fill(const LstmTcxPlan* p, TcxArgs& x, int B, int d0, int ndir, int hstride, const int* hoff) {
   x.no = p->no; x.no4 = 4 * p->no; x.CS = p->CS; x.KQ = p->KQ; x.nks = p->nks; x.nkc = p->nkc; x.nmt = p->nmt;
   x.ngroups = (B + kXL - 1) / kXL; x.d0 = d0; x.ndir = ndir; x.hstride = hstride; x.hoff[0] = hoff[0]; x.hoff[1] = hoff[1];
-  x.nlt = p->nlt; x.dbg = p->dbg; x.flags = p->flags;
+  x.nlt = p->nlt; x.dbg = p->dbg;
 }
 }
 
@@ -920,7 +1029,6 @@ LstmTcxPlan* lstm_tcx_create(int no, int num_sms) {
   p->tmem = true;
   if (const char* e = getenv("CLSTM_B200_TCX_TMEM")) p->tmem = (atoi(e) != 0) || p->KQ > 256;
   p->nlt = p->tmem ? std::min(p->nmt, (512 - 96 * p->nmt) / 64) : 0;
-  if (const char* e = getenv("CLSTM_B200_TCX_FLAGS")) p->flags = atoi(e);
   if (getenv("CLSTM_B200_TC_DBG") && cudaMalloc((void**)&p->dbg, sizeof p->dbg_host) == cudaSuccess) cudaMemset(p->dbg, 0, sizeof p->dbg_host);
   const size_t elems = (size_t)2 * p->CS * 128 * p->KQ;
   bool ok = cudaMalloc((void**)&p->a_hi, elems * 2) == cudaSuccess && cudaMalloc((void**)&p->a_lo, elems * 2) == cudaSuccess &&
