@@ -133,6 +133,8 @@ struct clstm_b200_net {
   float* W1T = nullptr;                    // W1^T [nfeat][nc]
   bool g_pending = false;
   bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
+  int gx_mode = 0;              // persistent TMA-fed GEMM (gemm_x.cu): 0 by size, 1 always, 2 never  (CLSTM_B200_GEMM=x / tc)
+  GxPlan* gx[2] = {nullptr, nullptr};   // operand-plane scratch of the main / side stream
   int lstm_mode = 0;            // recurrence: 0 auto (by size and batch), 1 always the lock-step tensor-core kernels, 2 never, 3 always the cluster-resident ones
 
   // ---- batch capacity and buffers.  The INPUT SET (x, metadata, tiles, their pinned staging, host geometry, Lines view)
@@ -574,11 +576,22 @@ bool vec_ok(const float* p, long long ld) { return (ld % 4 == 0) && ((reinterpre
 
 // C[M x N] = beta*C + A[M x K] * B^T (+bias) with A K-contiguous; B either K-contiguous ([N][K], b_mn=false) or
 // MN-contiguous ([K][N], b_mn=true)
+// The persistent TMA-fed GEMM pays two conversion launches per product: it takes over where the products are real GEMMs
+// (measured crossover on B200: a few GFLOP per product; BASELINE config 2 stays on the on-the-fly 3xTF32 kernels).
+bool want_gx(const clstm_b200_net* n, int side, double flops) {
+  if (!n->use_tc || !n->gx[side] || n->gx_mode == 2) return false;
+  return n->gx_mode == 1 || flops >= 8e9;
+}
 int dense_nt(clstm_b200_net* n, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
-             bool b_mn, float* C, long long ldc, const float* bias, float beta) {
+             bool b_mn, float* C, long long ldc, const float* bias, float beta, float scale_a = 16.f, float scale_b = 16.f) {
   if (!n->use_tc) {
     return gemm_f32(n->st, M, N, K, A, lda, 1, B, b_mn ? ldb : 1, b_mn ? 1 : ldb, C, ldc, bias, beta, nullptr, 0,
                     n->num_sms);
+  }
+  if (!b_mn && beta == 0.f && want_gx(n, 0, 2.0 * M * N * K)) {
+    const int r = gemm_x_nt(n->gx[0], n->st, M, N, K, A, lda, B, ldb, C, ldc, bias, scale_a, scale_b);
+    if (r >= 0) return r;
+    cudaGetLastError();                                         // (out of scratch memory: the on-the-fly kernels below need none)
   }
   TcArgs g{};
   g.M = M; g.N = N;
@@ -596,6 +609,19 @@ int dense_tn(clstm_b200_net* n, int M, int K, const float* A, long long lda, con
   cudaStream_t stream = side ? n->st2 : n->st;
   float* ws = side ? n->ws2 : n->ws;
   const size_t wsf = side ? n->ws2_floats : n->ws_floats;
+  if (want_gx(n, side ? 1 : 0, 2.0 * M * (n0 + n1 + 1) * K)) {
+    int splits = 1;
+    const int r = gemm_x_tn(n->gx[side ? 1 : 0], stream, M, K, A, lda, B0, n0, B1, n1, 256.f, 16.f, ws, wsf, &splits);
+    if (r >= 0) {
+      TcOut o{};
+      o.p[0] = out0; o.ld[0] = n0; o.len[0] = n0; o.nseg = 1;
+      if (B1) { o.p[1] = out1; o.ld[1] = n1; o.len[1] = n1; o.nseg = 2; }
+      o.bias = out_bias;
+      tc_reduce_scatter(stream, M, n0 + n1 + 1, splits, ws, o, 1.f, n->num_sms);
+      return r + 1;
+    }
+    cudaGetLastError();
+  }
   if (!n->use_tc) {
     int k = gemm_f32(stream, M, n0, K, A, 1, lda, B0, n0, 1, out0, n0, nullptr, 1.f, ws, wsf, n->num_sms);
     if (B1) k += gemm_f32(stream, M, n1, K, A, 1, lda, B1, n1, 1, out1, n1, nullptr, 1.f, ws, wsf, n->num_sms);
@@ -736,7 +762,7 @@ int run_backward(clstm_b200_net* n, bool defer_dx = false) {
       CU(cudaMemcpyAsync(last.dH, n->delta, (size_t)N * nc * sizeof(float), cudaMemcpyDeviceToDevice, n->st));
     } else {
       if (n->out_kind > 0) { full_backward(n->st, n->delta, n->out, (size_t)N * nc, n->out_kind); s.launches(1); }
-      if (n->use_tc) s.launches(dense_nt(n, N, nfeat, nc, n->delta, nc, n->W1T, nc, false, last.dH, nfeat, nullptr, 0.f));
+      if (n->use_tc) s.launches(dense_nt(n, N, nfeat, nc, n->delta, nc, n->W1T, nc, false, last.dH, nfeat, nullptr, 0.f, 256.f, 16.f));
       else s.launches(dense_nt(n, N, nfeat, nc, n->delta, nc, n->v + n->oW1, nfeat, true, last.dH, nfeat, nullptr, 0.f));
       // the W1 derivative product needs only delta and H: run it on the side stream, concurrently with the backward
       // recurrence (which occupies 2B of the 148 SMs), and join before anything consumes g
@@ -1016,11 +1042,13 @@ int clstm_b200_create_ex(const clstm_b200_cfg_ex* cfg, clstm_b200_net** out) {
   {
     const char* e = getenv("CLSTM_B200_GEMM");   // "simt" selects the fp32 SIMT tiles (A/B testing against tcgen05)
     n->use_tc = !(e && strcmp(e, "simt") == 0);
+    n->gx_mode = (e && strcmp(e, "x") == 0) ? 1 : ((e && strcmp(e, "tc") == 0) ? 2 : 0);   // "x": always the TMA-fed GEMM, "tc": never
   }
   {
     const char* e = getenv("CLSTM_B200_LSTM");   // "tc": always the batched tensor-core recurrence; "simt": never
     n->lstm_mode = (e && strcmp(e, "tc") == 0) ? 1 : ((e && strcmp(e, "simt") == 0) ? 2 : ((e && strcmp(e, "tcx") == 0) ? 3 : 0));
   }
+  if (n->use_tc) { n->gx[0] = gemm_x_create(n->num_sms); n->gx[1] = gemm_x_create(n->num_sms); }
   if (lstm_tc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   if (n->cell == 0 && n->lstm_mode != 2)
     for (int k = 0; k < n->nblk; k++)
@@ -1059,6 +1087,7 @@ void clstm_b200_destroy(clstm_b200_net* n) {
   for (int r = 0; r < kMaxPeers; r++)
     if (n->peer_buf[r] && r != n->rank) cudaIpcCloseMemHandle(n->peer_buf[r]);
   dev_free(n->v); dev_free(n->d); dev_free(n->comm_buf); n->g = nullptr; dev_free(n->W1T);
+  gemm_x_destroy(n->gx[0]); gemm_x_destroy(n->gx[1]); n->gx[0] = n->gx[1] = nullptr;
   for (int k = 0; k < 2; k++) {
     lstm_tc_destroy(n->blk[k].tc);
     n->blk[k].tc = nullptr;

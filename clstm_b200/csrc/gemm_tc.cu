@@ -645,6 +645,13 @@ int gemm_tc_configure() {
   return (int)e;
 }
 
+void tc_reduce_scatter(cudaStream_t st, int M, int N, int splits, const float* ws, const TcOut& o, float beta, int num_sms) {
+  const size_t total = (size_t)M * N;
+  size_t nb = (total + 255) / 256;
+  if (nb > (size_t)num_sms * 8) nb = (size_t)num_sms * 8;
+  tc_reduce_scatter_kernel<<<(int)nb, 256, 0, st>>>(M, N, splits, ws, o, beta);
+}
+
 int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms) {
   if (g.M <= 0 || g.N <= 0) return 0;
   // N tile: multiple of 16, <= 256, as few tiles as possible

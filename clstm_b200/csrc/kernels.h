@@ -58,6 +58,21 @@ struct TcArgs {
 // the scatter targets with `beta`.
 int gemm_tc(cudaStream_t st, TcArgs g, const TcOut* scatter, int num_sms);
 int gemm_tc_configure();
+// out(seg)[m][c] = beta*out + sum_z ws[z][m][c] (fixed order), scattered into the column blocks of `o`
+void tc_reduce_scatter(cudaStream_t st, int M, int N, int splits, const float* ws, const TcOut& o, float beta, int num_sms);
+
+// ---------------------------------------------------------------- gemm_x.cu (persistent TMA-fed tcgen05 GEMM on fp16 hi/lo planes)
+struct GxPlan;                                        // operand-plane scratch of one stream
+GxPlan* gemm_x_create(int num_sms);                   // nullptr: driver entry point missing
+void gemm_x_destroy(GxPlan* p);
+const char* gemm_x_error(const GxPlan* p);
+// C = A[M x K] * B[N x K]^T + bias (fp32 row-major operands; values are multiplied by scale_a / scale_b before the fp16 split:
+// |value * scale| must stay below 65504).  Returns kernels launched, < 0 on error.
+int gemm_x_nt(GxPlan* p, cudaStream_t st, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb, float* C,
+              long long ldc, const float* bias, float scale_a, float scale_b);
+// partials of A^T [B0 | B1 | 1] over the Kc rows (A [Kc x M], B blocks [Kc x n0 / n1]) into ws as [splits][M][n0 + n1 + 1]
+int gemm_x_tn(GxPlan* p, cudaStream_t st, int M, int Kc, const float* A, long long lda, const float* B0, int n0, const float* B1, int n1,
+              float scale_a, float scale_b, float* ws, size_t ws_floats, int* splits_out);
 
 // ---------------------------------------------------------------- lstm.cu
 // One recurrent block = up to two LSTMs over the same input: slot index d = 0 runs forward in time, d = 1 reversed

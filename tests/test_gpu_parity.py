@@ -194,6 +194,32 @@ def test_tcgen05_dense_products_match_simt(ffi, nh):
     assert err.max() < 1e-5, err
 
 
+@pytest.mark.parametrize("nh", [100, 400])
+def test_tma_fed_gemm_matches_simt(ffi, nh, monkeypatch):
+    # the persistent TMA-fed GEMM on fp16 hi/lo planes (gemm_x.cu), forced for every product size (CLSTM_B200_GEMM=x is read
+    # when the net is created): forward products with bias, both derivative products with column blocks + ones column
+    monkeypatch.setenv("CLSTM_B200_GEMM", "x")
+    net = ffi.Net(48, nh, 83)
+    err = net.selftest_gemm()
+    assert len(err) == 6
+    assert err.max() < 1e-5, err
+
+
+def test_tma_fed_gemm_training_steps_track_oracle(ffi, oracle, monkeypatch):
+    # whole training steps with every dense product on the TMA-fed GEMM (ragged batch, K and N tails, split-K derivative products)
+    monkeypatch.setenv("CLSTM_B200_GEMM", "x")
+    ni, nh, nc, B = 48, 100, 83, 7
+    x, Ts, labels, L = synth.make_lines(B, (5, 70), ni, nc, seed=13)
+    onet = oracle.BidiOracle(ni, nh, nc, seed=0.222)
+    onet.set_params(synth.trained_like(onet.nparams, 0.3, seed=7))
+    gnet = ffi.Net(ni, nh, nc)
+    gnet.set_params(onet.get_params())
+    for _ in range(3):
+        gnet.train_step(x, Ts, labels, L, 1e-3, 0.9)
+        onet.train_lines(x, Ts, labels, L, 1e-3, 0.9, threads=1, reps=1)
+    assert np.abs(gnet.get_params() - onet.get_params()).max() < 1e-4
+
+
 def test_long_lines_wide_net(ffi, oracle):
     # BASELINE config 3 shape in miniature: nhidden=200 (cluster recurrent kernels), ragged lines up to T=1500,
     # transcripts up to 75 labels (lattice lanes own 5 states each); alignment indices must be bit-exact.
