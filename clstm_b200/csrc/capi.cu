@@ -1048,7 +1048,10 @@ int clstm_b200_create_ex(const clstm_b200_cfg_ex* cfg, clstm_b200_net** out) {
     const char* e = getenv("CLSTM_B200_LSTM");   // "tc": always the batched tensor-core recurrence; "simt": never
     n->lstm_mode = (e && strcmp(e, "tc") == 0) ? 1 : ((e && strcmp(e, "simt") == 0) ? 2 : ((e && strcmp(e, "tcx") == 0) ? 3 : 0));
   }
-  if (n->use_tc) { n->gx[0] = gemm_x_create(n->num_sms); n->gx[1] = gemm_x_create(n->num_sms); }
+  if (n->use_tc && n->gx_mode != 2) {
+    n->gx[0] = gemm_x_create(n->num_sms); n->gx[1] = gemm_x_create(n->num_sms);
+    if (!n->gx[0] || !n->gx[1]) { clstm_b200_destroy(n); return fail("the TMA-fed GEMM (gemm_x.cu) could not be set up on this device"); }
+  }
   if (lstm_tc_configure() != 0) { clstm_b200_destroy(n); return fail("kernel image for sm_100a not usable on this device"); }
   if (n->cell == 0 && n->lstm_mode != 2)
     for (int k = 0; k < n->nblk; k++)

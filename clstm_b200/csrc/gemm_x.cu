@@ -272,6 +272,7 @@ int make_map_gx(CUtensorMap* m, const void* base, size_t rows, size_t kp, size_t
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
              ? 0 : 1;
 }
+constexpr size_t kGxSmemMax = 226 * 1024;   // dynamic part; the 227 KB limit of a CTA includes the kernel's static shared memory
 size_t gx_smem_bytes(int BN, int stages) { return (size_t)stages * (2 * GX_BM * 128 + 2 * (size_t)BN * 128) + 1024; }
 }  // namespace
 
@@ -285,7 +286,7 @@ struct GxPlan {
 
 GxPlan* gemm_x_create(int num_sms) {
   if (load_encode_gx() != 0) return nullptr;
-  if (cudaFuncSetAttribute(gemm_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+  if (cudaFuncSetAttribute(gemm_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGxSmemMax) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
@@ -344,7 +345,7 @@ int gx_launch(GxPlan* p, cudaStream_t st, int M, int N, int Kp, size_t pitch_a, 
   g.kb_per_split = (g.nkb + splits - 1) / splits;
   splits = (g.nkb + g.kb_per_split - 1) / g.kb_per_split;
   g.splits = splits;
-  g.stages = (gx_smem_bytes(g.BN, 4) <= 227 * 1024) ? 4 : (gx_smem_bytes(g.BN, 3) <= 227 * 1024 ? 3 : 2);
+  g.stages = (gx_smem_bytes(g.BN, 4) <= kGxSmemMax) ? 4 : (gx_smem_bytes(g.BN, 3) <= kGxSmemMax ? 3 : 2);
   g.C = C; g.ldc = ldc; g.bias = bias; g.ws = ws; g.out_scale = out_scale;
   CUtensorMap mAh, mAl, mBh, mBl;
   if (make_map_gx(&mAh, p->a[0], M, Kp, pitch_a, GX_BM) || make_map_gx(&mAl, p->a[1], M, Kp, pitch_a, GX_BM) ||
