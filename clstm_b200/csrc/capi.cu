@@ -588,7 +588,9 @@ int dense_nt(clstm_b200_net* n, int M, int N, int K, const float* A, long long l
     return gemm_f32(n->st, M, N, K, A, lda, 1, B, b_mn ? ldb : 1, b_mn ? 1 : ldb, C, ldc, bias, beta, nullptr, 0,
                     n->num_sms);
   }
-  if (!b_mn && beta == 0.f && want_gx(n, 0, 2.0 * M * N * K)) {
+  // (K < 128: the product is bound by writing its output -- the input projection, K = 48 -- and the 3xTF32 kernel's 128-bit row
+  // stores are faster there: 1.97 against 3.13 ms at nhidden 400 x 256 lines)
+  if (!b_mn && beta == 0.f && K >= 128 && want_gx(n, 0, 2.0 * M * N * K)) {
     const int r = gemm_x_nt(n->gx[0], n->st, M, N, K, A, lda, B, ldb, C, ldc, bias, scale_a, scale_b);
     if (r >= 0) return r;
     cudaGetLastError();                                         // (out of scratch memory: the on-the-fly kernels below need none)
