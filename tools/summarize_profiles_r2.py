@@ -13,7 +13,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
-PHASE = {"lstm_tc_fwd": "lstm_fwd", "lstm_tc_bwd": "lstm_bwd", "lstm_fwd": "lstm_fwd", "lstm_bwd": "lstm_bwd",
+PHASE = {"lstm_tcx_fwd": "lstm_fwd", "lstm_tcx_bwd": "lstm_bwd", "lstm_tc_fwd": "lstm_fwd", "lstm_tc_bwd": "lstm_bwd", "lstm_fwd": "lstm_fwd",
+         "lstm_bwd": "lstm_bwd", "gemm_x_kernel": "wgrad_gemm_x", "split_transpose_kernel": "wgrad_split",
          "gemm_tn_kernel": "wgrad_gemm", "ctc_": "ctc_align", "sgd_update": "sgd_update", "peer_allreduce": "allreduce"}
 
 
