@@ -82,16 +82,21 @@ __global__ void __launch_bounds__(TILE_THREADS) ctc_lmatch_kernel(Lines ln, CtcA
 }
 
 // ------------------------------------------------------------------------------------------------ lattice
-// One lattice pass by one warp.  rev=0: lr(t,s).  rev=1: processes i-th step on column T-1-i and state index jj
-// on real state S-1-jj, result stored at rl(T-1-i, S-1-jj)  (forwardbackward, ctc.cc:42-55).
-// Lane l owns KS consecutive states; a time step is one shuffle plus KS log_adds.  A single warp has nothing to
-// hide latency with, so the loop body is straight-line: running row pointers, a running -5*i, and lmatch rows
-// prefetched PF steps ahead into a register ring without bounds checks (the lattice buffers are padded by
-// kLatPad floats on both sides, so the prefetch may run past the line's rows).
-template <int KS, int PF>
-__device__ void lattice_pass(const float* __restrict__ lm, float* __restrict__ out, int T, int S, bool rev) {
+// One lattice pass by W warps (one direction of one line).  rev=0: lr(t,s).  rev=1: processes i-th step on column T-1-i and
+// state index jj on real state S-1-jj, result stored at rl(T-1-i, S-1-jj)  (forwardbackward, ctc.cc:42-55).
+// Thread tg of the group owns KS consecutive states; a time step is one shuffle plus KS log_adds -- every state's update is the
+// same expression whatever the distribution, so the lattices are bit-identical for every W.  W = 1 (short transcripts): a single
+// warp has nothing to hide latency with, so the loop body is straight-line: running row pointers, a running -5*i, and lmatch
+// rows prefetched PF steps ahead into a register ring without bounds checks (the lattice buffers are padded by kLatPad floats
+// on both sides, so the prefetch may run past the line's rows).  W = 2 / 4 (long transcripts: a lane of a single warp would own
+// up to 32 states = 64 MUFU operations per step on ONE scheduler): the warps of a direction sit on different schedulers; the
+// value that crosses a warp boundary (old v of the previous warp's last state) goes through a double-buffered shared-memory
+// slot and ONE named barrier per step.
+template <int KS, int PF, int W>
+__device__ void lattice_pass(const float* __restrict__ lm, float* __restrict__ out, int T, int S, bool rev, float* xch, int bar_id) {
   const int lane = threadIdx.x & 31;
-  const int j0 = lane * KS;
+  const int wg = (threadIdx.x >> 5) % W;                                   // warp inside the direction's group
+  const int j0 = (wg * 32 + lane) * KS;
   const int dirk = rev ? -1 : 1;
   const long long rowstep = rev ? -(long long)S : (long long)S;
   const long long first = (rev ? (long long)(T - 1) * S + (S - 1 - j0) : (long long)j0);
@@ -110,9 +115,15 @@ __device__ void lattice_pass(const float* __restrict__ lm, float* __restrict__ o
     for (int k = 0; k < KS; k++) mq[u][k] = ok[k] ? lp[u * rowstep + k * dirk] : 0.f;
   const float* lpn = lp + PF * rowstep;
   float skipv = 0.f;                                                      // w(0) = skip*i   ctc.cc:32
+  int par = 0;
   auto step = [&](float* m) {
+    if (W > 1) {                                                          // old v of my last state -> the next warp's first state
+      if (lane == 31) xch[par * W + wg] = v[KS - 1];
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * W) : "memory");
+    }
     float below = __shfl_up_sync(0xffffffffu, v[KS - 1], 1);              // old v(jj-1) of this lane's first state
-    below = (lane == 0) ? skipv : below;
+    if (lane == 0) below = (W == 1 || wg == 0) ? skipv : xch[par * W + wg - 1];
+    par ^= 1;
     skipv -= 5.f;
 #pragma unroll
     for (int k = KS - 1; k >= 0; k--) {
@@ -140,23 +151,37 @@ __device__ void lattice_pass(const float* __restrict__ lm, float* __restrict__ o
     if (u < rem) step(mq[u]);
 }
 
-__device__ void lattice_dispatch(const float* lm, float* out, int T, int S, bool rev) {
+constexpr int kLatWarps = 4;                     // warps per direction the launch provides
+// warps per direction actually used for a transcript of S states (ks = states per lane of a single warp)
+__device__ __forceinline__ int lattice_width(int S) {
   const int ks = (S + 31) / 32;
-  if (ks <= 1) lattice_pass<1, 8>(lm, out, T, S, rev);
-  else if (ks <= 2) lattice_pass<2, 8>(lm, out, T, S, rev);
-  else if (ks <= 4) lattice_pass<4, 4>(lm, out, T, S, rev);
-  else if (ks <= 8) lattice_pass<8, 2>(lm, out, T, S, rev);
-  else if (ks <= 16) lattice_pass<16, 1>(lm, out, T, S, rev);
-  else lattice_pass<32, 1>(lm, out, T, S, rev);
+  return ks <= 2 ? 1 : (ks <= 4 ? 2 : 4);
+}
+template <int W>
+__device__ void lattice_dispatch(const float* lm, float* out, int T, int S, bool rev, float* xch, int bar_id) {
+  const int ks = (S + 32 * W - 1) / (32 * W);
+  if (ks <= 1) lattice_pass<1, 8, W>(lm, out, T, S, rev, xch, bar_id);
+  else if (ks <= 2) lattice_pass<2, 8, W>(lm, out, T, S, rev, xch, bar_id);
+  else if (ks <= 4) lattice_pass<4, 4, W>(lm, out, T, S, rev, xch, bar_id);
+  else lattice_pass<8, 2, W>(lm, out, T, S, rev, xch, bar_id);        // S <= kCtcMaxStates = 1024 = 4 warps x 32 lanes x 8
 }
 
-__global__ void __launch_bounds__(64) ctc_lattice_kernel(Lines ln, CtcArgs a) {
+__global__ void __launch_bounds__(64 * kLatWarps) ctc_lattice_kernel(Lines ln, CtcArgs a) {
+  __shared__ float xch_s[2][2 * kLatWarps];      // [direction][parity x warp]
   const int b = ln.order[blockIdx.x];
   const int T = ln.T[b], L = ln.L[b];
   const int S = a.raw ? L : 2 * L + 1;
   const float* lm = a.lmatch + ln.lat_off[b];
-  if ((threadIdx.x >> 5) == 0) lattice_dispatch(lm, a.lr + ln.lat_off[b], T, S, false);
-  else lattice_dispatch(lm, a.rl + ln.lat_off[b], T, S, true);
+  const int W = lattice_width(S);
+  const int warp = threadIdx.x >> 5;
+  if (warp >= 2 * W) return;                     // (the named barriers below only count the 32 W threads of a direction)
+  const bool rev = warp >= W;
+  float* out = (rev ? a.rl : a.lr) + ln.lat_off[b];
+  float* xch = xch_s[rev ? 1 : 0];
+  const int bar_id = rev ? 2 : 1;
+  if (W == 1) lattice_dispatch<1>(lm, out, T, S, rev, xch, bar_id);
+  else if (W == 2) lattice_dispatch<2>(lm, out, T, S, rev, xch, bar_id);
+  else lattice_dispatch<4>(lm, out, T, S, rev, xch, bar_id);
 }
 
 // ------------------------------------------------------------------------------------------------ stats
@@ -299,7 +324,7 @@ int ctc_align(cudaStream_t st, const Lines& ln, const CtcArgs& a) {
   const size_t sm_a = (size_t)(TC * ncp + 2 * TC) * sizeof(float) + (size_t)kCtcMaxStates * sizeof(int);
   const size_t sm_d = (size_t)(8 * a.nc + kCtcMaxStates) * sizeof(double) + (size_t)kCtcMaxStates * sizeof(int);
   ctc_lmatch_kernel<<<ln.ntiles, TILE_THREADS, sm_a, st>>>(ln, a);
-  ctc_lattice_kernel<<<ln.B, 64, 0, st>>>(ln, a);
+  ctc_lattice_kernel<<<ln.B, 64 * kLatWarps, 0, st>>>(ln, a);
   ctc_max_kernel<<<dim3(ln.B, kStatSlices), 256, 0, st>>>(ln, a);
   ctc_sum_kernel<<<dim3(ln.B, kStatSlices), 256, 0, st>>>(ln, a);
   ctc_posterior_kernel<<<ln.ntiles, TILE_THREADS, sm_d, st>>>(ln, a);
