@@ -63,3 +63,26 @@ def test_batched_recurrence_is_tcgen05_with_tma_and_tmem():
     assert "REDG.E.ADD.STRONG.GPU" in s       # red.release.gpu on the step counters
     assert "HMMA" not in s.replace("UTCHMMA", "")
     assert "FENCE.VIEW.ASYNC" in s            # proxy fences between generic-proxy writes and TMA / tensor-core reads
+
+
+def test_cluster_resident_recurrence_keeps_weights_in_tensor_memory():
+    # lstm_tcx.cu: tcgen05.mma with the A operand (the weight slice) in TMEM, written there once by tcgen05.st; h and the partial
+    # sums travel between the CTAs of the cluster by bulk copies shared::cta -> shared::cluster; no cluster-scope acquire (which
+    # compiles to an L1 invalidate) inside the step loops
+    s = sass("lstm_tcx.o")
+    assert "sm_100a" in s
+    assert s.count("UTCHMMA tmem") >= 8 and "STTM" in s      # A-from-TMEM MMAs (the first operand after D is tmem[..]) + tcgen05.st
+    assert "UBLKCP.S.S" in s                                  # cp.async.bulk shared -> peer shared memory
+    assert "LDTM" in s and "UTCBAR" in s
+    assert "UTMALDG" in s                                     # shared-memory form of the weight slice (A/B runs) is TMA-loaded
+    assert s.count("CCTL.IVALL") <= 12                        # only the cluster barriers at group boundaries invalidate L1
+    assert "HMMA" not in s.replace("UTCHMMA", "")
+
+
+def test_persistent_gemm_is_tma_fed_tcgen05():
+    s = sass("gemm_x.o")
+    assert "sm_100a" in s
+    assert s.count("UTCHMMA") >= 12           # 3 MMAs (hi*hi + hi*lo + lo*hi) x 4 k slices per 64-wide k block
+    assert s.count("UTMALDG") >= 4            # A hi / lo and B hi / lo tiles by TMA
+    assert "LDTM" in s and "UTCBAR" in s
+    assert "HMMA" not in s.replace("UTCHMMA", "")
