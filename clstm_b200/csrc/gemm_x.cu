@@ -11,7 +11,7 @@
 // element, against operands that are re-read once per output tile.
 // Kernel: 6 warps.  Warp 0 = TMA producer (4 loads per 64-wide k block: A hi/lo [128 x 64], B hi/lo [BN x 64], ring of 2-3
 // stages, mbarrier expect_tx), warp 1 = MMA issuer (12 tcgen05.mma per k block from one elected thread, tcgen05.commit frees the
-// stage), warps 2-5 = epilogue (tcgen05.ld 32 columns at a time, transposed through a padded shared-memory tile, scale, bias, full 128-byte lines to global memory).  Two TMEM
+// stage), warps 2-5 = epilogue (tcgen05.ld 32 columns at a time, scale, bias from a shared-memory tile, 128-bit row stores).  Two TMEM
 // accumulators of 256 columns: the epilogue of tile i overlaps the main loop of tile i+1.  Persistent: CTA b walks tiles
 // b, b + grid, ... (n fastest, so neighbouring CTAs share the A tile in L2).  Split-K (derivative products) writes fp32 partials
 // to a workspace that gemm_tc.cu's fixed-order reduce-scatter kernel folds into the derivative blocks.
@@ -123,7 +123,7 @@ gemm_x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
   const unsigned smem0 = (smem_u32(gx_smem) + 1023u) & ~1023u;
   const unsigned a_bytes = GX_BM * 128u, b_bytes = (unsigned)g.BN * 128u;
   const unsigned stage_bytes = 2u * a_bytes + 2u * b_bytes;
-  const unsigned epi0 = smem0 + (unsigned)g.stages * stage_bytes;      // 4 epilogue tiles of 32 x 33 floats
+  const unsigned epi0 = smem0 + (unsigned)g.stages * stage_bytes;      // per-warp bias tiles of the epilogue (4 x 1 KB)
   const unsigned bar0 = smem_u32(&bars[0]);
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (GX_MAXST + s); };
@@ -215,32 +215,46 @@ gemm_x_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ 
       tfph ^= 1u << acc;
       tc_fence_after();
       const unsigned taddr = tmem_d + ((unsigned)(32 * lq) << 16) + 256u * (unsigned)acc;
-      // 32 rows x 32 columns per round: every thread holds one ROW of the chunk (TMEM lane = row); the chunk goes through a padded
-      // shared-memory tile so that one store instruction writes 32 consecutive floats of ONE row (a full 128-byte line) instead
-      // of 16 bytes of 32 different rows
-      const unsigned st_base = epi0 + (unsigned)(warp - 2) * (32u * 33u * 4u);
-      const int row_w0 = mt * GX_BM + 32 * lq;                 // first row of this warp
+      // every thread owns one ROW of the tile (TMEM lane = row) and writes 32 consecutive floats of it per round as 128-bit
+      // stores.  The bias tile is staged per warp in shared memory first: bias loads between the stores (possible aliasing keeps
+      // the compiler from hoisting them) cost ~100 cycles each, 25 000 per tile -- the input projection ran 1.6x slower than on
+      // the 3xTF32 kernel until they went.  (A transposed epilogue -- full 128-byte lines per store -- measured 2x slower.)
+      const unsigned bias_s = epi0 + (unsigned)(warp - 2) * 1024u;
+      const bool has_bias = g.bias && !g.ws;
+      if (has_bias) {
+        __syncwarp();
+        for (int i = lane; i < g.BN; i += 32) {
+          const float bv = (col0 + i < g.N) ? g.bias[col0 + i] : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * i), "f"(bv) : "memory");
+        }
+        __syncwarp();
+      }
+      const int row = mt * GX_BM + 32 * lq + lane;
+      float* __restrict__ dst = g.ws ? g.ws + ((size_t)z * g.M + row) * g.N : g.C + (size_t)row * g.ldc;
+      const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
       for (int cb = 0; cb < g.BN; cb += 32) {
         float v[32];
         tmem_ld<32>(taddr + (unsigned)cb, v);
+        if (row < g.M) {
 #pragma unroll
-        for (int e = 0; e < 32; e++)
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(st_base + (unsigned)(lane * 33 + e) * 4u), "f"(v[e]) : "memory");
-        __syncwarp();
-        const int col = col0 + cb + lane;
-        const bool colok = (cb + lane < g.BN) && (col < g.N);
-        const float bv = (g.bias && !g.ws && colok) ? g.bias[col] : 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {
-          float x;
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(st_base + (unsigned)(r * 33 + lane) * 4u) : "memory");
-          const int rw = row_w0 + r;
-          if (colok && rw < g.M) {
-            float* drow = g.ws ? g.ws + ((size_t)z * g.M + rw) * g.N : g.C + (size_t)rw * g.ldc;
-            drow[col] = fmaf(x, g.out_scale, bv);
+          for (int q = 0; q < 8; q++) {
+            const int col = col0 + cb + 4 * q;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_bias && cb + 4 * q < g.BN)
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(bias_s + 4u * (cb + 4 * q)));
+            const float o0 = fmaf(v[4 * q], g.out_scale, bb.x), o1 = fmaf(v[4 * q + 1], g.out_scale, bb.y);
+            const float o2 = fmaf(v[4 * q + 2], g.out_scale, bb.z), o3 = fmaf(v[4 * q + 3], g.out_scale, bb.w);
+            if (cb + 4 * q < g.BN) {
+              if (vec && col + 3 < g.N) *reinterpret_cast<float4*>(dst + col) = make_float4(o0, o1, o2, o3);
+              else {
+                if (col < g.N) dst[col] = o0;
+                if (col + 1 < g.N) dst[col + 1] = o1;
+                if (col + 2 < g.N) dst[col + 2] = o2;
+                if (col + 3 < g.N) dst[col + 3] = o3;
+              }
+            }
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -278,7 +292,7 @@ int make_map_gx(CUtensorMap* m, const void* base, size_t rows, size_t kp, size_t
              ? 0 : 1;
 }
 constexpr size_t kGxSmemMax = 226 * 1024;   // dynamic part; the 227 KB limit of a CTA includes the kernel's static shared memory
-size_t gx_smem_bytes(int BN, int stages) { return (size_t)stages * (2 * GX_BM * 128 + 2 * (size_t)BN * 128) + 4 * 32 * 33 * 4 + 1024; }
+size_t gx_smem_bytes(int BN, int stages) { return (size_t)stages * (2 * GX_BM * 128 + 2 * (size_t)BN * 128) + 4 * 1024 + 1024; }
 }  // namespace
 
 struct GxPlan {
