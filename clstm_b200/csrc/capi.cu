@@ -135,7 +135,7 @@ struct clstm_b200_net {
   bool use_tc = true;           // dense products on tcgen05 (3xTF32); false: fp32 SIMT tiles (A/B testing)
   int gx_mode = 0;              // persistent TMA-fed GEMM (gemm_x.cu): 0 by size, 1 always, 2 never  (CLSTM_B200_GEMM=x / tc)
   GxPlan* gx[2] = {nullptr, nullptr};   // operand-plane scratch of the main / side stream
-  bool gx_small_k = false;      // also products with K < 128 (CLSTM_B200_GX_SMALLK=1, A/B runs)
+  bool gx_small_k = true;       // also products with K < 128 (CLSTM_B200_GX_SMALLK=0 keeps them on the 3xTF32 kernel, A/B runs)
   int lstm_mode = 0;            // recurrence: 0 auto (by size and batch), 1 always the lock-step tensor-core kernels, 2 never, 3 always the cluster-resident ones
 
   // ---- batch capacity and buffers.  The INPUT SET (x, metadata, tiles, their pinned staging, host geometry, Lines view)
@@ -589,8 +589,8 @@ int dense_nt(clstm_b200_net* n, int M, int N, int K, const float* A, long long l
     return gemm_f32(n->st, M, N, K, A, lda, 1, B, b_mn ? ldb : 1, b_mn ? 1 : ldb, C, ldc, bias, beta, nullptr, 0,
                     n->num_sms);
   }
-  // (K < 128: the product is bound by writing its output -- the input projection, K = 48 -- and the 3xTF32 kernel's 128-bit row
-  // stores are faster there: 1.97 against 3.13 ms at nhidden 400 x 256 lines)
+  // (products with a short reduction -- the input projection, K = 48 -- are bound by writing their output; with the bias tile
+  // staged in shared memory the TMA-fed kernel wins there too: 1.57 against 1.97 ms at nhidden 400 x 256 lines)
   if (!b_mn && beta == 0.f && (K >= 128 || n->gx_small_k) && want_gx(n, 0, 2.0 * M * N * K)) {
     const int r = gemm_x_nt(n->gx[0], n->st, M, N, K, A, lda, B, ldb, C, ldc, bias, scale_a, scale_b);
     if (r >= 0) return r;
@@ -1047,7 +1047,7 @@ int clstm_b200_create_ex(const clstm_b200_cfg_ex* cfg, clstm_b200_net** out) {
     n->use_tc = !(e && strcmp(e, "simt") == 0);
     n->gx_mode = (e && strcmp(e, "x") == 0) ? 1 : ((e && strcmp(e, "tc") == 0) ? 2 : 0);   // "x": always the TMA-fed GEMM, "tc": never
     const char* e2 = getenv("CLSTM_B200_GX_SMALLK");
-    n->gx_small_k = (e2 && atoi(e2) != 0) || n->gx_mode == 1;
+    n->gx_small_k = !(e2 && atoi(e2) == 0) || n->gx_mode == 1;
   }
   {
     const char* e = getenv("CLSTM_B200_LSTM");   // "tc": always the batched tensor-core recurrence; "simt": never
