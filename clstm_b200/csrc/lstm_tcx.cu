@@ -52,7 +52,7 @@ constexpr int kXThreads = 32 * (kXEW + 1);   // + the loader / MMA warp
 //  0  all-lane barrier waits, the MMA warp issues the bulk copies, MMAs of a step back to back after the last chunk   18.6 / 18.2
 //  1  epilogue waits by one lane per warp                                                                            19.9 / 34.3
 //  2  MMA-warp waits by one lane                                                                                     22.9 / 32.2
-//  4  bulk copies issued by the epilogue warps, one each, behind a named barrier                                     18.0 / 29.9 -> no gain
+//  4  bulk copies issued by the epilogue warps, one each, behind a named barrier (no longer buildable)               18.0 / 29.9 -> no gain
 //  8  MMAs issued chunk by chunk as the chunks arrive (uniform chunk order)                                          22.5 / --
 // 16  backward: output tiles innermost (consecutive MMAs to different accumulators)                                   -- / 21.5
 // 32  pull form: the CTAs signal "staged", every CTA fetches the peers' blocks with ld.shared::cluster               17.8 / 25.0
@@ -62,6 +62,7 @@ constexpr int kXThreads = 32 * (kXEW + 1);   // + the loader / MMA warp
 #define CB200_TCX_FLAGS 0
 #endif
 constexpr int kXFlags = CB200_TCX_FLAGS;
+static_assert((kXFlags & 4) == 0, "variant 4 sent a CTA's own block with a bulk copy (shared::cta -> shared::cluster must target another CTA): kept as a measurement, not buildable");
 constexpr int kXDbgStep = 64;                // step whose timeline CTA 0 records when a debug buffer is given
 constexpr int kXMaxCS = 15;                  // CTAs per cluster (KQ = 480: D + both A planes fill the 512 TMEM columns)
 constexpr float kXScaleH = 16.f, kXScaleR = 16.f, kXScaleD = 256.f;
@@ -319,7 +320,10 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
         if (s >= 1) {
           const unsigned b = (unsigned)(s - 1) & 1u;            // h_{s-1} sits in buffer (s-1)&1
           const unsigned hb0 = bar0 + 8u * (b * kXMaxCS);
-          if (!pull && (unsigned)lane < CS) mbar_expect_tx(hb0 + 8u * lane, 2048u);
+          if (!pull && (unsigned)lane < CS) {                   // (the own chunk is copied locally, see below: a plain arrival keeps its barrier in phase)
+            if ((unsigned)lane == c) mbar_arrive(hb0 + 8u * lane);
+            else mbar_expect_tx(hb0 + 8u * lane, 2048u);
+          }
           __syncwarp();
           const unsigned ph = (hph >> b) & 1u;
           if (pull) {                                           // the epilogue warps have fetched every block of h_{s-1}
@@ -405,7 +409,18 @@ lstm_tcx_fwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           mbar_wait_sel(stagebar, stph, w1);
           stph ^= 1;
           const unsigned sb = (unsigned)s & 1u;
-          if ((unsigned)lane < CS) bulk_copy_to_peer(crdst0 + sb * bbytes, stg0 + sb * 2048u, 2048u, crbar0 + sb * (8u * kXMaxCS));
+          // the own chunk: staging -> own B buffer with plain shared-memory copies (a bulk copy shared::cta -> shared::cluster must
+          // target ANOTHER CTA); ordered before this warp's MMAs of the next step by program order + the proxy fence
+#pragma unroll
+          for (int qq = 0; qq < 4; qq++) {
+            const unsigned o = 16u * (unsigned)(lane + 32 * qq);
+            unsigned x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(stg0 + sb * 2048u + o) : "memory");
+            sts_v4(b0 + sb * bbytes + c * 2048u + o, x0, x1, x2, x3);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if ((unsigned)lane < CS && (unsigned)lane != c) bulk_copy_to_peer(crdst0 + sb * bbytes, stg0 + sb * 2048u, 2048u, crbar0 + sb * (8u * kXMaxCS));
           __syncwarp();
           if (rec) dbg_stamp(dbg, 11);
         }
@@ -595,7 +610,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
   long long* const dbg = (p.dbg && blockIdx.x == 0) ? p.dbg + 32 : nullptr;
 
   if (tid == 0) {
-    mbar_init(pbar0, 1); mbar_init(pbar1, 1); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, (kXFlags & 1) ? kXEW : 32 * kXEW); mbar_init(stagebar, kXEW); mbar_init(readybar0, CS); mbar_init(readybar0 + 8u, CS);
+    mbar_init(pbar0, 2); mbar_init(pbar1, 2); mbar_init(accbar, 1); mbar_init(abar, 1); mbar_init(bbar, (kXFlags & 1) ? kXEW : 32 * kXEW); mbar_init(stagebar, kXEW); mbar_init(readybar0, CS); mbar_init(readybar0 + 8u, CS);
     mbar_init_fence();
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo);
   }
@@ -722,7 +737,11 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           mbar_wait_sel(stagebar, stph, w1);                    // the partial sums are staged: one bulk copy per owner CTA
           stph ^= 1;
           const unsigned sb = (unsigned)it & 1u;
-          if ((unsigned)lane < CS) bulk_copy_to_peer(crdst0 + sb * rbytes, stg0 + sb * rbytes + (unsigned)lane * 2048u, 2048u, crbar0 + sb * 8u);
+          // the block of my own slots stays in the staging buffer (the reduction reads it there: a bulk copy must target ANOTHER CTA);
+          // this arrival publishes it to the epilogue warps together with the remote blocks
+          if (lane == 0) mbar_arrive(sb ? pbar1 : pbar0);
+          if ((unsigned)lane < CS && (unsigned)lane != c)
+            bulk_copy_to_peer(crdst0 + sb * rbytes, stg0 + sb * rbytes + (unsigned)lane * 2048u, 2048u, crbar0 + sb * 8u);
           __syncwarp();
           if (rec) dbg_stamp(dbg, 11);
         }
@@ -798,7 +817,7 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
             pull_blocks(r0 + b * rbytes, stg0 + b * rbytes + c * 2048u, p.CS, tid);
             epi_bar_sync();
           } else {
-            if (tid == 0) mbar_expect_tx(pb, pbytes);
+            if (tid == 0) mbar_expect_tx(pb, pbytes - 2048u);   // (CS - 1 remote blocks; the own one is read from the staging buffer)
             mbar_wait_sel(pb, b ? pph1 : pph0, (kXFlags & 1) != 0);
             if (b) pph1 ^= 1; else pph0 ^= 1;
           }
@@ -806,9 +825,10 @@ lstm_tcx_bwd(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__
           if (real && fs < myT - 1) {
             float r = 0.f;
             const unsigned ra = r0 + b * rbytes + red_off;
+            const unsigned own = (kXFlags & 32) ? ra + c * 2048u : stg0 + b * rbytes + c * 2048u + red_off;
             for (unsigned sc = 0; sc < CS; sc++) {
               float x;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(ra + sc * 2048u) : "memory");
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(sc == c ? own : ra + sc * 2048u) : "memory");
               r += x;
             }
             dh += r;
