@@ -581,6 +581,7 @@ bool vec_ok(const float* p, long long ld) { return (ld % 4 == 0) && ((reinterpre
 // (measured crossover on B200: a few GFLOP per product; BASELINE config 2 stays on the on-the-fly 3xTF32 kernels).
 bool want_gx(const clstm_b200_net* n, int side, double flops) {
   if (!n->use_tc || !n->gx[side] || n->gx_mode == 2) return false;
+  if (n->cell != 0 && n->gx_mode != 1) return false;   // LIN / RELU cells: outputs are unbounded, the fp16 hi/lo planes saturate at 4096
   return n->gx_mode == 1 || flops >= 8e9;
 }
 int dense_nt(clstm_b200_net* n, int M, int N, int K, const float* A, long long lda, const float* B, long long ldb,
